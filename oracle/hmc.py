@@ -1,0 +1,152 @@
+"""Restatement of BlackJAX's Euclidean metric, velocity-Verlet integrator and HMC kernel.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  float32, batched over chains [C, D].
+
+Follows:
+* metric           blackjax/mcmc/metrics.py:221-346 (gaussian_euclidean), :701-729 (_format_covariance),
+                   blackjax/util.py:23-61 (linear_map), :66-91 (generate_gaussian_noise)
+* integrator       blackjax/mcmc/integrators.py:62-152 (generalized_two_stage_integrator),
+                   :175-245 (euclidean position/momentum updates), :321-369 (coefficient tables)
+* HMC transition   blackjax/mcmc/hmc.py:90-92 (init), :95-112 (flip_momentum), :153-176 (generate),
+                   :279-312 (kernel); trajectory.py:136-167 (static_integration), :730-750 (hmc_energy);
+                   proposal.py:45-48 (safe_energy_diff), :214-235 (static_binomial_sampling)
+"""
+from typing import NamedTuple
+
+import numpy as np
+
+from . import prng
+
+F = np.float32
+
+VELOCITY_VERLET = (0.5, 1.0, 0.5)                                   # integrators.py:321
+_b1 = 0.1931833275037836
+MCLACHLAN = (_b1, 0.5, 1 - 2 * _b1, 0.5, _b1)                        # integrators.py:335-340
+_b1y, _a1y = 0.11888010966548, 0.29619504261126
+YOSHIDA = (_b1y, _a1y, 0.5 - _b1y, 1 - 2 * _a1y, 0.5 - _b1y, _a1y, _b1y)  # integrators.py:351-357
+
+
+class Metric:
+    """gaussian_euclidean(inverse_mass_matrix): 1-D => diagonal, 2-D => dense."""
+
+    def __init__(self, inverse_mass_matrix):
+        imm = np.asarray(inverse_mass_matrix, F)
+        self.imm = imm
+        if imm.ndim == 1:
+            self.dense = False
+            # metrics.py:703-708: mass_matrix_sqrt = 1/sqrt(M^-1)
+            self.mass_sqrt = (F(1.0) / np.sqrt(imm)).astype(F)
+        elif imm.ndim == 2:
+            self.dense = True
+            # metrics.py:712-715: L = chol(M^-1) lower ; mass_matrix_sqrt = L^-T
+            L = np.linalg.cholesky(imm.astype(np.float64))
+            self.mass_sqrt = np.linalg.solve(L.T, np.eye(L.shape[0])).astype(F)
+        else:
+            raise ValueError(
+                "The mass matrix has the wrong number of dimensions:"
+                f" expected 1 or 2, got {imm.ndim}."
+            )
+
+    def velocity(self, p):
+        """linear_map(M^-1, p) (util.py:57-61)."""
+        if self.dense:
+            return (p @ self.imm.T).astype(F)
+        return (self.imm * p).astype(F)
+
+    def sample_momentum(self, keys, dim):
+        """metrics.py:260-261 -> util.py:89-91: p = mass_matrix_sqrt (.) normal(key,(D,))."""
+        z = prng.normal(keys, (dim,))
+        if self.dense:
+            return (z @ self.mass_sqrt.T).astype(F)
+        return (self.mass_sqrt * z).astype(F)
+
+    def kinetic_energy(self, p):
+        """metrics.py:263-270: 0.5 * dot(M^-1 p, p)."""
+        return (F(0.5) * np.sum(self.velocity(p) * p, axis=-1, dtype=F)).astype(F)
+
+    def is_turning(self, p_left, p_right, p_sum):
+        """metrics.py:272-304 generalised U-turn (<=, OR)."""
+        rho = p_sum - (p_right + p_left) / F(2.0)
+        tl = np.sum(self.velocity(p_left) * rho, axis=-1, dtype=F) <= 0
+        tr = np.sum(self.velocity(p_right) * rho, axis=-1, dtype=F) <= 0
+        return tl | tr
+
+
+def integrator_step(target, metric, q, p, g, eps, coefficients=VELOCITY_VERLET):
+    """One palindromic two-stage step; eps is f32 scalar or [C,1] (signed)."""
+    eps = np.asarray(eps, F)
+    logp = None
+    v = None
+    for i, coef in enumerate(coefficients[:-1]):
+        if i % 2 == 0:
+            p = (p + (eps * F(coef)) * g).astype(F)          # integrators.py:235-239
+            v = metric.velocity(p)                            # :242 grad of kinetic energy
+        else:
+            q = (q + (eps * F(coef)) * v).astype(F)          # :199-203
+            logp, g = target(q)                               # :204
+    p = (p + (eps * F(coefficients[-1])) * g).astype(F)      # :134-141 last call
+    return q, p, logp, g
+
+
+def static_integration(target, metric, q, p, logp, g, eps, num_steps, coefficients=VELOCITY_VERLET):
+    """trajectory.py:155-165 fori_loop of num_steps integrator steps."""
+    for _ in range(int(num_steps)):
+        q, p, logp, g = integrator_step(target, metric, q, p, g, eps, coefficients)
+    return q, p, logp, g
+
+
+class HMCState(NamedTuple):
+    position: np.ndarray
+    logdensity: np.ndarray
+    logdensity_grad: np.ndarray
+
+
+class HMCInfo(NamedTuple):
+    momentum: np.ndarray
+    acceptance_rate: np.ndarray
+    is_accepted: np.ndarray
+    is_divergent: np.ndarray
+    energy: np.ndarray
+    proposal: tuple
+    num_integration_steps: int
+
+
+def init(position, target):
+    logp, g = target(np.asarray(position, F))
+    return HMCState(np.asarray(position, F), logp, g)
+
+
+def safe_energy_diff(e0, e1):
+    with np.errstate(invalid="ignore"):
+        d = (e0 - e1).astype(F)
+    return np.where(np.isnan(d), F(-np.inf), d).astype(F)
+
+
+def hmc_kernel(keys, state, target, step_size, inverse_mass_matrix, num_integration_steps,
+               divergence_threshold=1000.0, coefficients=VELOCITY_VERLET):
+    """One HMC transition for every chain.  keys: uint32[C,2] (per-chain rng_key)."""
+    metric = inverse_mass_matrix if isinstance(inverse_mass_matrix, Metric) else Metric(inverse_mass_matrix)
+    q0, logp0, g0 = state
+    C, D = q0.shape
+    ks = prng.split(keys, 2)                                         # hmc.py:299
+    key_momentum, key_integrator = ks[:, 0], ks[:, 1]
+    p0 = metric.sample_momentum(key_momentum, D)                      # hmc.py:302
+    eps = np.asarray(step_size, F)
+    if eps.ndim == 1:
+        eps = eps[:, None]
+    q1, p1, logp1, g1 = static_integration(target, metric, q0, p0, logp0, g0, eps,
+                                           num_integration_steps, coefficients)
+    p1 = (F(-1.0) * p1).astype(F)                                    # flip_momentum hmc.py:158
+    e0 = (-logp0 + metric.kinetic_energy(p0)).astype(F)              # hmc.py:159
+    e1 = (-logp1 + metric.kinetic_energy(p1)).astype(F)              # hmc.py:160
+    delta = safe_energy_diff(e0, e1)                                 # hmc.py:161
+    is_div = (-delta) > F(divergence_threshold)                      # hmc.py:162
+    with np.errstate(over="ignore"):
+        p_acc = np.minimum(np.exp(delta).astype(F), F(1.0))          # proposal.py:225
+    u = prng.uniform(key_integrator)                                  # proposal.py:226 (same key)
+    acc = u < p_acc
+    a = acc[:, None]
+    new = HMCState(np.where(a, q1, q0).astype(F), np.where(acc, logp1, logp0).astype(F),
+                   np.where(a, g1, g0).astype(F))
+    info = HMCInfo(p0, p_acc, acc, is_div, e1, (q1, p1, logp1, g1), int(num_integration_steps))
+    return new, info

@@ -1,0 +1,132 @@
+"""Analytic ``value_and_grad`` of the named targets (float32, batched over chains).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference differentiates arbitrary
+JAX callables with ``jax.value_and_grad`` (blackjax/mcmc/hmc.py:91,
+integrators.py:189,204); without JAX the named models are differentiated by hand:
+
+* ``StdNormal`` / ``DiagGaussian``  tests/fixtures.py:60-78 ``std_normal_logdensity``
+* ``Funnel``                        tests/fixtures.py:81-98 ``neal_funnel_logdensity``
+* ``DenseGaussian``                 tests/mcmc/test_mclmc_lrd.py:68-90,
+                                    tests/adaptation/test_staged_adaptation.py:1029-1040
+* ``Banana``                        tests/mcmc/test_trajectory.py:79-80
+* ``NormLogpdf``                    tests/mcmc/test_trajectory.py:27 (jax.scipy.stats.norm.logpdf)
+
+Each target maps ``q: f32[C, D]`` to ``(logp: f32[C], grad: f32[C, D])``.
+"""
+import numpy as np
+
+F = np.float32
+
+
+class DiagGaussian:
+    """logp = -1/2 sum (x_i/s_i)^2 ; grad_i = -x_i / s_i^2   (scale scalar or [D])."""
+
+    kind = "diag_gaussian"
+
+    def __init__(self, scale=1.0, dim=None):
+        s = np.asarray(scale, np.float64)
+        if s.ndim == 0:
+            assert dim is not None
+            s = np.full((dim,), float(s))
+        self.scale = s.astype(F)
+        # same constant the device path receives: 1/s^2 rounded once to f32
+        self.inv_var = (1.0 / (s * s)).astype(F)
+        self.dim = self.scale.shape[0]
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        t = q * self.inv_var
+        logp = F(-0.5) * np.sum(q * t, axis=-1, dtype=F)
+        return logp.astype(F), (-t).astype(F)
+
+
+def StdNormal(dim):
+    return DiagGaussian(1.0, dim)
+
+
+class Funnel:
+    """Neal's funnel: y=x[0]~N(0,3^2), x[1:]~N(0,e^y).
+
+    logp = -1/2 (y/3)^2 - 1/2 e^{-y} sum v^2 - 1/2 n y
+    d/dy = -y/9 + 1/2 e^{-y} sum v^2 - n/2 ;  d/dv_i = -e^{-y} v_i
+    """
+
+    kind = "funnel"
+
+    def __init__(self, dim):
+        self.dim = dim
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        y = q[..., 0]
+        v = q[..., 1:]
+        n = F(self.dim - 1)
+        with np.errstate(over="ignore", invalid="ignore"):
+            ey = np.exp(-y).astype(F)
+            ss = np.sum(v * v, axis=-1, dtype=F)
+            t = y / F(3.0)
+            logp = F(-0.5) * (t * t) + (F(-0.5) * ey * ss - F(0.5) * n * y)
+            g = np.empty_like(q)
+            g[..., 0] = -y / F(9.0) + F(0.5) * ey * ss - F(0.5) * n
+            g[..., 1:] = -(ey[..., None] * v)
+        return logp.astype(F), g.astype(F)
+
+
+class DenseGaussian:
+    """logp = -1/2 x^T P x ; grad = -P x   (P symmetric precision, [D, D])."""
+
+    kind = "dense_gaussian"
+
+    def __init__(self, precision, const=0.0):
+        self.precision = np.asarray(precision, F)
+        self.dim = self.precision.shape[0]
+        self.const = F(const)
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        Pq = (q @ self.precision.T).astype(F)
+        logp = F(-0.5) * np.sum(q * Pq, axis=-1, dtype=F) + self.const
+        return logp.astype(F), (-Pq).astype(F)
+
+
+class Banana:
+    """logp = -(1-x0)^2 - 1.5 (x1 - x0^2)^2   (tests/mcmc/test_trajectory.py:79-80)."""
+
+    kind = "banana"
+    dim = 2
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        x0, x1 = q[..., 0], q[..., 1]
+        r = x1 - x0 * x0
+        logp = -((F(1.0) - x0) ** 2) - F(1.5) * r * r
+        g = np.stack([F(2.0) * (F(1.0) - x0) + F(6.0) * r * x0, F(-3.0) * r], axis=-1)
+        return logp.astype(F), g.astype(F)
+
+
+class NormLogpdf:
+    """sum_i norm.logpdf(x_i) = -1/2 x^2 - 1/2 log(2 pi) (normalised standard normal)."""
+
+    kind = "norm_logpdf"
+
+    def __init__(self, dim=1):
+        self.dim = dim
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        logp = np.sum(F(-0.5) * q * q - F(0.5 * np.log(2 * np.pi)), axis=-1, dtype=F)
+        return logp.astype(F), (-q).astype(F)
+
+
+def correlated_gaussian(dim, seed=0, lo=-1.0, hi=1.0):
+    """BASELINE config 2 target: Sigma = Q diag(logspace(lo,hi,dim)) Q^T, Q from QR of a
+    default_rng(seed) normal matrix (recipe of tests/mcmc/test_mclmc_lrd.py:68-90).
+    Returns (cov f32, precision f32), both symmetrised in float64 before the cast."""
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+    eigs = np.logspace(lo, hi, dim)
+    cov = (Q * eigs) @ Q.T
+    prec = (Q / eigs) @ Q.T
+    cov = 0.5 * (cov + cov.T)
+    prec = 0.5 * (prec + prec.T)
+    return cov.astype(F), prec.astype(F)

@@ -1,0 +1,262 @@
+"""Pins the CPU oracle against every known-answer test the reference's own suite holds for the
+HMC/NUTS path, plus the JAX PRNG known answers.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import adaptation, hmc, nuts, prng, targets
+
+F = np.float32
+
+
+# ---- JAX PRNG known answers (jax 0.10.0 defaults: threefry2x32, partitionable) -------------
+def test_prng_split_key0():
+    got = prng.split(prng.key(0))
+    assert got.tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+
+
+def test_prng_fold_in_equals_split_child():
+    k = prng.key(1234)
+    assert (prng.fold_in(k, 3) == prng.split(k, 5)[3]).all()
+
+
+def test_prng_normal_known_answers():
+    assert prng.normal(prng.key(42)) == F(-0.028304616)
+    assert abs(float(prng.normal(prng.key(0))) - 1.622642) < 2e-6
+
+
+def test_prng_uniform_range_and_bits():
+    u = prng.uniform(prng.key(7), (4096,))
+    assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
+    b = prng.random_bits(prng.key(7), (8, 4))
+    o0, o1 = prng.threefry2x32(0, 7, 0, np.arange(32, dtype=np.uint32))
+    assert (b.ravel() == (o0 ^ o1)).all()
+
+
+def test_erfinv_matches_scipy():
+    from scipy.special import erfinv
+    x = np.linspace(-0.999999, 0.999999, 20001).astype(F)
+    ref = erfinv(x.astype(np.float64))
+    got = prng.erfinv_f32(x).astype(np.float64)
+    assert np.max(np.abs(got - ref) / np.maximum(1e-3, np.abs(ref))) < 5e-6
+
+
+# ---- tests/mcmc/test_integrators.py:74-103 golden end state ---------------------------------
+COV6 = np.array(
+    [[5.9959664, 1.1494889, -1.0420643, -0.6328479, -0.20363973, 2.1600752],
+     [1.1494889, 1.3504763, -0.3601517, -0.98311526, 1.1569028, -1.4185406],
+     [-1.0420643, -0.3601517, 6.3011055, -2.0662997, -0.10126236, 1.2898219],
+     [-0.6328479, -0.98311526, -2.0662997, 4.82699, -2.575554, 2.5724294],
+     [-0.20363973, 1.1569028, -0.10126236, -2.575554, 3.35319, -2.9411654],
+     [2.1600752, -1.4185406, 1.2898219, 2.5724294, -2.9411654, 6.3740206]])
+Q6_INIT = np.array([[0.0, 1.0, 2.0, 3.0, 1.0, 1.0]], F)
+P6_INIT = np.array([[0.53288144, 0.25310317, 1.3788314, -0.13486017, -0.59082425, 1.2088736]], F)
+Q6_END = np.array([0.38887993, 0.85231394, 2.7879136, 3.0339851, 0.5856687, 1.9291426])
+P6_END = np.array([0.46576163, 0.23854092, 1.2518811, -0.35647452, -0.742138, 1.2552949])
+
+
+def test_velocity_verlet_mvn_golden():
+    t = targets.DenseGaussian(np.linalg.inv(COV6))
+    m = hmc.Metric(COV6.astype(F))
+    lp, g = t(Q6_INIT)
+    q1, p1, lp1, _ = hmc.static_integration(t, m, Q6_INIT, P6_INIT, lp, g, F(0.005), 16)
+    np.testing.assert_allclose(q1[0], Q6_END, atol=2e-6)
+    np.testing.assert_allclose(p1[0], P6_END, atol=2e-6)
+    e0 = -lp + m.kinetic_energy(P6_INIT)
+    e1 = -lp1 + m.kinetic_energy(p1)
+    assert abs(float(e0[0] - e1[0])) < 1e-4          # reference precision for velocity_verlet
+
+
+@pytest.mark.parametrize("coeffs", [hmc.VELOCITY_VERLET, hmc.MCLACHLAN, hmc.YOSHIDA])
+def test_integrators_analytic(coeffs):
+    # free fall: U = g*x, q(1)=0.5?  reference examples use harmonic oscillator & free fall
+    t = targets.StdNormal(1)                         # harmonic oscillator: logp = -x^2/2
+    m = hmc.Metric(np.ones(1, F))
+    q = np.zeros((1, 1), F)
+    p = np.ones((1, 1), F)
+    lp, g = t(q)
+    q1, p1, _, _ = hmc.static_integration(t, m, q, p, lp, g, F(0.01), 100, coeffs)
+    assert abs(float(q1[0, 0]) - np.sin(1.0)) < 1e-2
+    assert abs(float(p1[0, 0]) - np.cos(1.0)) < 1e-2
+
+
+# ---- tests/mcmc/test_metrics.py:124-142,158-179 momentum identities ---------------------------
+def test_momentum_identity_diag():
+    m = hmc.Metric(np.array([0.25], F))
+    p = m.sample_momentum(prng.key(0)[None], 1)
+    assert p[0, 0] == F(2.0) * prng.normal(prng.key(0))
+    assert m.kinetic_energy(p)[0] == F(0.5) * (F(0.25) * p[0, 0]) * p[0, 0]
+
+
+def test_momentum_identity_dense():
+    imm = np.array([[2 / 3, 0.5], [0.5, 3 / 4]], F)
+    m = hmc.Metric(imm)
+    L = np.linalg.cholesky(imm.astype(np.float64))
+    z = prng.normal(prng.key(0), (2,)).astype(np.float64)
+    expected = np.linalg.solve(L.T, z)               # L^-T z
+    p = m.sample_momentum(prng.key(0)[None], 2)
+    np.testing.assert_allclose(p[0], expected, rtol=2e-6)
+    np.testing.assert_allclose(m.kinetic_energy(p)[0], 0.5 * expected @ imm.astype(np.float64) @ expected, rtol=1e-5)
+
+
+def test_metric_wrong_ndim():
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        hmc.Metric(np.ones((2, 2, 2), F))
+
+
+# ---- tests/mcmc/test_uturn.py:13-43 ------------------------------------------------------------
+@pytest.mark.parametrize("idxs, expected", [((3, 2), False), ((3, 3), True), ((0, 0), False),
+                                            ((0, 1), True), ((1, 3), True)])
+def test_iterative_uturn_table(idxs, expected):
+    m = hmc.Metric(np.ones(1, F))
+    ck_p = np.array([1.0, 2.0, 3.0, -2.0], F)[:, None]
+    ck_s = np.array([2.0, 4.0, 4.0, -1.0], F)[:, None]
+    got = nuts.is_iterative_turning(m, ck_p, ck_s, idxs[0], idxs[1], np.array([3.0], F), np.array([1.0], F))
+    assert got == expected
+
+
+def test_leaf_idx_to_ckpt_idxs():
+    # termination.py:77-82 docstring examples: idx_max 6->2, 7->2, 13->2 ; num_subtrees 6->0, 7->3, 13->1
+    assert [nuts.leaf_idx_to_ckpt_idxs(n)[1] for n in (6, 7, 13)] == [2, 2, 2]
+    assert [nuts.leaf_idx_to_ckpt_idxs(n) for n in (6, 7, 13)] == [(3, 2), (0, 2), (2, 2)]
+
+
+# ---- tests/mcmc/test_trajectory.py:20-74 sub-tree divergence -----------------------------------
+@pytest.mark.parametrize("step_size, should_diverge", [(0.0001, False), (1000, True)])
+def test_subtree_divergence(step_size, should_diverge):
+    t = targets.NormLogpdf(1)
+    m = hmc.Metric(np.ones(1, F))
+    k = prng.key(0)[None]
+    q = np.ones((1, 1), F)
+    p = m.sample_momentum(k, 1)
+    lp, g = t(q)
+    h0 = -lp + m.kinetic_energy(p)
+    out = nuts.subtree(t, m, k, q, p, lp, g, np.array([1], np.int32), np.zeros((1, 10, 1), F),
+                       np.zeros((1, 10, 1), F), 100, F(step_size), h0, np.array([True]))
+    assert bool(out["is_div"][0]) is should_diverge
+
+
+# ---- tests/mcmc/test_trajectory.py:193-260 tree-doubling outcomes --------------------------------
+@pytest.mark.parametrize("step_size, diverge, turn, doublings",
+                         [(1e-10, False, False, 10), (1.0, False, True, 2), (1e5, True, True, 1)])
+def test_dynamic_expansion_outcomes(step_size, diverge, turn, doublings):
+    t = targets.StdNormal(1)
+    m = hmc.Metric(np.ones(1, F))
+    k = prng.key(0)[None]
+    p0 = m.sample_momentum(k, 1)
+    q0 = np.zeros((1, 1), F)
+    lp, g = t(q0)
+    _, info = nuts.nuts_kernel(None, (q0, lp, g), t, F(step_size), m, 10, momentum=p0, key_integrator=k)
+    assert bool(info.is_divergent[0]) == diverge
+    assert bool(info.is_turning[0]) == turn
+    assert int(info.num_trajectory_expansions[0]) == doublings
+
+
+# ---- tests/mcmc/test_trajectory.py:76-191 progressive == recursive ------------------------------
+def test_progressive_equals_recursive():
+    t = targets.Banana()
+    m = hmc.Metric(np.array([[1.0, 0.5], [0.5, 1.25]], F))
+    rng_key = prng.key(23133)
+    rs = np.random.default_rng(5)
+    for i in range(50):
+        sub = prng.fold_in(rng_key, i)
+        k6 = prng.split(sub, 6)
+        direction = int(rs.choice([-1, 1]))
+        depth = int(rs.integers(2, 5))
+        q = prng.normal(k6[4], (2,))[None]
+        p = prng.normal(k6[5], (2,))[None]
+        eps = F(abs(float(prng.normal(k6[3]))) * 0.1)
+        lp, g = t(q)
+        h0 = -lp + m.kinetic_energy(p)
+        out = nuts.subtree(t, m, k6[0][None], q, p, lp, g, np.array([direction], np.int32),
+                           np.zeros((1, depth, 2), F), np.zeros((1, depth, 2), F), 2 ** depth, eps, h0,
+                           np.array([True]))
+        _, prop1, tr1, div1, turn1 = nuts.recursive_subtree(t, m, k6[0], (q[0], p[0], lp[0], g[0]),
+                                                            direction, depth, eps, h0[0])
+        assert bool(out["is_div"][0]) == div1
+        assert bool(out["has_term"][0]) == turn1
+        left0, right0 = (out["first"], out["last"]) if direction > 0 else (out["last"], out["first"])
+        for a, b in zip(left0, tr1["left"]):
+            np.testing.assert_allclose(np.asarray(a)[0], b, rtol=1e-5, atol=1e-6)
+        for a, b in zip(right0, tr1["right"]):
+            np.testing.assert_allclose(np.asarray(a)[0], b, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out["p_sum"][0], tr1["p_sum"], rtol=1e-5, atol=1e-6)
+        assert int(out["n"][0]) == tr1["n"]
+        np.testing.assert_allclose(out["prop"]["weight"][0], prop1["weight"], rtol=1e-5)
+        np.testing.assert_allclose(out["prop"]["slpa"][0], prop1["slpa"], rtol=1e-5)
+
+
+# ---- tests/adaptation/test_adaptation.py:27-49 ----------------------------------------------------
+@pytest.mark.parametrize("num_steps, expected", [
+    (19, [(0, False)] * 19),
+    (100, [(0, False)] * 15 + [(1, False)] * 74 + [(1, True)] + [(0, False)] * 10),
+    (200, [(0, False)] * 75 + [(1, False)] * 24 + [(1, True)] + [(1, False)] * 49 + [(1, True)]
+     + [(0, False)] * 50)])
+def test_adaptation_schedule(num_steps, expected):
+    s = adaptation.build_schedule(num_steps)
+    assert len(s) == num_steps and s == expected
+
+
+def test_welford_recovers_covariance():
+    # tests/adaptation/test_mass_matrix.py:14-44 (rtol 1e-1)
+    rs = np.random.default_rng(0)
+    cov = np.array([[1.0, 0.3], [0.3, 2.0]])
+    x = rs.multivariate_normal([0, 0], cov, 5000).astype(F)
+    w = adaptation.welford_init(2, diagonal=False)
+    wd = adaptation.welford_init(2, diagonal=True)
+    for xi in x:
+        w = adaptation.welford_update(w, xi)
+        wd = adaptation.welford_update(wd, xi)
+    np.testing.assert_allclose(w.m2 / (w.n - 1), cov, rtol=1e-1, atol=5e-2)
+    np.testing.assert_allclose(wd.m2 / (wd.n - 1), np.diag(cov), rtol=1e-1)
+    # CGL merge of two halves equals the sequential estimate
+    a = adaptation.welford_init(2, True)
+    b = adaptation.welford_init(2, True)
+    for xi in x[:2000]:
+        a = adaptation.welford_update(a, xi)
+    for xi in x[2000:]:
+        b = adaptation.welford_update(b, xi)
+    ab = adaptation.cgl_merge(a, b)
+    np.testing.assert_allclose(ab.m2, wd.m2, rtol=1e-3)
+    np.testing.assert_allclose(ab.mean, wd.mean, atol=1e-4)
+
+
+def test_dual_averaging_mean_pool_step_counter():
+    # tests/adaptation/test_meta_builders_e2e.py:1443-1700 semantics: one update per warm-up step
+    s = adaptation.da_init(1.0)
+    s2 = adaptation.da_update(s, 0.5)
+    assert s2.step == 2 and s.step == 1
+    assert s2.log_step_size_avg == F(1.0) * s.log_step_size      # eta_1 = 1 -> pre-update iterate
+    assert abs(float(s.mu) - np.log(10.0)) < 1e-6
+
+
+# ---- statistical end-to-end (tests/mcmc/test_sampling.py:1055-1119,1174-1186), 10% tolerance -------
+def test_univariate_normal_hmc_and_nuts():
+    t = targets.DiagGaussian(2.0, 1)
+
+    class Shifted:
+        dim = 1
+
+        def __call__(self, q):
+            lp, g = t(q - F(1.0))
+            return lp, g
+
+    tgt = Shifted()
+    C = 64
+    key = prng.key(12)
+    q = np.ones((C, 1), F)
+    for name, kern, kw in (("hmc", hmc.hmc_kernel, dict(num_integration_steps=30, step_size=F(3.9))),
+                           ("nuts", nuts.nuts_kernel, dict(step_size=F(1.0)))):
+        st = hmc.init(q, tgt)
+        draws = []
+        keys = prng.split(key, 400)
+        for i in range(400):
+            ck = prng.split(keys[i], C)
+            if name == "hmc":
+                st, _ = kern(ck, st, tgt, kw["step_size"], np.ones(1, F), kw["num_integration_steps"])
+            else:
+                st, _ = kern(ck, st, tgt, kw["step_size"], np.ones(1, F))
+            if i >= 100:
+                draws.append(st.position[:, 0].copy())
+        d = np.concatenate(draws)
+        assert abs(d.mean() - 1.0) < 0.1, name
+        assert abs(d.var() - 4.0) < 0.4, name
