@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- leapfrog-steps/sec (all chains) of the B200-native HMC hot path, with the HBM
+roofline of the vectorised leapfrog kernel and the CPU baseline timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N>1)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: CPU oracle twin
+
+A "step" is one HMC transition (L leapfrogs) over every chain of the workload.  `value` counts
+executed leapfrogs (C * L per step) with the chain state resident in HBM; `e2e` is the same metric
+through the public API with HOST buffers (pinned host -> device copy of the step's positions and keys,
+hmc.init, one step, device -> host copy of the new positions and acceptance rates, all inside the
+timed region).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "leapfrog-steps/sec (all chains)"
+UNIT = "leapfrog-steps/s"
+
+WORKLOADS = {
+    # the 65k x 1024 leapfrog shape the north star's HBM target names (diagonal mass matrix).
+    # BASELINE configs[1] proper (dense mass matrix + correlated Gaussian) needs the batched-GEMM path
+    # that is not built yet; this workload is the same (chains x dims x L) with a diagonal metric.
+    "hmc_diag_gaussian_65536x1024_L50": dict(C=65536, D=1024, L=50, eps=0.1),
+    # BASELINE configs[0]: the reference's own CPU-runnable case
+    "hmc_iso_gaussian_1024x100_L10": dict(C=1024, D=100, L=10, eps=0.2),
+}
+DEFAULT_WORKLOAD = "hmc_diag_gaussian_65536x1024_L50"
+
+
+def target_scale(D):
+    import numpy as np
+    return np.ones(D) if D == 100 else np.logspace(-0.5, 0.5, D)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the restated oracle's C twin (the reference itself needs jax, which cannot be installed here)
+# ------------------------------------------------------------------------------------------------------
+def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
+    """leapfrog-steps/s of the C/pthreads oracle twin on all host cores, on a bounded chain sample of the
+    same workload (same D, L, eps, target)."""
+    import numpy as np
+    from oracle import cport, prng
+    D, L, eps = wl["D"], wl["L"], wl["eps"]
+    s = target_scale(D)
+    inv_var = (1.0 / s ** 2).astype(np.float32)
+    imm = (s ** 2).astype(np.float32)
+    cores = cport.num_threads()
+
+    def run(Cs, n):
+        rs = np.random.default_rng(0)
+        q = (rs.standard_normal((Cs, D)) * s).astype(np.float32)
+        g = (-q * inv_var).astype(np.float32)
+        logp = (-0.5 * (q * q * inv_var).sum(1)).astype(np.float32)
+        keys = prng.split(prng.key(0), Cs)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cport.hmc_step(0, inv_var, imm, keys, q, logp, g, eps, L)
+        return time.perf_counter() - t0
+
+    probe_c = max(cores * 4, 64)
+    run(probe_c, 1)
+    t = run(probe_c, 1)
+    per_chain = t / probe_c
+    n_steps = max(1, steps)
+    Cs = int(min(wl["C"], max(probe_c, budget_s / max(per_chain * (n_steps + warmup), 1e-9))))
+    Cs = max(cores, (Cs // cores) * cores)
+    if warmup:
+        run(Cs, warmup)
+    t = run(Cs, n_steps)
+    rate = Cs * L * n_steps / t
+    return rate, cores, f"{Cs} of {wl['C']} chains x {D} dims x L={L}, {n_steps} transition(s), {t:.2f} s", t / n_steps * 1e3
+
+
+def run_reference(args, wl_name, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, cores, sample, ms = cpu_hmc_rate(wl, budget_s=20.0, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl_name, "note": "restated oracle (C/pthreads twin of oracle/hmc.py), not JAX: "
+                   "blackjax needs jax 0.10.0 which cannot be installed in this image"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, args.workload, wl)
+        return
+
+    import numpy as np
+    import torch
+
+    import blackjax_b200 as bj
+    from blackjax_b200 import _engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: blackjax_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    C, D, L, eps = wl["C"], wl["D"], wl["L"], wl["eps"]
+    K, W = args.steps, args.warmup
+    s = target_scale(D)
+    tgt = bj.targets.DiagGaussian(s)
+    imm = torch.from_numpy((s ** 2).astype(np.float32)).to(dev)
+    scale_t = torch.from_numpy(s.astype(np.float32)).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # chains are sharded over GPUs: this rank owns global chains [rank*C, (rank+1)*C)  (weak scaling)
+    q0 = torch.randn(C, D, device=dev, generator=gen) * scale_t
+    kernel = bj.hmc.build_kernel(inplace=True)
+    state = bj.hmc.init(q0.clone(), tgt)
+    step_keys = bj.random.split(bj.random.key(0, dev), W + K + 1)
+
+    def chain_keys(t):  # split(step_key, C_global)[rank shard]  -- one launch of k_prng_split
+        return bj.random.split(step_keys[t], C * world)[rank * C:(rank + 1) * C]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(W):
+        state, info = kernel(chain_keys(t), state, tgt, eps, imm, L)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(W, W + K):
+        state, info = kernel(chain_keys(t), state, tgt, eps, imm, L)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = 2 * K  # k_prng_split + k_hmc_transition per step
+    acc_mean = float(info.acceptance_rate.mean())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the vectorised single-step leapfrog kernel: the HBM roofline the north star names -------------
+    eng = _engine.get_engine(state.position, tgt)
+    p = eng.sample_momentum(chain_keys(W + K))
+    q1, lp1, g1 = state.position.clone(), state.logdensity.clone(), state.logdensity_grad.clone()
+    for _ in range(3):
+        eng.leapfrog_(q1, p, lp1, g1, eps, 1)
+    torch.cuda.synchronize()
+    n1 = 40
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n1):
+        eng.leapfrog_(q1, p, lp1, g1, eps, 1)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_1step = f0.elapsed_time(f1) / n1
+    del q1, p, g1
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------------------
+    q_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    q_host.copy_(state.position)
+    out_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    acc_host = torch.empty(C, dtype=torch.float32).pin_memory()
+    key_host = torch.empty(C, 2, dtype=torch.int32).pin_memory()
+    key_host.copy_(chain_keys(0).view(torch.int32))
+    q_dev = torch.empty(C, D, device=dev)
+    k_dev = torch.empty(C, 2, dtype=torch.int32, device=dev)
+    kernel_e2e = bj.hmc.build_kernel(inplace=True)
+    K_e2e = max(1, min(K, 10))
+
+    def e2e_step():
+        q_dev.copy_(q_host, non_blocking=True)
+        k_dev.copy_(key_host, non_blocking=True)
+        st = bj.hmc.init(q_dev, tgt)
+        st, inf = kernel_e2e(k_dev.view(torch.uint32), st, tgt, eps, imm, L)
+        out_host.copy_(st.position, non_blocking=True)
+        acc_host.copy_(inf.acceptance_rate, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    g0, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(K_e2e):
+        e2e_step()
+    g1e.record()
+    barrier()
+    ms_e2e = g0.elapsed_time(g1e)
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------
+    times = torch.tensor([ms_total, ms_e2e, ms_1step], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_1step = [float(x) for x in times]
+    value = n_gpus * C * L * K / (ms_total * 1e-3)
+    e2e_value = n_gpus * C * L * K_e2e / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        bytes_1step = 24.0 * C * D
+        achieved = bytes_1step / (ms_1step * 1e-3) / 1e9
+        ms_step = ms_total / K
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "chains_per_gpu": C, "dims": D, "leapfrogs_per_step": L,
+                       "step_size": eps, "mass_matrix": "diag", "parallelism": f"chains sharded x{n_gpus}, no data-path collective",
+                       "l2": "inputs larger than L2 (q,g = 2 x %.0f MB per GPU)" % (C * D * 4 / 1e6),
+                       "mean_acceptance": acc_mean},
+            "roofline": {"bound": "hbm", "kernel": "k_leapfrog (1 step/launch, 24*D B per chain)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "avg_launch_ms": ms_1step, "launches_timed": n1},
+            "fused_transition": {"kernel": "k_hmc_transition (L leapfrogs/launch, row resident in registers)",
+                                 "hbm_bytes_per_launch": 16.0 * C * D + 20.0 * C,
+                                 "equivalent_GBps_at_24D_per_leapfrog": 24.0 * C * D * L / (ms_step * 1e-3) / 1e9,
+                                 "speedup_vs_1step_launches": (ms_1step * L) / ms_step},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + C * 8,
+                    "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": K_e2e, "ms_per_step": ms_e2e / K_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and n_gpus == 1:
+            rate, cores, sample, _ = cpu_hmc_rate(wl, budget_s=12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "note": "restated oracle (C/pthreads), not JAX"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+"""Stan-style window adaptation (step-size dual averaging + diagonal Welford mass matrix) for the
+batched HMC/NUTS kernels.
+
+Mirrors ``blackjax.window_adaptation`` (blackjax/adaptation/window_adaptation.py:296-444 ->
+staged_adaptation.py:111-307,731-754,864-874,906-966).  Two modes:
+
+* ``shared=False`` (default): every chain adapts its own (step_size, inverse mass matrix) -- what a
+  BlackJAX user gets from ``jax.vmap(warmup.run)``.  Device-resident per-chain dual averaging and
+  Welford accumulators (libbjx ``bjx_da_*`` / ``bjx_welford_*``); no communication.
+* ``shared=True``: ONE step size and inverse mass matrix for all chains on all GPUs -- the
+  reference's multi-chain path (staged_adaptation.py:906-966): dual averaging is fed
+  ``mean(acceptance_rate)`` (one update per warm-up step, :153-171) and the mass matrix comes from the
+  chain-pooled Chan-Golub-LeVeque merge (metric_buffers.py:334-420).  Each GPU reduces its chains to a
+  ``(sum accept, n, mean[D], M2[D])`` block (``bjx_pooled_stats``); the blocks are exchanged with ONE
+  all-gather per warm-up step and merged identically on every rank.
+"""
+import math
+from typing import NamedTuple
+
+import torch
+
+from .. import random as bjx_random
+from .._lib import check, lib, ptr
+from ..base import AdaptationAlgorithm, AdaptationResults
+
+
+def build_schedule(num_steps, initial_buffer_size=75, final_buffer_size=50, first_window_size=25):
+    """blackjax/adaptation/staged_adaptation.py:315-405: list of (stage, is_middle_window_end)."""
+    schedule = []
+    if num_steps < 20:
+        schedule += [(0, False)] * num_steps
+    else:
+        if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
+            initial_buffer_size = int(0.15 * num_steps)
+            final_buffer_size = int(0.1 * num_steps)
+            first_window_size = num_steps - initial_buffer_size - final_buffer_size
+        schedule += [(0, False)] * initial_buffer_size
+        final_buffer_start = num_steps - final_buffer_size
+        next_window_size = first_window_size
+        next_window_start = initial_buffer_size
+        while next_window_start < final_buffer_start:
+            current_start, current_size = next_window_start, next_window_size
+            if 3 * current_size <= final_buffer_start - current_start:
+                next_window_size = 2 * current_size
+            else:
+                current_size = final_buffer_start - current_start
+            next_window_start = current_start + current_size
+            schedule += [(1, False)] * (next_window_start - 1 - current_start)
+            schedule.append((1, True))
+        schedule += [(0, False)] * (num_steps - final_buffer_start)
+    return schedule
+
+
+# ---- host-side float32 dual averaging for the shared-epsilon mode (one scalar state) -----------------
+class _DA(NamedTuple):
+    log_step: float
+    log_step_avg: float
+    step: int
+    avg_error: float
+    mu: float
+
+
+def _f32(x):
+    return torch.tensor(x, dtype=torch.float32).item()
+
+
+def _da_init(eps):
+    return _DA(_f32(math.log(_f32(eps))), 0.0, 1, 0.0, _f32(math.log(_f32(10.0 * _f32(eps)))))
+
+
+def _da_update(s, acceptance_rate, target, t0=10, gamma=0.05, kappa=0.75):
+    """optimizers/dual_averaging.py:101-123 in float32 (torch CPU scalars; O(1) host work)."""
+    f = lambda v: torch.tensor(v, dtype=torch.float32)
+    log_step, avg, step, avg_error, mu = (f(s.log_step), f(s.log_step_avg), s.step, f(s.avg_error), f(s.mu))
+    gradient = f(target) - f(acceptance_rate)
+    reg_step = f(float(step + t0))
+    eta_t = torch.pow(f(float(step)), f(-kappa))
+    avg_error = (f(1.0) - (f(1.0) / reg_step)) * avg_error + gradient / reg_step
+    log_x = mu - (torch.sqrt(f(float(step))) / f(gamma)) * avg_error
+    log_x_avg = eta_t * log_step + (f(1.0) - eta_t) * avg
+    return _DA(log_x.item(), log_x_avg.item(), step + 1, avg_error.item(), s.mu)
+
+
+def cgl_merge_blocks(blocks):
+    """Chan-Golub-LeVeque merge of per-GPU blocks [G, 2+2D] -> (sum_accept, n, mean[D], M2[D])
+    (metric_buffers.py:334-393), sequential in rank order so every rank computes identical bits."""
+    D = (blocks.shape[1] - 2) // 2
+    acc = blocks[0, 0].clone()
+    n = blocks[0, 1].clone()
+    mean = blocks[0, 2:2 + D].clone()
+    m2 = blocks[0, 2 + D:].clone()
+    for gidx in range(1, blocks.shape[0]):
+        nb = blocks[gidx, 1]
+        mb = blocks[gidx, 2:2 + D]
+        m2b = blocks[gidx, 2 + D:]
+        n_ab = n + nb
+        delta = mb - mean
+        mean = mean + delta * (nb / n_ab)
+        m2 = m2 + m2b + delta * delta * (n * nb / n_ab)
+        n = n_ab
+        acc = acc + blocks[gidx, 0]
+    return acc, n, mean, m2
+
+
+def _allgather_stats(block, group):
+    """ONE all-gather of the per-GPU summary block (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return block[None]
+    world = dist.get_world_size(group)
+    flat = block.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view((world,) + tuple(block.shape))
+
+
+def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = True,
+                      initial_step_size: float = 1.0, target_acceptance_rate: float = 0.80, shared: bool = False,
+                      process_group=None, **extra_parameters):
+    """blackjax/adaptation/window_adaptation.py:296-444.  ``algorithm`` is ``blackjax_b200.hmc`` or
+    ``blackjax_b200.nuts``; ``extra_parameters`` go to the kernel (``num_integration_steps`` /
+    ``max_num_doublings``).  Returns an :class:`AdaptationAlgorithm` with ``run(rng_key, position, num_steps)``."""
+    if not is_mass_matrix_diagonal:
+        raise NotImplementedError("dense window adaptation (welford_dense) is not built yet (SURVEY.md section 8a a21)")
+    mcmc_kernel = algorithm.build_kernel()
+
+    def run(rng_key, position, num_steps: int = 1000):
+        from .._engine import get_engine
+        position = position.contiguous()
+        C, D = position.shape
+        dev = position.device
+        state = algorithm.init(position, logdensity_fn)
+        eng = get_engine(position, logdensity_fn, max_tree_depth=extra_parameters.get("max_num_doublings", 10))
+        schedule = build_schedule(num_steps)
+        history = []
+        if shared:
+            # keys: split(rng_key, num_steps); per step split(step_key, C_global) and take this rank's slice
+            import torch.distributed as dist
+            world, rank = 1, 0
+            if dist.is_available() and dist.is_initialized():
+                world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+            step_keys = bjx_random.split(rng_key.to(dev), num_steps)
+            da = _da_init(initial_step_size)
+            eps = _f32(initial_step_size)
+            imm = torch.ones(D, dtype=torch.float32, device=dev)
+            w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+            stats = torch.empty(2 + 2 * D, dtype=torch.float32, device=dev)
+            for t, (stage, window_end) in enumerate(schedule):
+                ck = bjx_random.split(step_keys[t], C * world)[rank * C:(rank + 1) * C]
+                state, info = mcmc_kernel(ck, state, logdensity_fn, eps, imm, **extra_parameters)
+                check(lib().bjx_pooled_stats(eng.h, ptr(state.position), ptr(info.acceptance_rate), ptr(stats)), eng.h)
+                blocks = _allgather_stats(stats, process_group)
+                acc_sum, n_b, mean_b, m2_b = cgl_merge_blocks(blocks)
+                if stage == 1:  # CGL-merge this step's pooled block into the window accumulator
+                    if w_n == 0.0:
+                        w_n, w_mean, w_m2 = float(n_b), mean_b, m2_b
+                    else:
+                        nb = float(n_b)
+                        n_ab = w_n + nb
+                        delta = mean_b - w_mean
+                        w_mean = w_mean + delta * (nb / n_ab)
+                        w_m2 = w_m2 + m2_b + delta * delta * (w_n * nb / n_ab)
+                        w_n = n_ab
+                da = _da_update(da, (acc_sum / n_b).item(), target_acceptance_rate)
+                eps = _f32(math.exp(da.log_step))
+                if window_end:  # mass_matrix.py:335-357 + staged_adaptation.py:233-249
+                    cov = w_m2 / (w_n - 1.0)
+                    imm = ((w_n / (w_n + 5.0)) * cov + (5.0 / (w_n + 5.0)) * 1e-3).to(torch.float32).contiguous()
+                    w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+                    da = _da_init(_f32(math.exp(da.log_step_avg)))
+                    eps = _f32(math.exp(da.log_step))
+                history.append(eps)
+            step_size = _f32(math.exp(da.log_step_avg))
+            parameters = {"step_size": step_size, "inverse_mass_matrix": imm, **extra_parameters}
+            return AdaptationResults(state, parameters), history
+        # ---- per-chain adaptation, all state on the device ------------------------------------------------
+        if rng_key.ndim == 1:
+            chain_keys = bjx_random.split(rng_key.to(dev), C)
+        else:
+            chain_keys = rng_key
+        keys = bjx_random.split(chain_keys, num_steps)                      # [C, T, 2]   (util.py:203 per chain)
+        keys = keys.transpose(0, 1).contiguous()                            # [T, C, 2]
+        da_state = torch.empty(C, 5, dtype=torch.float32, device=dev)
+        eps = torch.full((C,), float(initial_step_size), dtype=torch.float32, device=dev)
+        check(lib().bjx_da_init(eng.h, ptr(da_state), ptr(eps), ptr(eps)), eng.h)
+        imm = torch.ones(C, D, dtype=torch.float32, device=dev)
+        w_mean = torch.zeros(C, D, dtype=torch.float32, device=dev)
+        w_m2 = torch.zeros(C, D, dtype=torch.float32, device=dev)
+        w_n = 0
+        for t, (stage, window_end) in enumerate(schedule):
+            state, info = mcmc_kernel(keys[t], state, logdensity_fn, eps, imm, **extra_parameters)
+            if stage == 1:
+                w_n += 1
+                check(lib().bjx_welford_update(eng.h, ptr(state.position), ptr(w_mean), ptr(w_m2), w_n), eng.h)
+            check(lib().bjx_da_update(eng.h, ptr(da_state), ptr(info.acceptance_rate), float(target_acceptance_rate),
+                                      ptr(eps)), eng.h)
+            if window_end:
+                new_imm = torch.empty_like(imm)
+                check(lib().bjx_welford_final(eng.h, ptr(w_mean), ptr(w_m2), w_n, ptr(new_imm)), eng.h)
+                imm = new_imm   # new tensor identity => the kernel re-derives mass_matrix_sqrt
+                w_n = 0
+                check(lib().bjx_da_reset(eng.h, ptr(da_state), ptr(eps)), eng.h)
+        step_size = torch.empty(C, dtype=torch.float32, device=dev)
+        check(lib().bjx_da_final(eng.h, ptr(da_state), ptr(step_size)), eng.h)
+        parameters = {"step_size": step_size, "inverse_mass_matrix": imm, **extra_parameters}
+        return AdaptationResults(state, parameters), history
+
+    return AdaptationAlgorithm(run)

@@ -1,0 +1,593 @@
+// C ABI of libbjx.so (include/bjx.h): handle management, argument checking, kernel dispatch and
+// the host-driven NUTS doubling loop.  No torch types, no exceptions across the boundary.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bjx.h"
+#include "bjx_internal.h"
+#include "bjx_launch.cuh"
+
+using namespace bjx;
+
+struct bjx_handle_s {
+  bjx_config cfg;
+  cudaStream_t stream;
+  int sc;              // SizeClass
+  int metric_kind;     // -1 until set
+  bool metric_small_dense;
+  const float* imm;    // caller-owned
+  float* msqrt;        // owned
+  size_t msqrt_elems;
+  // NUTS workspace (owned, lazily allocated)
+  NutsWs ws;
+  void* ws_block;
+  int ws_depth;
+  int* h_flag;         // pinned
+  int64_t last_leaf_launches, last_depth;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(bjx_handle_t h, int code, const std::string& msg) {
+  g_err = msg;
+  if (h) h->err = msg;
+  return code;
+}
+static int cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) {
+  return fail(h, (int)e, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define BJX_CUDA(call)                                            \
+  do {                                                            \
+    cudaError_t e_ = (call);                                      \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);        \
+  } while (0)
+#define BJX_CHECK_LAUNCH(where)                                   \
+  do {                                                            \
+    cudaError_t e_ = cudaGetLastError();                          \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, where);        \
+  } while (0)
+
+static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
+  if (t.dim != dim) return fail(h, BJX_E_INVALID, "target.dim != config.dim");
+  switch (t.kind) {
+    case BJX_TARGET_DIAG_GAUSSIAN:
+      if (!t.inv_var) return fail(h, BJX_E_INVALID, "DIAG_GAUSSIAN target needs inv_var");
+      break;
+    case BJX_TARGET_FUNNEL:
+      if (dim < 2) return fail(h, BJX_E_INVALID, "FUNNEL target needs dim >= 2");
+      break;
+    case BJX_TARGET_DENSE_GAUSSIAN:
+      if (!t.precision) return fail(h, BJX_E_INVALID, "DENSE_GAUSSIAN target needs precision");
+      if (dim > 128) return fail(h, BJX_E_UNSUPPORTED, "DENSE_GAUSSIAN target with dim > 128 needs the batched-GEMM path (not built yet)");
+      break;
+    case BJX_TARGET_BANANA:
+      if (dim != 2) return fail(h, BJX_E_INVALID, "BANANA target needs dim == 2");
+      break;
+    default:
+      return fail(h, BJX_E_INVALID, "unknown target kind");
+  }
+  return 0;
+}
+
+extern "C" int bjx_version(void) { return BJX_VERSION; }
+
+extern "C" const char* bjx_last_error(bjx_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
+  bjx_handle_t h = nullptr;
+  if (!cfg || !out) return fail(nullptr, BJX_E_INVALID, "null argument");
+  if (cfg->n_chains <= 0 || cfg->dim <= 0) return fail(nullptr, BJX_E_INVALID, "n_chains and dim must be positive");
+  if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 30) return fail(nullptr, BJX_E_INVALID, "max_tree_depth must be in [1, 30]");
+  const int sc = size_class_for(cfg->dim);
+  if (sc == SC_NONE)
+    return fail(nullptr, BJX_E_UNSUPPORTED, "dim must be <= 1024 with dim % 4 == 0, or <= 128 otherwise (warp-per-chain kernels)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount (no CUDA device: there is no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, BJX_E_INVALID, "bad device ordinal");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  h = new bjx_handle_s();
+  h->cfg = *cfg;
+  if (!(h->cfg.divergence_threshold > 0.f)) h->cfg.divergence_threshold = 1000.f;
+  h->stream = (cudaStream_t)cfg->stream;
+  h->sc = sc;
+  h->metric_kind = -1;
+  h->metric_small_dense = false;
+  h->imm = nullptr;
+  h->msqrt = nullptr;
+  h->msqrt_elems = 0;
+  memset(&h->ws, 0, sizeof(h->ws));
+  h->ws_block = nullptr;
+  h->ws_depth = 0;
+  h->h_flag = nullptr;
+  h->last_leaf_launches = 0;
+  h->last_depth = 0;
+  int rc = validate_target(h, cfg->target, cfg->dim);
+  if (rc) {
+    g_err = h->err;
+    delete h;
+    return rc;
+  }
+  e = cudaMallocHost((void**)&h->h_flag, 64 * sizeof(int));
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(nullptr, e, "cudaMallocHost");
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int bjx_destroy(bjx_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  if (h->msqrt) cudaFree(h->msqrt);
+  if (h->ws_block) cudaFree(h->ws_block);
+  if (h->h_flag) cudaFreeHost(h->h_flag);
+  delete h;
+  return 0;
+}
+
+extern "C" int bjx_set_target(bjx_handle_t h, const bjx_target_desc* t) {
+  if (!h || !t) return fail(h, BJX_E_INVALID, "null argument");
+  int rc = validate_target(h, *t, h->cfg.dim);
+  if (rc) return rc;
+  h->cfg.target = *t;
+  return 0;
+}
+
+extern "C" int bjx_synchronize(bjx_handle_t h) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  BJX_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
+  if (!h || !imm) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.dim, C = h->cfg.n_chains;
+  size_t elems;
+  if (kind == BJX_METRIC_DIAG) elems = D;
+  else if (kind == BJX_METRIC_DIAG_PER_CHAIN) elems = (size_t)C * D;
+  else if (kind == BJX_METRIC_DENSE) {
+    if (D > 128 || !size_class_is_small(h->sc))
+      return fail(h, BJX_E_UNSUPPORTED, "dense metric with dim > 128 needs the batched-GEMM path (not built yet)");
+    elems = (size_t)D * D;
+  } else
+    return fail(h, BJX_E_INVALID, "The mass matrix has the wrong number of dimensions: expected 1 or 2");  // metrics.py:724-728
+  if (elems > h->msqrt_elems) {
+    if (h->msqrt) BJX_CUDA(cudaFree(h->msqrt));
+    h->msqrt = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->msqrt, elems * sizeof(float)));
+    h->msqrt_elems = elems;
+  }
+  if (kind == BJX_METRIC_DENSE) {
+    // metrics.py:712-715: L = chol(M^-1) (lower); mass_matrix_sqrt = solve_triangular(L, I, lower, trans) = L^-T
+    std::vector<float> a((size_t)D * D);
+    BJX_CUDA(cudaMemcpyAsync(a.data(), imm, a.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    BJX_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> L((size_t)D * D, 0.0), Li((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double s = a[(size_t)i * D + j];
+        for (int k = 0; k < j; ++k) s -= L[(size_t)i * D + k] * L[(size_t)j * D + k];
+        if (i == j) {
+          if (!(s > 0.0)) return fail(h, BJX_E_INVALID, "inverse mass matrix is not positive definite");
+          L[(size_t)i * D + i] = sqrt(s);
+        } else
+          L[(size_t)i * D + j] = s / L[(size_t)j * D + j];
+      }
+    for (int c = 0; c < D; ++c) {  // Li = L^-1 by forward substitution, column c
+      for (int i = c; i < D; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) s -= L[(size_t)i * D + k] * Li[(size_t)k * D + c];
+        Li[(size_t)i * D + c] = s / L[(size_t)i * D + i];
+      }
+    }
+    std::vector<float> m((size_t)D * D);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) m[(size_t)i * D + j] = (float)Li[(size_t)j * D + i];  // (L^-1)^T
+    BJX_CUDA(cudaMemcpyAsync(h->msqrt, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    BJX_CUDA(cudaStreamSynchronize(h->stream));
+  } else {
+    launch_diag_mass_sqrt(imm, (long long)elems, h->msqrt, h->stream);
+    BJX_CHECK_LAUNCH("k_diag_mass_sqrt");
+  }
+  h->metric_kind = kind;
+  h->metric_small_dense = (kind == BJX_METRIC_DENSE);
+  h->imm = imm;
+  return 0;
+}
+
+extern "C" int bjx_get_mass_matrix_sqrt(bjx_handle_t h, const float** out) {
+  if (!h || !out) return fail(h, BJX_E_INVALID, "null argument");
+  if (h->metric_kind < 0) return fail(h, BJX_E_STATE, "metric not set");
+  *out = h->msqrt;
+  return 0;
+}
+
+static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
+  Params P;
+  P.C = h->cfg.n_chains;
+  P.D = h->cfg.dim;
+  P.inv_var = h->cfg.target.inv_var;
+  P.mean = h->cfg.target.mean;
+  P.prec = h->cfg.target.precision;
+  P.logp_offset = h->cfg.target.logp_offset;
+  P.imm = h->imm;
+  P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
+  P.msqrt = h->msqrt;
+  P.eps = eps;
+  P.eps_dev = eps_dev;
+  P.div_thr = h->cfg.divergence_threshold;
+  return P;
+}
+
+static int dispatch(bjx_handle_t h, int kernel_id, bool target_dependent, LaunchArgs& a) {
+  a.stream = h->stream;
+  const bool dm = h->metric_small_dense;
+  int rc;
+  const int tk = target_dependent ? h->cfg.target.kind : (int)BJX_TARGET_FUNNEL;
+  switch (tk) {
+    case BJX_TARGET_DIAG_GAUSSIAN: rc = Launcher<TK_DIAG>::launch(kernel_id, h->sc, dm, a); break;
+    case BJX_TARGET_FUNNEL: rc = Launcher<TK_FUNNEL>::launch(kernel_id, h->sc, dm, a); break;
+    case BJX_TARGET_DENSE_GAUSSIAN: rc = Launcher<TK_DENSE>::launch(kernel_id, h->sc, dm, a); break;
+    case BJX_TARGET_BANANA: rc = Launcher<TK_BANANA>::launch(kernel_id, h->sc, dm, a); break;
+    default: rc = -2;
+  }
+  if (rc) return fail(h, BJX_E_UNSUPPORTED, "kernel variant not built for this (target, dim, metric) combination");
+  BJX_CHECK_LAUNCH("kernel launch");
+  return 0;
+}
+
+static int check_ready(bjx_handle_t h, bool need_metric, const void* const* ptrs, int n) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  if (need_metric && h->metric_kind < 0) return fail(h, BJX_E_STATE, "metric not set: call bjx_set_metric first");
+  for (int i = 0; i < n; ++i) {
+    if (!ptrs[i]) return fail(h, BJX_E_INVALID, "null array argument");
+    if (size_class_is_vec(h->sc) && ((uintptr_t)ptrs[i] & 15u)) return fail(h, BJX_E_INVALID, "state arrays must be 16-byte aligned");
+  }
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  return 0;
+}
+
+extern "C" int bjx_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
+  const void* ptrs[] = {q, grad_out};
+  int rc = check_ready(h, false, ptrs, 2);
+  if (rc) return rc;
+  if (!logp_out) return fail(h, BJX_E_INVALID, "null array argument");
+  LaunchArgs a{};
+  a.P = make_params(h, 0.f, nullptr);
+  a.q_in = q;
+  a.logp_out = logp_out;
+  a.g_out = grad_out;
+  // k_init_state never reads the metric: route through the non-dense-metric variant unless only dm is built
+  return dispatch(h, K_INIT, true, a);
+}
+
+extern "C" int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out) {
+  const void* ptrs[] = {p_out};
+  int rc = check_ready(h, true, ptrs, 1);
+  if (rc) return rc;
+  if (!keys) return fail(h, BJX_E_INVALID, "null keys");
+  LaunchArgs a{};
+  a.P = make_params(h, 0.f, nullptr);
+  a.keys = keys;
+  a.p_io = p_out;
+  return dispatch(h, K_MOMENTUM, false, a);
+}
+
+extern "C" int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* grad, float step_size,
+                            const float* step_size_dev, int32_t n_steps) {
+  const void* ptrs[] = {q, p, grad};
+  int rc = check_ready(h, true, ptrs, 3);
+  if (rc) return rc;
+  if (!logp || n_steps < 0) return fail(h, BJX_E_INVALID, "bad argument");
+  LaunchArgs a{};
+  a.P = make_params(h, step_size, step_size_dev);
+  a.q_out = q;
+  a.p_io = p;
+  a.logp_out = logp;
+  a.g_out = grad;
+  a.n = n_steps;
+  return dispatch(h, K_LEAPFROG, true, a);
+}
+
+extern "C" int bjx_energy(bjx_handle_t h, const float* p, const float* logp, float* energy_out) {
+  const void* ptrs[] = {p};
+  int rc = check_ready(h, true, ptrs, 1);
+  if (rc) return rc;
+  if (!logp || !energy_out) return fail(h, BJX_E_INVALID, "null array argument");
+  LaunchArgs a{};
+  a.P = make_params(h, 0.f, nullptr);
+  a.p_io = const_cast<float*>(p);
+  a.logp_in = logp;
+  a.e_out = energy_out;
+  return dispatch(h, K_ENERGY, false, a);
+}
+
+extern "C" int bjx_is_turning(bjx_handle_t h, const float* pl, const float* pr, const float* ps, uint8_t* out) {
+  const void* ptrs[] = {pl, pr, ps};
+  int rc = check_ready(h, true, ptrs, 3);
+  if (rc) return rc;
+  if (!out) return fail(h, BJX_E_INVALID, "null array argument");
+  LaunchArgs a{};
+  a.P = make_params(h, 0.f, nullptr);
+  a.pl = pl;
+  a.pr = pr;
+  a.ps = ps;
+  a.out_u8 = out;
+  return dispatch(h, K_TURNING, false, a);
+}
+
+static InfoPtrs make_info(const bjx_info* info) {
+  InfoPtrs ip{};
+  if (info) {
+    ip.acceptance_rate = info->acceptance_rate;
+    ip.is_accepted = info->is_accepted;
+    ip.is_divergent = info->is_divergent;
+    ip.is_turning = info->is_turning;
+    ip.energy = info->energy;
+    ip.num_integration_steps = info->num_integration_steps;
+    ip.num_trajectory_expansions = info->num_trajectory_expansions;
+    ip.momentum = info->momentum;
+    ip.proposal_position = info->proposal_position;
+    ip.proposal_momentum = info->proposal_momentum;
+  }
+  return ip;
+}
+
+extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                            const float* grad_in, float* q_out, float* logp_out, float* grad_out, float step_size,
+                            const float* step_size_dev, int32_t L, const bjx_info* info) {
+  const void* ptrs[] = {q_in, grad_in, q_out, grad_out};
+  int rc = check_ready(h, true, ptrs, 4);
+  if (rc) return rc;
+  if (!keys || !logp_in || !logp_out || L < 0) return fail(h, BJX_E_INVALID, "bad argument");
+  if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
+    return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  LaunchArgs a{};
+  a.P = make_params(h, step_size, step_size_dev);
+  a.keys = keys;
+  a.q_in = q_in;
+  a.logp_in = logp_in;
+  a.g_in = grad_in;
+  a.q_out = q_out;
+  a.logp_out = logp_out;
+  a.g_out = grad_out;
+  a.n = L;
+  a.info = make_info(info);
+  return dispatch(h, K_HMC, true, a);
+}
+
+// ---- NUTS workspace -------------------------------------------------------------------------------------
+static int ensure_ws(bjx_handle_t h) {
+  const int depth = h->cfg.max_tree_depth;
+  if (h->ws_block && h->ws_depth == depth) return 0;
+  if (h->ws_block) {
+    BJX_CUDA(cudaFree(h->ws_block));
+    h->ws_block = nullptr;
+  }
+  const size_t C = h->cfg.n_chains, D = h->cfg.dim;
+  const size_t row = ((C * D * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t key = ((C * 2 * sizeof(uint32_t)) + 255) & ~(size_t)255;
+  const size_t ckpt = ((C * depth * D * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t n_counters = 4096;
+  const size_t total = 10 * row + 2 * ckpt + 13 * vec + 7 * vec + 3 * key + n_counters * sizeof(int) + 256;
+  BJX_CUDA(cudaMalloc(&h->ws_block, total));
+  BJX_CUDA(cudaMemsetAsync(h->ws_block, 0, total, h->stream));
+  char* p = (char*)h->ws_block;
+  auto takef = [&](size_t bytes) { float* r = (float*)p; p += bytes; return r; };
+  NutsWs& w = h->ws;
+  w.left_q = takef(row); w.left_p = takef(row); w.left_g = takef(row);
+  w.right_q = takef(row); w.right_p = takef(row); w.right_g = takef(row);
+  w.psum = takef(row); w.sub_psum = takef(row); w.sub_prop_q = takef(row); w.sub_prop_g = takef(row);
+  w.ckpt_p = takef(ckpt); w.ckpt_sum = takef(ckpt);
+  w.left_logp = takef(vec); w.right_logp = takef(vec); w.h0 = takef(vec);
+  w.prop_energy = takef(vec); w.prop_weight = takef(vec); w.prop_slpa = takef(vec);
+  w.sub_logp = takef(vec); w.sub_energy = takef(vec); w.sub_weight = takef(vec); w.sub_slpa = takef(vec);
+  w.n_states = (int*)takef(vec); w.sub_n = (int*)takef(vec); w.step = (int*)takef(vec);
+  w.is_div = (uint8_t*)takef(vec); w.is_turn = (uint8_t*)takef(vec); w.sub_div = (uint8_t*)takef(vec);
+  w.sub_term = (uint8_t*)takef(vec); w.run = (uint8_t*)takef(vec); w.active = (uint8_t*)takef(vec);
+  w.dir = (int8_t*)takef(vec);
+  w.key_int = (uint32_t*)takef(key); w.traj_key = (uint32_t*)takef(key); w.prop_key = (uint32_t*)takef(key);
+  w.counters = (int*)p;
+  w.max_depth = depth;
+  h->ws_depth = depth;
+  return 0;
+}
+
+static inline int popcount32(unsigned x) { return __builtin_popcount(x); }
+
+extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                             const float* grad_in, float* q_out, float* logp_out, float* grad_out, float step_size,
+                             const float* step_size_dev, int32_t max_num_doublings, const bjx_info* info,
+                             const float* momentum_override, const uint32_t* key_integrator_override) {
+  const void* ptrs[] = {q_in, grad_in, q_out, grad_out};
+  int rc = check_ready(h, true, ptrs, 4);
+  if (rc) return rc;
+  if (!logp_in || !logp_out) return fail(h, BJX_E_INVALID, "null array argument");
+  if ((momentum_override == nullptr) != (key_integrator_override == nullptr))
+    return fail(h, BJX_E_INVALID, "momentum_override and key_integrator_override go together");
+  if (!keys && !key_integrator_override) return fail(h, BJX_E_INVALID, "null keys");
+  if (max_num_doublings < 0 || max_num_doublings > h->cfg.max_tree_depth)
+    return fail(h, BJX_E_INVALID, "max_num_doublings exceeds the handle's max_tree_depth");
+  if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
+    return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  rc = ensure_ws(h);
+  if (rc) return rc;
+  const int C = h->cfg.n_chains;
+  const size_t n_counters = 4096;
+  BJX_CUDA(cudaMemsetAsync(h->ws.counters, 0, n_counters * sizeof(int), h->stream));
+
+  LaunchArgs a{};
+  a.P = make_params(h, step_size, step_size_dev);
+  a.ws = h->ws;
+  a.keys = keys;
+  a.q_in = q_in; a.logp_in = logp_in; a.g_in = grad_in;
+  a.q_out = q_out; a.logp_out = logp_out; a.g_out = grad_out;
+  a.mom_override = momentum_override;
+  a.keyint_override = key_integrator_override;
+  a.mom_out = info ? info->momentum : nullptr;
+  a.n = max_num_doublings;
+  rc = dispatch(h, K_NUTS_INIT, false, a);
+  if (rc) return rc;
+
+  // counters[d] = number of chains that run doubling d (written by init for d=0, by end(d-1) for d>0);
+  // counters[64 + k] = periodic within-depth "still active" counts.
+  int extra = 64;
+  int64_t leaves = 0;
+  int depth_reached = 0;
+  for (int d = 0; d < max_num_doublings; ++d) {
+    if (d > 0) {  // did any chain start doubling d?
+      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      BJX_CUDA(cudaStreamSynchronize(h->stream));
+      if (h->h_flag[0] == 0) break;
+    }
+    depth_reached = d + 1;
+    const int n_leaves = 1 << d;
+    for (int i = 0; i < n_leaves; ++i) {
+      // termination.py:75-84 checkpoint index range of leaf i
+      const int idx_max = popcount32((unsigned)i >> 1);
+      const int num_subtrees = popcount32((~(unsigned)i & ((unsigned)i + 1u)) - 1u);
+      const int idx_min = idx_max - num_subtrees + 1;
+      const bool probe = (n_leaves >= 64) && ((i & 31) == 31) && (i + 1 < n_leaves) && (extra < (int)n_counters);
+      a.i = i; a.idx_min = idx_min; a.idx_max = idx_max;
+      a.counter = probe ? h->ws.counters + extra : nullptr;
+      rc = dispatch(h, K_NUTS_LEAF, true, a);
+      if (rc) return rc;
+      ++leaves;
+      if (probe) {  // every 32 leaves of a deep sub-tree: stop launching once every chain has terminated
+        BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + extra, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        BJX_CUDA(cudaStreamSynchronize(h->stream));
+        ++extra;
+        if (h->h_flag[0] == 0) break;
+      }
+    }
+    a.n = max_num_doublings;
+    a.counter = h->ws.counters + d + 1;
+    rc = dispatch(h, K_NUTS_END, false, a);
+    if (rc) return rc;
+  }
+  k_nuts_finish<<<(C + 255) / 256, 256, 0, h->stream>>>(C, h->ws, make_info(info));
+  BJX_CHECK_LAUNCH("k_nuts_finish");
+  if (info) {
+    const size_t bytes = (size_t)C * h->cfg.dim * sizeof(float);
+    if (info->left_position) BJX_CUDA(cudaMemcpyAsync(info->left_position, h->ws.left_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (info->left_momentum) BJX_CUDA(cudaMemcpyAsync(info->left_momentum, h->ws.left_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (info->right_position) BJX_CUDA(cudaMemcpyAsync(info->right_position, h->ws.right_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (info->right_momentum) BJX_CUDA(cudaMemcpyAsync(info->right_momentum, h->ws.right_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->last_leaf_launches = leaves;
+  h->last_depth = depth_reached;
+  return 0;
+}
+
+extern "C" int bjx_nuts_last_stats(bjx_handle_t h, int64_t* leaf_launches, int64_t* depth_reached) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  if (leaf_launches) *leaf_launches = h->last_leaf_launches;
+  if (depth_reached) *depth_reached = h->last_depth;
+  return 0;
+}
+
+// ---- PRNG ----------------------------------------------------------------------------------------------
+// h may be NULL: the call then runs on the current device's legacy default stream.
+#define BJX_PRNG_PROLOGUE()                                                        \
+  if (!keys || !out || n_keys < 0) return fail(h, BJX_E_INVALID, "bad argument");  \
+  if (h) BJX_CUDA(cudaSetDevice(h->cfg.device));                                   \
+  cudaStream_t pstream = h ? h->stream : (cudaStream_t)0;
+
+extern "C" int bjx_prng_split(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out) {
+  BJX_PRNG_PROLOGUE();
+  if (num < 0) return fail(h, BJX_E_INVALID, "bad argument");
+  launch_prng_split(keys, n_keys, num, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_split");
+  return 0;
+}
+extern "C" int bjx_prng_fold_in(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, uint32_t data, uint32_t* out) {
+  BJX_PRNG_PROLOGUE();
+  launch_prng_fold_in(keys, n_keys, data, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_fold_in");
+  return 0;
+}
+extern "C" int bjx_prng_random_bits(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, uint32_t* out) {
+  BJX_PRNG_PROLOGUE();
+  if (per_key < 0 || per_key > 0xFFFFFFFFll) return fail(h, BJX_E_INVALID, "bad per_key");
+  launch_prng_draw(0, keys, n_keys, per_key, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_draw");
+  return 0;
+}
+extern "C" int bjx_prng_uniform(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out) {
+  BJX_PRNG_PROLOGUE();
+  if (per_key < 0 || per_key > 0xFFFFFFFFll) return fail(h, BJX_E_INVALID, "bad per_key");
+  launch_prng_draw(1, keys, n_keys, per_key, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_draw");
+  return 0;
+}
+extern "C" int bjx_prng_normal(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out) {
+  BJX_PRNG_PROLOGUE();
+  if (per_key < 0 || per_key > 0xFFFFFFFFll) return fail(h, BJX_E_INVALID, "bad per_key");
+  launch_prng_draw(2, keys, n_keys, per_key, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_draw");
+  return 0;
+}
+
+// ---- window adaptation ------------------------------------------------------------------------------------
+extern "C" int bjx_da_init(bjx_handle_t h, float* st, const float* eps0, float* eps_out) {
+  if (!h || !st || !eps0) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_da(0, h->cfg.n_chains, st, eps0, 0.f, eps_out, h->stream);
+  BJX_CHECK_LAUNCH("k_da_init");
+  return 0;
+}
+extern "C" int bjx_da_update(bjx_handle_t h, float* st, const float* acc, float target, float* eps_out) {
+  if (!h || !st || !acc) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_da(1, h->cfg.n_chains, st, acc, target, eps_out, h->stream);
+  BJX_CHECK_LAUNCH("k_da_update");
+  return 0;
+}
+extern "C" int bjx_da_reset(bjx_handle_t h, float* st, float* eps_out) {
+  if (!h || !st) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_da(2, h->cfg.n_chains, st, nullptr, 0.f, eps_out, h->stream);
+  BJX_CHECK_LAUNCH("k_da_reset");
+  return 0;
+}
+extern "C" int bjx_da_final(bjx_handle_t h, const float* st, float* eps_out) {
+  if (!h || !st || !eps_out) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_da(3, h->cfg.n_chains, const_cast<float*>(st), nullptr, 0.f, eps_out, h->stream);
+  BJX_CHECK_LAUNCH("k_da_final");
+  return 0;
+}
+extern "C" int bjx_welford_update(bjx_handle_t h, const float* q, float* mean, float* m2, int32_t new_count) {
+  if (!h || !q || !mean || !m2 || new_count < 1) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_welford_update((long long)h->cfg.n_chains * h->cfg.dim, q, mean, m2, new_count, h->stream);
+  BJX_CHECK_LAUNCH("k_welford_update");
+  return 0;
+}
+extern "C" int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t count, float* imm_out) {
+  if (!h || !mean || !m2 || !imm_out || count < 2) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_welford_final((long long)h->cfg.n_chains * h->cfg.dim, mean, m2, count, imm_out, h->stream);
+  BJX_CHECK_LAUNCH("k_welford_final");
+  return 0;
+}
+extern "C" int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acc, float* out) {
+  if (!h || !q || !acc || !out) return fail(h, BJX_E_INVALID, "null argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_pooled_stats(h->cfg.n_chains, h->cfg.dim, q, acc, out, h->stream);
+  BJX_CHECK_LAUNCH("k_pooled_stats");
+  return 0;
+}

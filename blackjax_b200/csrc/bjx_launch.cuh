@@ -1,0 +1,124 @@
+// Template dispatch: (target kind, size class, dense-small metric) -> kernel instantiation.
+// Each target kind is instantiated in its own translation unit (bjx_inst_*.cu) so the build
+// parallelises; bjx_api.cu only sees the declaration of Launcher<TK>::launch.
+#pragma once
+#include "bjx_kernels.cuh"
+
+namespace bjx {
+
+enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_NONE };
+enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_LEAF, K_NUTS_END };
+
+struct LaunchArgs {
+  Params P;
+  NutsWs ws;
+  InfoPtrs info;
+  const uint32_t* keys;
+  const float *q_in, *logp_in, *g_in;
+  float *q_out, *logp_out, *g_out;
+  float* p_io;
+  int n;  // n_steps | L | max_doublings
+  int i, idx_min, idx_max;
+  int* counter;
+  const float* mom_override;
+  const uint32_t* keyint_override;
+  float* mom_out;
+  const float *pl, *pr, *ps;
+  uint8_t* out_u8;
+  float* e_out;
+  cudaStream_t stream;
+};
+
+inline SizeClass size_class_for(int D) {
+  if (D <= 0) return SC_NONE;
+  if (D % 4 == 0 && D <= 1024) return D <= 128 ? SC_V1 : D <= 256 ? SC_V2 : D <= 512 ? SC_V4 : SC_V8;
+  if (D <= 32) return SC_S1;
+  if (D <= 128) return SC_S4;
+  return SC_NONE;
+}
+inline bool size_class_is_small(int sc) { return sc == SC_V1 || sc == SC_S1 || sc == SC_S4; }
+inline bool size_class_is_vec(int sc) { return sc <= SC_V8; }
+
+template <int TK>
+struct Launcher {
+  // returns 0, or -2 when the combination is not built
+  static int launch(int kernel_id, int sc, bool dm, const LaunchArgs& a);
+};
+
+#ifdef BJX_INSTANTIATE_TK
+template <class R, int TK, bool DM>
+static int launch_one(int kernel_id, const LaunchArgs& a) {
+  const dim3 grid((a.P.C + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
+  const size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
+  cudaStream_t st = a.stream;
+  switch (kernel_id) {
+    case K_INIT:
+      k_init_state<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.q_in, a.logp_out, a.g_out);
+      return 0;
+    case K_LEAPFROG:
+      k_leapfrog<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
+      return 0;
+    case K_HMC:
+      k_hmc_transition<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                              a.logp_out, a.g_out, a.n, a.info);
+      return 0;
+    case K_NUTS_LEAF:
+      k_nuts_leaf<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.i, a.idx_min, a.idx_max, a.counter);
+      return 0;
+    default:
+      break;
+  }
+  if constexpr (TK == TK_FUNNEL) {  // target-independent kernels are built once, under the funnel launcher
+    switch (kernel_id) {
+      case K_MOMENTUM:
+        k_sample_momentum<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.keys, a.p_io);
+        return 0;
+      case K_ENERGY:
+        k_energy<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.p_io, a.logp_in, a.e_out);
+        return 0;
+      case K_TURNING:
+        k_is_turning<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.pl, a.pr, a.ps, a.out_u8);
+        return 0;
+      case K_NUTS_INIT:
+        k_nuts_init<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                           a.logp_out, a.g_out, a.mom_override, a.keyint_override,
+                                                           a.mom_out, a.n);
+        return 0;
+      case K_NUTS_END:
+        k_nuts_end<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.n, a.counter);
+        return 0;
+      default:
+        break;
+    }
+  }
+  return -2;
+}
+
+template <int TK>
+int Launcher<TK>::launch(int kernel_id, int sc, bool dm, const LaunchArgs& a) {
+  constexpr bool small_only = (TK == TK_DENSE || TK == TK_BANANA);
+  switch (sc) {
+    case SC_V1:
+      return dm ? launch_one<Row<4, true>, TK, true>(kernel_id, a) : launch_one<Row<4, true>, TK, false>(kernel_id, a);
+    case SC_S1:
+      return dm ? launch_one<Row<1, false>, TK, true>(kernel_id, a) : launch_one<Row<1, false>, TK, false>(kernel_id, a);
+    case SC_S4:
+      return dm ? launch_one<Row<4, false>, TK, true>(kernel_id, a) : launch_one<Row<4, false>, TK, false>(kernel_id, a);
+    default:
+      break;
+  }
+  if constexpr (!small_only) {
+    if (dm) return -2;
+    switch (sc) {
+      case SC_V2: return launch_one<Row<8, true>, TK, false>(kernel_id, a);
+      case SC_V4: return launch_one<Row<16, true>, TK, false>(kernel_id, a);
+      case SC_V8: return launch_one<Row<32, true>, TK, false>(kernel_id, a);
+      default: break;
+    }
+  }
+  return -2;
+}
+template struct Launcher<BJX_INSTANTIATE_TK>;
+#endif
+
+}  // namespace bjx

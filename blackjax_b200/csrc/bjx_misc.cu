@@ -1,0 +1,200 @@
+// Small kernels around the hot path: PRNG entry points (KAT-able), metric preparation,
+// dual averaging / Welford window adaptation, chain-pooled summary statistics.
+#include "bjx_internal.h"
+#include "bjx_prng.cuh"
+
+namespace bjx {
+
+// ---- jax.random entry points --------------------------------------------------------------------------
+__global__ void k_prng_split(const uint32_t* __restrict__ keys, long long n_keys, int num, uint32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_keys * num) return;
+  const long long k = t / num;
+  const Key o = fold_in(Key{keys[2 * k], keys[2 * k + 1]}, (uint32_t)(t % num));
+  out[2 * t] = o.a;
+  out[2 * t + 1] = o.b;
+}
+__global__ void k_prng_fold_in(const uint32_t* __restrict__ keys, long long n_keys, uint32_t data, uint32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_keys) return;
+  const Key o = fold_in(Key{keys[2 * t], keys[2 * t + 1]}, data);
+  out[2 * t] = o.a;
+  out[2 * t + 1] = o.b;
+}
+template <int MODE>  // 0 bits, 1 uniform, 2 normal
+__global__ void k_prng_draw(const uint32_t* __restrict__ keys, long long n_keys, long long per_key, void* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_keys * per_key) return;
+  const long long k = t / per_key;
+  const uint32_t i = (uint32_t)(t % per_key);
+  const Key key{keys[2 * k], keys[2 * k + 1]};
+  if (MODE == 0) reinterpret_cast<uint32_t*>(out)[t] = random_bits(key, i);
+  if (MODE == 1) reinterpret_cast<float*>(out)[t] = bits_to_unit(random_bits(key, i));
+  if (MODE == 2) reinterpret_cast<float*>(out)[t] = normal_at(key, i);
+}
+
+static inline dim3 grid1d(long long n, int b = 256) { return dim3((unsigned)((n + b - 1) / b)); }
+
+void launch_prng_split(const uint32_t* keys, long long n, int num, uint32_t* out, cudaStream_t s) {
+  if (n * num > 0) k_prng_split<<<grid1d(n * num), 256, 0, s>>>(keys, n, num, out);
+}
+void launch_prng_fold_in(const uint32_t* keys, long long n, uint32_t data, uint32_t* out, cudaStream_t s) {
+  if (n > 0) k_prng_fold_in<<<grid1d(n), 256, 0, s>>>(keys, n, data, out);
+}
+void launch_prng_draw(int mode, const uint32_t* keys, long long n, long long per_key, void* out, cudaStream_t s) {
+  if (n * per_key <= 0) return;
+  if (mode == 0) k_prng_draw<0><<<grid1d(n * per_key), 256, 0, s>>>(keys, n, per_key, out);
+  if (mode == 1) k_prng_draw<1><<<grid1d(n * per_key), 256, 0, s>>>(keys, n, per_key, out);
+  if (mode == 2) k_prng_draw<2><<<grid1d(n * per_key), 256, 0, s>>>(keys, n, per_key, out);
+}
+
+// ---- metrics._format_covariance, diagonal branch (metrics.py:703-708): mass_matrix_sqrt = 1/sqrt(M^-1) ----
+__global__ void k_diag_mass_sqrt(const float* __restrict__ imm, long long n, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = 1.0f / sqrtf(imm[t]);
+}
+void launch_diag_mass_sqrt(const float* imm, long long n, float* out, cudaStream_t s) {
+  if (n > 0) k_diag_mass_sqrt<<<grid1d(n), 256, 0, s>>>(imm, n, out);
+}
+
+// ---- dual averaging (optimizers/dual_averaging.py:87-129), one state per chain ---------------------------
+// state [C,5] = (log_step, log_step_avg, step, avg_error, mu)
+__global__ void k_da_init(int C, float* __restrict__ st, const float* __restrict__ eps0, float* __restrict__ eps_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float x = eps0[c];
+  st[5 * c + 0] = logf(x);
+  st[5 * c + 1] = 0.f;
+  st[5 * c + 2] = 1.f;
+  st[5 * c + 3] = 0.f;
+  st[5 * c + 4] = logf(10.f * x);
+  if (eps_out) eps_out[c] = expf(st[5 * c + 0]);
+}
+__global__ void k_da_update(int C, float* __restrict__ st, const float* __restrict__ acc, float target,
+                            float* __restrict__ eps_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float log_step = st[5 * c + 0], avg_log_step = st[5 * c + 1], step = st[5 * c + 2];
+  float avg_error = st[5 * c + 3];
+  const float mu = st[5 * c + 4];
+  const float gradient = target - acc[c];
+  const float reg_step = step + 10.f;                    // t0 = 10
+  const float eta_t = powf(step, -0.75f);                // kappa = 0.75
+  avg_error = (1.f - (1.f / reg_step)) * avg_error + gradient / reg_step;
+  const float log_x = mu - (sqrtf(step) / 0.05f) * avg_error;  // gamma = 0.05
+  const float log_x_avg = eta_t * log_step + (1.f - eta_t) * avg_log_step;  // uses the PRE-update iterate (:122)
+  st[5 * c + 0] = log_x;
+  st[5 * c + 1] = log_x_avg;
+  st[5 * c + 2] = step + 1.f;
+  st[5 * c + 3] = avg_error;
+  if (eps_out) eps_out[c] = expf(log_x);
+}
+__global__ void k_da_reset(int C, float* __restrict__ st, float* __restrict__ eps_out) {  // staged_adaptation.py:233-249
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float x = expf(st[5 * c + 1]);
+  st[5 * c + 0] = logf(x);
+  st[5 * c + 1] = 0.f;
+  st[5 * c + 2] = 1.f;
+  st[5 * c + 3] = 0.f;
+  st[5 * c + 4] = logf(10.f * x);
+  if (eps_out) eps_out[c] = expf(st[5 * c + 0]);
+}
+__global__ void k_da_final(int C, const float* __restrict__ st, float* __restrict__ eps_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) eps_out[c] = expf(st[5 * c + 1]);
+}
+void launch_da(int op, int C, float* st, const float* in, float target, float* eps_out, cudaStream_t s) {
+  if (C <= 0) return;
+  if (op == 0) k_da_init<<<grid1d(C), 256, 0, s>>>(C, st, in, eps_out);
+  if (op == 1) k_da_update<<<grid1d(C), 256, 0, s>>>(C, st, in, target, eps_out);
+  if (op == 2) k_da_reset<<<grid1d(C), 256, 0, s>>>(C, st, eps_out);
+  if (op == 3) k_da_final<<<grid1d(C), 256, 0, s>>>(C, st, eps_out);
+}
+
+// ---- Welford, diagonal, one accumulator per chain (adaptation/mass_matrix.py:411-442) ----------------------
+__global__ void k_welford_update(long long n, const float* __restrict__ x, float* __restrict__ mean,
+                                 float* __restrict__ m2, float count) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float v = x[t];
+  const float m = mean[t];
+  const float delta = v - m;
+  const float nm = m + delta / count;
+  mean[t] = nm;
+  m2[t] = m2[t] + delta * (v - nm);
+}
+// regularised inverse mass matrix (mass_matrix.py:335-357) and accumulator reset
+__global__ void k_welford_final(long long n, float* __restrict__ mean, float* __restrict__ m2, float count,
+                                float* __restrict__ imm) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float cov = m2[t] / (count - 1.f);
+  const float denom = count + 5.f;
+  imm[t] = count / denom * cov + 5.f / denom * 1e-3f;
+  mean[t] = 0.f;
+  m2[t] = 0.f;
+}
+void launch_welford_update(long long n, const float* x, float* mean, float* m2, int count, cudaStream_t s) {
+  if (n > 0) k_welford_update<<<grid1d(n), 256, 0, s>>>(n, x, mean, m2, (float)count);
+}
+void launch_welford_final(long long n, float* mean, float* m2, int count, float* imm, cudaStream_t s) {
+  if (n > 0) k_welford_final<<<grid1d(n), 256, 0, s>>>(n, mean, m2, (float)count, imm);
+}
+
+// ---- chain-pooled summary block (metric_buffers.py:396-420 cgl_update_batch statistics) -------------------
+// out[0] = sum acceptance_rate, out[1] = C, out[2:2+D] = mean over chains, out[2+D:2+2D] = sum (x-mean)^2.
+// Column reductions over the chain axis: block (32 x 8) owns 32 columns, threads stride over chains
+// (coalesced 128-byte rows), deterministic shared-memory tree, two passes (mean, then centred M2).
+__global__ void k_pooled_colstats(int C, int D, const float* __restrict__ x, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (col < D)
+    for (int c = threadIdx.y; c < C; c += 8) acc += x[(size_t)c * D + col];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float mean = 0.f;
+  if (threadIdx.y == 0) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    red[0][threadIdx.x] = s / (float)C;
+  }
+  __syncthreads();
+  mean = red[0][threadIdx.x];
+  __syncthreads();
+  acc = 0.f;
+  if (col < D)
+    for (int c = threadIdx.y; c < C; c += 8) {
+      const float d = x[(size_t)c * D + col] - mean;
+      acc = fmaf(d, d, acc);
+    }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    out[2 + col] = mean;
+    out[2 + D + col] = s;
+  }
+}
+__global__ void k_pooled_accept(int C, const float* __restrict__ acc, float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) a += acc[c];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += red[k];
+    out[0] = s;
+    out[1] = (float)C;
+  }
+}
+void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s) {
+  k_pooled_accept<<<1, 1024, 0, s>>>(C, acc, out);
+  k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, x, out);
+}
+
+}  // namespace bjx

@@ -1,0 +1,294 @@
+// Warp-owns-a-chain row primitives for the HMC/NUTS kernels.
+//
+// Layout: state arrays are float32 [C, D] row-major.  One warp owns one chain row; lane l holds
+// NS "slots" of the row in registers.  VEC layout (D % 4 == 0): slot s = 4*j + v is element
+// (j*32 + l)*4 + v, so each j is one coalesced 512-byte LDG.128/STG.128 per warp.  Scalar layout
+// (any D <= 32*NS): slot s is element s*32 + l.  Slots past D are held as 0 so that per-chain
+// reductions (log-density, kinetic energy, U-turn dot products) need no masks and finish with
+// __shfl_xor_sync inside the owning warp -- no shared memory, no cross-CTA traffic.
+//
+// The build uses -fmad=false: elementwise integrator updates round exactly like the float32
+// reference expression `x + (eps*coef)*grad` (blackjax/mcmc/integrators.py:200,236); reductions
+// use explicit fmaf.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bjx_prng.cuh"
+
+namespace bjx {
+
+enum { TK_DIAG = 0, TK_FUNNEL = 1, TK_DENSE = 2, TK_BANANA = 3 };
+
+struct Params {
+  int C, D;
+  // target
+  const float* inv_var;
+  const float* mean;
+  const float* prec;
+  float logp_offset;
+  // metric
+  const float* imm;        // diag: [D] or [C,D]; dense: [D,D]
+  long long imm_stride;    // 0 (shared) or D (per chain)
+  const float* msqrt;      // mass_matrix_sqrt, same layout as imm
+  // step size
+  float eps;
+  const float* eps_dev;    // [C] or nullptr
+  float div_thr;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NS_, bool VEC_>
+struct Row {
+  static constexpr int NS = NS_;
+  static constexpr bool VEC = VEC_;
+  static_assert(!VEC_ || (NS_ % 4 == 0), "vector layout needs NS % 4 == 0");
+
+  __device__ static __forceinline__ int idx(int s, int lane) {
+    return VEC ? (((s >> 2) * 32 + lane) * 4 + (s & 3)) : (s * 32 + lane);
+  }
+
+  // streaming (evict-first) loads/stores for the [C,D] state arrays
+  __device__ static __forceinline__ void load(float (&x)[NS], const float* __restrict__ row, int D, int lane) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < D) t = __ldcs(reinterpret_cast<const float4*>(row + e));
+        x[4 * j + 0] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int e = s * 32 + lane;
+        x[s] = (e < D) ? __ldcs(row + e) : 0.f;
+      }
+    }
+  }
+  // cached loads for small shared vectors (inverse mass, target scales)
+  __device__ static __forceinline__ void load_const(float (&x)[NS], const float* __restrict__ row, int D, int lane) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < D) t = __ldg(reinterpret_cast<const float4*>(row + e));
+        x[4 * j + 0] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int e = s * 32 + lane;
+        x[s] = (e < D) ? __ldg(row + e) : 0.f;
+      }
+    }
+  }
+  __device__ static __forceinline__ void store(const float (&x)[NS], float* __restrict__ row, int D, int lane) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        if (e < D) __stcs(reinterpret_cast<float4*>(row + e), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int e = s * 32 + lane;
+        if (e < D) __stcs(row + e, x[s]);
+      }
+    }
+  }
+  __device__ static __forceinline__ float dot(const float (&a)[NS], const float (&b)[NS]) {
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc = fmaf(a[s], b[s], acc);
+    return warp_sum(acc);
+  }
+};
+
+// y = M x for a small dense [D,D] matrix: the warp stages x in its shared-memory slice and each
+// lane forms the rows it owns.  Used for dense metrics/targets with D <= 128 (KAT-sized problems);
+// large dense problems go through the batched GEMM path instead.
+template <class R>
+__device__ __forceinline__ void matvec_small(const float* __restrict__ M, const float (&x)[R::NS], float (&y)[R::NS],
+                                             float* sm, int D, int lane) {
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) {
+    const int e = R::idx(s, lane);
+    if (e < D) sm[e] = x[s];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) {
+    const int e = R::idx(s, lane);
+    float acc = 0.f;
+    if (e < D) {
+      const float* mr = M + (size_t)e * D;
+      for (int j = 0; j < D; ++j) acc = fmaf(__ldg(mr + j), sm[j], acc);
+    }
+    y[s] = acc;
+  }
+  __syncwarp();
+}
+
+// Per-warp constant context: target scales and inverse mass held in registers for the whole kernel.
+template <class R, int TK, bool DM>
+struct Ctx {
+  float tw[(TK == TK_DIAG) ? R::NS : 1];  // target 1/s^2
+  float mw[DM ? 1 : R::NS];               // diagonal inverse mass
+  float* sm;                              // shared-memory slice (small dense paths)
+  int lane;
+
+  __device__ __forceinline__ void init(const Params& P, int chain, int lane_, float* sm_) {
+    lane = lane_;
+    sm = sm_;
+    if constexpr (TK == TK_DIAG) R::load_const(tw, P.inv_var, P.D, lane);
+    if constexpr (!DM) R::load_const(mw, P.imm + (size_t)chain * P.imm_stride, P.D, lane);
+  }
+
+  // linear_map(M^-1, p)   blackjax/util.py:57-61
+  __device__ __forceinline__ void velocity(const Params& P, const float (&p)[R::NS], float (&v)[R::NS]) {
+    if constexpr (DM) {
+      matvec_small<R>(P.imm, p, v, sm, P.D, lane);
+    } else {
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) v[s] = mw[s] * p[s];
+    }
+  }
+
+  // kinetic_energy  blackjax/mcmc/metrics.py:263-270: 0.5 * dot(M^-1 p, p)
+  __device__ __forceinline__ float kinetic(const Params& P, const float (&p)[R::NS]) {
+    float v[R::NS];
+    velocity(P, p, v);
+    return 0.5f * R::dot(v, p);
+  }
+
+  // value_and_grad of the target at q
+  __device__ __forceinline__ void value_and_grad(const Params& P, const float (&q)[R::NS], float (&g)[R::NS], float& logp) {
+    if constexpr (TK == TK_DIAG) {
+      float acc = 0.f;
+      if (P.mean != nullptr) {
+        float mu[R::NS];
+        R::load_const(mu, P.mean, P.D, lane);
+#pragma unroll
+        for (int s = 0; s < R::NS; ++s) {
+          const float d = q[s] - mu[s];
+          const float t = d * tw[s];
+          acc = fmaf(d, t, acc);
+          g[s] = -t;
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < R::NS; ++s) {
+          const float t = q[s] * tw[s];
+          acc = fmaf(q[s], t, acc);
+          g[s] = -t;
+        }
+      }
+      logp = -0.5f * warp_sum(acc) + P.logp_offset;
+    } else if constexpr (TK == TK_FUNNEL) {
+      const float y = __shfl_sync(0xffffffffu, q[0], 0);
+      float acc = 0.f;
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) {
+        const bool neck = (s == 0) && (lane == 0);
+        acc = neck ? acc : fmaf(q[s], q[s], acc);
+      }
+      const float ss = warp_sum(acc);
+      const float ey = expf(-y);
+      const float n = (float)(P.D - 1);
+      const float t = y / 3.0f;
+      logp = -0.5f * (t * t) + (-0.5f * ey * ss - 0.5f * n * y) + P.logp_offset;
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) g[s] = -(ey * q[s]);
+      if (lane == 0) g[0] = -y / 9.0f + 0.5f * ey * ss - 0.5f * n;
+    } else if constexpr (TK == TK_DENSE) {
+      matvec_small<R>(P.prec, q, g, sm, P.D, lane);
+      logp = -0.5f * R::dot(q, g) + P.logp_offset;
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) g[s] = -g[s];
+    } else {  // TK_BANANA, D == 2, scalar layout: x0 at lane 0, x1 at lane 1
+      const float x0 = __shfl_sync(0xffffffffu, q[0], 0);
+      const float x1 = __shfl_sync(0xffffffffu, q[0], 1);
+      const float r = x1 - x0 * x0;
+      const float a = 1.0f - x0;
+      logp = -(a * a) - 1.5f * r * r + P.logp_offset;
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) g[s] = 0.f;
+      if (lane == 0) g[0] = 2.0f * a + 6.0f * r * x0;
+      if (lane == 1) g[0] = -3.0f * r;
+    }
+  }
+
+  // one velocity-Verlet step, coefficients [0.5, 1.0, 0.5]
+  // (blackjax/mcmc/integrators.py:104-150,199-203,235-245,321-322)
+  __device__ __forceinline__ void leapfrog(const Params& P, float (&q)[R::NS], float (&p)[R::NS], float (&g)[R::NS],
+                                           float& logp, float eps) {
+    const float eh = eps * 0.5f;
+    const float e1 = eps * 1.0f;
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) p[s] = p[s] + eh * g[s];
+    {
+      float v[R::NS];
+      velocity(P, p, v);
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) q[s] = q[s] + e1 * v[s];
+    }
+    value_and_grad(P, q, g, logp);
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) p[s] = p[s] + eh * g[s];
+  }
+
+  // metric.sample_momentum  metrics.py:260-261 -> util.py:89-91: p = mass_matrix_sqrt (.) normal(key,(D,))
+  __device__ __forceinline__ void sample_momentum(const Params& P, int chain, Key key, float (&p)[R::NS]) {
+    float z[R::NS];
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) {
+      const int e = R::idx(s, lane);
+      z[s] = (e < P.D) ? normal_at(key, (uint32_t)e) : 0.f;
+    }
+    if constexpr (DM) {
+      matvec_small<R>(P.msqrt, z, p, sm, P.D, lane);
+    } else {
+      float ms[R::NS];
+      R::load_const(ms, P.msqrt + (size_t)chain * P.imm_stride, P.D, lane);
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) p[s] = ms[s] * z[s];
+    }
+  }
+
+  // gaussian_euclidean.is_turning  metrics.py:272-304 (<=, OR)
+  __device__ __forceinline__ bool is_turning(const Params& P, const float (&pl)[R::NS], const float (&pr)[R::NS],
+                                             const float (&psum)[R::NS]) {
+    float rho[R::NS], v[R::NS];
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) rho[s] = psum[s] - (pr[s] + pl[s]) / 2.0f;
+    velocity(P, pl, v);
+    const float dl = R::dot(v, rho);
+    velocity(P, pr, v);
+    const float dr = R::dot(v, rho);
+    return (dl <= 0.f) || (dr <= 0.f);
+  }
+};
+
+__device__ __forceinline__ float safe_energy_diff(float e0, float e1) {  // proposal.py:45-48
+  const float d = e0 - e1;
+  return isnan(d) ? -__int_as_float(0x7f800000) : d;
+}
+
+__device__ __forceinline__ float logaddexp_f(float a, float b) {  // jnp.logaddexp
+  const float amax = fmaxf(a, b);
+  const float delta = a - b;
+  if (isnan(delta)) return a + b;
+  return amax + log1pf(expf(-fabsf(delta)));
+}
+
+__device__ __forceinline__ float expit_f(float x) { return 1.0f / (1.0f + expf(-x)); }  // jax.scipy.special.expit
+
+}  // namespace bjx

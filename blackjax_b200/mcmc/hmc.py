@@ -1,0 +1,107 @@
+"""HMC behind BlackJAX's ``init / build_kernel / as_top_level_api`` surface (blackjax/mcmc/hmc.py).
+
+Intentional surface difference: the chain axis is explicit -- ``position`` is a
+``[n_chains, dim]`` CUDA tensor and ``rng_key`` is either one raw key ``uint32[2]`` (split into one key
+per chain, the reference's step-major pattern ``vmap(kernel)(split(key, C), states)``,
+docs/examples/howto_sample_multiple_chains.md:116-129) or per-chain keys ``uint32[C, 2]``.
+``logdensity_fn`` is a :mod:`blackjax_b200.targets` descriptor.
+"""
+from typing import NamedTuple, Optional
+
+import torch
+
+from .. import random as bjx_random
+from .._engine import get_engine
+from ..base import build_sampling_algorithm
+
+__all__ = ["HMCState", "HMCInfo", "init", "build_kernel", "as_top_level_api"]
+
+velocity_verlet = "velocity_verlet"  # the only integrator built so far (integrators.py:321-322)
+
+
+class HMCState(NamedTuple):
+    """blackjax/mcmc/hmc.py:38-49, batched: position [C,D], logdensity [C], logdensity_grad [C,D]."""
+
+    position: torch.Tensor
+    logdensity: torch.Tensor
+    logdensity_grad: torch.Tensor
+
+
+class IntegratorState(NamedTuple):
+    """blackjax/mcmc/integrators.py:43-53."""
+
+    position: torch.Tensor
+    momentum: torch.Tensor
+    logdensity: Optional[torch.Tensor]
+    logdensity_grad: Optional[torch.Tensor]
+
+
+class HMCInfo(NamedTuple):
+    """blackjax/mcmc/hmc.py:52-87.  D-sized fields (momentum, proposal) are materialised only with
+    ``build_kernel(..., full_info=True)``; otherwise they are None."""
+
+    momentum: Optional[torch.Tensor]
+    acceptance_rate: torch.Tensor
+    is_accepted: torch.Tensor
+    is_divergent: torch.Tensor
+    energy: torch.Tensor
+    proposal: Optional[IntegratorState]
+    num_integration_steps: int
+
+
+def init(position, logdensity_fn):
+    """blackjax/mcmc/hmc.py:90-92."""
+    eng = get_engine(position, logdensity_fn)
+    position = position.contiguous()
+    logp, grad = eng.init_state(position)
+    return HMCState(position, logp, grad)
+
+
+def per_chain_keys(rng_key, n_chains, device):
+    if rng_key.ndim == 1:
+        return bjx_random.split(rng_key.to(device), n_chains)
+    return rng_key
+
+
+def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000, build_proposal=None,
+                 full_info: bool = False, inplace: bool = False):
+    """blackjax/mcmc/hmc.py:251-314.  ``inplace=True`` overwrites the input state's tensors (no
+    allocation; the returned state aliases the input)."""
+    if integrator != velocity_verlet:
+        raise NotImplementedError("only velocity_verlet is built (SURVEY.md section 8f item 2)")
+    if build_proposal is not None:
+        raise NotImplementedError("custom proposals are not supported by the fused transition kernel")
+
+    def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps):
+        q, logp, g = state
+        eng = get_engine(q, logdensity_fn, divergence_threshold=divergence_threshold)
+        if eng._imm_key is not inverse_mass_matrix:
+            eng.set_metric(inverse_mass_matrix)
+            eng._imm_key = inverse_mass_matrix
+        keys = per_chain_keys(rng_key, eng.C, eng.device)
+        C, dev = eng.C, eng.device
+        fields = dict(acceptance_rate=torch.empty(C, dtype=torch.float32, device=dev),
+                      is_accepted=torch.empty(C, dtype=torch.uint8, device=dev),
+                      is_divergent=torch.empty(C, dtype=torch.uint8, device=dev),
+                      energy=torch.empty(C, dtype=torch.float32, device=dev))
+        if full_info:
+            fields.update(momentum=torch.empty_like(q), proposal_position=torch.empty_like(q),
+                          proposal_momentum=torch.empty_like(q))
+        out = (q, logp, g) if inplace else None
+        qo, lo, go = eng.hmc_step(keys, q, logp, g, step_size, num_integration_steps, out=out, info_fields=fields)
+        proposal = None
+        if full_info:
+            proposal = IntegratorState(fields["proposal_position"], fields["proposal_momentum"], None, None)
+        info = HMCInfo(fields.get("momentum"), fields["acceptance_rate"], fields["is_accepted"].bool(),
+                       fields["is_divergent"].bool(), fields["energy"], proposal, num_integration_steps)
+        return HMCState(qo, lo, go), info
+
+    return kernel
+
+
+def as_top_level_api(logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps, *,
+                     divergence_threshold: int = 1000, integrator=velocity_verlet, **kw):
+    """blackjax/mcmc/hmc.py:317-414."""
+    kernel = build_kernel(integrator, divergence_threshold, **kw)
+    return build_sampling_algorithm(kernel, init, logdensity_fn,
+                                    kernel_args=(step_size, inverse_mass_matrix, num_integration_steps))

@@ -1,0 +1,114 @@
+"""Log-density targets with a fused device ``value_and_grad``.
+
+BlackJAX accepts any JAX callable as ``logdensity_fn`` and differentiates it with
+``jax.value_and_grad`` (blackjax/mcmc/hmc.py:91, integrators.py:189).  Without a tracing compiler the
+B200 path takes a *target descriptor* in the ``logdensity_fn`` slot instead: one of the named models
+below, each with a hand-derived gradient fused into the leapfrog kernels
+(blackjax_b200/csrc/bjx_row.cuh ``Ctx::value_and_grad``).  This is the deliberate scope limit of the
+drop-in (SURVEY.md section 7 "logdensity boundary").
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Target:
+    kind = None
+    dim = None
+
+    def _desc(self, device):
+        raise NotImplementedError
+
+    def desc(self, device):
+        """bjx_target_desc for ``device`` (parameter tensors are cached per device)."""
+        return self._desc(torch.device(device))
+
+    def _cached(self, name, host_array, device):
+        cache = self.__dict__.setdefault("_dev", {})
+        k = (name, str(device))
+        if k not in cache:
+            cache[k] = torch.as_tensor(np.ascontiguousarray(host_array, dtype=np.float32)).to(device)
+        return cache[k]
+
+
+class DiagGaussian(Target):
+    """``std_normal_logdensity(x, scale)`` (tests/fixtures.py:60-78): -1/2 sum ((x-mean)/scale)^2 + offset."""
+
+    kind = _lib.TARGET_DIAG_GAUSSIAN
+
+    def __init__(self, scale=1.0, dim=None, mean=None, logp_offset=0.0):
+        s = np.asarray(scale, np.float64)
+        if s.ndim == 0:
+            if dim is None:
+                raise ValueError("dim is required with a scalar scale")
+            s = np.full((dim,), float(s))
+        self.scale = s
+        self.dim = int(s.shape[0])
+        self.inv_var = (1.0 / (s * s)).astype(np.float32)
+        self.mean = None if mean is None else np.broadcast_to(np.asarray(mean, np.float32), (self.dim,)).copy()
+        self.logp_offset = float(logp_offset)
+
+    def _desc(self, device):
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        d.inv_var = self._cached("inv_var", self.inv_var, device).data_ptr()
+        d.mean = None if self.mean is None else self._cached("mean", self.mean, device).data_ptr()
+        d.precision = None
+        d.logp_offset = self.logp_offset
+        return d
+
+
+def StdNormal(dim):
+    return DiagGaussian(1.0, dim)
+
+
+class Funnel(Target):
+    """``neal_funnel_logdensity`` (tests/fixtures.py:81-98)."""
+
+    kind = _lib.TARGET_FUNNEL
+
+    def __init__(self, dim):
+        if dim < 2:
+            raise ValueError("funnel needs dim >= 2")
+        self.dim = int(dim)
+
+    def _desc(self, device):
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        d.logp_offset = 0.0
+        return d
+
+
+class DenseGaussian(Target):
+    """-1/2 x^T P x + offset (tests/mcmc/test_mclmc_lrd.py:86-88)."""
+
+    kind = _lib.TARGET_DENSE_GAUSSIAN
+
+    def __init__(self, precision, logp_offset=0.0):
+        p = np.asarray(precision, np.float32)
+        if p.ndim != 2 or p.shape[0] != p.shape[1]:
+            raise ValueError("precision must be a square matrix")
+        self.precision = p
+        self.dim = int(p.shape[0])
+        self.logp_offset = float(logp_offset)
+
+    def _desc(self, device):
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        d.precision = self._cached("precision", self.precision, device).data_ptr()
+        d.logp_offset = self.logp_offset
+        return d
+
+
+class Banana(Target):
+    """-(1-x0)^2 - 1.5 (x1 - x0^2)^2 (tests/mcmc/test_trajectory.py:79-80)."""
+
+    kind = _lib.TARGET_BANANA
+    dim = 2
+
+    def _desc(self, device):
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, 2
+        d.logp_offset = 0.0
+        return d

@@ -1,0 +1,172 @@
+/*
+ * bjx.h -- C ABI of the B200-native HMC/NUTS hot path (libbjx.so).
+ *
+ * Drop-in boundary for BlackJAX's `blackjax.hmc` / `blackjax.nuts` / `window_adaptation`
+ * path (reference: blackjax-devs/blackjax @ 63912a4).  The reference has no FFI of its own
+ * (it is pure Python on JAX), so every entry point below cites the reference *function* it
+ * replaces; `INTEGRATION.md` shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - All array pointers are DEVICE pointers owned by the caller unless marked "host".
+ *  - State arrays are row-major float32 [n_chains, dim] (chain-major, dimension contiguous);
+ *    per-chain scalars are [n_chains]; PRNG keys are uint32 [n_chains, 2] (raw threefry keys,
+ *    i.e. jax.random.key_data layout).
+ *  - Every call is asynchronous and ordered on the handle's stream, except bjx_nuts_step
+ *    which synchronises the stream once per tree doubling (host-driven tree building).
+ *  - Return value: 0 ok; <0 invalid argument / unsupported configuration (BJX_E_*);
+ *    >0 a cudaError_t.  bjx_last_error(handle) returns the text.  No exceptions or
+ *    callbacks cross this ABI.  A handle is not thread-safe; distinct handles are independent.
+ *  - There is NO CPU fallback: every entry point fails with a CUDA error if no device exists.
+ */
+#ifndef BJX_H_
+#define BJX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BJX_VERSION 100
+
+/* error codes (negative) */
+#define BJX_OK 0
+#define BJX_E_INVALID (-1)     /* bad argument / shape */
+#define BJX_E_UNSUPPORTED (-2) /* configuration not built (e.g. dim % 4 != 0 with dim > 128) */
+#define BJX_E_STATE (-3)       /* call order (e.g. metric not set) */
+
+/* log-density targets with a fused analytic value_and_grad (replaces jax.value_and_grad of the
+ * user callable: blackjax/mcmc/hmc.py:91, integrators.py:189,204). */
+enum bjx_target_kind {
+  BJX_TARGET_DIAG_GAUSSIAN = 0,  /* -1/2 sum ((x-mean)/s)^2 + offset   tests/fixtures.py:60-78   */
+  BJX_TARGET_FUNNEL = 1,         /* Neal's funnel                       tests/fixtures.py:81-98   */
+  BJX_TARGET_DENSE_GAUSSIAN = 2, /* -1/2 x^T P x + offset               tests/mcmc/test_mclmc_lrd.py:86-88 */
+  BJX_TARGET_BANANA = 3          /* -(1-x0)^2 - 1.5 (x1-x0^2)^2, dim=2  tests/mcmc/test_trajectory.py:79-80 */
+};
+
+/* inverse-mass-matrix layouts (metrics.py:701-729: 1-D => diagonal, 2-D => dense) */
+enum bjx_metric_kind {
+  BJX_METRIC_DIAG = 0,          /* imm [dim]                                    */
+  BJX_METRIC_DENSE = 1,         /* imm [dim, dim] symmetric positive definite   */
+  BJX_METRIC_DIAG_PER_CHAIN = 2 /* imm [n_chains, dim] (vmapped window adaptation) */
+};
+
+typedef struct {
+  int32_t kind;           /* bjx_target_kind */
+  int32_t dim;
+  const float* inv_var;   /* DIAG_GAUSSIAN: [dim] 1/s^2 (device)           */
+  const float* mean;      /* DIAG_GAUSSIAN: [dim] or NULL (device)         */
+  const float* precision; /* DENSE_GAUSSIAN: [dim, dim] symmetric (device) */
+  float logp_offset;      /* constant added to every log-density           */
+} bjx_target_desc;
+
+typedef struct {
+  int32_t device;              /* CUDA ordinal */
+  int32_t n_chains;            /* chains held by THIS process/GPU */
+  int32_t dim;
+  int32_t max_tree_depth;      /* NUTS checkpoint capacity (max_num_doublings upper bound), >= 1 */
+  float divergence_threshold;  /* default 1000 (hmc.py:120, trajectory.py:325) */
+  void* stream;                /* cudaStream_t to order all work on (NULL = legacy default stream) */
+  bjx_target_desc target;
+} bjx_config;
+
+/* Optional per-transition outputs (NULL => not written).  Mirrors HMCInfo (hmc.py:52-87) and
+ * NUTSInfo (nuts.py:36-74); D-sized fields only on request. */
+typedef struct {
+  float* acceptance_rate;          /* [C]                                              */
+  uint8_t* is_accepted;            /* [C]   HMC only                                   */
+  uint8_t* is_divergent;           /* [C]                                              */
+  uint8_t* is_turning;             /* [C]   NUTS only                                  */
+  float* energy;                   /* [C]   energy of the proposal                     */
+  int32_t* num_integration_steps;  /* [C]                                              */
+  int32_t* num_trajectory_expansions; /* [C] NUTS only                                 */
+  float* momentum;                 /* [C,D] momentum drawn at the start of the transition */
+  float* proposal_position;        /* [C,D] HMC: end state (before accept/reject)      */
+  float* proposal_momentum;        /* [C,D] HMC: flipped end momentum                  */
+  float* left_position;            /* [C,D] NUTS trajectory_leftmost_state.position    */
+  float* left_momentum;            /* [C,D]                                            */
+  float* right_position;           /* [C,D] NUTS trajectory_rightmost_state.position   */
+  float* right_momentum;           /* [C,D]                                            */
+} bjx_info;
+
+typedef struct bjx_handle_s* bjx_handle_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int bjx_version(void);
+int bjx_create(const bjx_config* cfg, bjx_handle_t* out);
+int bjx_destroy(bjx_handle_t h);
+const char* bjx_last_error(bjx_handle_t h); /* h may be NULL: last global error */
+int bjx_set_target(bjx_handle_t h, const bjx_target_desc* target);
+int bjx_synchronize(bjx_handle_t h);
+
+/* metrics.default_metric / gaussian_euclidean (metrics.py:180-218,221-346): precomputes
+ * mass_matrix_sqrt = 1/sqrt(M^-1) (diag) or L^-T with L = chol(M^-1) (dense), metrics.py:701-729.
+ * The dense factorisation runs on the host in float64 and synchronises the stream. */
+int bjx_set_metric(bjx_handle_t h, int32_t metric_kind, const float* inverse_mass_matrix);
+/* device pointer to mass_matrix_sqrt as precomputed by bjx_set_metric (for tests) */
+int bjx_get_mass_matrix_sqrt(bjx_handle_t h, const float** out);
+
+/* ---- building blocks (KAT-able; each maps to one reference function) -------------------------- */
+/* hmc.init (hmc.py:90-92): logp, grad = value_and_grad(logdensity)(q) */
+int bjx_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out);
+/* metric.sample_momentum (metrics.py:260-261 -> util.py:66-91): p = mass_matrix_sqrt (.) normal(key,(D,)) */
+int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out);
+/* static_integration (trajectory.py:136-167) of velocity_verlet (integrators.py:62-152,321-322):
+ * n_steps leapfrogs in place.  step_size_dev ([C], signed) overrides step_size when non-NULL. */
+int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* grad, float step_size,
+                 const float* step_size_dev, int32_t n_steps);
+/* hmc_energy (trajectory.py:730-750): -logp + 1/2 p^T M^-1 p */
+int bjx_energy(bjx_handle_t h, const float* p, const float* logp, float* energy_out);
+/* metrics.is_turning (metrics.py:272-304) on explicit momenta (for the U-turn truth table) */
+int bjx_is_turning(bjx_handle_t h, const float* p_left, const float* p_right, const float* p_sum,
+                   uint8_t* out);
+
+/* ---- transitions ------------------------------------------------------------------------------ */
+/* hmc.build_kernel(...).kernel (hmc.py:279-312).  (q,logp,grad)_in -> (q,logp,grad)_out; out may
+ * alias in (in-place).  keys: one rng_key per chain. */
+int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                 const float* grad_in, float* q_out, float* logp_out, float* grad_out,
+                 float step_size, const float* step_size_dev, int32_t num_integration_steps,
+                 const bjx_info* info);
+/* nuts.build_kernel(...).kernel (nuts.py:113-145) with iterative_nuts_proposal (nuts.py:223-321).
+ * Tree doubling is driven from the host; each leapfrog leaf is one kernel launch over all chains.
+ * momentum_override/key_integrator_override (both or neither, for KATs): skip the key split and
+ * the momentum draw and use the given momentum [C,D] and integrator keys [C,2]. */
+int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                  const float* grad_in, float* q_out, float* logp_out, float* grad_out,
+                  float step_size, const float* step_size_dev, int32_t max_num_doublings,
+                  const bjx_info* info, const float* momentum_override,
+                  const uint32_t* key_integrator_override);
+/* total leapfrog launches / leaf evaluations performed by the last bjx_nuts_step (host ints) */
+int bjx_nuts_last_stats(bjx_handle_t h, int64_t* leaf_launches, int64_t* depth_reached);
+
+/* ---- PRNG (jax.random restated; keys raw uint32 pairs) ----------------------------------------- */
+/* h may be NULL for the PRNG entry points: current device, legacy default stream */
+int bjx_prng_split(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);
+int bjx_prng_fold_in(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, uint32_t data, uint32_t* out);
+int bjx_prng_random_bits(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, uint32_t* out);
+int bjx_prng_uniform(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out);
+int bjx_prng_normal(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out);
+
+/* ---- window adaptation (staged_adaptation.py:111-307) -------------------------------------------- */
+/* Per-chain dual averaging (optimizers/dual_averaging.py:87-129).  da_state float32 [C,5] =
+ * (log_step, log_step_avg, step, avg_error, mu).  step_size_out [C] = exp(log_step). */
+int bjx_da_init(bjx_handle_t h, float* da_state, const float* initial_step_size /*[C]*/, float* step_size_out);
+int bjx_da_update(bjx_handle_t h, float* da_state, const float* acceptance_rate, float target, float* step_size_out);
+/* slow-window end: re-initialise DA at exp(log_step_avg) (staged_adaptation.py:233-249) */
+int bjx_da_reset(bjx_handle_t h, float* da_state, float* step_size_out);
+int bjx_da_final(bjx_handle_t h, const float* da_state, float* step_size_out);
+/* Per-chain diagonal Welford (adaptation/mass_matrix.py:411-442): mean,m2 [C,D]; count is a host int */
+int bjx_welford_update(bjx_handle_t h, const float* q, float* mean, float* m2, int32_t new_count);
+/* regularised IMM (mass_matrix.py:335-357): imm = n/(n+5) m2/(n-1) + 1e-3*5/(n+5); resets mean,m2 */
+int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t count, float* imm_out);
+/* Chain-pooled summary block of THIS GPU's chains for the shared-epsilon warm-up
+ * (staged_adaptation.py:153-171,906-966; metric_buffers.py:396-420):
+ * stats_out float32 [2 + 2*D] = (sum acceptance_rate, n_chains, mean[D], M2[D]).
+ * The blocks of all GPUs are exchanged with ONE all-gather and CGL-merged on every rank. */
+int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BJX_H_ */

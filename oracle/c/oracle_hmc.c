@@ -1,0 +1,181 @@
+/*
+ * C/pthreads twin of the numpy oracle's HMC transition (oracle/hmc.py), used ONLY as the CPU
+ * timing stand-in (bench.py cpu_baseline / --impl reference) and cross-checked against the numpy
+ * oracle in tests/test_oracle_c.py.  TEST INFRASTRUCTURE -- never linked into the product.
+ *
+ * "restated oracle, not JAX": the reference (blackjax-devs/blackjax) needs jax 0.10.0, which is not
+ * installable here, so this restates blackjax/mcmc/hmc.py:279-312 (kernel), integrators.py:104-150
+ * (velocity Verlet), metrics.py:260-270 (momentum draw, kinetic energy), proposal.py:214-235
+ * (Metropolis accept) and the jax.random threefry2x32 PRNG, float32, chains split across pthreads --
+ * the per-chain program that jax.vmap batches on CPU.
+ *
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -pthread -shared -fPIC oracle_hmc.c -o liboracle_hmc.so -lm
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+static inline uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+static void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o0, uint32_t* o1) {
+  static const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0];
+  x1 += ks[1];
+  for (int i = 0; i < 5; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      x0 += x1;
+      x1 = rotl(x1, R[i & 1][j]);
+      x1 ^= x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+  *o0 = x0;
+  *o1 = x1;
+}
+
+static inline float bits_to_unit(uint32_t b) {
+  union { uint32_t u; float f; } c;
+  c.u = (b >> 9) | 0x3F800000u;
+  return c.f - 1.0f;
+}
+
+static float erfinv_f32(float x) {
+  static const float A[9] = {2.81022636e-08f, 3.43273939e-07f, -3.5233877e-06f, -4.39150654e-06f, 0.00021858087f,
+                             -0.00125372503f, -0.00417768164f, 0.246640727f, 1.50140941f};
+  static const float B[9] = {-0.000200214257f, 0.000100950558f, 0.00134934322f, -0.00367342844f, 0.00573950773f,
+                             -0.0076224613f, 0.00943887047f, 1.00167406f, 2.83297682f};
+  float w = -log1pf(-(x * x));
+  const float* c = (w < 5.0f) ? A : B;
+  float ww = (w < 5.0f) ? (w - 2.5f) : (sqrtf(w) - 3.0f);
+  float p = c[0];
+  for (int i = 1; i < 9; ++i) p = c[i] + p * ww;
+  if (fabsf(x) == 1.0f) return x * INFINITY;
+  return p * x;
+}
+
+static inline float normal_at(uint32_t k0, uint32_t k1, uint32_t i) {
+  uint32_t a, b;
+  threefry2x32(k0, k1, 0u, i, &a, &b);
+  const float lo = -0.99999994f;
+  float u = bits_to_unit(a ^ b) * (1.0f - lo) + lo;
+  if (u < lo) u = lo;
+  return 1.41421356237309515f * erfinv_f32(u);
+}
+
+/* target kinds: 0 diagonal Gaussian (inv_var[D]), 1 Neal's funnel */
+static float value_and_grad(int kind, int D, const float* inv_var, const float* q, float* g) {
+  if (kind == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < D; ++i) {
+      float t = q[i] * inv_var[i];
+      acc += q[i] * t;
+      g[i] = -t;
+    }
+    return -0.5f * acc;
+  }
+  float y = q[0], ss = 0.f;
+  for (int i = 1; i < D; ++i) ss += q[i] * q[i];
+  float ey = expf(-y), n = (float)(D - 1), t = y / 3.0f;
+  for (int i = 1; i < D; ++i) g[i] = -(ey * q[i]);
+  g[0] = -y / 9.0f + 0.5f * ey * ss - 0.5f * n;
+  return -0.5f * (t * t) + (-0.5f * ey * ss - 0.5f * n * y);
+}
+
+typedef struct {
+  int c0, c1, D, kind, L;
+  const float *inv_var, *imm, *msqrt;
+  const uint32_t* keys;
+  float *q, *logp, *g, eps, *acc_rate;
+  unsigned char* accepted;
+} job_t;
+
+static void* worker(void* arg) {
+  job_t* J = (job_t*)arg;
+  const int D = J->D, L = J->L;
+  const float *imm = J->imm, *msqrt = J->msqrt, eps = J->eps;
+  float* p = (float*)malloc(sizeof(float) * D * 3);
+  float* q1 = p + D;
+  float* g1 = q1 + D;
+  for (int c = J->c0; c < J->c1; ++c) {
+    uint32_t km0, km1, ki0, ki1;
+    threefry2x32(J->keys[2 * c], J->keys[2 * c + 1], 0u, 0u, &km0, &km1); /* split(rng_key, 2) hmc.py:299 */
+    threefry2x32(J->keys[2 * c], J->keys[2 * c + 1], 0u, 1u, &ki0, &ki1);
+    float* qc = J->q + (size_t)c * D;
+    float* gc = J->g + (size_t)c * D;
+    float k0 = 0.f;
+    for (int i = 0; i < D; ++i) {
+      p[i] = msqrt[i] * normal_at(km0, km1, (uint32_t)i);
+      k0 += (imm[i] * p[i]) * p[i];
+    }
+    const float e0 = -J->logp[c] + 0.5f * k0;
+    memcpy(q1, qc, sizeof(float) * D);
+    memcpy(g1, gc, sizeof(float) * D);
+    float lp = J->logp[c];
+    const float eh = eps * 0.5f, e1s = eps * 1.0f;
+    for (int s = 0; s < L; ++s) { /* integrators.py:104-150 */
+      for (int i = 0; i < D; ++i) {
+        p[i] = p[i] + eh * g1[i];
+        q1[i] = q1[i] + e1s * (imm[i] * p[i]);
+      }
+      lp = value_and_grad(J->kind, D, J->inv_var, q1, g1);
+      for (int i = 0; i < D; ++i) p[i] = p[i] + eh * g1[i];
+    }
+    float k1 = 0.f;
+    for (int i = 0; i < D; ++i) {
+      float pf = -1.0f * p[i];
+      k1 += (imm[i] * pf) * pf;
+    }
+    const float e1 = -lp + 0.5f * k1;
+    float delta = e0 - e1;
+    if (isnan(delta)) delta = -INFINITY;
+    float pa = expf(delta);
+    if (pa > 1.0f) pa = 1.0f;
+    uint32_t a, b;
+    threefry2x32(ki0, ki1, 0u, 0u, &a, &b);
+    const float u = bits_to_unit(a ^ b);
+    const int acc = u < pa;
+    if (acc) {
+      memcpy(qc, q1, sizeof(float) * D);
+      memcpy(gc, g1, sizeof(float) * D);
+      J->logp[c] = lp;
+    }
+    if (J->acc_rate) J->acc_rate[c] = pa;
+    if (J->accepted) J->accepted[c] = (unsigned char)acc;
+  }
+  free(p);
+  return NULL;
+}
+
+int oracle_num_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+/* One HMC transition for chains [0, C): in-place on q, logp, g.  Returns the number of leapfrogs done. */
+long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const float* imm /*[D]*/,
+                          const uint32_t* keys /*[C,2]*/, float* q, float* logp, float* g, float eps, int L,
+                          float* acc_rate /*[C] or NULL*/, unsigned char* accepted /*[C] or NULL*/, int n_threads) {
+  float* msqrt = (float*)malloc(sizeof(float) * D);
+  for (int i = 0; i < D; ++i) msqrt[i] = 1.0f / sqrtf(imm[i]);
+  int T = n_threads > 0 ? n_threads : oracle_num_threads();
+  if (T > C) T = C;
+  if (T < 1) T = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * T);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * T);
+  for (int t = 0; t < T; ++t) {
+    job_t j = {(int)((long long)C * t / T), (int)((long long)C * (t + 1) / T), D, kind, L, inv_var, imm, msqrt, keys,
+               q, logp, g, eps, acc_rate, accepted};
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+  free(msqrt);
+  return (long long)C * L;
+}

@@ -23,7 +23,7 @@ class DiagGaussian:
 
     kind = "diag_gaussian"
 
-    def __init__(self, scale=1.0, dim=None):
+    def __init__(self, scale=1.0, dim=None, mean=None, logp_offset=0.0):
         s = np.asarray(scale, np.float64)
         if s.ndim == 0:
             assert dim is not None
@@ -32,11 +32,14 @@ class DiagGaussian:
         # same constant the device path receives: 1/s^2 rounded once to f32
         self.inv_var = (1.0 / (s * s)).astype(F)
         self.dim = self.scale.shape[0]
+        self.mean = None if mean is None else np.broadcast_to(np.asarray(mean, F), (self.dim,)).copy()
+        self.logp_offset = F(logp_offset)
 
     def __call__(self, q):
         q = np.asarray(q, F)
-        t = q * self.inv_var
-        logp = F(-0.5) * np.sum(q * t, axis=-1, dtype=F)
+        d = q if self.mean is None else (q - self.mean).astype(F)
+        t = d * self.inv_var
+        logp = F(-0.5) * np.sum(d * t, axis=-1, dtype=F) + self.logp_offset
         return logp.astype(F), (-t).astype(F)
 
 

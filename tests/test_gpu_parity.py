@@ -1,0 +1,514 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the blackjax_b200 API) against the CPU
+oracle on the same seeded inputs, plus size-independent properties at BASELINE.json's full shapes.
+
+Tolerances (stated per BASELINE.md section 4): PRNG integers and uniform variates bit-exact; one
+transition from an identical (state, key) within 1e-5 relative (abs floor 1e-5 x typical scale);
+discrete decisions (accept, direction, turning, tree size) identical except where the deciding float
+comparison is within float32 rounding of a tie.
+"""
+import numpy as np
+import pytest
+import torch
+
+import blackjax_b200 as bj
+from blackjax_b200 import _engine, targets as T
+from oracle import adaptation as oadapt
+from oracle import hmc as ohmc
+from oracle import nuts as onuts
+from oracle import prng as oprng
+from oracle import targets as otargets
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+DEV = "cuda:0"
+
+
+def tk(keys_np):
+    """numpy uint32 keys -> torch uint32 CUDA tensor."""
+    return torch.from_numpy(np.ascontiguousarray(keys_np).view(np.int32)).to(DEV).view(torch.uint32)
+
+
+def tf(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=1e-5, scale=None):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    s = np.max(np.abs(b)) if scale is None else scale
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * max(s, 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PRNG: bit-exact
+# ---------------------------------------------------------------------------------------------------------
+def test_prng_bit_exact():
+    k0 = bj.random.key(0, DEV)
+    assert npy(bj.random.split(k0)).tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+    keys = oprng.split(oprng.key(123), 257)
+    dk = tk(keys)
+    assert (npy(bj.random.split(dk, 3)) == oprng.split(keys, 3)).all()
+    assert (npy(bj.random.fold_in(dk, 77)) == oprng.fold_in(keys, 77)).all()
+    assert (npy(bj.random.bits(dk, (33,))) == oprng.random_bits(keys, (33,))).all()
+    assert (npy(bj.random.uniform(dk, (33,))) == oprng.uniform(keys, (33,))).all()
+    n_dev = npy(bj.random.normal(dk, (130,)))
+    n_ref = oprng.normal(keys, (130,))
+    assert np.max(np.abs(n_dev - n_ref)) < 2e-6
+    assert float(npy(bj.random.normal(bj.random.key(42, DEV)))) == pytest.approx(-0.028304616, abs=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------------------------------------
+def make_target(kind, D, rs):
+    if kind == "std":
+        return T.StdNormal(D), otargets.StdNormal(D)
+    if kind == "diag":
+        s = np.exp(rs.uniform(-1, 1, D))
+        mean = rs.standard_normal(D).astype(F)
+        return T.DiagGaussian(s, mean=mean, logp_offset=0.25), otargets.DiagGaussian(s, mean=mean, logp_offset=0.25)
+    if kind == "funnel":
+        return T.Funnel(D), otargets.Funnel(D)
+    if kind == "dense":
+        A = rs.standard_normal((D, D))
+        P = A @ A.T / D + np.eye(D)
+        return T.DenseGaussian(P), otargets.DenseGaussian(P)
+    if kind == "banana":
+        return T.Banana(), otargets.Banana()
+    raise ValueError(kind)
+
+
+SHAPES = [("std", 100), ("diag", 1024), ("diag", 516), ("diag", 7), ("diag", 97), ("funnel", 128),
+          ("funnel", 10), ("funnel", 260), ("dense", 6), ("dense", 64), ("banana", 2), ("std", 1)]
+
+
+@pytest.mark.parametrize("kind, D", SHAPES)
+def test_init_state_matches_oracle(kind, D):
+    rs = np.random.default_rng(1)
+    tgt, otgt = make_target(kind, D, rs)
+    C = 37
+    q = rs.standard_normal((C, D)).astype(F)
+    st = bj.hmc.init(tf(q), tgt)
+    lp, g = otgt(q)
+    close(npy(st.logdensity), lp, rtol=2e-6, scale=np.max(np.abs(lp)) + 1)
+    close(npy(st.logdensity_grad), g, rtol=2e-6)
+
+
+@pytest.mark.parametrize("D, dense", [(100, False), (1024, False), (7, False), (6, True), (64, True)])
+def test_sample_momentum_matches_oracle(D, dense):
+    rs = np.random.default_rng(2)
+    C = 33
+    if dense:
+        A = rs.standard_normal((D, D))
+        imm = (A @ A.T / D + np.eye(D)).astype(F)
+    else:
+        imm = np.exp(rs.uniform(-2, 2, D)).astype(F)
+    tgt = T.StdNormal(D)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    keys = oprng.split(oprng.key(5), C)
+    p = npy(eng.sample_momentum(tk(keys)))
+    ref = ohmc.Metric(imm).sample_momentum(keys, D)
+    close(p, ref, rtol=3e-6)
+    # kinetic energy through bjx_energy
+    e = npy(eng.energy(tf(ref), tf(np.zeros(C, F))))
+    close(e, ohmc.Metric(imm).kinetic_energy(ref), rtol=2e-6)
+
+
+def test_dense_metric_factorisation_identity():
+    # tests/mcmc/test_metrics.py:158-179: p = L^-T z for M^-1 = [[2/3, .5], [.5, 3/4]]
+    imm = np.array([[2 / 3, 0.5], [0.5, 3 / 4]], F)
+    eng = _engine.Engine(DEV, 1, 2, T.StdNormal(2))
+    eng.set_metric(tf(imm))
+    p = npy(eng.sample_momentum(tk(oprng.key(0)[None])))
+    L = np.linalg.cholesky(imm.astype(np.float64))
+    z = oprng.normal(oprng.key(0), (2,)).astype(np.float64)
+    close(p[0], np.linalg.solve(L.T, z), rtol=3e-6)
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        eng.set_metric(torch.ones(2, 2, 2, device=DEV))
+
+
+def test_momentum_identity_diag_quarter():
+    # tests/mcmc/test_metrics.py:124-142: M^-1 = [1/4] -> p = 2 * normal(key)
+    eng = _engine.Engine(DEV, 1, 1, T.StdNormal(1))
+    eng.set_metric(tf(np.array([0.25], F)))
+    p = npy(eng.sample_momentum(tk(oprng.key(0)[None])))
+    assert abs(p[0, 0] - 2.0 * float(oprng.normal(oprng.key(0)))) < 1e-6
+
+
+def test_velocity_verlet_mvn_golden():
+    # tests/mcmc/test_integrators.py:74-103 golden end state through bjx_leapfrog (dense metric + dense target)
+    from test_oracle_kat import COV6, P6_END, P6_INIT, Q6_END, Q6_INIT
+    tgt = T.DenseGaussian(np.linalg.inv(COV6))
+    eng = _engine.Engine(DEV, 1, 6, tgt)
+    eng.set_metric(tf(COV6))
+    q = tf(Q6_INIT)
+    p = tf(P6_INIT)
+    logp, g = eng.init_state(q)
+    eng.leapfrog_(q, p, logp, g, 0.005, 16)
+    np.testing.assert_allclose(npy(q)[0], Q6_END, atol=3e-6)
+    np.testing.assert_allclose(npy(p)[0], P6_END, atol=3e-6)
+
+
+@pytest.mark.parametrize("kind, D", [("std", 100), ("diag", 1024), ("diag", 97), ("funnel", 128), ("dense", 6)])
+def test_leapfrog_matches_oracle(kind, D):
+    rs = np.random.default_rng(3)
+    tgt, otgt = make_target(kind, D, rs)
+    C = 19
+    imm = np.exp(rs.uniform(-1, 1, D)).astype(F)
+    q = (0.3 * rs.standard_normal((C, D))).astype(F)
+    p = rs.standard_normal((C, D)).astype(F)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    dq, dp = tf(q), tf(p)
+    logp, g = eng.init_state(dq)
+    eps = F(0.05)
+    eng.leapfrog_(dq, dp, logp, g, float(eps), 7)
+    lp0, g0 = otgt(q)
+    q1, p1, lp1, g1 = ohmc.static_integration(otgt, ohmc.Metric(imm), q, p, lp0, g0, eps, 7)
+    if kind in ("std", "diag"):  # purely elementwise dynamics: bit-exact with the float32 oracle
+        assert (npy(dq) == q1).all() and (npy(dp) == p1).all() and (npy(g) == g1).all()
+    else:
+        close(npy(dq), q1)
+        close(npy(dp), p1)
+        close(npy(g), g1)
+    close(npy(logp), lp1, rtol=3e-6, scale=np.max(np.abs(lp1)) + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# HMC transition (teacher-forced: identical state + key on both sides)
+# ---------------------------------------------------------------------------------------------------------
+def run_hmc_case(kind, D, C, L, eps, imm_kind="diag", per_chain_eps=False, seed=11):
+    rs = np.random.default_rng(seed)
+    tgt, otgt = make_target(kind, D, rs)
+    if imm_kind == "diag":
+        imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    elif imm_kind == "ones":
+        imm = np.ones(D, F)
+    elif imm_kind == "dense":
+        A = rs.standard_normal((D, D))
+        imm = (A @ A.T / D + np.eye(D)).astype(F)
+    else:  # per-chain diagonal
+        imm = np.exp(rs.uniform(-0.5, 0.5, (C, D))).astype(F)
+    q = (0.5 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(seed), C)
+    eps_np = (eps * np.exp(rs.uniform(-0.3, 0.3, C))).astype(F) if per_chain_eps else F(eps)
+    ometric = oadapt._PerChainDiag(imm) if imm_kind == "per_chain" else ohmc.Metric(imm)
+    ostate = ohmc.init(q, otgt)
+    onew, oinfo = ohmc.hmc_kernel(keys, ostate, otgt, eps_np, ometric, L)
+
+    kernel = bj.hmc.build_kernel(full_info=True)
+    state = bj.hmc.init(tf(q), tgt)
+    step = tf(eps_np) if per_chain_eps else float(eps_np)
+    new, info = kernel(tk(keys), state, tgt, step, tf(imm), L)
+    torch.cuda.synchronize()
+    # energies and acceptance probability
+    close(npy(info.energy), oinfo.energy, rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + 1)
+    close(npy(info.acceptance_rate), oinfo.acceptance_rate, rtol=1e-4, scale=1.0)
+    close(npy(info.momentum), oinfo.momentum, rtol=3e-6)
+    close(npy(info.proposal.position), oinfo.proposal[0])
+    close(npy(info.proposal.momentum), oinfo.proposal[1])
+    # accept decisions: identical except within rounding of a tie
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    acc_dev = npy(info.is_accepted)
+    tie = np.abs(u - oinfo.acceptance_rate) < 1e-5
+    assert ((acc_dev == oinfo.is_accepted) | tie).all()
+    assert (npy(info.is_divergent) == oinfo.is_divergent).all()
+    same = acc_dev == oinfo.is_accepted
+    close(npy(new.position)[same], onew.position[same])
+    close(npy(new.logdensity_grad)[same], onew.logdensity_grad[same])
+    close(npy(new.logdensity)[same], onew.logdensity[same], rtol=1e-5, scale=np.max(np.abs(onew.logdensity)) + 1)
+    return acc_dev.mean()
+
+
+def test_hmc_config1_iso_gaussian_1024x100():
+    # BASELINE config 1: HMC, 100-D isotropic Gaussian, 1024 chains, diag mass, 10 leapfrog steps
+    rate = run_hmc_case("std", 100, 1024, 10, 0.2, imm_kind="ones")
+    assert 0.5 < rate <= 1.0
+
+
+@pytest.mark.parametrize("kind, D, C, L, eps, imm_kind, pce", [
+    ("diag", 1024, 64, 10, 0.05, "diag", False),
+    ("diag", 516, 33, 5, 0.1, "diag", True),
+    ("diag", 97, 40, 8, 0.1, "per_chain", True),
+    ("diag", 7, 40, 8, 0.2, "diag", False),
+    ("funnel", 128, 96, 10, 0.05, "ones", False),
+    ("funnel", 10, 50, 20, 0.1, "diag", False),
+    ("dense", 6, 30, 10, 0.1, "dense", False),
+    ("dense", 64, 20, 5, 0.05, "dense", False),
+    ("banana", 2, 64, 12, 0.1, "dense", False),
+    ("std", 1, 64, 30, 3.9, "ones", False),     # tests/mcmc/test_sampling.py:1055-1119 HMC settings
+    ("std", 100, 64, 10, 30.0, "ones", False),  # wildly unstable step: divergences / NaN energies -> reject
+])
+def test_hmc_transition_matches_oracle(kind, D, C, L, eps, imm_kind, pce):
+    run_hmc_case(kind, D, C, L, eps, imm_kind, pce)
+
+
+def test_hmc_inplace_and_out_of_place_agree():
+    tgt = T.StdNormal(64)
+    q = torch.randn(128, 64, device=DEV)
+    keys = bj.random.split(bj.random.key(3, DEV), 128)
+    st = bj.hmc.init(q.clone(), tgt)
+    imm = torch.ones(64, device=DEV)
+    a, ia = bj.hmc.build_kernel()(keys, st, tgt, 0.3, imm, 5)
+    st2 = bj.hmc.init(q.clone(), tgt)
+    b, ib = bj.hmc.build_kernel(inplace=True)(keys, st2, tgt, 0.3, imm, 5)
+    assert torch.equal(a.position, b.position) and torch.equal(a.logdensity_grad, b.logdensity_grad)
+    assert b.position.data_ptr() == st2.position.data_ptr()
+    assert torch.equal(st.position, q)  # the out-of-place call left its input untouched
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NUTS
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("step_size, diverge, turn, doublings",
+                         [(1e-10, False, False, 10), (1.0, False, True, 2), (1e5, True, True, 1)])
+def test_nuts_expansion_outcomes_kat(step_size, diverge, turn, doublings):
+    # tests/mcmc/test_trajectory.py:193-260 through bjx_nuts_step
+    tgt = T.StdNormal(1)
+    imm = torch.ones(1, device=DEV)
+    k = oprng.key(0)[None]
+    p0 = ohmc.Metric(np.ones(1, F)).sample_momentum(k, 1)
+    st = bj.nuts.init(torch.zeros(1, 1, device=DEV), tgt)
+    kern = bj.nuts.build_kernel()
+    _, info = kern(None, st, tgt, step_size, imm, 10, _momentum=tf(p0), _key_integrator=tk(k))
+    assert bool(info.is_divergent[0]) == diverge
+    assert bool(info.is_turning[0]) == turn
+    assert int(info.num_trajectory_expansions[0]) == doublings
+
+
+def run_nuts_case(kind, D, C, eps, imm_kind="ones", max_doublings=10, seed=21, min_match=0.97):
+    rs = np.random.default_rng(seed)
+    tgt, otgt = make_target(kind, D, rs)
+    if imm_kind == "ones":
+        imm = np.ones(D, F)
+    elif imm_kind == "diag":
+        imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    else:
+        A = rs.standard_normal((D, D))
+        imm = (A @ A.T / D + np.eye(D)).astype(F)
+    q = (0.1 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(seed), C)
+    ostate = ohmc.init(q, otgt)
+    onew, oinfo = onuts.nuts_kernel(keys, ostate, otgt, F(eps), imm, max_doublings)
+    kern = bj.nuts.build_kernel(full_info=True, max_tree_depth=max_doublings)
+    st = bj.nuts.init(tf(q), tgt)
+    new, info = kern(tk(keys), st, tgt, float(eps), tf(imm), max_doublings)
+    torch.cuda.synchronize()
+    close(npy(info.momentum), oinfo.momentum, rtol=3e-6)
+    n_dev, n_ref = npy(info.num_integration_steps), oinfo.num_integration_steps
+    same = ((n_dev == n_ref) & (npy(info.num_trajectory_expansions) == oinfo.num_trajectory_expansions)
+            & (npy(info.is_turning) == oinfo.is_turning) & (npy(info.is_divergent) == oinfo.is_divergent))
+    pos_same = np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1)
+    frac = float(np.mean(same & pos_same))
+    # discrete tree decisions sit on float comparisons (U-turn dot products, multinomial draws): chains whose
+    # deciding comparison is within rounding of a tie may legitimately differ; everything else must agree.
+    assert frac >= min_match, f"only {frac:.3f} of chains match the oracle"
+    ok = same & pos_same
+    close(npy(info.acceptance_rate)[ok], oinfo.acceptance_rate[ok], rtol=1e-4, scale=1.0)
+    close(npy(info.energy)[ok], oinfo.energy[ok], rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + 1)
+    close(npy(new.logdensity_grad)[ok], onew.logdensity_grad[ok], rtol=1e-4)
+    close(npy(info.trajectory_leftmost_state.position)[ok], oinfo.trajectory_leftmost_state[0][ok], rtol=1e-4)
+    close(npy(info.trajectory_rightmost_state.momentum)[ok], oinfo.trajectory_rightmost_state[1][ok], rtol=1e-4)
+    return n_dev
+
+
+@pytest.mark.parametrize("kind, D, C, eps, imm_kind, md", [
+    ("std", 1, 64, 1.0, "ones", 10),          # tests/mcmc/test_sampling.py:1174-1186 NUTS settings
+    ("std", 100, 64, 0.2, "ones", 10),
+    ("diag", 64, 48, 0.15, "diag", 10),
+    ("diag", 97, 32, 0.15, "diag", 6),        # scalar layout
+    ("funnel", 128, 64, 0.1, "ones", 10),     # BASELINE config 3 target/shape (fewer chains)
+    ("funnel", 10, 64, 0.3, "ones", 10),
+    ("banana", 2, 64, 0.1, "dense", 10),      # dense metric through the small in-warp path
+    ("dense", 6, 32, 0.2, "dense", 8),
+    ("std", 8, 64, 1e-4, "ones", 4),          # never turns: hits max depth
+    ("std", 8, 32, 1e4, "ones", 10),          # diverges on the first leaf
+])
+def test_nuts_transition_matches_oracle(kind, D, C, eps, imm_kind, md):
+    run_nuts_case(kind, D, C, eps, imm_kind, md)
+
+
+def test_nuts_step_count_stats():
+    n = run_nuts_case("std", 16, 256, 0.5, "ones", 10)
+    assert n.min() >= 1 and n.max() <= 1023
+
+
+# ---------------------------------------------------------------------------------------------------------
+# window adaptation
+# ---------------------------------------------------------------------------------------------------------
+def test_dual_averaging_and_welford_kernels():
+    from blackjax_b200._lib import check, lib, ptr
+    C, D = 50, 12
+    rs = np.random.default_rng(4)
+    eng = _engine.Engine(DEV, C, D, T.StdNormal(D))
+    st = torch.empty(C, 5, device=DEV)
+    eps0 = tf(np.exp(rs.uniform(-1, 1, C)))
+    eps = torch.empty(C, device=DEV)
+    check(lib().bjx_da_init(eng.h, ptr(st), ptr(eps0), ptr(eps)), eng.h)
+    o = [oadapt.da_init(e) for e in npy(eps0)]
+    for it in range(12):
+        acc = rs.uniform(0, 1, C).astype(F)
+        check(lib().bjx_da_update(eng.h, ptr(st), ptr(tf(acc)), 0.8, ptr(eps)), eng.h)
+        o = [oadapt.da_update(s, a, 0.8) for s, a in zip(o, acc)]
+        close(npy(eps), [np.exp(s.log_step_size) for s in o], rtol=1e-5)
+    fin = torch.empty(C, device=DEV)
+    check(lib().bjx_da_final(eng.h, ptr(st), ptr(fin)), eng.h)
+    close(npy(fin), [oadapt.da_final(s) for s in o], rtol=1e-5)
+    check(lib().bjx_da_reset(eng.h, ptr(st), ptr(eps)), eng.h)
+    close(npy(eps), [np.exp(oadapt.da_init(oadapt.da_final(s)).log_step_size) for s in o], rtol=1e-5)
+    # Welford
+    mean = torch.zeros(C, D, device=DEV)
+    m2 = torch.zeros(C, D, device=DEV)
+    ws = [oadapt.welford_init(D) for _ in range(C)]
+    for n in range(1, 9):
+        x = rs.standard_normal((C, D)).astype(F)
+        check(lib().bjx_welford_update(eng.h, ptr(tf(x)), ptr(mean), ptr(m2), n), eng.h)
+        ws = [oadapt.welford_update(w, xi) for w, xi in zip(ws, x)]
+    close(npy(mean), np.stack([w.mean for w in ws]), rtol=1e-5)
+    close(npy(m2), np.stack([w.m2 for w in ws]), rtol=1e-5)
+    imm = torch.empty(C, D, device=DEV)
+    check(lib().bjx_welford_final(eng.h, ptr(mean), ptr(m2), 8, ptr(imm)), eng.h)
+    close(npy(imm), np.stack([oadapt.welford_final(w) for w in ws]), rtol=1e-5)
+    assert float(mean.abs().max()) == 0.0
+    # pooled block
+    x = rs.standard_normal((C, D)).astype(F) * 3 + 1
+    acc = rs.uniform(0, 1, C).astype(F)
+    out = torch.empty(2 + 2 * D, device=DEV)
+    check(lib().bjx_pooled_stats(eng.h, ptr(tf(x)), ptr(tf(acc)), ptr(out)), eng.h)
+    o = npy(out)
+    assert o[1] == C
+    close(o[0], acc.sum(), rtol=1e-5)
+    close(o[2:2 + D], x.mean(0), rtol=1e-5)
+    close(o[2 + D:], ((x - x.mean(0)) ** 2).sum(0), rtol=1e-4)
+
+
+@pytest.mark.parametrize("algo", ["hmc", "nuts"])
+def test_window_adaptation_per_chain_matches_oracle(algo):
+    D, C, T_ = 8, 16, 60
+    scale = np.logspace(-0.5, 0.5, D)
+    tgt, otgt = T.DiagGaussian(scale), otargets.DiagGaussian(scale)
+    rs = np.random.default_rng(9)
+    q = rs.standard_normal((C, D)).astype(F)
+    ckeys = oprng.split(oprng.key(77), C)
+    if algo == "hmc":
+        okern = lambda k, s, t, e, m, **kw: ohmc.hmc_kernel(k, s, t, e, m, 8)
+        extra = dict(num_integration_steps=8)
+        alg = bj.hmc
+    else:
+        okern = lambda k, s, t, e, m, **kw: onuts.nuts_kernel(k, s, t, e, m, 6)
+        extra = dict(max_num_doublings=6)
+        alg = bj.nuts
+    ost, oeps, oimm, ohist = oadapt.window_adaptation_run(okern, otgt, ckeys, q, T_)
+    warm = bj.window_adaptation(alg, tgt, **extra)
+    (st, params), _ = warm.run(tk(ckeys), tf(q), T_)
+    torch.cuda.synchronize()
+    # free-running for 60 adaptive transitions: rounding differences feed back through accept decisions, so
+    # compare the adapted quantities loosely per chain and tightly in aggregate.
+    eps_dev, imm_dev = npy(params["step_size"]), npy(params["inverse_mass_matrix"])
+    match = np.isclose(eps_dev, oeps, rtol=1e-3)
+    assert match.mean() >= 0.75
+    assert np.isclose(imm_dev[match], oimm[match], rtol=1e-2, atol=1e-4).mean() > 0.98
+    assert abs(np.median(eps_dev) / np.median(oeps) - 1) < 0.05
+
+
+def test_window_adaptation_shared_matches_oracle_and_recovers_scales():
+    D, C, T_ = 16, 256, 120
+    scale = np.logspace(-0.5, 0.5, D)
+    tgt, otgt = T.DiagGaussian(scale), otargets.DiagGaussian(scale)
+    rs = np.random.default_rng(10)
+    q = rs.standard_normal((C, D)).astype(F)
+    okern = lambda k, s, t, e, m, **kw: onuts.nuts_kernel(k, s, t, e, m, 5)
+    ost, oeps, oimm, ohist = oadapt.window_adaptation_run(okern, otgt, oprng.key(5), q, T_, shared=True)
+    warm = bj.window_adaptation(bj.nuts, tgt, shared=True, max_num_doublings=5)
+    (st, params), hist = warm.run(bj.random.key(5, DEV), tf(q), T_)
+    # pooled statistics over 256 chains damp single-chain decision flips: the two runs track closely
+    assert abs(params["step_size"] / float(oeps) - 1) < 0.05
+    np.testing.assert_allclose(npy(params["inverse_mass_matrix"]), oimm, rtol=0.1)
+    np.testing.assert_allclose(npy(params["inverse_mass_matrix"]), scale ** 2, rtol=0.35)
+    np.testing.assert_allclose(np.array(hist[:20]), ohist[:20], rtol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_fullsize_leapfrog_reversibility_and_energy_65536x1024():
+    C, D, L = 65536, 1024, 50
+    s = np.logspace(-0.5, 0.5, D)
+    tgt = T.DiagGaussian(s)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    imm = torch.from_numpy((s ** 2).astype(F)).to(DEV)
+    eng.set_metric(imm)
+    g_ = torch.Generator(device=DEV).manual_seed(0)
+    q0 = torch.randn(C, D, device=DEV, generator=g_) * torch.from_numpy(s.astype(F)).to(DEV)
+    p0 = eng.sample_momentum(bj.random.split(bj.random.key(1, DEV), C))
+    q, p = q0.clone(), p0.clone()
+    logp, g = eng.init_state(q)
+    e0 = eng.energy(p, logp)
+    eng.leapfrog_(q, p, logp, g, 0.1, L)
+    e1 = eng.energy(p, logp)
+    # symplectic integrator: energy error O(eps^2) and bounded
+    assert float((e1 - e0).abs().max() / e0.abs().mean()) < 5e-3
+    # time reversibility: flip momentum, integrate back, recover the start (float32 round-off only)
+    p.neg_()
+    eng.leapfrog_(q, p, logp, g, 0.1, L)
+    assert float((q - q0).abs().max()) < 5e-4 * float(q0.abs().max())
+    assert float((p + p0).abs().max()) < 5e-4 * float(p0.abs().max())
+    # n_steps composition: 50 one-step launches == one 50-step launch, bit for bit
+    qa, pa = q0.clone(), p0.clone()
+    la, ga = eng.init_state(qa)
+    qb, pb = q0.clone(), p0.clone()
+    lb, gb = eng.init_state(qb)
+    eng.leapfrog_(qa, pa, la, ga, 0.1, 5)
+    for _ in range(5):
+        eng.leapfrog_(qb, pb, lb, gb, 0.1, 1)
+    assert torch.equal(qa, qb) and torch.equal(pa, pb) and torch.equal(ga, gb)
+
+
+def test_fullsize_hmc_65536x1024_detailed_balance_stats():
+    C, D, L = 65536, 1024, 50
+    tgt = T.StdNormal(D)
+    imm = torch.ones(D, device=DEV)
+    g_ = torch.Generator(device=DEV).manual_seed(1)
+    q = torch.randn(C, D, device=DEV, generator=g_)
+    st = bj.hmc.init(q, tgt)
+    kern = bj.hmc.build_kernel()
+    keys = bj.random.split(bj.random.key(2, DEV), 3)
+    acc = []
+    for t in range(3):
+        st, info = kern(keys[t], st, tgt, 0.12, imm, L)
+        acc.append(float(info.acceptance_rate.mean()))
+        # accepted rows moved, rejected rows kept the old state (checked through the log-density identity)
+        lp = -0.5 * (st.position.double() ** 2).sum(1)
+        assert float((lp - st.logdensity.double()).abs().max()) < 1e-2
+    assert 0.6 < np.mean(acc) < 0.999
+    # stationary: started from the target, the second moment stays 1 within Monte-Carlo error
+    assert abs(float(st.position.var()) - 1.0) < 5e-3
+
+
+def test_fullsize_nuts_funnel_65536x128():
+    # BASELINE config 3: NUTS, Neal's funnel D=128, 65536 chains, diag mass, max_tree_depth=10
+    C, D = 65536, 128
+    tgt = T.Funnel(D)
+    imm = torch.ones(D, device=DEV)
+    q = 0.1 * bj.random.normal(bj.random.split(bj.random.key(0, DEV), C), (D,))
+    st = bj.nuts.init(q, tgt)
+    kern = bj.nuts.build_kernel()
+    st2, info = kern(bj.random.key(1, DEV), st, tgt, 0.1, imm, 10)
+    n = info.num_integration_steps
+    d = info.num_trajectory_expansions
+    assert int(n.min()) >= 1 and int(n.max()) <= 1023
+    # a tree of depth d holds between 2^(d-1) and 2^d - 1 leaves (last sub-tree may stop early)
+    assert bool(((n <= (2 ** d.long()) - 1) & (n >= 2 ** (d.long() - 1))).all())
+    ar = info.acceptance_rate
+    assert bool(((ar >= 0) & (ar <= 1)).all())
+    # returned state is self-consistent: logdensity/grad are those of the returned position
+    lp, g = _engine.get_engine(st2.position, tgt).init_state(st2.position)
+    assert float((lp - st2.logdensity).abs().max()) < 1e-2 * (1 + float(lp.abs().max()) * 1e-3)
+    torch.testing.assert_close(g, st2.logdensity_grad, rtol=1e-4, atol=1e-3)
+    # identical keys + identical state => identical result (determinism, no atomics in the data path)
+    st3, info3 = kern(bj.random.key(1, DEV), st, tgt, 0.1, imm, 10)
+    assert torch.equal(st2.position, st3.position) and torch.equal(n, info3.num_integration_steps)

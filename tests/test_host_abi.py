@@ -1,0 +1,169 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/bjx.h declares, argument
+errors surface as they should without a GPU, and the host-side adaptation logic (schedule, shared-epsilon
+dual averaging, CGL merge, the one all-gather under gloo with world_size 2) matches the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bjx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bjx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from blackjax_b200 import _lib
+    lib = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bjx.h but not exported by libbjx.so"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared      # the ctypes binding covers the whole header
+    assert lib.bjx_version() == 100
+
+
+def test_struct_layouts_match_header():
+    from blackjax_b200 import _lib
+    # bjx_target_desc: 2 x int32, 3 pointers, float (+pad); bjx_info: 14 pointers
+    assert C.sizeof(_lib.TargetDesc) == 40
+    assert C.sizeof(_lib.Info) == 14 * 8
+    assert C.sizeof(_lib.Config) == 16 + 8 + 8 + 40
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_fails_loudly():
+    import blackjax_b200 as bj
+    from blackjax_b200 import _lib
+    cfg = _lib.Config()
+    cfg.device, cfg.n_chains, cfg.dim, cfg.max_tree_depth = 0, 4, 8, 10
+    cfg.target.kind, cfg.target.dim = _lib.TARGET_FUNNEL, 8
+    h = C.c_void_p()
+    rc = _lib.lib().bjx_create(C.byref(cfg), C.byref(h))
+    assert rc > 0                                          # a cudaError_t, not a silent CPU path
+    assert b"no CPU fallback" in _lib.lib().bjx_last_error(None)
+    with pytest.raises(TypeError, match="CUDA tensor"):
+        bj.hmc.init(torch.zeros(4, 8), bj.targets.Funnel(8))
+
+
+def test_argument_validation_without_gpu():
+    from blackjax_b200 import _lib
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.bjx_create(None, C.byref(h)) == -1
+    cfg = _lib.Config()
+    cfg.device, cfg.n_chains, cfg.dim, cfg.max_tree_depth = 0, 0, 8, 10
+    assert lib.bjx_create(C.byref(cfg), C.byref(h)) == -1
+    cfg.n_chains, cfg.dim = 4, 1030                        # dim % 4 != 0 and > 128
+    assert lib.bjx_create(C.byref(cfg), C.byref(h)) == -2
+    assert lib.bjx_init_state(None, None, None, None) == -1
+
+
+def test_api_surface_mirrors_blackjax():
+    import inspect
+
+    import blackjax_b200 as bj
+    for alg in (bj.hmc, bj.nuts):
+        assert callable(alg) and callable(alg.init) and callable(alg.build_kernel)
+        assert list(inspect.signature(alg.init).parameters)[:2] == ["position", "logdensity_fn"]
+    k = bj.hmc.build_kernel()
+    assert list(inspect.signature(k).parameters) == ["rng_key", "state", "logdensity_fn", "step_size",
+                                                     "inverse_mass_matrix", "num_integration_steps"]
+    k = bj.nuts.build_kernel()
+    assert list(inspect.signature(k).parameters)[:6] == ["rng_key", "state", "logdensity_fn", "step_size",
+                                                         "inverse_mass_matrix", "max_num_doublings"]
+    alg = bj.nuts(bj.targets.Funnel(8), 0.1, torch.ones(8))
+    assert isinstance(alg, bj.SamplingAlgorithm)
+    assert list(inspect.signature(alg.step).parameters) == ["rng_key", "state"]
+    assert bj.nuts.init is bj.hmc.init                     # blackjax/mcmc/nuts.py:33
+
+
+def test_schedule_matches_reference_kat():
+    import blackjax_b200 as bj
+    from oracle.adaptation import build_schedule as ob
+    for n in (0, 5, 19, 20, 37, 100, 150, 200, 1000):
+        assert bj.build_schedule(n) == ob(n)
+    assert bj.build_schedule(100) == [(0, False)] * 15 + [(1, False)] * 74 + [(1, True)] + [(0, False)] * 10
+
+
+def test_shared_dual_averaging_host_matches_oracle():
+    import importlib
+    wa = importlib.import_module("blackjax_b200.adaptation.window_adaptation")
+    from oracle import adaptation as oa
+    rs = np.random.default_rng(0)
+    s, o = wa._da_init(0.7), oa.da_init(0.7)
+    for _ in range(40):
+        a = float(rs.uniform(0, 1))
+        s, o = wa._da_update(s, a, 0.8), oa.da_update(o, a, 0.8)
+        assert s.log_step == pytest.approx(float(o.log_step_size), rel=1e-6, abs=1e-7)
+        assert s.log_step_avg == pytest.approx(float(o.log_step_size_avg), rel=1e-6, abs=1e-7)
+        assert s.step == o.step
+
+
+def test_cgl_merge_blocks_matches_oracle():
+    from blackjax_b200.adaptation.window_adaptation import cgl_merge_blocks
+    from oracle import adaptation as oa
+    rs = np.random.default_rng(1)
+    D, G = 7, 4
+    xs = [rs.standard_normal((50 + 10 * g, D)).astype(np.float32) * (g + 1) for g in range(G)]
+    blocks = []
+    for x in xs:
+        m = x.mean(0)
+        blocks.append(np.concatenate([[x[:, 0].sum()], [len(x)], m, ((x - m) ** 2).sum(0)]))
+    acc, n, mean, m2 = cgl_merge_blocks(torch.tensor(np.stack(blocks), dtype=torch.float32))
+    allx = np.concatenate(xs)
+    assert float(n) == len(allx)
+    np.testing.assert_allclose(mean.numpy(), allx.mean(0), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m2.numpy(), ((allx - allx.mean(0)) ** 2).sum(0), rtol=1e-4)
+    w = oa.Welford(blocks[0][2:2 + D].astype(np.float32), blocks[0][2 + D:].astype(np.float32), len(xs[0]))
+    for b, x in zip(blocks[1:], xs[1:]):
+        w = oa.cgl_merge(w, oa.Welford(b[2:2 + D].astype(np.float32), b[2 + D:].astype(np.float32), len(x)))
+    np.testing.assert_allclose(m2.numpy(), w.m2, rtol=1e-5)
+
+
+_GLOO_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from blackjax_b200.adaptation.window_adaptation import _allgather_stats, cgl_merge_blocks
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rs = np.random.default_rng(0)
+D = 5
+x_all = rs.standard_normal((64, D)).astype(np.float32) * 2 + 1
+acc_all = rs.uniform(0, 1, 64).astype(np.float32)
+x, a = x_all[rank * 32:(rank + 1) * 32], acc_all[rank * 32:(rank + 1) * 32]        # chain shard of this rank
+m = x.mean(0)
+block = torch.tensor(np.concatenate([[a.sum()], [32.0], m, ((x - m) ** 2).sum(0)]), dtype=torch.float32)
+blocks = _allgather_stats(block, None)                                            # the ONE collective
+acc, n, mean, m2 = cgl_merge_blocks(blocks)
+assert blocks.shape == (2, 2 + 2 * D) and float(n) == 64
+np.testing.assert_allclose(float(acc) / float(n), acc_all.mean(), rtol=1e-5)
+np.testing.assert_allclose(mean.numpy(), x_all.mean(0), rtol=1e-5, atol=1e-6)
+np.testing.assert_allclose(m2.numpy(), ((x_all - x_all.mean(0)) ** 2).sum(0), rtol=1e-4)
+# every rank must hold bit-identical merged statistics (no broadcast follows)
+gathered = [torch.empty_like(m2) for _ in range(2)]
+dist.all_gather(gathered, m2)
+assert torch.equal(gathered[0], gathered[1])
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_allgather_merge_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + (os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "OK" in o

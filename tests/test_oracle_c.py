@@ -1,0 +1,31 @@
+"""The C/pthreads oracle twin (CPU timing stand-in) agrees with the numpy oracle."""
+import numpy as np
+import pytest
+
+from oracle import cport, hmc, prng, targets
+
+F = np.float32
+
+
+@pytest.mark.parametrize("kind, D", [("diag", 100), ("diag", 37), ("funnel", 16)])
+def test_c_twin_matches_numpy_oracle(kind, D):
+    rs = np.random.default_rng(0)
+    C, L, eps = 64, 10, F(0.1)
+    if kind == "diag":
+        t = targets.DiagGaussian(np.exp(rs.uniform(-1, 1, D)))
+        inv_var, k = t.inv_var, 0
+    else:
+        t = targets.Funnel(D)
+        inv_var, k = np.ones(D, F), 1
+    imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    q = (0.5 * rs.standard_normal((C, D))).astype(F)
+    keys = prng.split(prng.key(3), C)
+    st = hmc.init(q, t)
+    new, info = hmc.hmc_kernel(keys, st, t, eps, imm, L)
+    qc, lc, gc = q.copy(), st.logdensity.copy(), st.logdensity_grad.copy()
+    acc, ok = cport.hmc_step(k, inv_var, imm, keys, qc, lc, gc, eps, L)
+    np.testing.assert_allclose(acc, info.acceptance_rate, rtol=2e-4, atol=2e-5)
+    same = ok == info.is_accepted
+    assert same.mean() > 0.98
+    np.testing.assert_allclose(qc[same], new.position[same], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gc[same], new.logdensity_grad[same], rtol=1e-5, atol=1e-5)
