@@ -381,8 +381,8 @@ static int ensure_ws(bjx_handle_t h) {
   const size_t vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
   const size_t key = ((C * 2 * sizeof(uint32_t)) + 255) & ~(size_t)255;
   const size_t ckpt = ((C * depth * D * sizeof(float)) + 255) & ~(size_t)255;
-  const size_t n_counters = 4096;
-  const size_t total = 10 * row + 2 * ckpt + 13 * vec + 7 * vec + 3 * key + n_counters * sizeof(int) + 256;
+  const size_t n_counters = 64;
+  const size_t total = 9 * row + 2 * ckpt + 12 * vec + key + n_counters * sizeof(int) + 256;
   BJX_CUDA(cudaMalloc(&h->ws_block, total));
   BJX_CUDA(cudaMemsetAsync(h->ws_block, 0, total, h->stream));
   char* p = (char*)h->ws_block;
@@ -390,23 +390,19 @@ static int ensure_ws(bjx_handle_t h) {
   NutsWs& w = h->ws;
   w.left_q = takef(row); w.left_p = takef(row); w.left_g = takef(row);
   w.right_q = takef(row); w.right_p = takef(row); w.right_g = takef(row);
-  w.psum = takef(row); w.sub_psum = takef(row); w.sub_prop_q = takef(row); w.sub_prop_g = takef(row);
+  w.psum = takef(row); w.sub_prop_q = takef(row); w.sub_prop_g = takef(row);
   w.ckpt_p = takef(ckpt); w.ckpt_sum = takef(ckpt);
   w.left_logp = takef(vec); w.right_logp = takef(vec); w.h0 = takef(vec);
   w.prop_energy = takef(vec); w.prop_weight = takef(vec); w.prop_slpa = takef(vec);
-  w.sub_logp = takef(vec); w.sub_energy = takef(vec); w.sub_weight = takef(vec); w.sub_slpa = takef(vec);
-  w.n_states = (int*)takef(vec); w.sub_n = (int*)takef(vec); w.step = (int*)takef(vec);
-  w.is_div = (uint8_t*)takef(vec); w.is_turn = (uint8_t*)takef(vec); w.sub_div = (uint8_t*)takef(vec);
-  w.sub_term = (uint8_t*)takef(vec); w.run = (uint8_t*)takef(vec); w.active = (uint8_t*)takef(vec);
-  w.dir = (int8_t*)takef(vec);
-  w.key_int = (uint32_t*)takef(key); w.traj_key = (uint32_t*)takef(key); w.prop_key = (uint32_t*)takef(key);
+  w.n_states = (int*)takef(vec); w.step = (int*)takef(vec);
+  w.is_div = (uint8_t*)takef(vec); w.is_turn = (uint8_t*)takef(vec);
+  w.list_a = (int*)takef(vec); w.list_b = (int*)takef(vec);
+  w.key_int = (uint32_t*)takef(key);
   w.counters = (int*)p;
   w.max_depth = depth;
   h->ws_depth = depth;
   return 0;
 }
-
-static inline int popcount32(unsigned x) { return __builtin_popcount(x); }
 
 extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
                              const float* grad_in, float* q_out, float* logp_out, float* grad_out, float step_size,
@@ -426,8 +422,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   rc = ensure_ws(h);
   if (rc) return rc;
   const int C = h->cfg.n_chains;
-  const size_t n_counters = 4096;
-  BJX_CUDA(cudaMemsetAsync(h->ws.counters, 0, n_counters * sizeof(int), h->stream));
+  BJX_CUDA(cudaMemsetAsync(h->ws.counters, 0, 64 * sizeof(int), h->stream));
 
   LaunchArgs a{};
   a.P = make_params(h, step_size, step_size_dev);
@@ -442,41 +437,30 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   rc = dispatch(h, K_NUTS_INIT, false, a);
   if (rc) return rc;
 
-  // counters[d] = number of chains that run doubling d (written by init for d=0, by end(d-1) for d>0);
-  // counters[64 + k] = periodic within-depth "still active" counts.
-  int extra = 64;
-  int64_t leaves = 0;
+  // Host-driven tree doubling (trajectory.py:616-725): one launch per doubling over the chains that are
+  // still expanding.  counters[d+1] = number of chains that continue after doubling d; their indices are
+  // compacted into list_a/list_b (ping-pong).  One pinned-memory readback per doubling.
+  int n_active = C;
+  const int* list_in = nullptr;
+  int64_t launches = 0;
   int depth_reached = 0;
-  for (int d = 0; d < max_num_doublings; ++d) {
-    if (d > 0) {  // did any chain start doubling d?
-      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      BJX_CUDA(cudaStreamSynchronize(h->stream));
-      if (h->h_flag[0] == 0) break;
-    }
-    depth_reached = d + 1;
-    const int n_leaves = 1 << d;
-    for (int i = 0; i < n_leaves; ++i) {
-      // termination.py:75-84 checkpoint index range of leaf i
-      const int idx_max = popcount32((unsigned)i >> 1);
-      const int num_subtrees = popcount32((~(unsigned)i & ((unsigned)i + 1u)) - 1u);
-      const int idx_min = idx_max - num_subtrees + 1;
-      const bool probe = (n_leaves >= 64) && ((i & 31) == 31) && (i + 1 < n_leaves) && (extra < (int)n_counters);
-      a.i = i; a.idx_min = idx_min; a.idx_max = idx_max;
-      a.counter = probe ? h->ws.counters + extra : nullptr;
-      rc = dispatch(h, K_NUTS_LEAF, true, a);
-      if (rc) return rc;
-      ++leaves;
-      if (probe) {  // every 32 leaves of a deep sub-tree: stop launching once every chain has terminated
-        BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + extra, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        BJX_CUDA(cudaStreamSynchronize(h->stream));
-        ++extra;
-        if (h->h_flag[0] == 0) break;
-      }
-    }
-    a.n = max_num_doublings;
+  for (int d = 0; d < max_num_doublings && n_active > 0; ++d) {
+    int* list_out = (d & 1) ? h->ws.list_b : h->ws.list_a;
+    a.depth = d;
+    a.list_in = list_in;
+    a.n_in = n_active;
+    a.list_out = list_out;
     a.counter = h->ws.counters + d + 1;
-    rc = dispatch(h, K_NUTS_END, false, a);
+    rc = dispatch(h, K_NUTS_DOUBLING, true, a);
     if (rc) return rc;
+    ++launches;
+    depth_reached = d + 1;
+    if (d + 1 < max_num_doublings) {
+      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + d + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      BJX_CUDA(cudaStreamSynchronize(h->stream));
+      n_active = h->h_flag[0];
+      list_in = list_out;
+    }
   }
   k_nuts_finish<<<(C + 255) / 256, 256, 0, h->stream>>>(C, h->ws, make_info(info));
   BJX_CHECK_LAUNCH("k_nuts_finish");
@@ -487,7 +471,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
     if (info->right_position) BJX_CUDA(cudaMemcpyAsync(info->right_position, h->ws.right_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
     if (info->right_momentum) BJX_CUDA(cudaMemcpyAsync(info->right_momentum, h->ws.right_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
   }
-  h->last_leaf_launches = leaves;
+  h->last_leaf_launches = launches;
   h->last_depth = depth_reached;
   return 0;
 }

@@ -168,58 +168,37 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
 // =====================================================================================================
 // NUTS (nuts.py:223-321, trajectory.py:273-393,616-725, termination.py:31-106)
 //
-// Host C++ drives the doubling loop; per-chain tree state lives in this workspace.  A sub-tree is
-// integrated IN PLACE on the tree endpoint it extends (the last leaf always becomes the new
-// endpoint after the merge, trajectory.py:376-385,697-704), so a leaf costs one read and one write
-// of (q,p,g) plus the momentum-sum / checkpoint traffic.
+// Chains never interact, so nothing forces them through the tree in lock step.  Host C++ drives the
+// doubling loop (one launch per doubling over the chains that are still expanding, compacted into an
+// index list); inside a launch each warp integrates its chain's WHOLE sub-tree -- up to 2^d leapfrog
+// leaves -- with the moving endpoint (q, p, grad) and the sub-tree momentum sum resident in
+// registers, stopping early on divergence / U-turn.  A sub-tree is integrated IN PLACE on the tree
+// endpoint it extends (the last leaf always becomes the new endpoint after the merge,
+// trajectory.py:376-385,697-704).  Per leaf the only global traffic is the U-turn checkpoint row
+// (store on even leaves, loads on odd leaves) and the proposal row when the multinomial draw accepts.
 // =====================================================================================================
 struct NutsWs {
   float *left_q, *left_p, *left_g, *right_q, *right_p, *right_g;  // [C,D] trajectory endpoints
-  float *psum, *sub_psum;                                         // [C,D] momentum sums
+  float* psum;                                                    // [C,D] trajectory momentum sum
   float *sub_prop_q, *sub_prop_g;                                 // [C,D] sub-tree proposal
   float *ckpt_p, *ckpt_sum;                                       // [C,depth,D] U-turn checkpoints
   float *left_logp, *right_logp, *h0;
   float *prop_energy, *prop_weight, *prop_slpa;
-  float *sub_logp, *sub_energy, *sub_weight, *sub_slpa;
-  int *n_states, *sub_n, *step;
-  uint8_t *is_div, *is_turn, *sub_div, *sub_term, *run, *active;
-  int8_t* dir;
-  uint32_t *key_int, *traj_key, *prop_key;                        // [C,2]
-  int* counters;                                                  // [depth+2 + extra] device counters
+  int *n_states, *step;
+  uint8_t *is_div, *is_turn;
+  uint32_t* key_int;                                              // [C,2]
+  int *list_a, *list_b;                                           // [C] compacted indices of expanding chains
+  int* counters;                                                  // [depth+2]
   int max_depth;                                                  // checkpoint capacity
 };
 
-// trajectory.py:642-655 for the doubling about to start (run by all lanes, lane 0 writes)
-__device__ __forceinline__ void nuts_begin(const NutsWs& ws, int chain, int lane, int max_doublings, int* counter) {
-  const int step = ws.step[chain];
-  const bool run = (step < max_doublings) && !ws.is_div[chain] && !ws.is_turn[chain];  // trajectory.py:622-630
-  if (lane == 0) {
-    ws.run[chain] = run;
-    ws.active[chain] = run;
-    if (run) {
-      const Key ki{ws.key_int[2 * chain], ws.key_int[2 * chain + 1]};
-      const Key sub = fold_in(ki, (uint32_t)step);           // :645
-      const Key dk = fold_in(sub, 0u);                       // split(subkey, 3)  :646
-      const Key tk = fold_in(sub, 1u);
-      const Key pk = fold_in(sub, 2u);
-      ws.dir[chain] = (uniform01(dk) < 0.5f) ? 1 : -1;       // :650
-      ws.traj_key[2 * chain] = tk.a; ws.traj_key[2 * chain + 1] = tk.b;
-      ws.prop_key[2 * chain] = pk.a; ws.prop_key[2 * chain + 1] = pk.b;
-      ws.sub_div[chain] = 0;
-      ws.sub_term[chain] = 0;
-      ws.sub_n[chain] = 0;
-      atomicAdd(counter, 1);
-    }
-  }
-}
-
-// nuts.py:133-136,278-294: key split, momentum draw, initial proposal/trajectory, then begin(depth 0)
+// nuts.py:133-136,278-294: key split, momentum draw, initial proposal / trajectory / termination state
 template <class R, int TK, bool DM>
 __global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, const uint32_t* __restrict__ keys,
                                                         const float* q_in, const float* logp_in, const float* g_in,
                                                         float* q_out, float* logp_out, float* g_out,
                                                         const float* mom_override, const uint32_t* keyint_override,
-                                                        float* mom_out, int max_doublings) {
+                                                        float* mom_out) {
   BJX_WARP_PROLOGUE();
   Ctx<R, TK_FUNNEL, DM> c;
   c.init(P, chain, lane, sm);
@@ -264,147 +243,189 @@ __global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, con
     ws.key_int[2 * chain] = key_integrator.a;
     ws.key_int[2 * chain + 1] = key_integrator.b;
   }
-  __syncwarp();
-  nuts_begin(ws, chain, lane, max_doublings, ws.counters + 0);
 }
 
-// One leaf of every active sub-tree (trajectory.py:318-355): leapfrog from the endpoint being
-// extended, energy/weight, progressive uniform sampling, momentum sum, checkpoint store (even leaf)
-// and iterative U-turn scan (termination.py:56-104).  leaf index i and its checkpoint range are the
-// same for all chains, so they are kernel arguments computed on the host (termination.py:75-84).
+// is_turning(ckpt_p, p, p_sum - ckpt_sum + ckpt_p) against one checkpoint row (termination.py:96-103,
+// metrics.py:272-304), streaming the checkpoint through registers a slot at a time.
 template <class R, int TK, bool DM>
-__global__ void __launch_bounds__(kThreads) k_nuts_leaf(Params P, NutsWs ws, int i, int idx_min, int idx_max,
-                                                        int* active_counter) {
-  BJX_WARP_PROLOGUE();
-  if (!ws.active[chain]) return;
+__device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const Params& P, const float* __restrict__ cp_row,
+                                                      const float* __restrict__ cs_row, const float (&p)[R::NS],
+                                                      const float (&ps)[R::NS], int lane) {
+  if constexpr (DM) {
+    float cp[R::NS], cs[R::NS];
+    R::load(cp, cp_row, P.D, lane);
+    R::load(cs, cs_row, P.D, lane);
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) cs[s] = ps[s] - cs[s] + cp[s];
+    return c.is_turning(P, cp, p, cs);
+  } else {
+    float al = 0.f, ar = 0.f;
+    if constexpr (R::VEC) {
+#pragma unroll
+      for (int j = 0; j < R::NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (e < P.D) {
+          a = *reinterpret_cast<const float4*>(cp_row + e);
+          b = *reinterpret_cast<const float4*>(cs_row + e);
+        }
+        const float cpv[4] = {a.x, a.y, a.z, a.w}, csv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int s = 4 * j + v;
+          const float sub = ps[s] - csv[v] + cpv[v];
+          const float rho = sub - (p[s] + cpv[v]) / 2.0f;
+          al = fmaf(c.mw[s] * cpv[v], rho, al);
+          ar = fmaf(c.mw[s] * p[s], rho, ar);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) {
+        const int e = s * 32 + lane;
+        const float cpv = (e < P.D) ? cp_row[e] : 0.f;
+        const float csv = (e < P.D) ? cs_row[e] : 0.f;
+        const float sub = ps[s] - csv + cpv;
+        const float rho = sub - (p[s] + cpv) / 2.0f;
+        al = fmaf(c.mw[s] * cpv, rho, al);
+        ar = fmaf(c.mw[s] * p[s], rho, ar);
+      }
+    }
+    al = warp_sum(al);
+    ar = warp_sum(ar);
+    return (al <= 0.f) || (ar <= 0.f);
+  }
+}
+
+// One tree doubling for every chain still expanding (trajectory.py:642-717): draw the direction, integrate
+// the sub-tree of up to 2^d leaves (trajectory.py:318-372) with progressive uniform sampling
+// (proposal.py:118-143) and the iterative U-turn checkpoints (termination.py:56-104), then update the
+// proposal (biased progressive sampling, proposal.py:146-176), merge the trajectories and test the
+// full-trajectory U-turn.  Chains that keep expanding are appended to list_out.
+template <class R, int TK, bool DM>
+__global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d, int max_doublings,
+                                                            const int* __restrict__ list_in, int n_in,
+                                                            int* __restrict__ list_out, int* counter_out,
+                                                            float* q_out, float* logp_out, float* g_out) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  extern __shared__ float bjx_smem[];
+  float* sm = bjx_smem + (size_t)(threadIdx.x >> 5) * P.D;
+  if (w >= n_in) return;
+  const int chain = list_in ? list_in[w] : w;
+  const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK, DM> c;
-  const int dir = ws.dir[chain];
+
+  // ---- begin: direction and keys of this doubling (trajectory.py:645-655) --------------------------------
+  const Key ki{ws.key_int[2 * chain], ws.key_int[2 * chain + 1]};
+  const Key sub = fold_in(ki, (uint32_t)d);
+  const Key tk = fold_in(sub, 1u), pk = fold_in(sub, 2u);
+  const int dir = (uniform01(fold_in(sub, 0u)) < 0.5f) ? 1 : -1;
   float* eq = dir > 0 ? ws.right_q : ws.left_q;
   float* ep = dir > 0 ? ws.right_p : ws.left_p;
   float* eg = dir > 0 ? ws.right_g : ws.left_g;
-  float q[R::NS], p[R::NS], g[R::NS];
+  float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
   R::load(q, eq + roff, P.D, lane);
   R::load(p, ep + roff, P.D, lane);
   R::load(g, eg + roff, P.D, lane);
   c.init(P, chain, lane, sm);
   const float eps = (float)dir * (P.eps_dev ? P.eps_dev[chain] : P.eps);  // direction * step_size  :323
-  float logp;
-  c.leapfrog(P, q, p, g, logp, eps);
+  const float h0 = ws.h0[chain];
+  const size_t coff = (size_t)chain * ws.max_depth * P.D;
+  const float ninf = -__int_as_float(0x7f800000);
+
+  // ---- the sub-tree (trajectory.py:318-372) ---------------------------------------------------------------
+  float sub_weight = ninf, sub_slpa = ninf, sub_logp = 0.f, sub_energy = 0.f, logp = 0.f;
+  bool sub_div = false, sub_term = false;
+  int n = 0;
+  const int n_leaves = 1 << d;
+  for (int i = 0; i < n_leaves; ++i) {
+    c.leapfrog(P, q, p, g, logp, eps);
+    const float e_new = -logp + c.kinetic(P, p);
+    const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
+    const float slpa_new = fminf(w_new, 0.f);
+    const bool is_div = (-w_new) > P.div_thr;         // :325
+    bool take;
+    if (i == 0) {  // :329-334 the first leaf is taken unconditionally
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) ps[s] = p[s];
+      take = true;
+      sub_weight = w_new;
+      sub_slpa = slpa_new;
+    } else {  // :335-338 append + progressive uniform sampling
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
+      const float p_accept = expit_f(w_new - sub_weight);
+      take = uniform01(fold_in(tk, (uint32_t)i)) < p_accept;
+      sub_weight = logaddexp_f(sub_weight, w_new);
+      sub_slpa = logaddexp_f(sub_slpa, slpa_new);
+    }
+    if (take) {
+      R::store(q, ws.sub_prop_q + roff, P.D, lane);
+      R::store(g, ws.sub_prop_g + roff, P.D, lane);
+      sub_logp = logp;
+      sub_energy = e_new;
+    }
+    n = i + 1;
+    // termination.py:75-84 checkpoint index range of leaf i
+    const int idx_max = __popc((unsigned)i >> 1);
+    const int idx_min = idx_max - __popc((~(unsigned)i & ((unsigned)i + 1u)) - 1u) + 1;
+    if ((i & 1) == 0) {  // termination.py:66-72
+      R::store(p, ws.ckpt_p + coff + (size_t)idx_max * P.D, P.D, lane);
+      R::store(ps, ws.ckpt_sum + coff + (size_t)idx_max * P.D, P.D, lane);
+    }
+    bool turning = false;
+    for (int k = idx_max; k >= idx_min && !turning; --k)  // termination.py:96-103
+      turning = turning_vs_checkpoint<R, TK, DM>(c, P, ws.ckpt_p + coff + (size_t)k * P.D,
+                                                 ws.ckpt_sum + coff + (size_t)k * P.D, p, ps, lane);
+    sub_div = is_div;
+    sub_term = turning;
+    if (is_div || turning) break;
+  }
+  // the last leaf is the new endpoint of the merged trajectory (trajectory.py:376-385,697-704)
   R::store(q, eq + roff, P.D, lane);
   R::store(p, ep + roff, P.D, lane);
   R::store(g, eg + roff, P.D, lane);
-  const float e_new = -logp + c.kinetic(P, p);
-  const float w_new = safe_energy_diff(ws.h0[chain], e_new);  // proposal.py:94-98
-  const float slpa_new = fminf(w_new, 0.f);
-  const bool is_div = (-w_new) > P.div_thr;                   // :325
-  float ps[R::NS];
-  bool take;
-  float w_tot, slpa_tot;
-  if (i == 0) {  // :329-334 first leaf is taken unconditionally
-#pragma unroll
-    for (int s = 0; s < R::NS; ++s) ps[s] = p[s];
-    take = true;
-    w_tot = w_new;
-    slpa_tot = slpa_new;
-  } else {  // :335-338 append + progressive uniform sampling (proposal.py:118-143)
-    R::load(ps, ws.sub_psum + roff, P.D, lane);
-#pragma unroll
-    for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
-    const Key tk{ws.traj_key[2 * chain], ws.traj_key[2 * chain + 1]};
-    const float w_old = ws.sub_weight[chain];
-    const float p_accept = expit_f(w_new - w_old);
-    take = uniform01(fold_in(tk, (uint32_t)i)) < p_accept;
-    w_tot = logaddexp_f(w_old, w_new);
-    slpa_tot = logaddexp_f(ws.sub_slpa[chain], slpa_new);
-  }
-  R::store(ps, ws.sub_psum + roff, P.D, lane);
-  if (take) {
-    R::store(q, ws.sub_prop_q + roff, P.D, lane);
-    R::store(g, ws.sub_prop_g + roff, P.D, lane);
-  }
-  const size_t coff = (size_t)chain * ws.max_depth * P.D;
-  if ((i & 1) == 0) {  // termination.py:66-72
-    R::store(p, ws.ckpt_p + coff + (size_t)idx_max * P.D, P.D, lane);
-    R::store(ps, ws.ckpt_sum + coff + (size_t)idx_max * P.D, P.D, lane);
-  }
-  bool turning = false;
-  for (int k = idx_max; k >= idx_min && !turning; --k) {  // termination.py:96-103
-    float cp[R::NS], cs[R::NS];
-    R::load(cp, ws.ckpt_p + coff + (size_t)k * P.D, P.D, lane);
-    R::load(cs, ws.ckpt_sum + coff + (size_t)k * P.D, P.D, lane);
-#pragma unroll
-    for (int s = 0; s < R::NS; ++s) cs[s] = ps[s] - cs[s] + cp[s];
-    turning = c.is_turning(P, cp, p, cs);
-  }
-  if (lane == 0) {
-    if (dir > 0) ws.right_logp[chain] = logp; else ws.left_logp[chain] = logp;
-    if (take) {
-      ws.sub_logp[chain] = logp;
-      ws.sub_energy[chain] = e_new;
-    }
-    ws.sub_weight[chain] = w_tot;
-    ws.sub_slpa[chain] = slpa_tot;
-    ws.sub_n[chain] = i + 1;
-    ws.sub_div[chain] = is_div;
-    ws.sub_term[chain] = turning;
-    const bool still = !(is_div || turning);
-    ws.active[chain] = still;
-    if (active_counter && still) atomicAdd(active_counter, 1);
-  }
-}
 
-// End of a doubling (trajectory.py:672-717): proposal update (biased progressive sampling or only
-// sum_log_p_accept), merge, full-trajectory U-turn, then begin the next doubling.
-template <class R, int TK, bool DM>
-__global__ void __launch_bounds__(kThreads) k_nuts_end(Params P, NutsWs ws, float* q_out, float* logp_out,
-                                                       float* g_out, int max_doublings, int* next_counter) {
-  BJX_WARP_PROLOGUE();
-  if (!ws.run[chain]) return;
-  Ctx<R, TK_FUNNEL, DM> c;
-  c.init(P, chain, lane, sm);
-  const bool sub_div = ws.sub_div[chain], sub_term = ws.sub_term[chain];
+  // ---- end of the doubling (trajectory.py:672-717) ---------------------------------------------------------
   const bool bad = sub_div || sub_term;
-  const float pw = ws.prop_weight[chain], sw = ws.sub_weight[chain];
-  const float new_slpa = logaddexp_f(ws.prop_slpa[chain], ws.sub_slpa[chain]);
-  bool take = false;
-  if (!bad) {  // proposal.py:146-176
-    const float p_accept = clip_max1(expf(sw - pw));
-    const Key pk{ws.prop_key[2 * chain], ws.prop_key[2 * chain + 1]};
-    take = uniform01(pk) < p_accept;
-  }
-  if (take) {
+  const float pw = ws.prop_weight[chain];
+  const float new_slpa = logaddexp_f(ws.prop_slpa[chain], sub_slpa);
+  bool take2 = false;
+  if (!bad) take2 = uniform01(pk) < clip_max1(expf(sub_weight - pw));  // proposal.py:155-156
+  if (take2) {
     float t[R::NS];
     R::load(t, ws.sub_prop_q + roff, P.D, lane);
     R::store(t, q_out + roff, P.D, lane);
     R::load(t, ws.sub_prop_g + roff, P.D, lane);
     R::store(t, g_out + roff, P.D, lane);
   }
-  float pl[R::NS], pr[R::NS], ps[R::NS];
   {
-    float sp[R::NS];
-    R::load(ps, ws.psum + roff, P.D, lane);
-    R::load(sp, ws.sub_psum + roff, P.D, lane);
+    float t[R::NS];
+    R::load(t, ws.psum + roff, P.D, lane);
 #pragma unroll
-    for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + sp[s];  // merge_trajectories  trajectory.py:102-125
+    for (int s = 0; s < R::NS; ++s) ps[s] = t[s] + ps[s];  // merge_trajectories  trajectory.py:102-125
     R::store(ps, ws.psum + roff, P.D, lane);
-  }
-  R::load(pl, ws.left_p + roff, P.D, lane);
-  R::load(pr, ws.right_p + roff, P.D, lane);
-  const bool turning = c.is_turning(P, pl, pr, ps);  // :706-710
-  if (lane == 0) {
-    if (take) {
-      logp_out[chain] = ws.sub_logp[chain];
-      ws.prop_energy[chain] = ws.sub_energy[chain];
+    R::load(t, (dir > 0 ? ws.left_p : ws.right_p) + roff, P.D, lane);  // the endpoint that did not move
+    // :706-710 is_turning(p_left, p_right, p_sum)
+    const bool turning = (dir > 0) ? c.is_turning(P, t, p, ps) : c.is_turning(P, p, t, ps);
+    const bool is_turn = sub_term || turning;  // :715
+    const bool run_next = (d + 1 < max_doublings) && !sub_div && !is_turn;
+    if (lane == 0) {
+      if (dir > 0) ws.right_logp[chain] = logp; else ws.left_logp[chain] = logp;
+      if (take2) {
+        logp_out[chain] = sub_logp;
+        ws.prop_energy[chain] = sub_energy;
+      }
+      if (!bad) ws.prop_weight[chain] = logaddexp_f(pw, sub_weight);
+      ws.prop_slpa[chain] = new_slpa;
+      ws.n_states[chain] += n;
+      ws.step[chain] = d + 1;
+      ws.is_div[chain] = sub_div;
+      ws.is_turn[chain] = is_turn;
+      if (run_next) list_out[atomicAdd(counter_out, 1)] = chain;
     }
-    if (!bad) ws.prop_weight[chain] = logaddexp_f(pw, sw);
-    ws.prop_slpa[chain] = new_slpa;
-    ws.n_states[chain] += ws.sub_n[chain];
-    ws.step[chain] += 1;
-    ws.is_div[chain] = sub_div;
-    ws.is_turn[chain] = sub_term || turning;  // :715
   }
-  __syncwarp();
-  nuts_begin(ws, chain, lane, max_doublings, next_counter);
 }
 
 // nuts.py:303-319: acceptance_rate = exp(sum_log_p_accept) / num_states and the NUTSInfo scalars

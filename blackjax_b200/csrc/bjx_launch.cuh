@@ -7,7 +7,7 @@
 namespace bjx {
 
 enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_NONE };
-enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_LEAF, K_NUTS_END };
+enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING };
 
 struct LaunchArgs {
   Params P;
@@ -18,7 +18,10 @@ struct LaunchArgs {
   float *q_out, *logp_out, *g_out;
   float* p_io;
   int n;  // n_steps | L | max_doublings
-  int i, idx_min, idx_max;
+  int depth;            // current doubling
+  const int* list_in;   // compacted chain indices (nullptr = identity)
+  int n_in;             // number of warps to launch (0 = all chains)
+  int* list_out;
   int* counter;
   const float* mom_override;
   const uint32_t* keyint_override;
@@ -48,7 +51,8 @@ struct Launcher {
 #ifdef BJX_INSTANTIATE_TK
 template <class R, int TK, bool DM>
 static int launch_one(int kernel_id, const LaunchArgs& a) {
-  const dim3 grid((a.P.C + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
+  const int n_rows = (kernel_id == K_NUTS_DOUBLING) ? a.n_in : a.P.C;
+  const dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
   const size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
   cudaStream_t st = a.stream;
   switch (kernel_id) {
@@ -62,8 +66,9 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       k_hmc_transition<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
                                                               a.logp_out, a.g_out, a.n, a.info);
       return 0;
-    case K_NUTS_LEAF:
-      k_nuts_leaf<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.i, a.idx_min, a.idx_max, a.counter);
+    case K_NUTS_DOUBLING:
+      k_nuts_doubling<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in, a.list_out,
+                                                           a.counter, a.q_out, a.logp_out, a.g_out);
       return 0;
     default:
       break;
@@ -82,10 +87,7 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       case K_NUTS_INIT:
         k_nuts_init<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
                                                            a.logp_out, a.g_out, a.mom_override, a.keyint_override,
-                                                           a.mom_out, a.n);
-        return 0;
-      case K_NUTS_END:
-        k_nuts_end<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.n, a.counter);
+                                                           a.mom_out);
         return 0;
       default:
         break;

@@ -129,7 +129,8 @@ int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const 
                  float step_size, const float* step_size_dev, int32_t num_integration_steps,
                  const bjx_info* info);
 /* nuts.build_kernel(...).kernel (nuts.py:113-145) with iterative_nuts_proposal (nuts.py:223-321).
- * Tree doubling is driven from the host; each leapfrog leaf is one kernel launch over all chains.
+ * Tree doubling is driven from the host: one launch per doubling over the chains still expanding; each
+ * warp integrates its chain's whole sub-tree (up to 2^d leapfrog leaves) inside the launch.
  * momentum_override/key_integrator_override (both or neither, for KATs): skip the key split and
  * the momentum draw and use the given momentum [C,D] and integrator keys [C,2]. */
 int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
@@ -137,8 +138,8 @@ int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   float step_size, const float* step_size_dev, int32_t max_num_doublings,
                   const bjx_info* info, const float* momentum_override,
                   const uint32_t* key_integrator_override);
-/* total leapfrog launches / leaf evaluations performed by the last bjx_nuts_step (host ints) */
-int bjx_nuts_last_stats(bjx_handle_t h, int64_t* leaf_launches, int64_t* depth_reached);
+/* doubling launches and doublings reached by the last bjx_nuts_step (host ints) */
+int bjx_nuts_last_stats(bjx_handle_t h, int64_t* doubling_launches, int64_t* depth_reached);
 
 /* ---- PRNG (jax.random restated; keys raw uint32 pairs) ----------------------------------------- */
 /* h may be NULL for the PRNG entry points: current device, legacy default stream */

@@ -352,7 +352,8 @@ def test_dual_averaging_and_welford_kernels():
     o = [oadapt.da_init(e) for e in npy(eps0)]
     for it in range(12):
         acc = rs.uniform(0, 1, C).astype(F)
-        check(lib().bjx_da_update(eng.h, ptr(st), ptr(tf(acc)), 0.8, ptr(eps)), eng.h)
+        dacc = tf(acc)
+        check(lib().bjx_da_update(eng.h, ptr(st), ptr(dacc), 0.8, ptr(eps)), eng.h)
         o = [oadapt.da_update(s, a, 0.8) for s, a in zip(o, acc)]
         close(npy(eps), [np.exp(s.log_step_size) for s in o], rtol=1e-5)
     fin = torch.empty(C, device=DEV)
@@ -366,7 +367,8 @@ def test_dual_averaging_and_welford_kernels():
     ws = [oadapt.welford_init(D) for _ in range(C)]
     for n in range(1, 9):
         x = rs.standard_normal((C, D)).astype(F)
-        check(lib().bjx_welford_update(eng.h, ptr(tf(x)), ptr(mean), ptr(m2), n), eng.h)
+        dx = tf(x)
+        check(lib().bjx_welford_update(eng.h, ptr(dx), ptr(mean), ptr(m2), n), eng.h)
         ws = [oadapt.welford_update(w, xi) for w, xi in zip(ws, x)]
     close(npy(mean), np.stack([w.mean for w in ws]), rtol=1e-5)
     close(npy(m2), np.stack([w.m2 for w in ws]), rtol=1e-5)
@@ -378,7 +380,8 @@ def test_dual_averaging_and_welford_kernels():
     x = rs.standard_normal((C, D)).astype(F) * 3 + 1
     acc = rs.uniform(0, 1, C).astype(F)
     out = torch.empty(2 + 2 * D, device=DEV)
-    check(lib().bjx_pooled_stats(eng.h, ptr(tf(x)), ptr(tf(acc)), ptr(out)), eng.h)
+    dx, dacc = tf(x), tf(acc)   # keep both alive: the caching allocator would hand a freed block to the next tensor
+    check(lib().bjx_pooled_stats(eng.h, ptr(dx), ptr(dacc), ptr(out)), eng.h)
     o = npy(out)
     assert o[1] == C
     close(o[0], acc.sum(), rtol=1e-5)
@@ -388,31 +391,75 @@ def test_dual_averaging_and_welford_kernels():
 
 @pytest.mark.parametrize("algo", ["hmc", "nuts"])
 def test_window_adaptation_per_chain_matches_oracle(algo):
+    """Per-chain warm-up (what ``jax.vmap(warmup.run)`` computes), checked TEACHER-FORCED: at every one of the
+    60 warm-up steps the oracle is restarted from the device's current (state, step size, inverse mass matrix,
+    dual-averaging state, Welford accumulators) and must reproduce the device's next values.  (Free-running
+    chains cannot be compared element-wise: early dual-averaging iterates put the integrator in its unstable
+    regime, which amplifies float32 rounding differences exponentially -- BASELINE.md section 4.)"""
+    from blackjax_b200._lib import check, lib, ptr
     D, C, T_ = 8, 16, 60
     scale = np.logspace(-0.5, 0.5, D)
     tgt, otgt = T.DiagGaussian(scale), otargets.DiagGaussian(scale)
     rs = np.random.default_rng(9)
     q = rs.standard_normal((C, D)).astype(F)
     ckeys = oprng.split(oprng.key(77), C)
+    keys_np = oprng.split(ckeys, T_)                      # [C,T,2]  util.py:203 per chain
     if algo == "hmc":
-        okern = lambda k, s, t, e, m, **kw: ohmc.hmc_kernel(k, s, t, e, m, 8)
-        extra = dict(num_integration_steps=8)
-        alg = bj.hmc
+        okern = lambda k, s, e, m: ohmc.hmc_kernel(k, s, otgt, e, m, 8)
+        extra, alg = dict(num_integration_steps=8), bj.hmc
     else:
-        okern = lambda k, s, t, e, m, **kw: onuts.nuts_kernel(k, s, t, e, m, 6)
-        extra = dict(max_num_doublings=6)
-        alg = bj.nuts
-    ost, oeps, oimm, ohist = oadapt.window_adaptation_run(okern, otgt, ckeys, q, T_)
+        okern = lambda k, s, e, m: onuts.nuts_kernel(k, s, otgt, e, m, 6)
+        extra, alg = dict(max_num_doublings=6), bj.nuts
+    kern = alg.build_kernel()
+    state = alg.init(tf(q), tgt)
+    eng = _engine.get_engine(state.position, tgt)
+    da_state = torch.empty(C, 5, device=DEV)
+    eps = torch.full((C,), 1.0, device=DEV)
+    check(lib().bjx_da_init(eng.h, ptr(da_state), ptr(eps), ptr(eps)), eng.h)
+    imm = torch.ones(C, D, device=DEV)
+    w_mean, w_m2, w_n = torch.zeros(C, D, device=DEV), torch.zeros(C, D, device=DEV), 0
+    eps_trace = []
+    for t, (stage, wend) in enumerate(bj.build_schedule(T_)):
+        ost = ohmc.HMCState(npy(state.position), npy(state.logdensity), npy(state.logdensity_grad))
+        oeps, oimm = npy(eps).copy(), npy(imm).copy()
+        onew, oinfo = okern(keys_np[:, t], ost, oeps, oadapt._PerChainDiag(oimm))
+        state, info = kern(tk(keys_np[:, t]), state, tgt, eps, imm, **extra)
+        torch.cuda.synchronize()
+        if algo == "hmc":
+            ok = npy(info.is_accepted) == oinfo.is_accepted
+        else:
+            ok = npy(info.num_integration_steps) == oinfo.num_integration_steps
+            ok &= np.all(np.isclose(npy(state.position), onew.position, rtol=1e-4, atol=1e-5), axis=1)
+        assert ok.mean() >= 0.9
+        close(npy(state.position)[ok], onew.position[ok], rtol=1e-4)
+        close(npy(info.acceptance_rate)[ok], oinfo.acceptance_rate[ok], rtol=1e-4, scale=1.0)
+        st_np, acc_np = npy(da_state).copy(), npy(info.acceptance_rate)
+        odas = [oadapt.da_update(oadapt.DAState(F(r[0]), F(r[1]), int(r[2]), F(r[3]), F(r[4])), a, 0.8)
+                for r, a in zip(st_np, acc_np)]
+        if stage == 1:
+            w_n += 1
+            check(lib().bjx_welford_update(eng.h, ptr(state.position), ptr(w_mean), ptr(w_m2), w_n), eng.h)
+        check(lib().bjx_da_update(eng.h, ptr(da_state), ptr(info.acceptance_rate), 0.8, ptr(eps)), eng.h)
+        close(npy(eps), [np.exp(s.log_step_size) for s in odas], rtol=1e-5)
+        if wend:
+            m2_np, mean_np = npy(w_m2).copy(), npy(w_mean).copy()
+            new_imm = torch.empty_like(imm)
+            check(lib().bjx_welford_final(eng.h, ptr(w_mean), ptr(w_m2), w_n, ptr(new_imm)), eng.h)
+            close(npy(new_imm), np.stack([oadapt.welford_final(oadapt.Welford(mean_np[c], m2_np[c], w_n))
+                                          for c in range(C)]), rtol=1e-5)
+            imm, w_n = new_imm, 0
+            check(lib().bjx_da_reset(eng.h, ptr(da_state), ptr(eps)), eng.h)
+        eps_trace.append(npy(eps).copy())
+    fin = torch.empty(C, device=DEV)
+    check(lib().bjx_da_final(eng.h, ptr(da_state), ptr(fin)), eng.h)
+    # the packaged driver runs exactly this loop: identical bits
     warm = bj.window_adaptation(alg, tgt, **extra)
-    (st, params), _ = warm.run(tk(ckeys), tf(q), T_)
-    torch.cuda.synchronize()
-    # free-running for 60 adaptive transitions: rounding differences feed back through accept decisions, so
-    # compare the adapted quantities loosely per chain and tightly in aggregate.
-    eps_dev, imm_dev = npy(params["step_size"]), npy(params["inverse_mass_matrix"])
-    match = np.isclose(eps_dev, oeps, rtol=1e-3)
-    assert match.mean() >= 0.75
-    assert np.isclose(imm_dev[match], oimm[match], rtol=1e-2, atol=1e-4).mean() > 0.98
-    assert abs(np.median(eps_dev) / np.median(oeps) - 1) < 0.05
+    (st2, params), _ = warm.run(tk(ckeys), tf(q), T_)
+    assert torch.equal(params["step_size"], fin)
+    assert torch.equal(params["inverse_mass_matrix"], imm)
+    assert torch.equal(st2.position, state.position)
+    # and it adapts: the pooled step size lands in a sane range for this target (stable below 2*min scale)
+    assert 0.05 < float(np.median(npy(fin))) < 2.5
 
 
 def test_window_adaptation_shared_matches_oracle_and_recovers_scales():
@@ -504,7 +551,8 @@ def test_fullsize_nuts_funnel_65536x128():
     # a tree of depth d holds between 2^(d-1) and 2^d - 1 leaves (last sub-tree may stop early)
     assert bool(((n <= (2 ** d.long()) - 1) & (n >= 2 ** (d.long() - 1))).all())
     ar = info.acceptance_rate
-    assert bool(((ar >= 0) & (ar <= 1)).all())
+    # exp(logaddexp-accumulated log sum)/n can exceed 1 by float32 rounding when every leaf has min(w,0)=0
+    assert bool(((ar >= 0) & (ar <= 1 + 1e-5)).all())
     # returned state is self-consistent: logdensity/grad are those of the returned position
     lp, g = _engine.get_engine(st2.position, tgt).init_state(st2.position)
     assert float((lp - st2.logdensity).abs().max()) < 1e-2 * (1 + float(lp.abs().max()) * 1e-3)
