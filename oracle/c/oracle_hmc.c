@@ -9,7 +9,7 @@
  * (Metropolis accept) and the jax.random threefry2x32 PRNG, float32, chains split across pthreads --
  * the per-chain program that jax.vmap batches on CPU.
  *
- * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -pthread -shared -fPIC oracle_hmc.c -o liboracle_hmc.so -lm
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=fast -pthread -shared -fPIC oracle_hmc.c -o liboracle_hmc.so -lm
  */
 #include <math.h>
 #include <stdint.h>

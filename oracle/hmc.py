@@ -26,6 +26,20 @@ _b1y, _a1y = 0.11888010966548, 0.29619504261126
 YOSHIDA = (_b1y, _a1y, 0.5 - _b1y, 1 - 2 * _a1y, 0.5 - _b1y, _a1y, _b1y)  # integrators.py:351-357
 
 
+# XLA:CPU compiles with llvm::FPOpFusion::Fast, so `x + (eps*coef)*grad` lowers to ONE fused multiply-add
+# on FMA-capable hosts; the CUDA path contracts the same way.  Emulated here through float64 (the product of
+# two float32 is exact in float64; the double rounding differs from a true FMA with probability ~2^-29).
+FMA_CONTRACT = True
+
+
+def axpy(x, a, y):
+    """x + a*y in float32, as a fused multiply-add when FMA_CONTRACT."""
+    if FMA_CONTRACT:
+        with np.errstate(over="ignore", invalid="ignore"):
+            return (np.asarray(x, np.float64) + np.asarray(a, np.float64) * np.asarray(y, np.float64)).astype(F)
+    return (x + a * y).astype(F)
+
+
 class Metric:
     """gaussian_euclidean(inverse_mass_matrix): 1-D => diagonal, 2-D => dense."""
 
@@ -79,12 +93,12 @@ def integrator_step(target, metric, q, p, g, eps, coefficients=VELOCITY_VERLET):
     v = None
     for i, coef in enumerate(coefficients[:-1]):
         if i % 2 == 0:
-            p = (p + (eps * F(coef)) * g).astype(F)          # integrators.py:235-239
+            p = axpy(p, eps * F(coef), g)                    # integrators.py:235-239
             v = metric.velocity(p)                            # :242 grad of kinetic energy
         else:
-            q = (q + (eps * F(coef)) * v).astype(F)          # :199-203
+            q = axpy(q, eps * F(coef), v)                    # :199-203
             logp, g = target(q)                               # :204
-    p = (p + (eps * F(coefficients[-1])) * g).astype(F)      # :134-141 last call
+    p = axpy(p, eps * F(coefficients[-1]), g)                # :134-141 last call
     return q, p, logp, g
 
 
