@@ -47,6 +47,91 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- Blackwell packed FP32 (FFMA2 / FMUL2 / FADD2): two IEEE round-to-nearest operations per issue slot ----
+// sm_100 adds fma/mul/add.rn.f32x2 on 64-bit register pairs.  The leapfrog inner loop is FP32-issue bound
+// once the chain row lives in registers, so every elementwise update below goes through these helpers
+// (pairs of adjacent slots; odd slot counts fall back to scalar ops).  Results are bit-identical to the
+// scalar fmaf / * / + they replace.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+template <int NS>
+struct Vec {
+  // x = fma(a, y, x)
+  __device__ static __forceinline__ void axpy(float (&x)[NS], float a, const float (&y)[NS]) {
+    if constexpr (NS % 2 == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s += 2) fma2(x[s], x[s + 1], a, a, y[s], y[s + 1], x[s], x[s + 1]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) x[s] = fmaf(a, y[s], x[s]);
+    }
+  }
+  // d = a * b
+  __device__ static __forceinline__ void mul(float (&d)[NS], const float (&a)[NS], const float (&b)[NS]) {
+    if constexpr (NS % 2 == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s += 2) mul2(d[s], d[s + 1], a[s], a[s + 1], b[s], b[s + 1]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) d[s] = a[s] * b[s];
+    }
+  }
+  // d = a * b (scalar a)
+  __device__ static __forceinline__ void scale(float (&d)[NS], float a, const float (&b)[NS]) {
+    if constexpr (NS % 2 == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s += 2) mul2(d[s], d[s + 1], a, a, b[s], b[s + 1]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) d[s] = a * b[s];
+    }
+  }
+  // d = a + b
+  __device__ static __forceinline__ void add(float (&d)[NS], const float (&a)[NS], const float (&b)[NS]) {
+    if constexpr (NS % 2 == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s += 2) add2(d[s], d[s + 1], a[s], a[s + 1], b[s], b[s + 1]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) d[s] = a[s] + b[s];
+    }
+  }
+  // per-lane partial of sum_s a[s]*b[s] (two interleaved accumulators when packed)
+  __device__ static __forceinline__ float dot_partial(const float (&a)[NS], const float (&b)[NS]) {
+    if constexpr (NS % 2 == 0) {
+      float e = 0.f, o = 0.f;
+#pragma unroll
+      for (int s = 0; s < NS; s += 2) fma2(e, o, a[s], a[s + 1], b[s], b[s + 1], e, o);
+      return e + o;
+    } else {
+      float acc = 0.f;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc = fmaf(a[s], b[s], acc);
+      return acc;
+    }
+  }
+};
+
 template <int NS_, bool VEC_>
 struct Row {
   static constexpr int NS = NS_;
@@ -109,10 +194,7 @@ struct Row {
     }
   }
   __device__ static __forceinline__ float dot(const float (&a)[NS], const float (&b)[NS]) {
-    float acc = 0.f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) acc = fmaf(a[s], b[s], acc);
-    return warp_sum(acc);
+    return warp_sum(Vec<NS>::dot_partial(a, b));
   }
 };
 
@@ -144,7 +226,7 @@ __device__ __forceinline__ void matvec_small(const float* __restrict__ M, const 
 // Per-warp constant context: target scales and inverse mass held in registers for the whole kernel.
 template <class R, int TK, bool DM>
 struct Ctx {
-  float tw[(TK == TK_DIAG) ? R::NS : 1];  // target 1/s^2
+  float tw[(TK == TK_DIAG) ? R::NS : 1];  // target -1/s^2 (negated once: grad = q * tw, exactly -(q/s^2))
   float mw[DM ? 1 : R::NS];               // diagonal inverse mass
   float* sm;                              // shared-memory slice (small dense paths)
   int lane;
@@ -152,7 +234,11 @@ struct Ctx {
   __device__ __forceinline__ void init(const Params& P, int chain, int lane_, float* sm_) {
     lane = lane_;
     sm = sm_;
-    if constexpr (TK == TK_DIAG) R::load_const(tw, P.inv_var, P.D, lane);
+    if constexpr (TK == TK_DIAG) {
+      R::load_const(tw, P.inv_var, P.D, lane);
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) tw[s] = -tw[s];
+    }
     if constexpr (!DM) R::load_const(mw, P.imm + (size_t)chain * P.imm_stride, P.D, lane);
   }
 
@@ -161,8 +247,7 @@ struct Ctx {
     if constexpr (DM) {
       matvec_small<R>(P.imm, p, v, sm, P.D, lane);
     } else {
-#pragma unroll
-      for (int s = 0; s < R::NS; ++s) v[s] = mw[s] * p[s];
+      Vec<R::NS>::mul(v, mw, p);
     }
   }
 
@@ -176,42 +261,38 @@ struct Ctx {
   // value_and_grad of the target at q
   __device__ __forceinline__ void value_and_grad(const Params& P, const float (&q)[R::NS], float (&g)[R::NS], float& logp) {
     if constexpr (TK == TK_DIAG) {
-      float acc = 0.f;
+      // g = (q - mean) * (-1/s^2);  logp = 0.5 * sum (q - mean) * g   (negation is exact, so this equals
+      // -0.5 * sum d * (d / s^2) bit for bit)
+      float acc;
       if (P.mean != nullptr) {
-        float mu[R::NS];
-        R::load_const(mu, P.mean, P.D, lane);
+        float d[R::NS];
+        R::load_const(d, P.mean, P.D, lane);
 #pragma unroll
-        for (int s = 0; s < R::NS; ++s) {
-          const float d = q[s] - mu[s];
-          const float t = d * tw[s];
-          acc = fmaf(d, t, acc);
-          g[s] = -t;
-        }
+        for (int s = 0; s < R::NS; ++s) d[s] = -d[s];
+        Vec<R::NS>::add(d, q, d);
+        Vec<R::NS>::mul(g, d, tw);
+        acc = Vec<R::NS>::dot_partial(d, g);
       } else {
-#pragma unroll
-        for (int s = 0; s < R::NS; ++s) {
-          const float t = q[s] * tw[s];
-          acc = fmaf(q[s], t, acc);
-          g[s] = -t;
-        }
+        Vec<R::NS>::mul(g, q, tw);
+        acc = Vec<R::NS>::dot_partial(q, g);
       }
-      logp = -0.5f * warp_sum(acc) + P.logp_offset;
+      logp = 0.5f * warp_sum(acc) + P.logp_offset;
     } else if constexpr (TK == TK_FUNNEL) {
       const float y = __shfl_sync(0xffffffffu, q[0], 0);
-      float acc = 0.f;
+      const float q0 = q[0];
+      {  // sum of v^2 over the funnel coordinates (the neck slot contributes an exact 0)
+        float qq[R::NS];
 #pragma unroll
-      for (int s = 0; s < R::NS; ++s) {
-        const bool neck = (s == 0) && (lane == 0);
-        acc = neck ? acc : fmaf(q[s], q[s], acc);
+        for (int s = 0; s < R::NS; ++s) qq[s] = q[s];
+        if (lane == 0) qq[0] = 0.f;
+        const float ss = warp_sum(Vec<R::NS>::dot_partial(qq, qq));
+        const float ey = expf(-y);
+        const float n = (float)(P.D - 1);
+        const float t = y / 3.0f;
+        logp = -0.5f * (t * t) + (-0.5f * ey * ss - 0.5f * n * y) + P.logp_offset;
+        Vec<R::NS>::scale(g, -ey, q);
+        if (lane == 0) g[0] = -q0 / 9.0f + 0.5f * ey * ss - 0.5f * n;
       }
-      const float ss = warp_sum(acc);
-      const float ey = expf(-y);
-      const float n = (float)(P.D - 1);
-      const float t = y / 3.0f;
-      logp = -0.5f * (t * t) + (-0.5f * ey * ss - 0.5f * n * y) + P.logp_offset;
-#pragma unroll
-      for (int s = 0; s < R::NS; ++s) g[s] = -(ey * q[s]);
-      if (lane == 0) g[0] = -y / 9.0f + 0.5f * ey * ss - 0.5f * n;
     } else if constexpr (TK == TK_DENSE) {
       matvec_small<R>(P.prec, q, g, sm, P.D, lane);
       logp = -0.5f * R::dot(q, g) + P.logp_offset;
@@ -236,17 +317,14 @@ struct Ctx {
                                            float& logp, float eps) {
     const float eh = eps * 0.5f;
     const float e1 = eps * 1.0f;
-#pragma unroll
-    for (int s = 0; s < R::NS; ++s) p[s] = p[s] + eh * g[s];
+    Vec<R::NS>::axpy(p, eh, g);
     {
       float v[R::NS];
       velocity(P, p, v);
-#pragma unroll
-      for (int s = 0; s < R::NS; ++s) q[s] = q[s] + e1 * v[s];
+      Vec<R::NS>::axpy(q, e1, v);
     }
     value_and_grad(P, q, g, logp);
-#pragma unroll
-    for (int s = 0; s < R::NS; ++s) p[s] = p[s] + eh * g[s];
+    Vec<R::NS>::axpy(p, eh, g);
   }
 
   // metric.sample_momentum  metrics.py:260-261 -> util.py:89-91: p = mass_matrix_sqrt (.) normal(key,(D,))
