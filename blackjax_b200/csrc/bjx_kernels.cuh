@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(kThreads) k_leapfrog(Params P, float* __restri
   c.init(P, chain, lane, sm);
   const float eps = P.eps_dev ? P.eps_dev[chain] : P.eps;
   float logp = 0.f;
-  for (int i = 0; i < n_steps; ++i) c.leapfrog(P, q, p, g, logp, eps);
+  for (int i = 0; i + 1 < n_steps; ++i) c.template leapfrog<false>(P, q, p, g, logp, eps);
+  if (n_steps > 0) c.template leapfrog<true>(P, q, p, g, logp, eps);
   R::store(q, q_io + roff, P.D, lane);
   R::store(p, p_io + roff, P.D, lane);
   R::store(g, g_io + roff, P.D, lane);
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   const float e0 = -logp0 + c.kinetic(P, p);    // hmc.py:159
   const float eps = P.eps_dev ? P.eps_dev[chain] : P.eps;
   float logp = logp0;
-  for (int i = 0; i < L; ++i) c.leapfrog(P, q, p, g, logp, eps);  // trajectory.py:165
+  for (int i = 0; i + 1 < L; ++i) c.template leapfrog<false>(P, q, p, g, logp, eps);  // trajectory.py:165
+  if (L > 0) c.template leapfrog<true>(P, q, p, g, logp, eps);
 #pragma unroll
   for (int s = 0; s < R::NS; ++s) p[s] = -1.0f * p[s];              // flip_momentum hmc.py:158
   const float e1 = -logp + c.kinetic(P, p);                         // hmc.py:160

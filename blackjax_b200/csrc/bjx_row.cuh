@@ -258,7 +258,9 @@ struct Ctx {
     return 0.5f * R::dot(v, p);
   }
 
-  // value_and_grad of the target at q
+  // value_and_grad of the target at q.  WANT_LOGP=false skips the log-density reduction where only the
+  // gradient is consumed (interior steps of a fixed-length trajectory: the value is dead there).
+  template <bool WANT_LOGP = true>
   __device__ __forceinline__ void value_and_grad(const Params& P, const float (&q)[R::NS], float (&g)[R::NS], float& logp) {
     if constexpr (TK == TK_DIAG) {
       // g = (q - mean) * (-1/s^2);  logp = 0.5 * sum (q - mean) * g   (negation is exact, so this equals
@@ -271,12 +273,12 @@ struct Ctx {
         for (int s = 0; s < R::NS; ++s) d[s] = -d[s];
         Vec<R::NS>::add(d, q, d);
         Vec<R::NS>::mul(g, d, tw);
-        acc = Vec<R::NS>::dot_partial(d, g);
+        acc = WANT_LOGP ? Vec<R::NS>::dot_partial(d, g) : 0.f;
       } else {
         Vec<R::NS>::mul(g, q, tw);
-        acc = Vec<R::NS>::dot_partial(q, g);
+        acc = WANT_LOGP ? Vec<R::NS>::dot_partial(q, g) : 0.f;
       }
-      logp = 0.5f * warp_sum(acc) + P.logp_offset;
+      if (WANT_LOGP) logp = 0.5f * warp_sum(acc) + P.logp_offset;
     } else if constexpr (TK == TK_FUNNEL) {
       const float y = __shfl_sync(0xffffffffu, q[0], 0);
       const float q0 = q[0];
@@ -313,6 +315,7 @@ struct Ctx {
 
   // one velocity-Verlet step, coefficients [0.5, 1.0, 0.5]
   // (blackjax/mcmc/integrators.py:104-150,199-203,235-245,321-322)
+  template <bool WANT_LOGP = true>
   __device__ __forceinline__ void leapfrog(const Params& P, float (&q)[R::NS], float (&p)[R::NS], float (&g)[R::NS],
                                            float& logp, float eps) {
     const float eh = eps * 0.5f;
@@ -323,7 +326,7 @@ struct Ctx {
       velocity(P, p, v);
       Vec<R::NS>::axpy(q, e1, v);
     }
-    value_and_grad(P, q, g, logp);
+    value_and_grad<WANT_LOGP>(P, q, g, logp);
     Vec<R::NS>::axpy(p, eh, g);
   }
 
