@@ -10,37 +10,36 @@
 #include "../../include/bjx.h"
 #include "bjx_internal.h"
 #include "bjx_launch.cuh"
+#include "bjx_handle.h"
 
 using namespace bjx;
 
-struct bjx_handle_s {
-  bjx_config cfg;
-  cudaStream_t stream;
-  int sc;              // SizeClass
-  int metric_kind;     // -1 until set
-  bool metric_small_dense;
-  const float* imm;    // caller-owned
-  float* msqrt;        // owned
-  size_t msqrt_elems;
-  // NUTS workspace (owned, lazily allocated)
-  NutsWs ws;
-  void* ws_block;
-  int ws_depth;
-  int* h_flag;         // pinned
-  int64_t last_leaf_launches, last_depth;
-  std::string err;
-};
-
 static thread_local std::string g_err;
 
-static int fail(bjx_handle_t h, int code, const std::string& msg) {
+int bjx_fail(bjx_handle_t h, int code, const std::string& msg) {
   g_err = msg;
   if (h) h->err = msg;
   return code;
 }
-static int cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) {
-  return fail(h, (int)e, std::string(where) + ": " + cudaGetErrorString(e));
+int bjx_cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) {
+  return bjx_fail(h, (int)e, std::string(where) + ": " + cudaGetErrorString(e));
 }
+static int fail(bjx_handle_t h, int code, const std::string& msg) { return bjx_fail(h, code, msg); }
+static int cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) { return bjx_cuda_fail(h, e, where); }
+
+// large-D dense path (bjx_dense.cu)
+int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out);
+int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out);
+int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out);
+int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n);
+int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
+                       float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
+                       const bjx::InfoPtrs& info);
+static inline bool target_large_dense(bjx_handle_t h) {
+  return h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN && h->cfg.dim > 128;
+}
+static inline bool metric_large_dense(bjx_handle_t h) { return h->metric_kind == BJX_METRIC_DENSE && h->cfg.dim > 128; }
+static inline bool use_dense_path(bjx_handle_t h) { return target_large_dense(h) || metric_large_dense(h); }
 #define BJX_CUDA(call)                                            \
   do {                                                            \
     cudaError_t e_ = (call);                                      \
@@ -63,7 +62,7 @@ static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
       break;
     case BJX_TARGET_DENSE_GAUSSIAN:
       if (!t.precision) return fail(h, BJX_E_INVALID, "DENSE_GAUSSIAN target needs precision");
-      if (dim > 128) return fail(h, BJX_E_UNSUPPORTED, "DENSE_GAUSSIAN target with dim > 128 needs the batched-GEMM path (not built yet)");
+      if (dim > 128 && dim % 4 != 0) return fail(h, BJX_E_UNSUPPORTED, "DENSE_GAUSSIAN target with dim > 128 needs dim % 4 == 0 (tensor-core GEMM path)");
       break;
     case BJX_TARGET_BANANA:
       if (dim != 2) return fail(h, BJX_E_INVALID, "BANANA target needs dim == 2");
@@ -108,6 +107,10 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->h_flag = nullptr;
   h->last_leaf_launches = 0;
   h->last_depth = 0;
+  h->dense_block = nullptr;
+  h->dense_bytes = 0;
+  h->gemm_ws = nullptr;
+  h->gemm_ws_bytes = 0;
   int rc = validate_target(h, cfg->target, cfg->dim);
   if (rc) {
     g_err = h->err;
@@ -129,6 +132,8 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   cudaStreamSynchronize(h->stream);
   if (h->msqrt) cudaFree(h->msqrt);
   if (h->ws_block) cudaFree(h->ws_block);
+  if (h->dense_block) cudaFree(h->dense_block);
+  if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->h_flag) cudaFreeHost(h->h_flag);
   delete h;
   return 0;
@@ -157,8 +162,8 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
   if (kind == BJX_METRIC_DIAG) elems = D;
   else if (kind == BJX_METRIC_DIAG_PER_CHAIN) elems = (size_t)C * D;
   else if (kind == BJX_METRIC_DENSE) {
-    if (D > 128 || !size_class_is_small(h->sc))
-      return fail(h, BJX_E_UNSUPPORTED, "dense metric with dim > 128 needs the batched-GEMM path (not built yet)");
+    if (D > 128 && D % 4 != 0)
+      return fail(h, BJX_E_UNSUPPORTED, "dense metric with dim > 128 needs dim % 4 == 0 (tensor-core GEMM path)");
     elems = (size_t)D * D;
   } else
     return fail(h, BJX_E_INVALID, "The mass matrix has the wrong number of dimensions: expected 1 or 2");  // metrics.py:724-728
@@ -201,7 +206,7 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
     BJX_CHECK_LAUNCH("k_diag_mass_sqrt");
   }
   h->metric_kind = kind;
-  h->metric_small_dense = (kind == BJX_METRIC_DENSE);
+  h->metric_small_dense = (kind == BJX_METRIC_DENSE) && D <= 128;
   h->imm = imm;
   return 0;
 }
@@ -264,6 +269,7 @@ extern "C" int bjx_init_state(bjx_handle_t h, const float* q, float* logp_out, f
   int rc = check_ready(h, false, ptrs, 2);
   if (rc) return rc;
   if (!logp_out) return fail(h, BJX_E_INVALID, "null array argument");
+  if (target_large_dense(h)) return bjx_dense_init_state(h, q, logp_out, grad_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.q_in = q;
@@ -278,6 +284,7 @@ extern "C" int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* 
   int rc = check_ready(h, true, ptrs, 1);
   if (rc) return rc;
   if (!keys) return fail(h, BJX_E_INVALID, "null keys");
+  if (metric_large_dense(h)) return bjx_dense_sample_momentum(h, keys, p_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.keys = keys;
@@ -291,6 +298,7 @@ extern "C" int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, flo
   int rc = check_ready(h, true, ptrs, 3);
   if (rc) return rc;
   if (!logp || n_steps < 0) return fail(h, BJX_E_INVALID, "bad argument");
+  if (use_dense_path(h)) return bjx_dense_leapfrog(h, q, p, logp, grad, step_size, step_size_dev, n_steps);
   LaunchArgs a{};
   a.P = make_params(h, step_size, step_size_dev);
   a.q_out = q;
@@ -306,6 +314,7 @@ extern "C" int bjx_energy(bjx_handle_t h, const float* p, const float* logp, flo
   int rc = check_ready(h, true, ptrs, 1);
   if (rc) return rc;
   if (!logp || !energy_out) return fail(h, BJX_E_INVALID, "null array argument");
+  if (metric_large_dense(h)) return bjx_dense_energy(h, p, logp, energy_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.p_io = const_cast<float*>(p);
@@ -319,6 +328,7 @@ extern "C" int bjx_is_turning(bjx_handle_t h, const float* pl, const float* pr, 
   int rc = check_ready(h, true, ptrs, 3);
   if (rc) return rc;
   if (!out) return fail(h, BJX_E_INVALID, "null array argument");
+  if (metric_large_dense(h)) return fail(h, BJX_E_UNSUPPORTED, "U-turn test with a dense metric needs dim <= 128");
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.pl = pl;
@@ -354,6 +364,9 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
   if (!keys || !logp_in || !logp_out || L < 0) return fail(h, BJX_E_INVALID, "bad argument");
   if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  if (use_dense_path(h))
+    return bjx_dense_hmc_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev, L,
+                              make_info(info));
   LaunchArgs a{};
   a.P = make_params(h, step_size, step_size_dev);
   a.keys = keys;
@@ -419,6 +432,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
     return fail(h, BJX_E_INVALID, "max_num_doublings exceeds the handle's max_tree_depth");
   if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  if (use_dense_path(h)) return fail(h, BJX_E_UNSUPPORTED, "NUTS with a dense metric / dense target needs dim <= 128");
   rc = ensure_ws(h);
   if (rc) return rc;
   const int C = h->cfg.n_chains;

@@ -1,0 +1,342 @@
+// Large-D dense path (D > 128): HMC with a dense inverse mass matrix and/or a dense Gaussian target
+// (BASELINE config 2: 1024-D correlated Gaussian, dense mass matrix).  The two linear maps of every
+// leapfrog -- v = M^-1 p (blackjax/mcmc/integrators.py:242 -> metrics.py:263-270 -> util.py:57-61) and
+// grad = -P q (the target's autodiff) -- are [C,D] x [D,D] GEMMs on the tensor cores (bjx_gemm.cu); the
+// elementwise glue (half kicks, energies, accept/select) are the streaming row kernels below.
+#include <vector>
+
+#include "bjx_handle.h"
+#include "bjx_internal.h"
+#include "bjx_prng.cuh"
+
+using namespace bjx;
+
+namespace bjx {
+size_t gemm_workspace_bytes(int M, int N, int K);
+int gemm_xa(const float* X, const float* A_nk, float* Y, const float* Cin, float alpha, float beta, int M, int N, int K,
+            void* workspace, cudaStream_t stream);
+
+constexpr int kRowWarps = 8;
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// z[c, i] = normal(split(rng_key_c, 2)[0], (D,))[i]   (hmc.py:299,302 -> util.py:89-91)
+__global__ void k_dense_normal(int C, int D, const uint32_t* __restrict__ keys, float* __restrict__ z) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = (long long)C * D / 4;
+  if (t >= n4) return;
+  const long long e = t * 4;
+  const int c = (int)(e / D);
+  const uint32_t i = (uint32_t)(e % D);
+  const Key km = fold_in(Key{keys[2 * c], keys[2 * c + 1]}, 0u);
+  float4 o;
+  o.x = normal_at(km, i);
+  o.y = normal_at(km, i + 1);
+  o.z = normal_at(km, i + 2);
+  o.w = normal_at(km, i + 3);
+  reinterpret_cast<float4*>(z)[t] = o;
+}
+
+// y[c,:] = a[:] * x[c,:]  (diagonal metric with a dense target)
+__global__ void k_rows_scale(int C, int D, const float* __restrict__ a, long long a_stride, const float* __restrict__ x,
+                             float* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = (long long)C * D / 4;
+  if (t >= n4) return;
+  const long long e = t * 4;
+  const int c = (int)(e / D);
+  const int i = (int)(e % D);
+  const float4 av = *reinterpret_cast<const float4*>(a + (size_t)c * a_stride + i);
+  const float4 xv = __ldcs(reinterpret_cast<const float4*>(x) + t);
+  __stcs(reinterpret_cast<float4*>(y) + t, make_float4(av.x * xv.x, av.y * xv.y, av.z * xv.z, av.w * xv.w));
+}
+
+// x[c,:] += (eps_c * coef) * y[c,:]     (integrators.py:199-203,235-239)
+__global__ void k_rows_axpy(int C, int D, float* __restrict__ x, const float* __restrict__ y, float eps,
+                            const float* __restrict__ eps_dev, float coef) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = (long long)C * D / 4;
+  if (t >= n4) return;
+  const int c = (int)(t * 4 / D);
+  const float a = (eps_dev ? eps_dev[c] : eps) * coef;
+  float4 xv = __ldcs(reinterpret_cast<const float4*>(x) + t);
+  const float4 yv = __ldcs(reinterpret_cast<const float4*>(y) + t);
+  xv.x = fmaf(a, yv.x, xv.x); xv.y = fmaf(a, yv.y, xv.y); xv.z = fmaf(a, yv.z, xv.z); xv.w = fmaf(a, yv.w, xv.w);
+  __stcs(reinterpret_cast<float4*>(x) + t, xv);
+}
+
+// e[c] = -logp[c] + 0.5 * sum_i v[c,i] p[c,i]      (trajectory.py:745-748, metrics.py:263-270)
+__global__ void k_rows_energy(int C, int D, const float* __restrict__ v, const float* __restrict__ p,
+                              const float* __restrict__ logp, float* __restrict__ e, float p_sign) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const float4* vr = reinterpret_cast<const float4*>(v + (size_t)c * D);
+  const float4* pr = reinterpret_cast<const float4*>(p + (size_t)c * D);
+  float acc = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 a = __ldcs(vr + i), b = __ldcs(pr + i);
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  }
+  acc = wsum(acc);
+  if (lane == 0) e[c] = -logp[c] + 0.5f * acc * p_sign;
+}
+
+// Gradient + second half kick for one leapfrog, streaming the row:
+//   TARGET 2 (dense Gaussian): aux = P q from the GEMM; g = -aux; logp = -1/2 q.aux + offset
+//   TARGET 0 (diag Gaussian) : g = -(q - mean) / s^2;      logp = -1/2 sum (q-mean)^2/s^2 + offset
+//   then (if p != null) p += (eps_c * 0.5) * g                                  (integrators.py:134-141)
+template <int TARGET>
+__global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, const float* __restrict__ aux,
+                                 const float* __restrict__ inv_var, const float* __restrict__ mean, float offset,
+                                 float* __restrict__ p, float eps, const float* __restrict__ eps_dev,
+                                 float* __restrict__ g_out, float* __restrict__ logp_out) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const size_t ro = (size_t)c * D;
+  const float eh = (eps_dev ? eps_dev[c] : eps) * 0.5f;
+  float acc = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 qv = __ldcs(reinterpret_cast<const float4*>(q + ro) + i);
+    float4 gv;
+    if (TARGET == 2) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(aux + ro) + i);
+      gv = make_float4(-a.x, -a.y, -a.z, -a.w);
+      acc = fmaf(qv.x, gv.x, acc); acc = fmaf(qv.y, gv.y, acc); acc = fmaf(qv.z, gv.z, acc); acc = fmaf(qv.w, gv.w, acc);
+    } else {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(inv_var) + i);
+      float4 d = qv;
+      if (mean) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + i);
+        d = make_float4(qv.x - m.x, qv.y - m.y, qv.z - m.z, qv.w - m.w);
+      }
+      gv = make_float4(d.x * -w.x, d.y * -w.y, d.z * -w.z, d.w * -w.w);
+      acc = fmaf(d.x, gv.x, acc); acc = fmaf(d.y, gv.y, acc); acc = fmaf(d.z, gv.z, acc); acc = fmaf(d.w, gv.w, acc);
+    }
+    __stcs(reinterpret_cast<float4*>(g_out + ro) + i, gv);
+    if (p) {
+      float4 pv = __ldcs(reinterpret_cast<const float4*>(p + ro) + i);
+      pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
+      __stcs(reinterpret_cast<float4*>(p + ro) + i, pv);
+    }
+  }
+  acc = wsum(acc);
+  if (lane == 0) logp_out[c] = 0.5f * acc + offset;
+}
+
+// Metropolis accept + select (hmc.py:158-163, proposal.py:214-235) for the dense path
+__global__ void k_rows_accept(int C, int D, const uint32_t* __restrict__ keys, const float* __restrict__ e0,
+                              const float* __restrict__ e1, float div_thr, const float* __restrict__ qw,
+                              const float* __restrict__ gw, const float* __restrict__ lw, const float* q_in,
+                              const float* g_in, const float* l_in, float* q_out, float* g_out, float* l_out, int L,
+                              InfoPtrs info) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const Key ki = fold_in(Key{keys[2 * c], keys[2 * c + 1]}, 1u);
+  float delta = e0[c] - e1[c];
+  if (isnan(delta)) delta = -__int_as_float(0x7f800000);
+  const bool is_div = (-delta) > div_thr;
+  float pa = expf(delta);
+  pa = pa > 1.0f ? 1.0f : pa;
+  const bool acc = uniform01(ki) < pa;
+  const size_t ro = (size_t)c * D;
+  if (acc || q_out != q_in) {
+    const float4* sq = reinterpret_cast<const float4*>((acc ? qw : q_in) + ro);
+    const float4* sg = reinterpret_cast<const float4*>((acc ? gw : g_in) + ro);
+    for (int i = lane; i < D / 4; i += 32) {
+      __stcs(reinterpret_cast<float4*>(q_out + ro) + i, __ldcs(sq + i));
+      __stcs(reinterpret_cast<float4*>(g_out + ro) + i, __ldcs(sg + i));
+    }
+    if (lane == 0) l_out[c] = acc ? lw[c] : l_in[c];
+  }
+  if (lane == 0) {
+    if (info.acceptance_rate) info.acceptance_rate[c] = pa;
+    if (info.is_accepted) info.is_accepted[c] = acc;
+    if (info.is_divergent) info.is_divergent[c] = is_div;
+    if (info.energy) info.energy[c] = e1[c];
+    if (info.num_integration_steps) info.num_integration_steps[c] = L;
+  }
+}
+}  // namespace bjx
+
+#define DN_CUDA(call)                                                \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) return bjx_cuda_fail(h, e_, #call);       \
+  } while (0)
+#define DN_LAUNCH(where)                                             \
+  do {                                                               \
+    cudaError_t e_ = cudaGetLastError();                             \
+    if (e_ != cudaSuccess) return bjx_cuda_fail(h, e_, where);       \
+  } while (0)
+
+static inline dim3 g4(long long n4) { return dim3((unsigned)((n4 + 255) / 256)); }
+static inline dim3 grow(int C) { return dim3((C + kRowWarps - 1) / kRowWarps); }
+
+struct DenseWs {
+  float *p, *v, *q, *g, *lw, *e0, *e1;
+};
+
+static int dense_ws(bjx_handle_t h, DenseWs& w) {
+  const size_t C = h->cfg.n_chains, D = h->cfg.dim;
+  const size_t row = ((C * D * sizeof(float)) + 255) & ~(size_t)255, vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t need = 4 * row + 3 * vec;
+  if (h->dense_bytes < need) {
+    if (h->dense_block) DN_CUDA(cudaFree(h->dense_block));
+    h->dense_block = nullptr;
+    DN_CUDA(cudaMalloc((void**)&h->dense_block, need));
+    h->dense_bytes = need;
+  }
+  const size_t gw = gemm_workspace_bytes((int)C, (int)D, (int)D);
+  if (gw > h->gemm_ws_bytes) {
+    if (h->gemm_ws) DN_CUDA(cudaFree(h->gemm_ws));
+    h->gemm_ws = nullptr;
+    DN_CUDA(cudaMalloc(&h->gemm_ws, gw));
+    h->gemm_ws_bytes = gw;
+  }
+  char* b = (char*)h->dense_block;
+  w.p = (float*)b; w.v = (float*)(b + row); w.q = (float*)(b + 2 * row); w.g = (float*)(b + 3 * row);
+  w.lw = (float*)(b + 4 * row); w.e0 = (float*)(b + 4 * row + vec); w.e1 = (float*)(b + 4 * row + 2 * vec);
+  return 0;
+}
+
+static int gemm(bjx_handle_t h, const float* X, const float* A, float* Y, const float* Cin, float alpha, float beta) {
+  const int rc = gemm_xa(X, A, Y, Cin, alpha, beta, h->cfg.n_chains, h->cfg.dim, h->cfg.dim, h->gemm_ws, h->stream);
+  if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
+  DN_LAUNCH("gemm");
+  return 0;
+}
+
+// v = M^-1 p
+static int dense_velocity(bjx_handle_t h, const float* p, float* v) {
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, p, h->imm, v, nullptr, 1.f, 0.f);
+  const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
+  k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->imm, stride, p, v);
+  DN_LAUNCH("k_rows_scale");
+  return 0;
+}
+
+// g, logp = value_and_grad(q); optionally p += eh * g.  aux: [C,D] scratch for P q.
+static int dense_grad(bjx_handle_t h, const float* q, float* aux, float* p, float eps, const float* eps_dev, float* g,
+                      float* logp) {
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  const bjx_target_desc& t = h->cfg.target;
+  if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
+    int rc = gemm(h, q, t.precision, aux, nullptr, 1.f, 0.f);
+    if (rc) return rc;
+    k_rows_grad_kick<2><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, aux, nullptr, nullptr, t.logp_offset, p, eps,
+                                                                 eps_dev, g, logp);
+  } else if (t.kind == BJX_TARGET_DIAG_GAUSSIAN) {
+    k_rows_grad_kick<0><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, nullptr, t.inv_var, t.mean, t.logp_offset, p,
+                                                                 eps, eps_dev, g, logp);
+  } else {
+    return bjx_fail(h, BJX_E_UNSUPPORTED, "large-D dense path supports DENSE_GAUSSIAN and DIAG_GAUSSIAN targets");
+  }
+  DN_LAUNCH("k_rows_grad_kick");
+  return 0;
+}
+
+int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  return dense_grad(h, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out);
+}
+
+int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  float* z = (h->metric_kind == BJX_METRIC_DENSE) ? w.v : p_out;
+  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z);
+  DN_LAUNCH("k_dense_normal");
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, z, h->msqrt, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
+  const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
+  k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->msqrt, stride, z, p_out);
+  DN_LAUNCH("k_rows_scale");
+  return 0;
+}
+
+int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  rc = dense_velocity(h, p, w.v);
+  if (rc) return rc;
+  k_rows_energy<<<grow(h->cfg.n_chains), kRowWarps * 32, 0, h->stream>>>(h->cfg.n_chains, h->cfg.dim, w.v, p, logp, e_out, 1.f);
+  DN_LAUNCH("k_rows_energy");
+  return 0;
+}
+
+// n velocity-Verlet steps in place (integrators.py:104-150)
+static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, float* q, float* p, float* logp, float* g, float eps,
+                               const float* eps_dev, int n_steps) {
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  const long long n4 = (long long)C * D / 4;
+  for (int s = 0; s < n_steps; ++s) {
+    k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, p, g, eps, eps_dev, 0.5f);  // p += (eps/2) g
+    DN_LAUNCH("k_rows_axpy");
+    int rc;
+    if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
+      rc = gemm(h, p, h->imm, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
+      if (rc) return rc;
+    } else {
+      rc = dense_velocity(h, p, w.v);
+      if (rc) return rc;
+      k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, q, w.v, eps, eps_dev, 1.0f);
+      DN_LAUNCH("k_rows_axpy");
+    }
+    rc = dense_grad(h, q, w.v, p, eps, eps_dev, g, logp);  // g, logp at the new q; p += (eps/2) g
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev,
+                       int n_steps) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  return dense_leapfrog_core(h, w, q, p, logp, g, eps, eps_dev, n_steps);
+}
+
+int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
+                       float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
+                       const InfoPtrs& info) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  const size_t bytes = (size_t)C * D * sizeof(float);
+  rc = bjx_dense_sample_momentum(h, keys, w.p);  // hmc.py:299-302
+  if (rc) return rc;
+  if (info.momentum) DN_CUDA(cudaMemcpyAsync(info.momentum, w.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  rc = dense_velocity(h, w.p, w.v);
+  if (rc) return rc;
+  k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, logp_in, w.e0, 1.f);  // hmc.py:159
+  DN_LAUNCH("k_rows_energy");
+  DN_CUDA(cudaMemcpyAsync(w.q, q_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  DN_CUDA(cudaMemcpyAsync(w.g, g_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  DN_CUDA(cudaMemcpyAsync(w.lw, logp_in, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  rc = dense_leapfrog_core(h, w, w.q, w.p, w.lw, w.g, eps, eps_dev, L);  // trajectory.py:165
+  if (rc) return rc;
+  rc = dense_velocity(h, w.p, w.v);  // kinetic energy of the (flipped) end momentum: (-p)^T M^-1 (-p) = p^T M^-1 p
+  if (rc) return rc;
+  k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, w.lw, w.e1, 1.f);  // hmc.py:160
+  DN_LAUNCH("k_rows_energy");
+  if (info.proposal_position) DN_CUDA(cudaMemcpyAsync(info.proposal_position, w.q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (info.proposal_momentum) {  // flipped momentum (hmc.py:158)
+    DN_CUDA(cudaMemsetAsync(info.proposal_momentum, 0, bytes, h->stream));
+    k_rows_axpy<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, info.proposal_momentum, w.p, -1.0f, nullptr, 1.0f);
+    DN_LAUNCH("k_rows_axpy");
+  }
+  k_rows_accept<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, keys, w.e0, w.e1, h->cfg.divergence_threshold, w.q, w.g,
+                                                          w.lw, q_in, g_in, logp_in, q_out, g_out, logp_out, L, info);
+  DN_LAUNCH("k_rows_accept");
+  return 0;
+}

@@ -1,0 +1,34 @@
+// The opaque handle behind include/bjx.h (internal).
+#pragma once
+#include <string>
+
+#include "../../include/bjx.h"
+#include "bjx_kernels.cuh"
+
+struct bjx_handle_s {
+  bjx_config cfg;
+  cudaStream_t stream;
+  int sc;              // SizeClass
+  int metric_kind;     // -1 until set
+  bool metric_small_dense;
+  const float* imm;    // caller-owned
+  float* msqrt;        // owned
+  size_t msqrt_elems;
+  // NUTS workspace (owned, lazily allocated)
+  bjx::NutsWs ws;
+  void* ws_block;
+  int ws_depth;
+  int* h_flag;         // pinned
+  int64_t last_leaf_launches, last_depth;
+  // large-D dense path (bjx_dense.cu): working rows p, v, q, g [C,D] + GEMM workspace
+  float* dense_block;
+  size_t dense_bytes;
+  void* gemm_ws;
+  size_t gemm_ws_bytes;
+  std::string err;
+};
+
+int bjx_fail(bjx_handle_t h, int code, const std::string& msg);
+int bjx_cuda_fail(bjx_handle_t h, cudaError_t e, const char* where);
+
+

@@ -264,6 +264,112 @@ def test_hmc_inplace_and_out_of_place_agree():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# large-D dense path: tensor-core GEMMs (float32-accurate operand split) for M^-1 p, -P x, L^-T z
+# ---------------------------------------------------------------------------------------------------------
+def dense_problem(D, C, seed=31, metric="dense", target="dense"):
+    rs = np.random.default_rng(seed)
+    cov, prec = otargets.correlated_gaussian(D, seed=seed, lo=-0.5, hi=0.5)
+    if target == "dense":
+        tgt, otgt = T.DenseGaussian(prec), otargets.DenseGaussian(prec)
+    else:
+        s = np.exp(rs.uniform(-0.5, 0.5, D))
+        tgt, otgt = T.DiagGaussian(s), otargets.DiagGaussian(s)
+    imm = cov if metric == "dense" else np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    q = (0.5 * rs.standard_normal((C, D))).astype(F)
+    return tgt, otgt, imm, q
+
+
+@pytest.mark.parametrize("D, C, metric, target", [(256, 100, "dense", "dense"), (512, 37, "dense", "dense"),
+                                                  (256, 64, "diag", "dense"), (256, 64, "dense", "diag")])
+def test_dense_path_building_blocks(D, C, metric, target):
+    tgt, otgt, imm, q = dense_problem(D, C, metric=metric, target=target)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    om = ohmc.Metric(imm)
+    dq = tf(q)
+    logp, g = eng.init_state(dq)
+    lp0, g0 = otgt(q)
+    close(npy(g), g0, rtol=1e-5)
+    close(npy(logp), lp0, rtol=1e-5, scale=np.max(np.abs(lp0)) + 1)
+    keys = oprng.split(oprng.key(9), C)
+    p = eng.sample_momentum(tk(keys))
+    p_ref = om.sample_momentum(keys, D)
+    close(npy(p), p_ref, rtol=1e-5)
+    e = eng.energy(tf(p_ref), logp)
+    close(npy(e), -lp0 + om.kinetic_energy(p_ref), rtol=1e-5, scale=np.max(np.abs(lp0)) + D)
+    dp = tf(p_ref)
+    eng.leapfrog_(dq, dp, logp, g, 0.05, 4)
+    q1, p1, lp1, g1 = ohmc.static_integration(otgt, om, q, p_ref, lp0, g0, F(0.05), 4)
+    close(npy(dq), q1, rtol=2e-5)
+    close(npy(dp), p1, rtol=2e-5)
+    close(npy(g), g1, rtol=2e-5)
+    close(npy(logp), lp1, rtol=2e-5, scale=np.max(np.abs(lp1)) + 1)
+
+
+@pytest.mark.parametrize("D, C, L, pce", [(256, 96, 6, False), (384, 40, 4, True)])
+def test_dense_hmc_transition_matches_oracle(D, C, L, pce):
+    tgt, otgt, imm, q = dense_problem(D, C)
+    keys = oprng.split(oprng.key(17), C)
+    rs = np.random.default_rng(3)
+    eps_np = (0.08 * np.exp(rs.uniform(-0.2, 0.2, C))).astype(F) if pce else F(0.08)
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, eps_np, ohmc.Metric(imm), L)
+    kernel = bj.hmc.build_kernel(full_info=True)
+    st = bj.hmc.init(tf(q), tgt)
+    new, info = kernel(tk(keys), st, tgt, tf(eps_np) if pce else float(eps_np), tf(imm), L)
+    torch.cuda.synchronize()
+    close(npy(info.momentum), oinfo.momentum, rtol=1e-5)
+    close(npy(info.proposal.position), oinfo.proposal[0], rtol=3e-5)
+    close(npy(info.proposal.momentum), oinfo.proposal[1], rtol=3e-5)
+    close(npy(info.energy), oinfo.energy, rtol=3e-5, scale=np.max(np.abs(oinfo.energy)) + D)
+    close(npy(info.acceptance_rate), oinfo.acceptance_rate, rtol=2e-3, scale=1.0)
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    tie = np.abs(u - oinfo.acceptance_rate) < 2e-3
+    acc = npy(info.is_accepted)
+    assert ((acc == oinfo.is_accepted) | tie).all()
+    same = acc == oinfo.is_accepted
+    close(npy(new.position)[same], onew.position[same], rtol=3e-5)
+    close(npy(new.logdensity_grad)[same], onew.logdensity_grad[same], rtol=3e-5)
+
+
+def test_dense_unsupported_combinations_fail_loudly():
+    tgt, _, imm, q = dense_problem(256, 8)
+    st = bj.nuts.init(tf(q), tgt)
+    with pytest.raises(bj.BjxError, match="dim <= 128"):
+        bj.nuts.build_kernel()(bj.random.key(0, DEV), st, tgt, 0.1, tf(imm), 5)
+
+
+def test_fullsize_dense_config2_65536x1024():
+    # BASELINE config 2 shape: 1024-D correlated Gaussian, 65536 chains, dense mass matrix.  Size-independent
+    # properties: energy conservation of the symplectic integrator, time reversibility, and linearity of the
+    # dynamics (Gaussian target + Gaussian kinetic energy => the flow map is linear in (q, p)).
+    C, D = 65536, 1024
+    cov, prec = otargets.correlated_gaussian(D, seed=0)
+    tgt = T.DenseGaussian(prec)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(cov))
+    g_ = torch.Generator(device=DEV).manual_seed(0)
+    q0 = 0.1 * torch.randn(C, D, device=DEV, generator=g_)
+    p0 = eng.sample_momentum(bj.random.split(bj.random.key(1, DEV), C))
+    q, p = q0.clone(), p0.clone()
+    logp, g = eng.init_state(q)
+    e0 = eng.energy(p, logp)
+    eng.leapfrog_(q, p, logp, g, 0.5, 3)
+    e1 = eng.energy(p, logp)
+    assert float((e1 - e0).abs().max() / e0.abs().mean()) < 0.2          # eps=0.5 is near the stability limit
+    p.neg_()
+    eng.leapfrog_(q, p, logp, g, 0.5, 3)
+    assert float((q - q0).abs().max()) < 2e-3 * float(q0.abs().max() + p0.abs().max())
+    # linearity: flow(2 q0, 2 p0) == 2 flow(q0, p0)
+    qa, pa = q0.clone(), p0.clone()
+    la, ga = eng.init_state(qa)
+    eng.leapfrog_(qa, pa, la, ga, 0.5, 2)
+    qb, pb = 2 * q0, 2 * p0
+    lb, gb = eng.init_state(qb)
+    eng.leapfrog_(qb, pb, lb, gb, 0.5, 2)
+    torch.testing.assert_close(qb, 2 * qa, rtol=1e-4, atol=1e-4 * float(qa.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # NUTS
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("step_size, diverge, turn, doublings",
