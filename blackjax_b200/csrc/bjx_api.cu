@@ -29,7 +29,7 @@ static int cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) { return 
 
 // large-D dense path (bjx_dense.cu)
 int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out);
-int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out);
+int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out, bool split_first);
 int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out);
 int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n);
 int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
@@ -284,7 +284,7 @@ extern "C" int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* 
   int rc = check_ready(h, true, ptrs, 1);
   if (rc) return rc;
   if (!keys) return fail(h, BJX_E_INVALID, "null keys");
-  if (metric_large_dense(h)) return bjx_dense_sample_momentum(h, keys, p_out);
+  if (metric_large_dense(h)) return bjx_dense_sample_momentum(h, keys, p_out, false);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.keys = keys;

@@ -24,15 +24,16 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-// z[c, i] = normal(split(rng_key_c, 2)[0], (D,))[i]   (hmc.py:299,302 -> util.py:89-91)
-__global__ void k_dense_normal(int C, int D, const uint32_t* __restrict__ keys, float* __restrict__ z) {
+// z[c, i] = normal(key_c, (D,))[i] with key_c = split(rng_key_c, 2)[0] when split_first (hmc.py:299,302 -> util.py:89-91)
+__global__ void k_dense_normal(int C, int D, const uint32_t* __restrict__ keys, float* __restrict__ z, bool split_first) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n4 = (long long)C * D / 4;
   if (t >= n4) return;
   const long long e = t * 4;
   const int c = (int)(e / D);
   const uint32_t i = (uint32_t)(e % D);
-  const Key km = fold_in(Key{keys[2 * c], keys[2 * c + 1]}, 0u);
+  Key km{keys[2 * c], keys[2 * c + 1]};
+  if (split_first) km = fold_in(km, 0u);
   float4 o;
   o.x = normal_at(km, i);
   o.y = normal_at(km, i + 1);
@@ -247,13 +248,13 @@ int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float*
   return dense_grad(h, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out);
 }
 
-int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out) {
+int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out, bool split_first) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   float* z = (h->metric_kind == BJX_METRIC_DENSE) ? w.v : p_out;
-  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z);
+  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z, split_first);
   DN_LAUNCH("k_dense_normal");
   if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, z, h->msqrt, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
   const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
@@ -313,7 +314,7 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
   if (rc) return rc;
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   const size_t bytes = (size_t)C * D * sizeof(float);
-  rc = bjx_dense_sample_momentum(h, keys, w.p);  // hmc.py:299-302
+  rc = bjx_dense_sample_momentum(h, keys, w.p, true);  // hmc.py:299-302
   if (rc) return rc;
   if (info.momentum) DN_CUDA(cudaMemcpyAsync(info.momentum, w.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
   rc = dense_velocity(h, w.p, w.v);
