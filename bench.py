@@ -27,19 +27,33 @@ METRIC = "leapfrog-steps/sec (all chains)"
 UNIT = "leapfrog-steps/s"
 
 WORKLOADS = {
-    # the 65k x 1024 leapfrog shape the north star's HBM target names (diagonal mass matrix).
-    # BASELINE configs[1] proper (dense mass matrix + correlated Gaussian) needs the batched-GEMM path
-    # that is not built yet; this workload is the same (chains x dims x L) with a diagonal metric.
-    "hmc_diag_gaussian_65536x1024_L50": dict(C=65536, D=1024, L=50, eps=0.1),
+    # BASELINE configs[1]: HMC, 1024-D correlated Gaussian (Sigma = Q diag(logspace(-1,1)) Q^T), 65536 chains,
+    # dense mass matrix M^-1 = Sigma, 50 leapfrog steps, 1 GPU (SURVEY section 8d fixed inputs: eps 0.5, q0 = 0.1 N(0,1))
+    "hmc_dense_gaussian_65536x1024_L50": dict(C=65536, D=1024, L=50, eps=0.5, dense=True),
+    # the same chains x dims x L with a diagonal mass matrix / diagonal Gaussian: the HBM-bound leapfrog shape the
+    # north star's ">= 60 % of HBM roofline at 65k chains x 1024 dims" names
+    "hmc_diag_gaussian_65536x1024_L50": dict(C=65536, D=1024, L=50, eps=0.1, dense=False),
     # BASELINE configs[0]: the reference's own CPU-runnable case
-    "hmc_iso_gaussian_1024x100_L10": dict(C=1024, D=100, L=10, eps=0.2),
+    "hmc_iso_gaussian_1024x100_L10": dict(C=1024, D=100, L=10, eps=0.2, dense=False),
 }
-DEFAULT_WORKLOAD = "hmc_diag_gaussian_65536x1024_L50"
+DEFAULT_WORKLOAD = "hmc_dense_gaussian_65536x1024_L50"
 
 
 def target_scale(D):
     import numpy as np
     return np.ones(D) if D == 100 else np.logspace(-0.5, 0.5, D)
+
+
+def dense_matrices(D):
+    """Synthetic inputs of configs[1]: Sigma = Q diag(logspace(-1, 1, D)) Q^T with Q from the QR of a
+    default_rng(0) normal matrix (recipe of tests/mcmc/test_mclmc_lrd.py:68-90); returns (cov, precision) float32."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    eigs = np.logspace(-1.0, 1.0, D)
+    cov = (Q * eigs) @ Q.T
+    prec = (Q / eigs) @ Q.T
+    return (0.5 * (cov + cov.T)).astype(np.float32), (0.5 * (prec + prec.T)).astype(np.float32)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -107,23 +121,38 @@ def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
     import numpy as np
     from oracle import cport, prng
     D, L, eps = wl["D"], wl["L"], wl["eps"]
-    s = target_scale(D)
-    inv_var = (1.0 / s ** 2).astype(np.float32)
-    imm = (s ** 2).astype(np.float32)
     cores = cport.num_threads()
+    if wl.get("dense"):
+        cov, prec = dense_matrices(D)
+        msqrt = cport.dense_mass_sqrt(cov)
 
-    def run(Cs, n):
-        rs = np.random.default_rng(0)
-        q = (rs.standard_normal((Cs, D)) * s).astype(np.float32)
-        g = (-q * inv_var).astype(np.float32)
-        logp = (-0.5 * (q * q * inv_var).sum(1)).astype(np.float32)
-        keys = prng.split(prng.key(0), Cs)
-        t0 = time.perf_counter()
-        for _ in range(n):
-            cport.hmc_step(0, inv_var, imm, keys, q, logp, g, eps, L)
-        return time.perf_counter() - t0
+        def run(Cs, n):
+            rs = np.random.default_rng(0)
+            q = (0.1 * rs.standard_normal((Cs, D))).astype(np.float32)
+            g = (-(q @ prec.T)).astype(np.float32)
+            logp = (0.5 * (q * g).sum(1)).astype(np.float32)
+            keys = prng.split(prng.key(0), Cs)
+            t0 = time.perf_counter()
+            for _ in range(n):
+                cport.hmc_dense_step(prec, cov, keys, q, logp, g, eps, L, msqrt=msqrt)
+            return time.perf_counter() - t0
+    else:
+        s = target_scale(D)
+        inv_var = (1.0 / s ** 2).astype(np.float32)
+        imm = (s ** 2).astype(np.float32)
 
-    probe_c = max(cores * 4, 64)
+        def run(Cs, n):
+            rs = np.random.default_rng(0)
+            q = (rs.standard_normal((Cs, D)) * s).astype(np.float32)
+            g = (-q * inv_var).astype(np.float32)
+            logp = (-0.5 * (q * q * inv_var).sum(1)).astype(np.float32)
+            keys = prng.split(prng.key(0), Cs)
+            t0 = time.perf_counter()
+            for _ in range(n):
+                cport.hmc_step(0, inv_var, imm, keys, q, logp, g, eps, L)
+            return time.perf_counter() - t0
+
+    probe_c = max(cores * (16 if wl.get("dense") else 4), 64)
     run(probe_c, 1)
     t = run(probe_c, 1)
     per_chain = t / probe_c
@@ -194,13 +223,20 @@ def main():
 
     C, D, L, eps = wl["C"], wl["D"], wl["L"], wl["eps"]
     K, W = args.steps, args.warmup
+    dense = bool(wl.get("dense"))
     s = target_scale(D)
-    tgt = bj.targets.DiagGaussian(s)
-    imm = torch.from_numpy((s ** 2).astype(np.float32)).to(dev)
-    scale_t = torch.from_numpy(s.astype(np.float32)).to(dev)
+    diag_tgt = bj.targets.DiagGaussian(s)
+    diag_imm = torch.from_numpy((s ** 2).astype(np.float32)).to(dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # chains are sharded over GPUs: this rank owns global chains [rank*C, (rank+1)*C)  (weak scaling)
-    q0 = torch.randn(C, D, device=dev, generator=gen) * scale_t
+    if dense:
+        cov, prec = dense_matrices(D)
+        tgt = bj.targets.DenseGaussian(prec)
+        imm = torch.from_numpy(cov).to(dev)
+        q0 = 0.1 * torch.randn(C, D, device=dev, generator=gen)
+    else:
+        tgt, imm = diag_tgt, diag_imm
+        q0 = torch.randn(C, D, device=dev, generator=gen) * torch.from_numpy(s.astype(np.float32)).to(dev)
     kernel = bj.hmc.build_kernel(inplace=True)
     state = bj.hmc.init(q0.clone(), tgt)
     step_keys = bj.random.split(bj.random.key(0, dev), W + K + 1)
@@ -226,26 +262,48 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = 2 * K  # k_prng_split + k_hmc_transition per step
+    # our kernels per step: k_prng_split + (diag) k_hmc_transition | (dense) normal, 2L+3 GEMMs, L axpy, L grad_kick,
+    # 2 energy, accept
+    launches = K * (2 if not dense else 1 + 1 + (2 * L + 3) + 2 * L + 2 + 1)
     acc_mean = float(info.acceptance_rate.mean())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the vectorised single-step leapfrog kernel: the HBM roofline the north star names -------------
     eng = _engine.get_engine(state.position, tgt)
-    p = eng.sample_momentum(chain_keys(W + K))
-    q1, lp1, g1 = state.position.clone(), state.logdensity.clone(), state.logdensity_grad.clone()
+    ms_gemm = 0.0
+    if dense:  # the dominant kernel of the dense workload: v = M^-1 p for all chains = one [C,D]x[D,D] tensor-core GEMM
+        pv = eng.sample_momentum(chain_keys(W + K))
+        for _ in range(3):
+            vv = eng.velocity(pv)
+        torch.cuda.synchronize()
+        n_g = 20
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(n_g):
+            vv = eng.velocity(pv)
+        f1.record()
+        torch.cuda.synchronize()
+        ms_gemm = f0.elapsed_time(f1) / n_g
+        del pv, vv
+    # the vectorised one-step leapfrog kernel (diagonal metric) at the same chains x dims: the HBM roofline kernel
+    qd = torch.randn(C, D, device=dev, generator=gen)
+    deng = _engine.Engine(dev, C, D, diag_tgt)
+    deng.set_metric(diag_imm)
+    p = deng.sample_momentum(chain_keys(W + K))
+    lp1, g1 = deng.init_state(qd)
+    q1 = qd
     for _ in range(3):
-        eng.leapfrog_(q1, p, lp1, g1, eps, 1)
+        deng.leapfrog_(q1, p, lp1, g1, 0.1, 1)
     torch.cuda.synchronize()
     n1 = 40
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(n1):
-        eng.leapfrog_(q1, p, lp1, g1, eps, 1)
+        deng.leapfrog_(q1, p, lp1, g1, 0.1, 1)
     f1.record()
     torch.cuda.synchronize()
     ms_1step = f0.elapsed_time(f1) / n1
-    del q1, p, g1
+    del q1, p, g1, qd, deng
 
     # ---- end to end through the public API with HOST buffers ----------------------------------------------
     q_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
@@ -279,10 +337,10 @@ def main():
     ms_e2e = g0.elapsed_time(g1e)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    times = torch.tensor([ms_total, ms_e2e, ms_1step], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e, ms_1step, ms_gemm], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_1step = [float(x) for x in times]
+    ms_total, ms_e2e, ms_1step, ms_gemm = [float(x) for x in times]
     value = n_gpus * C * L * K / (ms_total * 1e-3)
     e2e_value = n_gpus * C * L * K_e2e / (ms_e2e * 1e-3)
 
@@ -297,21 +355,37 @@ def main():
         bytes_1step = 24.0 * C * D
         achieved = bytes_1step / (ms_1step * 1e-3) / 1e9
         ms_step = ms_total / K
+        hbm_roofline = {"bound": "hbm", "kernel": "k_leapfrog (diag metric, 1 step/launch, 24*D B per chain)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": peak_src, "avg_launch_ms": ms_1step, "launches_timed": n1}
+        if dense:
+            tpeak = float(peaks.get("bf16_tflops", 1590.0))
+            tf_achieved = 2.0 * C * D * D / (ms_gemm * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "tcgen05 FastF32 GEMM [C,D]x[D,D] (v = M^-1 p; float32-accurate: 9 bf16 "
+                        "UTCHMMA per float32 product)", "achieved": tf_achieved, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": tf_achieved / tpeak, "traffic": None,
+                        "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
+                                        else "fallback 1590 TFLOP/s"),
+                        "avg_launch_ms": ms_gemm, "launches_timed": 20,
+                        "note": "algorithmic flops 2*C*D^2 per launch; the hardware executes 9x that in bf16 MMAs",
+                        "gemms_per_step": 2 * L + 3, "gemm_share_of_step": (2 * L + 3) * ms_gemm / ms_step}
+            extra = {"roofline_hbm_leapfrog": hbm_roofline}
+        else:
+            roofline = hbm_roofline
+            extra = {"fused_transition": {"kernel": "k_hmc_transition (L leapfrogs/launch, row resident in registers)",
+                                          "hbm_bytes_per_launch": 16.0 * C * D + 20.0 * C,
+                                          "equivalent_GBps_at_24D_per_leapfrog": 24.0 * C * D * L / (ms_step * 1e-3) / 1e9,
+                                          "speedup_vs_1step_launches": (ms_1step * L) / ms_step}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "chains_per_gpu": C, "dims": D, "leapfrogs_per_step": L,
-                       "step_size": eps, "mass_matrix": "diag", "parallelism": f"chains sharded x{n_gpus}, no data-path collective",
+                       "step_size": eps, "mass_matrix": "dense" if dense else "diag",
+                       "parallelism": f"chains sharded x{n_gpus}, no data-path collective",
                        "l2": "inputs larger than L2 (q,g = 2 x %.0f MB per GPU)" % (C * D * 4 / 1e6),
                        "mean_acceptance": acc_mean},
-            "roofline": {"bound": "hbm", "kernel": "k_leapfrog (1 step/launch, 24*D B per chain)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "avg_launch_ms": ms_1step, "launches_timed": n1},
-            "fused_transition": {"kernel": "k_hmc_transition (L leapfrogs/launch, row resident in registers)",
-                                 "hbm_bytes_per_launch": 16.0 * C * D + 20.0 * C,
-                                 "equivalent_GBps_at_24D_per_leapfrog": 24.0 * C * D * L / (ms_step * 1e-3) / 1e9,
-                                 "speedup_vs_1step_launches": (ms_1step * L) / ms_step},
+            "roofline": roofline, **extra,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + C * 8,
                     "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": K_e2e, "ms_per_step": ms_e2e / K_e2e},
             "gpu_launches": launches,

@@ -116,6 +116,12 @@ class Engine:
                                  ptr(_f32(logp, (self.C,))), ptr(_f32(g, (self.C, self.D))), eps, ptr(eps_dev),
                                  int(n_steps)), self.h)
 
+    def velocity(self, p):
+        """linear_map(M^-1, p) for every chain (dim > 128)."""
+        v = torch.empty(self.C, self.D, dtype=torch.float32, device=self.device)
+        check(lib().bjx_metric_velocity(self.h, ptr(_f32(p, (self.C, self.D))), ptr(v)), self.h)
+        return v
+
     def energy(self, p, logp):
         e = torch.empty(self.C, dtype=torch.float32, device=self.device)
         check(lib().bjx_energy(self.h, ptr(_f32(p, (self.C, self.D))), ptr(_f32(logp, (self.C,))), ptr(e)), self.h)

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bjx_init_state": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_sample_momentum": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "bjx_leapfrog": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, C.c_int32]),
+    "bjx_metric_velocity": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "bjx_energy": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_is_turning": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p]),
     "bjx_hmc_step": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,

@@ -31,6 +31,7 @@ static int cuda_fail(bjx_handle_t h, cudaError_t e, const char* where) { return 
 int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out);
 int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out, bool split_first);
 int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out);
+int bjx_dense_velocity(bjx_handle_t h, const float* p, float* v);
 int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n);
 int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
                        float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
@@ -307,6 +308,17 @@ extern "C" int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, flo
   a.g_out = grad;
   a.n = n_steps;
   return dispatch(h, K_LEAPFROG, true, a);
+}
+
+extern "C" int bjx_metric_velocity(bjx_handle_t h, const float* p, float* v_out) {
+  const void* ptrs[] = {p, v_out};
+  int rc = check_ready(h, true, ptrs, 2);
+  if (rc) return rc;
+  if (h->cfg.dim > 128) {
+    if (h->cfg.dim % 4) return fail(h, BJX_E_UNSUPPORTED, "bjx_metric_velocity needs dim % 4 == 0 for dim > 128");
+    return bjx_dense_velocity(h, p, v_out);
+  }
+  return fail(h, BJX_E_UNSUPPORTED, "bjx_metric_velocity is built for dim > 128 (use bjx_energy / bjx_leapfrog below)");
 }
 
 extern "C" int bjx_energy(bjx_handle_t h, const float* p, const float* logp, float* energy_out) {

@@ -90,11 +90,13 @@ __global__ void k_rows_energy(int C, int D, const float* __restrict__ v, const f
 //   TARGET 2 (dense Gaussian): aux = P q from the GEMM; g = -aux; logp = -1/2 q.aux + offset
 //   TARGET 0 (diag Gaussian) : g = -(q - mean) / s^2;      logp = -1/2 sum (q-mean)^2/s^2 + offset
 //   then (if p != null) p += (eps_c * 0.5) * g                                  (integrators.py:134-141)
+//   and, when another leapfrog follows (kicks == 2), that step's first half kick p += (eps_c * 0.5) * g
+//   (integrators.py:235-239) -- same gradient, two separately rounded FMAs, one pass over the row.
 template <int TARGET>
 __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, const float* __restrict__ aux,
                                  const float* __restrict__ inv_var, const float* __restrict__ mean, float offset,
                                  float* __restrict__ p, float eps, const float* __restrict__ eps_dev,
-                                 float* __restrict__ g_out, float* __restrict__ logp_out) {
+                                 float* __restrict__ g_out, float* __restrict__ logp_out, int kicks) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   const size_t ro = (size_t)c * D;
@@ -121,6 +123,9 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
     if (p) {
       float4 pv = __ldcs(reinterpret_cast<const float4*>(p + ro) + i);
       pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
+      if (kicks == 2) {
+        pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
+      }
       __stcs(reinterpret_cast<float4*>(p + ro) + i, pv);
     }
   }
@@ -223,22 +228,29 @@ static int dense_velocity(bjx_handle_t h, const float* p, float* v) {
 
 // g, logp = value_and_grad(q); optionally p += eh * g.  aux: [C,D] scratch for P q.
 static int dense_grad(bjx_handle_t h, const float* q, float* aux, float* p, float eps, const float* eps_dev, float* g,
-                      float* logp) {
+                      float* logp, int kicks = 1) {
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   const bjx_target_desc& t = h->cfg.target;
   if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
     int rc = gemm(h, q, t.precision, aux, nullptr, 1.f, 0.f);
     if (rc) return rc;
     k_rows_grad_kick<2><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, aux, nullptr, nullptr, t.logp_offset, p, eps,
-                                                                 eps_dev, g, logp);
+                                                                 eps_dev, g, logp, kicks);
   } else if (t.kind == BJX_TARGET_DIAG_GAUSSIAN) {
     k_rows_grad_kick<0><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, nullptr, t.inv_var, t.mean, t.logp_offset, p,
-                                                                 eps, eps_dev, g, logp);
+                                                                 eps, eps_dev, g, logp, kicks);
   } else {
     return bjx_fail(h, BJX_E_UNSUPPORTED, "large-D dense path supports DENSE_GAUSSIAN and DIAG_GAUSSIAN targets");
   }
   DN_LAUNCH("k_rows_grad_kick");
   return 0;
+}
+
+int bjx_dense_velocity(bjx_handle_t h, const float* p, float* v) {
+  DenseWs w;
+  int rc = dense_ws(h, w);
+  if (rc) return rc;
+  return dense_velocity(h, p, v);
 }
 
 int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
@@ -279,9 +291,11 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, float* q, float* p, f
                                const float* eps_dev, int n_steps) {
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   const long long n4 = (long long)C * D / 4;
-  for (int s = 0; s < n_steps; ++s) {
-    k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, p, g, eps, eps_dev, 0.5f);  // p += (eps/2) g
+  if (n_steps > 0) {
+    k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, p, g, eps, eps_dev, 0.5f);  // first half kick p += (eps/2) g
     DN_LAUNCH("k_rows_axpy");
+  }
+  for (int s = 0; s < n_steps; ++s) {
     int rc;
     if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
       rc = gemm(h, p, h->imm, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
@@ -292,7 +306,8 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, float* q, float* p, f
       k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, q, w.v, eps, eps_dev, 1.0f);
       DN_LAUNCH("k_rows_axpy");
     }
-    rc = dense_grad(h, q, w.v, p, eps, eps_dev, g, logp);  // g, logp at the new q; p += (eps/2) g
+    // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick when one follows
+    rc = dense_grad(h, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
     if (rc) return rc;
   }
   return 0;

@@ -33,22 +33,24 @@ using LayoutB = cutlass::layout::ColumnMajor;  // B(k, n) = A[n*K + k]: row-majo
 using LayoutC = cutlass::layout::RowMajor;
 constexpr int kAlign = 4;                       // 16-byte TMA alignment
 
-using MmaTileShape = Shape<_128, _128, _16>;
-using ClusterShape = Shape<_1, _1, _1>;
+template <class MmaTileShape, class ClusterShape, class Schedule>
+struct GemmCfg {
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
+      cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, kAlign, ElementC,
+      LayoutC, kAlign, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlign, ElementB, LayoutB, kAlign,
+      ElementAcc, MmaTileShape, ClusterShape,
+      cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      Schedule>::CollectiveOp;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+};
 
-using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
-    cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, kAlign, ElementC,
-    LayoutC, kAlign, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
-
-using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlign, ElementB, LayoutB, kAlign,
-    ElementAcc, MmaTileShape, ClusterShape,
-    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-    cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32SmemSm100>::CollectiveOp;
-
-using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
-using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+// CTA pair (cta_group::2): a 256x128 accumulator tile shared by two SMs, operands split between them
+using Gemm = GemmCfg<Shape<_256, _128, _16>, Shape<_2, _1, _1>,
+                     cutlass::gemm::KernelTmaWarpSpecialized2SmFastFP32SmemSm100>::Gemm;
 
 size_t gemm_workspace_bytes(int M, int N, int K) {
   typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}};

@@ -115,6 +115,9 @@ int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out);
  * n_steps leapfrogs in place.  step_size_dev ([C], signed) overrides step_size when non-NULL. */
 int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* grad, float step_size,
                  const float* step_size_dev, int32_t n_steps);
+/* linear_map(inverse_mass_matrix, p) (blackjax/util.py:23-61; the kinetic-energy gradient of
+ * integrators.py:242): v = M^-1 p for every chain.  Dense metric with dim > 128: one tensor-core GEMM. */
+int bjx_metric_velocity(bjx_handle_t h, const float* p, float* v_out);
 /* hmc_energy (trajectory.py:730-750): -logp + 1/2 p^T M^-1 p */
 int bjx_energy(bjx_handle_t h, const float* p, const float* logp, float* energy_out);
 /* metrics.is_turning (metrics.py:272-304) on explicit momenta (for the U-turn truth table) */

@@ -179,3 +179,120 @@ long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const fl
   free(msqrt);
   return (long long)C * L;
 }
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense variant (BASELINE config 2): dense Gaussian target logp = -1/2 x^T P x, dense inverse mass matrix.
+ * Chains are processed in blocks of BLK so every matrix row is reused BLK times from L1 (a small GEMM).
+ * ------------------------------------------------------------------------------------------------------ */
+#define BLK 16
+typedef struct {
+  int c0, c1, D, L;
+  const float *prec, *imm, *msqrt;
+  const uint32_t* keys;
+  float *q, *logp, *g, eps, *acc_rate;
+  unsigned char* accepted;
+} djob_t;
+
+/* Y[b][i] = sum_j A[i][j] X[b][j]   (A row-major [D,D]) */
+static void matmul_blk(int nb, int D, const float* A, const float* X, float* Y) {
+  for (int i = 0; i < D; ++i) {
+    const float* row = A + (size_t)i * D;
+    for (int b = 0; b < nb; ++b) {
+      const float* x = X + (size_t)b * D;
+      float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
+      for (int j = 0; j < D; ++j) acc += row[j] * x[j];
+      Y[(size_t)b * D + i] = acc;
+    }
+  }
+}
+
+static void* dworker(void* arg) {
+  djob_t* J = (djob_t*)arg;
+  const int D = J->D, L = J->L;
+  const float eps = J->eps, eh = eps * 0.5f, e1s = eps * 1.0f;
+  float* buf = (float*)malloc(sizeof(float) * (size_t)BLK * D * 5);
+  float *p = buf, *v = p + (size_t)BLK * D, *q1 = v + (size_t)BLK * D, *g1 = q1 + (size_t)BLK * D, *z = g1 + (size_t)BLK * D;
+  for (int c0 = J->c0; c0 < J->c1; c0 += BLK) {
+    const int nb = (c0 + BLK <= J->c1) ? BLK : (J->c1 - c0);
+    uint32_t ki0[BLK], ki1[BLK];
+    float e0[BLK], lp[BLK];
+    for (int b = 0; b < nb; ++b) {
+      const int c = c0 + b;
+      uint32_t km0, km1;
+      threefry2x32(J->keys[2 * c], J->keys[2 * c + 1], 0u, 0u, &km0, &km1);
+      threefry2x32(J->keys[2 * c], J->keys[2 * c + 1], 0u, 1u, &ki0[b], &ki1[b]);
+      for (int i = 0; i < D; ++i) z[(size_t)b * D + i] = normal_at(km0, km1, (uint32_t)i);
+      memcpy(q1 + (size_t)b * D, J->q + (size_t)c * D, sizeof(float) * D);
+      memcpy(g1 + (size_t)b * D, J->g + (size_t)c * D, sizeof(float) * D);
+      lp[b] = J->logp[c];
+    }
+    matmul_blk(nb, D, J->msqrt, z, p); /* p = L^-T z */
+    matmul_blk(nb, D, J->imm, p, v);
+    for (int b = 0; b < nb; ++b) {
+      float k = 0.f;
+      for (int i = 0; i < D; ++i) k += v[(size_t)b * D + i] * p[(size_t)b * D + i];
+      e0[b] = -lp[b] + 0.5f * k;
+    }
+    for (int s = 0; s < L; ++s) {
+      for (size_t t = 0; t < (size_t)nb * D; ++t) p[t] = p[t] + eh * g1[t];
+      matmul_blk(nb, D, J->imm, p, v);
+      for (size_t t = 0; t < (size_t)nb * D; ++t) q1[t] = q1[t] + e1s * v[t];
+      matmul_blk(nb, D, J->prec, q1, v); /* P q */
+      for (int b = 0; b < nb; ++b) {
+        float acc = 0.f;
+        for (int i = 0; i < D; ++i) {
+          const size_t t = (size_t)b * D + i;
+          g1[t] = -v[t];
+          acc += q1[t] * g1[t];
+          p[t] = p[t] + eh * g1[t];
+        }
+        lp[b] = 0.5f * acc;
+      }
+    }
+    matmul_blk(nb, D, J->imm, p, v);
+    for (int b = 0; b < nb; ++b) {
+      const int c = c0 + b;
+      float k = 0.f;
+      for (int i = 0; i < D; ++i) k += v[(size_t)b * D + i] * p[(size_t)b * D + i];
+      const float e1 = -lp[b] + 0.5f * k;
+      float delta = e0[b] - e1;
+      if (isnan(delta)) delta = -INFINITY;
+      float pa = expf(delta);
+      if (pa > 1.0f) pa = 1.0f;
+      uint32_t a, bb;
+      threefry2x32(ki0[b], ki1[b], 0u, 0u, &a, &bb);
+      const int acc = bits_to_unit(a ^ bb) < pa;
+      if (acc) {
+        memcpy(J->q + (size_t)c * D, q1 + (size_t)b * D, sizeof(float) * D);
+        memcpy(J->g + (size_t)c * D, g1 + (size_t)b * D, sizeof(float) * D);
+        J->logp[c] = lp[b];
+      }
+      if (J->acc_rate) J->acc_rate[c] = pa;
+      if (J->accepted) J->accepted[c] = (unsigned char)acc;
+    }
+  }
+  free(buf);
+  return NULL;
+}
+
+long long oracle_hmc_dense_step(int C, int D, const float* prec, const float* imm, const float* msqrt,
+                                const uint32_t* keys, float* q, float* logp, float* g, float eps, int L, float* acc_rate,
+                                unsigned char* accepted, int n_threads) {
+  int T = n_threads > 0 ? n_threads : oracle_num_threads();
+  int nblk = (C + BLK - 1) / BLK;
+  if (T > nblk) T = nblk;
+  if (T < 1) T = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * T);
+  djob_t* jobs = (djob_t*)malloc(sizeof(djob_t) * T);
+  for (int t = 0; t < T; ++t) {
+    int b0 = (int)((long long)nblk * t / T), b1 = (int)((long long)nblk * (t + 1) / T);
+    djob_t j = {b0 * BLK, b1 * BLK < C ? b1 * BLK : C, D, L, prec, imm, msqrt, keys, q, logp, g, eps, acc_rate, accepted};
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, dworker, &jobs[t]);
+  }
+  for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+  return (long long)C * L;
+}

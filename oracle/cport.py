@@ -24,6 +24,9 @@ def lib():
         l.oracle_hmc_step.restype = C.c_longlong
         l.oracle_hmc_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        l.oracle_hmc_dense_step.restype = C.c_longlong
+        l.oracle_hmc_dense_step.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         l.oracle_num_threads.restype = C.c_int
         _lib = l
     return _lib
@@ -46,4 +49,27 @@ def hmc_step(kind, inv_var, imm, keys, q, logp, g, eps, L, n_threads=0):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     lib().oracle_hmc_step(Cn, D, int(kind), p(inv_var), p(imm), p(keys), p(q), p(logp), p(g), float(eps), int(L),
                           p(acc), p(ok), int(n_threads))
+    return acc, ok.astype(bool)
+
+
+def dense_mass_sqrt(imm):
+    """L^-T with L = chol(M^-1)  (metrics.py:712-715), float64 then cast."""
+    Lc = np.linalg.cholesky(np.asarray(imm, np.float64))
+    return np.ascontiguousarray(np.linalg.solve(Lc.T, np.eye(Lc.shape[0])), np.float32)
+
+
+def hmc_dense_step(prec, imm, keys, q, logp, g, eps, L, n_threads=0, msqrt=None):
+    """In-place HMC transition, dense Gaussian target (precision ``prec``) and dense inverse mass matrix ``imm``."""
+    Cn, D = q.shape
+    for a in (q, logp, g):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    prec = np.ascontiguousarray(prec, np.float32)
+    imm = np.ascontiguousarray(imm, np.float32)
+    msqrt = dense_mass_sqrt(imm) if msqrt is None else np.ascontiguousarray(msqrt, np.float32)
+    keys = np.ascontiguousarray(keys, np.uint32)
+    acc = np.empty(Cn, np.float32)
+    ok = np.empty(Cn, np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().oracle_hmc_dense_step(Cn, D, p(prec), p(imm), p(msqrt), p(keys), p(q), p(logp), p(g), float(eps), int(L),
+                                p(acc), p(ok), int(n_threads))
     return acc, ok.astype(bool)

@@ -297,6 +297,7 @@ def test_dense_path_building_blocks(D, C, metric, target):
     close(npy(p), p_ref, rtol=1e-5)
     e = eng.energy(tf(p_ref), logp)
     close(npy(e), -lp0 + om.kinetic_energy(p_ref), rtol=1e-5, scale=np.max(np.abs(lp0)) + D)
+    close(npy(eng.velocity(tf(p_ref))), om.velocity(p_ref), rtol=1e-5)
     dp = tf(p_ref)
     eng.leapfrog_(dq, dp, logp, g, 0.05, 4)
     q1, p1, lp1, g1 = ohmc.static_integration(otgt, om, q, p_ref, lp0, g0, F(0.05), 4)

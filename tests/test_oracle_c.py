@@ -29,3 +29,20 @@ def test_c_twin_matches_numpy_oracle(kind, D):
     assert same.mean() > 0.98
     np.testing.assert_allclose(qc[same], new.position[same], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(gc[same], new.logdensity_grad[same], rtol=1e-5, atol=1e-5)
+
+
+def test_c_twin_dense_matches_numpy_oracle():
+    D, C, L, eps = 48, 40, 6, F(0.1)
+    cov, prec = targets.correlated_gaussian(D, seed=2, lo=-0.5, hi=0.5)
+    t = targets.DenseGaussian(prec)
+    rs = np.random.default_rng(1)
+    q = (0.5 * rs.standard_normal((C, D))).astype(F)
+    keys = prng.split(prng.key(4), C)
+    st = hmc.init(q, t)
+    new, info = hmc.hmc_kernel(keys, st, t, eps, cov, L)
+    qc, lc, gc = q.copy(), st.logdensity.copy(), st.logdensity_grad.copy()
+    acc, ok = cport.hmc_dense_step(prec, cov, keys, qc, lc, gc, eps, L)
+    np.testing.assert_allclose(acc, info.acceptance_rate, rtol=1e-3, atol=1e-4)
+    same = ok == info.is_accepted
+    assert same.mean() > 0.95
+    np.testing.assert_allclose(qc[same], new.position[same], rtol=1e-4, atol=1e-5)
