@@ -159,6 +159,8 @@ def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
     n_steps = max(1, steps)
     Cs = int(min(wl["C"], max(probe_c, budget_s / max(per_chain * (n_steps + warmup), 1e-9))))
     Cs = max(cores, (Cs // cores) * cores)
+    if steps <= 1:  # cpu_baseline leg: fill the ~budget_s of CPU work with more transitions when all chains fit
+        n_steps = int(max(1, min(200, budget_s / max(per_chain * Cs, 1e-9))))
     if warmup:
         run(Cs, warmup)
     t = run(Cs, n_steps)
