@@ -363,13 +363,15 @@ def main():
         if dense:
             tpeak = float(peaks.get("bf16_tflops", 1590.0))
             tf_achieved = 2.0 * C * D * D / (ms_gemm * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "tcgen05 FastF32 GEMM [C,D]x[D,D] (v = M^-1 p; float32-accurate: 9 bf16 "
-                        "UTCHMMA per float32 product)", "achieved": tf_achieved, "peak": tpeak, "unit": "TFLOP/s",
+            roofline = {"bound": "tensor", "kernel": "v = M^-1 p for all chains: k_rows_split3 + tcgen05 bf16 GEMM [C,6D]x[6D,D] "
+                        "(float32-accurate: 6 bf16 products per float32 product)", "achieved": tf_achieved, "peak": tpeak,
+                        "unit": "TFLOP/s",
                         "frac": tf_achieved / tpeak, "traffic": None,
                         "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
                                         else "fallback 1590 TFLOP/s"),
                         "avg_launch_ms": ms_gemm, "launches_timed": 20,
-                        "note": "algorithmic flops 2*C*D^2 per launch; the hardware executes 9x that in bf16 MMAs",
+                        "note": "algorithmic float32 flops 2*C*D^2 per call; the hardware executes 6x that in bf16 MMAs; "
+                                "the timed call includes the operand-split kernel",
                         "gemms_per_step": 2 * L + 3, "gemm_share_of_step": (2 * L + 3) * ms_gemm / ms_step}
             extra = {"roofline_hbm_leapfrog": hbm_roofline}
         else:

@@ -112,6 +112,9 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->dense_bytes = 0;
   h->gemm_ws = nullptr;
   h->gemm_ws_bytes = 0;
+  for (int m = 0; m < 3; ++m) { h->dense_mat_s[m] = nullptr; h->dense_mat_src[m] = nullptr; h->dense_mat_ver[m] = 0; }
+  h->dense_version = 1;
+  h->dense_bytes_built = 0;
   int rc = validate_target(h, cfg->target, cfg->dim);
   if (rc) {
     g_err = h->err;
@@ -145,6 +148,7 @@ extern "C" int bjx_set_target(bjx_handle_t h, const bjx_target_desc* t) {
   int rc = validate_target(h, *t, h->cfg.dim);
   if (rc) return rc;
   h->cfg.target = *t;
+  h->dense_version++;
   return 0;
 }
 
@@ -206,6 +210,7 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
     launch_diag_mass_sqrt(imm, (long long)elems, h->msqrt, h->stream);
     BJX_CHECK_LAUNCH("k_diag_mass_sqrt");
   }
+  h->dense_version++;
   h->metric_kind = kind;
   h->metric_small_dense = (kind == BJX_METRIC_DENSE) && D <= 128;
   h->imm = imm;

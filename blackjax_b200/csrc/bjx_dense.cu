@@ -7,14 +7,16 @@
 
 #include "bjx_handle.h"
 #include "bjx_internal.h"
+#include <cuda_bf16.h>
+
 #include "bjx_prng.cuh"
 
 using namespace bjx;
 
 namespace bjx {
-size_t gemm_workspace_bytes(int M, int N, int K);
-int gemm_xa(const float* X, const float* A_nk, float* Y, const float* Cin, float alpha, float beta, int M, int N, int K,
-            void* workspace, cudaStream_t stream);
+size_t gemm_workspace_bytes(int M, int N, int K6);
+int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, float alpha, float beta, int M, int N, int K6,
+               void* workspace, cudaStream_t stream);
 
 constexpr int kRowWarps = 8;
 
@@ -22,6 +24,42 @@ __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---- float32 -> 3 x bfloat16 operand split (see bjx_gemm.cu) ------------------------------------------------
+__device__ __forceinline__ void split3(float x, uint16_t& b1, uint16_t& b2, uint16_t& b3) {
+  const __nv_bfloat16 h1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h1);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(h2);
+  const __nv_bfloat16 h3 = __float2bfloat16_rn(r2);
+  b1 = __bfloat16_as_ushort(h1);
+  b2 = __bfloat16_as_ushort(h2);
+  b3 = __bfloat16_as_ushort(h3);
+}
+__device__ __forceinline__ uint2 pack4(const uint16_t (&v)[4]) {
+  return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+}
+// rows: X [R, K] float32 -> X' [R, 6K] bf16.  MATRIX=false (activations): planes (x1,x2,x3,x1,x2,x1);
+// MATRIX=true (constant matrices): planes (a1,a1,a1,a2,a2,a3); plane j of row r starts at r*6K + j*K.
+template <bool MATRIX>
+__global__ void k_rows_split3(long long R, int K, const float* __restrict__ x, uint16_t* __restrict__ xs) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * K / 4) return;
+  const long long e = t * 4;
+  const long long r = e / K;
+  const int k = (int)(e % K);
+  const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + t);
+  uint16_t p1[4], p2[4], p3[4];
+  split3(v.x, p1[0], p2[0], p3[0]);
+  split3(v.y, p1[1], p2[1], p3[1]);
+  split3(v.z, p1[2], p2[2], p3[2]);
+  split3(v.w, p1[3], p2[3], p3[3]);
+  const uint2 u1 = pack4(p1), u2 = pack4(p2), u3 = pack4(p3);
+  uint16_t* row = xs + r * 6 * K + k;
+  auto st = [&](int j, uint2 u) { *reinterpret_cast<uint2*>(row + (size_t)j * K) = u; };
+  if (MATRIX) { st(0, u1); st(1, u1); st(2, u1); st(3, u2); st(4, u2); st(5, u3); }
+  else        { st(0, u1); st(1, u2); st(2, u3); st(3, u1); st(4, u2); st(5, u1); }
 }
 
 // z[c, i] = normal(key_c, (D,))[i] with key_c = split(rng_key_c, 2)[0] when split_first (hmc.py:299,302 -> util.py:89-91)
@@ -184,19 +222,23 @@ static inline dim3 grow(int C) { return dim3((C + kRowWarps - 1) / kRowWarps); }
 
 struct DenseWs {
   float *p, *v, *q, *g, *lw, *e0, *e1;
+  uint16_t* xs;  // [C, 6D] bf16 split activations
 };
+enum { MAT_IMM = 0, MAT_MSQRT = 1, MAT_PREC = 2 };
 
 static int dense_ws(bjx_handle_t h, DenseWs& w) {
   const size_t C = h->cfg.n_chains, D = h->cfg.dim;
   const size_t row = ((C * D * sizeof(float)) + 255) & ~(size_t)255, vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
-  const size_t need = 4 * row + 3 * vec;
+  const size_t xsb = ((C * 6 * D * sizeof(uint16_t)) + 255) & ~(size_t)255;
+  const size_t mat = ((D * 6 * D * sizeof(uint16_t)) + 255) & ~(size_t)255;
+  const size_t need = 4 * row + 3 * vec + xsb + 3 * mat;
   if (h->dense_bytes < need) {
     if (h->dense_block) DN_CUDA(cudaFree(h->dense_block));
     h->dense_block = nullptr;
     DN_CUDA(cudaMalloc((void**)&h->dense_block, need));
     h->dense_bytes = need;
   }
-  const size_t gw = gemm_workspace_bytes((int)C, (int)D, (int)D);
+  const size_t gw = gemm_workspace_bytes((int)C, (int)D, (int)(6 * D));
   if (gw > h->gemm_ws_bytes) {
     if (h->gemm_ws) DN_CUDA(cudaFree(h->gemm_ws));
     h->gemm_ws = nullptr;
@@ -206,20 +248,42 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
   char* b = (char*)h->dense_block;
   w.p = (float*)b; w.v = (float*)(b + row); w.q = (float*)(b + 2 * row); w.g = (float*)(b + 3 * row);
   w.lw = (float*)(b + 4 * row); w.e0 = (float*)(b + 4 * row + vec); w.e1 = (float*)(b + 4 * row + 2 * vec);
+  w.xs = (uint16_t*)(b + 4 * row + 3 * vec);
+  for (int m = 0; m < 3; ++m) h->dense_mat_s[m] = (uint16_t*)(b + 4 * row + 3 * vec + xsb + m * mat);
+  if (h->dense_bytes_built != need) {  // fresh block: every split matrix must be rebuilt
+    for (int m = 0; m < 3; ++m) h->dense_mat_src[m] = nullptr;
+    h->dense_bytes_built = need;
+  }
+  // (re)build the split copies of the constant matrices whose source changed (set_metric / set_target)
+  const float* src[3] = {h->metric_kind == BJX_METRIC_DENSE ? h->imm : nullptr,
+                         h->metric_kind == BJX_METRIC_DENSE ? h->msqrt : nullptr,
+                         h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN ? h->cfg.target.precision : nullptr};
+  for (int m = 0; m < 3; ++m) {
+    if (src[m] && (h->dense_mat_src[m] != src[m] || h->dense_mat_ver[m] != h->dense_version)) {
+      k_rows_split3<true><<<g4((long long)D * D / 4), 256, 0, h->stream>>>((long long)D, (int)D, src[m], h->dense_mat_s[m]);
+      DN_LAUNCH("k_rows_split3<matrix>");
+      h->dense_mat_src[m] = src[m];
+      h->dense_mat_ver[m] = h->dense_version;
+    }
+  }
   return 0;
 }
 
-static int gemm(bjx_handle_t h, const float* X, const float* A, float* Y, const float* Cin, float alpha, float beta) {
-  const int rc = gemm_xa(X, A, Y, Cin, alpha, beta, h->cfg.n_chains, h->cfg.dim, h->cfg.dim, h->gemm_ws, h->stream);
+// Y = alpha * X . A^T + beta * Cin with A one of the handle's constant matrices (float32-accurate, see bjx_gemm.cu)
+static int gemm(bjx_handle_t h, DenseWs& w, const float* X, int mat, float* Y, const float* Cin, float alpha, float beta) {
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  k_rows_split3<false><<<g4((long long)C * D / 4), 256, 0, h->stream>>>((long long)C, D, X, w.xs);
+  DN_LAUNCH("k_rows_split3");
+  const int rc = gemm_split(w.xs, h->dense_mat_s[mat], Y, Cin, alpha, beta, C, D, 6 * D, h->gemm_ws, h->stream);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
   DN_LAUNCH("gemm");
   return 0;
 }
 
 // v = M^-1 p
-static int dense_velocity(bjx_handle_t h, const float* p, float* v) {
+static int dense_velocity(bjx_handle_t h, DenseWs& w, const float* p, float* v) {
   const int C = h->cfg.n_chains, D = h->cfg.dim;
-  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, p, h->imm, v, nullptr, 1.f, 0.f);
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, p, MAT_IMM, v, nullptr, 1.f, 0.f);
   const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
   k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->imm, stride, p, v);
   DN_LAUNCH("k_rows_scale");
@@ -227,12 +291,12 @@ static int dense_velocity(bjx_handle_t h, const float* p, float* v) {
 }
 
 // g, logp = value_and_grad(q); optionally p += eh * g.  aux: [C,D] scratch for P q.
-static int dense_grad(bjx_handle_t h, const float* q, float* aux, float* p, float eps, const float* eps_dev, float* g,
-                      float* logp, int kicks = 1) {
+static int dense_grad(bjx_handle_t h, DenseWs& w, const float* q, float* aux, float* p, float eps, const float* eps_dev,
+                      float* g, float* logp, int kicks = 1) {
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   const bjx_target_desc& t = h->cfg.target;
   if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
-    int rc = gemm(h, q, t.precision, aux, nullptr, 1.f, 0.f);
+    int rc = gemm(h, w, q, MAT_PREC, aux, nullptr, 1.f, 0.f);
     if (rc) return rc;
     k_rows_grad_kick<2><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, aux, nullptr, nullptr, t.logp_offset, p, eps,
                                                                  eps_dev, g, logp, kicks);
@@ -250,14 +314,14 @@ int bjx_dense_velocity(bjx_handle_t h, const float* p, float* v) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  return dense_velocity(h, p, v);
+  return dense_velocity(h, w, p, v);
 }
 
 int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  return dense_grad(h, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out);
+  return dense_grad(h, w, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out);
 }
 
 int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out, bool split_first) {
@@ -268,7 +332,7 @@ int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out
   float* z = (h->metric_kind == BJX_METRIC_DENSE) ? w.v : p_out;
   k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z, split_first);
   DN_LAUNCH("k_dense_normal");
-  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, z, h->msqrt, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, z, MAT_MSQRT, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
   const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
   k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->msqrt, stride, z, p_out);
   DN_LAUNCH("k_rows_scale");
@@ -279,7 +343,7 @@ int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  rc = dense_velocity(h, p, w.v);
+  rc = dense_velocity(h, w, p, w.v);
   if (rc) return rc;
   k_rows_energy<<<grow(h->cfg.n_chains), kRowWarps * 32, 0, h->stream>>>(h->cfg.n_chains, h->cfg.dim, w.v, p, logp, e_out, 1.f);
   DN_LAUNCH("k_rows_energy");
@@ -298,16 +362,16 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, float* q, float* p, f
   for (int s = 0; s < n_steps; ++s) {
     int rc;
     if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
-      rc = gemm(h, p, h->imm, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
+      rc = gemm(h, w, p, MAT_IMM, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
       if (rc) return rc;
     } else {
-      rc = dense_velocity(h, p, w.v);
+      rc = dense_velocity(h, w, p, w.v);
       if (rc) return rc;
       k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, q, w.v, eps, eps_dev, 1.0f);
       DN_LAUNCH("k_rows_axpy");
     }
     // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick when one follows
-    rc = dense_grad(h, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
+    rc = dense_grad(h, w, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
     if (rc) return rc;
   }
   return 0;
@@ -332,7 +396,7 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
   rc = bjx_dense_sample_momentum(h, keys, w.p, true);  // hmc.py:299-302
   if (rc) return rc;
   if (info.momentum) DN_CUDA(cudaMemcpyAsync(info.momentum, w.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  rc = dense_velocity(h, w.p, w.v);
+  rc = dense_velocity(h, w, w.p, w.v);
   if (rc) return rc;
   k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, logp_in, w.e0, 1.f);  // hmc.py:159
   DN_LAUNCH("k_rows_energy");
@@ -341,7 +405,7 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
   DN_CUDA(cudaMemcpyAsync(w.lw, logp_in, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   rc = dense_leapfrog_core(h, w, w.q, w.p, w.lw, w.g, eps, eps_dev, L);  // trajectory.py:165
   if (rc) return rc;
-  rc = dense_velocity(h, w.p, w.v);  // kinetic energy of the (flipped) end momentum: (-p)^T M^-1 (-p) = p^T M^-1 p
+  rc = dense_velocity(h, w, w.p, w.v);  // kinetic energy of the (flipped) end momentum: (-p)^T M^-1 (-p) = p^T M^-1 p
   if (rc) return rc;
   k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, w.lw, w.e1, 1.f);  // hmc.py:160
   DN_LAUNCH("k_rows_energy");
