@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbjx.so")
 
-TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL, TARGET_DENSE_GAUSSIAN, TARGET_BANANA = 0, 1, 2, 3
+TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL, TARGET_DENSE_GAUSSIAN, TARGET_BANANA, TARGET_HIER_LOGIT = 0, 1, 2, 3, 4
 METRIC_DIAG, METRIC_DENSE, METRIC_DIAG_PER_CHAIN = 0, 1, 2
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -14,7 +14,8 @@ _f32p = C.c_void_p  # device pointers travel as integers
 
 class TargetDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("inv_var", C.c_void_p), ("mean", C.c_void_p),
-                ("precision", C.c_void_p), ("logp_offset", C.c_float)]
+                ("precision", C.c_void_p), ("logp_offset", C.c_float), ("data_x", C.c_void_p), ("data_y", C.c_void_p),
+                ("n_groups", C.c_int32)]
 
 
 class Config(C.Structure):

@@ -41,6 +41,16 @@ static inline bool target_large_dense(bjx_handle_t h) {
 }
 static inline bool metric_large_dense(bjx_handle_t h) { return h->metric_kind == BJX_METRIC_DENSE && h->cfg.dim > 128; }
 static inline bool use_dense_path(bjx_handle_t h) { return target_large_dense(h) || metric_large_dense(h); }
+
+// CTA-per-chain path for 1024 < dim <= 18432 (bjx_big.cu)
+int bjx_big_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out);
+int bjx_big_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out);
+int bjx_big_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out);
+int bjx_big_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n);
+int bjx_big_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
+                     float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
+                     const bjx::InfoPtrs& info);
+static inline bool use_big_path(bjx_handle_t h) { return h->sc == SC_BIG && !use_dense_path(h); }
 #define BJX_CUDA(call)                                            \
   do {                                                            \
     cudaError_t e_ = (call);                                      \
@@ -68,6 +78,12 @@ static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
     case BJX_TARGET_BANANA:
       if (dim != 2) return fail(h, BJX_E_INVALID, "BANANA target needs dim == 2");
       break;
+    case BJX_TARGET_HIER_LOGIT:
+      if (!t.data_x || !t.data_y || t.n_groups < 1 || dim != 4 + t.n_groups)
+        return fail(h, BJX_E_INVALID, "HIER_LOGIT target needs data_x, data_y and dim == 4 + n_groups");
+      if (dim <= 1024 || dim % 4 != 0)
+        return fail(h, BJX_E_UNSUPPORTED, "HIER_LOGIT target is built for 1024 < dim <= 18432, dim % 4 == 0 (CTA-per-chain kernels)");
+      break;
     default:
       return fail(h, BJX_E_INVALID, "unknown target kind");
   }
@@ -85,7 +101,7 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 30) return fail(nullptr, BJX_E_INVALID, "max_tree_depth must be in [1, 30]");
   const int sc = size_class_for(cfg->dim);
   if (sc == SC_NONE)
-    return fail(nullptr, BJX_E_UNSUPPORTED, "dim must be <= 1024 with dim % 4 == 0, or <= 128 otherwise (warp-per-chain kernels)");
+    return fail(nullptr, BJX_E_UNSUPPORTED, "dim must be <= 18432 with dim % 4 == 0, or <= 128 otherwise");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount (no CUDA device: there is no CPU fallback)");
@@ -276,6 +292,7 @@ extern "C" int bjx_init_state(bjx_handle_t h, const float* q, float* logp_out, f
   if (rc) return rc;
   if (!logp_out) return fail(h, BJX_E_INVALID, "null array argument");
   if (target_large_dense(h)) return bjx_dense_init_state(h, q, logp_out, grad_out);
+  if (h->sc == SC_BIG) return bjx_big_init_state(h, q, logp_out, grad_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.q_in = q;
@@ -291,6 +308,7 @@ extern "C" int bjx_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* 
   if (rc) return rc;
   if (!keys) return fail(h, BJX_E_INVALID, "null keys");
   if (metric_large_dense(h)) return bjx_dense_sample_momentum(h, keys, p_out, false);
+  if (h->sc == SC_BIG) return bjx_big_sample_momentum(h, keys, p_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.keys = keys;
@@ -305,6 +323,7 @@ extern "C" int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, flo
   if (rc) return rc;
   if (!logp || n_steps < 0) return fail(h, BJX_E_INVALID, "bad argument");
   if (use_dense_path(h)) return bjx_dense_leapfrog(h, q, p, logp, grad, step_size, step_size_dev, n_steps);
+  if (use_big_path(h)) return bjx_big_leapfrog(h, q, p, logp, grad, step_size, step_size_dev, n_steps);
   LaunchArgs a{};
   a.P = make_params(h, step_size, step_size_dev);
   a.q_out = q;
@@ -332,6 +351,7 @@ extern "C" int bjx_energy(bjx_handle_t h, const float* p, const float* logp, flo
   if (rc) return rc;
   if (!logp || !energy_out) return fail(h, BJX_E_INVALID, "null array argument");
   if (metric_large_dense(h)) return bjx_dense_energy(h, p, logp, energy_out);
+  if (h->sc == SC_BIG) return bjx_big_energy(h, p, logp, energy_out);
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.p_io = const_cast<float*>(p);
@@ -346,6 +366,7 @@ extern "C" int bjx_is_turning(bjx_handle_t h, const float* pl, const float* pr, 
   if (rc) return rc;
   if (!out) return fail(h, BJX_E_INVALID, "null array argument");
   if (metric_large_dense(h)) return fail(h, BJX_E_UNSUPPORTED, "U-turn test with a dense metric needs dim <= 128");
+  if (h->sc == SC_BIG) return fail(h, BJX_E_UNSUPPORTED, "U-turn test / NUTS are built for dim <= 1024");
   LaunchArgs a{};
   a.P = make_params(h, 0.f, nullptr);
   a.pl = pl;
@@ -384,6 +405,9 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
   if (use_dense_path(h))
     return bjx_dense_hmc_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev, L,
                               make_info(info));
+  if (use_big_path(h))
+    return bjx_big_hmc_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev, L,
+                            make_info(info));
   LaunchArgs a{};
   a.P = make_params(h, step_size, step_size_dev);
   a.keys = keys;
@@ -450,6 +474,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
   if (use_dense_path(h)) return fail(h, BJX_E_UNSUPPORTED, "NUTS with a dense metric / dense target needs dim <= 128");
+  if (h->sc == SC_BIG) return fail(h, BJX_E_UNSUPPORTED, "NUTS is built for dim <= 1024");
   rc = ensure_ws(h);
   if (rc) return rc;
   const int C = h->cfg.n_chains;

@@ -1,0 +1,358 @@
+// Large rows (1024 < D <= 18432, D % 4 == 0): one CTA owns one chain and keeps the whole row triple
+// (q, p, grad) in shared memory for the entire launch -- the same "state never round-trips HBM between
+// leapfrogs" design as the warp-per-chain kernels (bjx_kernels.cuh), for rows that no longer fit a warp's
+// registers.  BASELINE config 5 (hierarchical logistic regression, D = 10000) runs here: at 3 x 40 KB of
+// shared memory per chain one CTA is resident per SM, and the step is bound by the 8*G sigmoid / softplus
+// evaluations per leapfrog (SFU), not by HBM.
+//
+// Same reference functions as the warp kernels: hmc.py:90-92 (init), metrics.py:260-270 (momentum draw,
+// kinetic energy), integrators.py:104-150 (velocity Verlet), hmc.py:279-312 (transition),
+// proposal.py:45-48,214-235 (accept).  Diagonal metrics only; NUTS is not built for this size class.
+#include "bjx_handle.h"
+#include "bjx_internal.h"
+#include "bjx_prng.cuh"
+
+using namespace bjx;
+
+namespace bjx {
+
+constexpr int kBigThreads = 256;
+
+struct BigParams {
+  int C, D;
+  int kind;
+  const float* inv_var;
+  const float* mean;
+  float logp_offset;
+  const float* data_x;
+  const uint8_t* data_y;
+  int G;
+  const float* imm;
+  long long imm_stride;
+  const float* msqrt;
+  float eps;
+  const float* eps_dev;
+  float div_thr;
+};
+
+// block-wide sum of up to NV values per thread (result valid in all threads)
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[NV*8]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  __syncthreads();  // protect red from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[k * 8 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBigThreads / 32; ++w) s += red[k * 8 + w];
+    v[k] = s;
+  }
+}
+
+// value_and_grad of the target at the row q (shared memory) -> g (shared memory), returns logp (all threads)
+template <int TK>
+__device__ __forceinline__ float big_value_and_grad(const BigParams& P, const float* q, float* g, float* red) {
+  const int D = P.D, tid = threadIdx.x;
+  if constexpr (TK == BJX_TARGET_DIAG_GAUSSIAN) {
+    float acc[1] = {0.f};
+    for (int i = tid; i < D; i += kBigThreads) {
+      const float d = P.mean ? q[i] - __ldg(P.mean + i) : q[i];
+      const float t = d * -__ldg(P.inv_var + i);
+      acc[0] = fmaf(d, t, acc[0]);
+      g[i] = t;
+    }
+    block_sum<1>(acc, red);
+    return 0.5f * acc[0] + P.logp_offset;
+  } else if constexpr (TK == BJX_TARGET_FUNNEL) {
+    const float y = q[0];
+    float acc[1] = {0.f};
+    for (int i = tid; i < D; i += kBigThreads) acc[0] = (i == 0) ? acc[0] : fmaf(q[i], q[i], acc[0]);
+    block_sum<1>(acc, red);
+    const float ss = acc[0], ey = expf(-y), n = (float)(D - 1), t = y / 3.0f;
+    for (int i = tid; i < D; i += kBigThreads) g[i] = (i == 0) ? (-y / 9.0f + 0.5f * ey * ss - 0.5f * n) : -(ey * q[i]);
+    return -0.5f * (t * t) + (-0.5f * ey * ss - 0.5f * n * y) + P.logp_offset;
+  } else {  // BJX_TARGET_HIER_LOGIT
+    const float mu = q[0], lt = q[1], b0 = q[2], b1 = q[3];
+    const float e2 = expf(-2.0f * lt);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // ll, sum d, sum d^2, grad b0, grad b1
+    for (int gi = tid; gi < P.G; gi += kBigThreads) {
+      const float alpha = q[4 + gi];
+      const float d = alpha - mu;
+      const float4* xr = reinterpret_cast<const float4*>(P.data_x + (size_t)gi * 16);
+      const unsigned bits = __ldg(P.data_y + gi);
+      float ga = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float4 xv = __ldg(xr + k2);  // (x_{2k2,0}, x_{2k2,1}, x_{2k2+1,0}, x_{2k2+1,1})
+        const float xs[2][2] = {{xv.x, xv.y}, {xv.z, xv.w}};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float yv = (float)((bits >> (2 * k2 + u)) & 1u);
+          const float eta = alpha + b0 * xs[u][0] + b1 * xs[u][1];
+          const float ex = expf(-fabsf(eta));
+          const float sig = (eta >= 0.f) ? 1.0f / (1.0f + ex) : ex / (1.0f + ex);
+          const float softplus = fmaxf(eta, 0.f) + log1pf(ex);
+          const float r = yv - sig;
+          acc[0] += yv * eta - softplus;
+          ga += r;
+          acc[3] = fmaf(r, xs[u][0], acc[3]);
+          acc[4] = fmaf(r, xs[u][1], acc[4]);
+        }
+      }
+      acc[1] += d;
+      acc[2] = fmaf(d, d, acc[2]);
+      g[4 + gi] = -d * e2 + ga;
+    }
+    block_sum<5>(acc, red);
+    if (tid == 0) {
+      g[0] = -0.01f * mu + e2 * acc[1];
+      g[1] = -lt + e2 * acc[2] - (float)P.G;
+      g[2] = -0.16f * b0 + acc[3];
+      g[3] = -0.16f * b1 + acc[4];
+    }
+    return -0.005f * mu * mu - 0.5f * lt * lt - 0.08f * (b0 * b0 + b1 * b1) + (-0.5f * e2 * acc[2] - (float)P.G * lt) +
+           acc[0] + P.logp_offset;
+  }
+}
+
+__device__ __forceinline__ float big_kinetic(const BigParams& P, const float* imm, const float* p, float* red) {
+  float acc[1] = {0.f};
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) acc[0] = fmaf(__ldg(imm + i) * p[i], p[i], acc[0]);
+  block_sum<1>(acc, red);
+  return 0.5f * acc[0];
+}
+
+template <int TK>
+__device__ __forceinline__ float big_leapfrog(const BigParams& P, const float* imm, float* q, float* p, float* g,
+                                              float eps, float* red) {
+  const float eh = eps * 0.5f, e1 = eps * 1.0f;
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) {
+    const float pn = fmaf(eh, g[i], p[i]);
+    p[i] = pn;
+    q[i] = fmaf(e1, __ldg(imm + i) * pn, q[i]);
+  }
+  __syncthreads();
+  const float logp = big_value_and_grad<TK>(P, q, g, red);
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) p[i] = fmaf(eh, g[i], p[i]);
+  __syncthreads();
+  return logp;
+}
+
+__device__ __forceinline__ void big_load(float* dst, const float* __restrict__ src, int D) {
+  for (int i = threadIdx.x; i < D / 4; i += kBigThreads)
+    reinterpret_cast<float4*>(dst)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+}
+__device__ __forceinline__ void big_store(float* __restrict__ dst, const float* src, int D) {
+  for (int i = threadIdx.x; i < D / 4; i += kBigThreads)
+    __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(src)[i]);
+}
+
+template <int TK>
+__global__ void __launch_bounds__(kBigThreads) k_big_init(BigParams P, const float* __restrict__ q_in,
+                                                          float* __restrict__ logp_out, float* __restrict__ g_out) {
+  extern __shared__ __align__(16) float sm[];
+  float *q = sm, *g = sm + P.D, *red = sm + 2 * (size_t)P.D;
+  const size_t ro = (size_t)blockIdx.x * P.D;
+  big_load(q, q_in + ro, P.D);
+  __syncthreads();
+  const float logp = big_value_and_grad<TK>(P, q, g, red);
+  __syncthreads();
+  big_store(g_out + ro, g, P.D);
+  if (threadIdx.x == 0) logp_out[blockIdx.x] = logp;
+}
+
+__global__ void __launch_bounds__(kBigThreads) k_big_momentum(BigParams P, const uint32_t* __restrict__ keys,
+                                                              float* __restrict__ p_out) {
+  const int c = blockIdx.x;
+  const Key k{keys[2 * c], keys[2 * c + 1]};
+  const float* ms = P.msqrt + (size_t)c * P.imm_stride;
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) p_out[(size_t)c * P.D + i] = __ldg(ms + i) * normal_at(k, (uint32_t)i);
+}
+
+__global__ void __launch_bounds__(kBigThreads) k_big_energy(BigParams P, const float* __restrict__ p_in,
+                                                            const float* __restrict__ logp, float* __restrict__ e) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const float* imm = P.imm + (size_t)c * P.imm_stride;
+  float acc[1] = {0.f};
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) {
+    const float pv = p_in[(size_t)c * P.D + i];
+    acc[0] = fmaf(__ldg(imm + i) * pv, pv, acc[0]);
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) e[c] = -logp[c] + 0.5f * acc[0];
+}
+
+template <int TK>
+__global__ void __launch_bounds__(kBigThreads) k_big_leapfrog(BigParams P, float* q_io, float* p_io, float* logp_io,
+                                                              float* g_io, int n_steps) {
+  extern __shared__ __align__(16) float sm[];
+  float *q = sm, *p = sm + P.D, *g = sm + 2 * (size_t)P.D, *red = sm + 3 * (size_t)P.D;
+  const int c = blockIdx.x;
+  const size_t ro = (size_t)c * P.D;
+  big_load(q, q_io + ro, P.D);
+  big_load(p, p_io + ro, P.D);
+  big_load(g, g_io + ro, P.D);
+  __syncthreads();
+  const float* imm = P.imm + (size_t)c * P.imm_stride;
+  const float eps = P.eps_dev ? P.eps_dev[c] : P.eps;
+  float logp = 0.f;
+  for (int s = 0; s < n_steps; ++s) logp = big_leapfrog<TK>(P, imm, q, p, g, eps, red);
+  big_store(q_io + ro, q, P.D);
+  big_store(p_io + ro, p, P.D);
+  big_store(g_io + ro, g, P.D);
+  if (threadIdx.x == 0 && n_steps > 0) logp_io[c] = logp;
+}
+
+// whole HMC transition (hmc.py:279-312) with the row resident in shared memory
+template <int TK>
+__global__ void __launch_bounds__(kBigThreads) k_big_hmc(BigParams P, const uint32_t* __restrict__ keys, const float* q_in,
+                                                         const float* logp_in, const float* g_in, float* q_out,
+                                                         float* logp_out, float* g_out, int L, InfoPtrs info) {
+  extern __shared__ __align__(16) float sm[];
+  float *q = sm, *p = sm + P.D, *g = sm + 2 * (size_t)P.D, *red = sm + 3 * (size_t)P.D;
+  const int c = blockIdx.x;
+  const size_t ro = (size_t)c * P.D;
+  big_load(q, q_in + ro, P.D);
+  big_load(g, g_in + ro, P.D);
+  const Key rng{keys[2 * c], keys[2 * c + 1]};
+  const Key km = fold_in(rng, 0u), ki = fold_in(rng, 1u);  // hmc.py:299
+  const float* imm = P.imm + (size_t)c * P.imm_stride;
+  const float* ms = P.msqrt + (size_t)c * P.imm_stride;
+  for (int i = threadIdx.x; i < P.D; i += kBigThreads) {
+    const float pv = __ldg(ms + i) * normal_at(km, (uint32_t)i);  // hmc.py:302
+    p[i] = pv;
+    if (info.momentum) info.momentum[ro + i] = pv;
+  }
+  __syncthreads();
+  const float logp0 = logp_in[c];
+  const float e0 = -logp0 + big_kinetic(P, imm, p, red);  // hmc.py:159
+  const float eps = P.eps_dev ? P.eps_dev[c] : P.eps;
+  float logp = logp0;
+  for (int s = 0; s < L; ++s) logp = big_leapfrog<TK>(P, imm, q, p, g, eps, red);  // trajectory.py:165
+  const float e1 = -logp + big_kinetic(P, imm, p, red);  // hmc.py:160 (kinetic energy is even in p: the flip is implicit)
+  float delta = e0 - e1;
+  if (isnan(delta)) delta = -__int_as_float(0x7f800000);  // proposal.py:45-48
+  const bool is_div = (-delta) > P.div_thr;
+  float pa = expf(delta);
+  pa = pa > 1.0f ? 1.0f : pa;                             // proposal.py:225
+  const bool acc = uniform01(ki) < pa;                    // proposal.py:226
+  if (info.proposal_position) big_store(info.proposal_position + ro, q, P.D);
+  if (info.proposal_momentum)
+    for (int i = threadIdx.x; i < P.D; i += kBigThreads) info.proposal_momentum[ro + i] = -1.0f * p[i];  // hmc.py:158
+  if (acc) {
+    big_store(q_out + ro, q, P.D);
+    big_store(g_out + ro, g, P.D);
+  } else if (q_out != q_in) {
+    for (int i = threadIdx.x; i < P.D / 4; i += kBigThreads) {
+      __stcs(reinterpret_cast<float4*>(q_out + ro) + i, __ldcs(reinterpret_cast<const float4*>(q_in + ro) + i));
+      __stcs(reinterpret_cast<float4*>(g_out + ro) + i, __ldcs(reinterpret_cast<const float4*>(g_in + ro) + i));
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (acc || q_out != q_in) logp_out[c] = acc ? logp : logp0;
+    if (info.acceptance_rate) info.acceptance_rate[c] = pa;
+    if (info.is_accepted) info.is_accepted[c] = acc;
+    if (info.is_divergent) info.is_divergent[c] = is_div;
+    if (info.energy) info.energy[c] = e1;
+    if (info.num_integration_steps) info.num_integration_steps[c] = L;
+  }
+}
+}  // namespace bjx
+
+#define BG_LAUNCH(where)                                           \
+  do {                                                             \
+    cudaError_t e_ = cudaGetLastError();                           \
+    if (e_ != cudaSuccess) return bjx_cuda_fail(h, e_, where);     \
+  } while (0)
+
+static BigParams big_params(bjx_handle_t h, float eps, const float* eps_dev) {
+  BigParams P;
+  P.C = h->cfg.n_chains;
+  P.D = h->cfg.dim;
+  P.kind = h->cfg.target.kind;
+  P.inv_var = h->cfg.target.inv_var;
+  P.mean = h->cfg.target.mean;
+  P.logp_offset = h->cfg.target.logp_offset;
+  P.data_x = h->cfg.target.data_x;
+  P.data_y = h->cfg.target.data_y;
+  P.G = h->cfg.target.n_groups;
+  P.imm = h->imm;
+  P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
+  P.msqrt = h->msqrt;
+  P.eps = eps;
+  P.eps_dev = eps_dev;
+  P.div_thr = h->cfg.divergence_threshold;
+  return P;
+}
+
+template <class K>
+static int big_smem(bjx_handle_t h, K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return bjx_cuda_fail(h, e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  return 0;
+}
+
+#define BIG_DISPATCH(KERNEL, ROWS, ...)                                                                   \
+  do {                                                                                                    \
+    const size_t smem_ = ((size_t)(ROWS)*h->cfg.dim + 64) * sizeof(float);                                \
+    int rc_ = 0;                                                                                          \
+    switch (h->cfg.target.kind) {                                                                         \
+      case BJX_TARGET_DIAG_GAUSSIAN:                                                                      \
+        if ((rc_ = big_smem(h, KERNEL<BJX_TARGET_DIAG_GAUSSIAN>, smem_))) return rc_;                     \
+        KERNEL<BJX_TARGET_DIAG_GAUSSIAN><<<h->cfg.n_chains, kBigThreads, smem_, h->stream>>>(__VA_ARGS__); \
+        break;                                                                                            \
+      case BJX_TARGET_FUNNEL:                                                                             \
+        if ((rc_ = big_smem(h, KERNEL<BJX_TARGET_FUNNEL>, smem_))) return rc_;                            \
+        KERNEL<BJX_TARGET_FUNNEL><<<h->cfg.n_chains, kBigThreads, smem_, h->stream>>>(__VA_ARGS__);       \
+        break;                                                                                            \
+      case BJX_TARGET_HIER_LOGIT:                                                                         \
+        if ((rc_ = big_smem(h, KERNEL<BJX_TARGET_HIER_LOGIT>, smem_))) return rc_;                        \
+        KERNEL<BJX_TARGET_HIER_LOGIT><<<h->cfg.n_chains, kBigThreads, smem_, h->stream>>>(__VA_ARGS__);   \
+        break;                                                                                            \
+      default:                                                                                            \
+        return bjx_fail(h, BJX_E_UNSUPPORTED, "target not built for dim > 1024");                         \
+    }                                                                                                     \
+    BG_LAUNCH(#KERNEL);                                                                                   \
+  } while (0)
+
+int bjx_big_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
+  BigParams P = big_params(h, 0.f, nullptr);
+  BIG_DISPATCH(k_big_init, 2, P, q, logp_out, grad_out);
+  return 0;
+}
+int bjx_big_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out) {
+  BigParams P = big_params(h, 0.f, nullptr);
+  k_big_momentum<<<h->cfg.n_chains, kBigThreads, 0, h->stream>>>(P, keys, p_out);
+  BG_LAUNCH("k_big_momentum");
+  return 0;
+}
+int bjx_big_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out) {
+  BigParams P = big_params(h, 0.f, nullptr);
+  k_big_energy<<<h->cfg.n_chains, kBigThreads, 0, h->stream>>>(P, p, logp, e_out);
+  BG_LAUNCH("k_big_energy");
+  return 0;
+}
+int bjx_big_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n) {
+  BigParams P = big_params(h, eps, eps_dev);
+  BIG_DISPATCH(k_big_leapfrog, 3, P, q, p, logp, g, n);
+  return 0;
+}
+int bjx_big_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
+                     float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
+                     const InfoPtrs& info) {
+  BigParams P = big_params(h, eps, eps_dev);
+  BIG_DISPATCH(k_big_hmc, 3, P, keys, q_in, logp_in, g_in, q_out, logp_out, g_out, L, info);
+  return 0;
+}

@@ -6,7 +6,7 @@
 
 namespace bjx {
 
-enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_NONE };
+enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_BIG, SC_NONE };  // SC_BIG: CTA-per-chain (bjx_big.cu)
 enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING };
 
 struct LaunchArgs {
@@ -37,10 +37,11 @@ inline SizeClass size_class_for(int D) {
   if (D % 4 == 0 && D <= 1024) return D <= 128 ? SC_V1 : D <= 256 ? SC_V2 : D <= 512 ? SC_V4 : SC_V8;
   if (D <= 32) return SC_S1;
   if (D <= 128) return SC_S4;
+  if (D % 4 == 0 && D <= 18432) return SC_BIG;
   return SC_NONE;
 }
 inline bool size_class_is_small(int sc) { return sc == SC_V1 || sc == SC_S1 || sc == SC_S4; }
-inline bool size_class_is_vec(int sc) { return sc <= SC_V8; }
+inline bool size_class_is_vec(int sc) { return sc <= SC_V8 || sc == SC_BIG; }
 
 template <int TK>
 struct Launcher {

@@ -112,3 +112,50 @@ class Banana(Target):
         d.kind, d.dim = self.kind, 2
         d.logp_offset = 0.0
         return d
+
+
+class HierLogit(Target):
+    """Hierarchical logistic regression (BASELINE config 5; builder-defined, not in the reference).
+
+    x = [mu, log_tau, beta0, beta1, alpha_0 .. alpha_{G-1}];  G groups, 8 Bernoulli-logit observations per group
+    with two covariates:  eta_gk = alpha_g + beta . x_gk,  alpha_g ~ N(mu, tau^2),  mu ~ N(0, 10^2),
+    log_tau ~ N(0, 1) (density on log_tau itself),  beta_j ~ N(0, 2.5^2).
+
+      logp = -mu^2/200 - lt^2/2 - (b0^2+b1^2)/12.5 + sum_g [-(alpha_g-mu)^2 e^{-2 lt}/2 - lt]
+             + sum_gk [y_gk eta_gk - softplus(eta_gk)]
+    """
+
+    kind = _lib.TARGET_HIER_LOGIT
+
+    def __init__(self, covariates, outcomes_bits):
+        x = np.ascontiguousarray(covariates, np.float32)
+        y = np.ascontiguousarray(outcomes_bits, np.uint8)
+        if x.ndim != 3 or x.shape[1:] != (8, 2) or y.shape != (x.shape[0],):
+            raise ValueError("covariates must be [G, 8, 2] and outcomes_bits uint8 [G]")
+        self.x, self.y = x, y
+        self.n_groups = int(x.shape[0])
+        self.dim = 4 + self.n_groups
+
+    @staticmethod
+    def synthetic_data(n_groups, seed=1):
+        """Covariates ~ N(0,1) and outcomes drawn from the model at mu=0.5, tau=0.7, beta=(1,-0.5); default_rng(seed)."""
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n_groups, 8, 2)).astype(np.float32)
+        alpha = 0.5 + 0.7 * rng.standard_normal(n_groups)
+        eta = alpha[:, None] + x[:, :, 0] * 1.0 + x[:, :, 1] * (-0.5)
+        y = rng.uniform(size=(n_groups, 8)) < 1.0 / (1.0 + np.exp(-eta))
+        bits = (y.astype(np.uint8) << np.arange(8, dtype=np.uint8)).sum(axis=1).astype(np.uint8)
+        return x, bits
+
+    def _desc(self, device):
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        d.data_x = self._cached("x", self.x, device).data_ptr()
+        cache = self.__dict__.setdefault("_dev", {})
+        k = ("y", str(device))
+        if k not in cache:
+            cache[k] = torch.as_tensor(self.y).to(device)
+        d.data_y = cache[k].data_ptr()
+        d.n_groups = self.n_groups
+        d.logp_offset = 0.0
+        return d

@@ -41,7 +41,9 @@ enum bjx_target_kind {
   BJX_TARGET_DIAG_GAUSSIAN = 0,  /* -1/2 sum ((x-mean)/s)^2 + offset   tests/fixtures.py:60-78   */
   BJX_TARGET_FUNNEL = 1,         /* Neal's funnel                       tests/fixtures.py:81-98   */
   BJX_TARGET_DENSE_GAUSSIAN = 2, /* -1/2 x^T P x + offset               tests/mcmc/test_mclmc_lrd.py:86-88 */
-  BJX_TARGET_BANANA = 3          /* -(1-x0)^2 - 1.5 (x1-x0^2)^2, dim=2  tests/mcmc/test_trajectory.py:79-80 */
+  BJX_TARGET_BANANA = 3,         /* -(1-x0)^2 - 1.5 (x1-x0^2)^2, dim=2  tests/mcmc/test_trajectory.py:79-80 */
+  BJX_TARGET_HIER_LOGIT = 4      /* hierarchical logistic regression (BASELINE config 5; builder-defined, see
+                                    DESIGN.md): x = [mu, log tau, beta0, beta1, alpha_0..alpha_{G-1}], dim = 4 + G */
 };
 
 /* inverse-mass-matrix layouts (metrics.py:701-729: 1-D => diagonal, 2-D => dense) */
@@ -58,6 +60,9 @@ typedef struct {
   const float* mean;      /* DIAG_GAUSSIAN: [dim] or NULL (device)         */
   const float* precision; /* DENSE_GAUSSIAN: [dim, dim] symmetric (device) */
   float logp_offset;      /* constant added to every log-density           */
+  const float* data_x;    /* HIER_LOGIT: covariates [G, 8, 2] (device)     */
+  const uint8_t* data_y;  /* HIER_LOGIT: outcomes, bit k of byte g = y_gk  */
+  int32_t n_groups;       /* HIER_LOGIT: G (dim = 4 + G)                   */
 } bjx_target_desc;
 
 typedef struct {

@@ -133,3 +133,41 @@ def correlated_gaussian(dim, seed=0, lo=-1.0, hi=1.0):
     cov = 0.5 * (cov + cov.T)
     prec = 0.5 * (prec + prec.T)
     return cov.astype(F), prec.astype(F)
+
+
+class HierLogit:
+    """Hierarchical logistic regression, BASELINE config 5 (builder-defined; see blackjax_b200/targets.py HierLogit).
+    x = [mu, log_tau, beta0, beta1, alpha_0..alpha_{G-1}]; covariates [G,8,2]; outcomes: bit k of byte g."""
+
+    kind = "hier_logit"
+
+    def __init__(self, covariates, outcomes_bits):
+        self.x = np.asarray(covariates, F)
+        bits = np.asarray(outcomes_bits, np.uint8)
+        self.y = ((bits[:, None] >> np.arange(8, dtype=np.uint8)) & 1).astype(F)      # [G, 8]
+        self.G = self.x.shape[0]
+        self.dim = 4 + self.G
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        mu, lt, b0, b1 = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+        alpha = q[..., 4:]                                                             # [C, G]
+        with np.errstate(over="ignore", invalid="ignore"):
+            e2 = np.exp(F(-2.0) * lt).astype(F)
+            d = (alpha - mu[..., None]).astype(F)
+            eta = (alpha[..., None] + b0[..., None, None] * self.x[:, :, 0] + b1[..., None, None] * self.x[:, :, 1]).astype(F)
+            sig = (F(1.0) / (F(1.0) + np.exp(-eta))).astype(F)
+            softplus = (np.maximum(eta, F(0.0)) + np.log1p(np.exp(-np.abs(eta)))).astype(F)
+            r = (self.y - sig).astype(F)
+            ll = np.sum(self.y * eta - softplus, axis=(-1, -2), dtype=F)
+            sd = np.sum(d, axis=-1, dtype=F)
+            sd2 = np.sum(d * d, axis=-1, dtype=F)
+            logp = (F(-0.005) * mu * mu - F(0.5) * lt * lt - F(0.08) * (b0 * b0 + b1 * b1)
+                    + (F(-0.5) * e2 * sd2 - F(self.G) * lt) + ll)
+            g = np.empty_like(q)
+            g[..., 0] = F(-0.01) * mu + e2 * sd
+            g[..., 1] = -lt + e2 * sd2 - F(self.G)
+            g[..., 2] = F(-0.16) * b0 + np.sum(r * self.x[:, :, 0], axis=(-1, -2), dtype=F)
+            g[..., 3] = F(-0.16) * b1 + np.sum(r * self.x[:, :, 1], axis=(-1, -2), dtype=F)
+            g[..., 4:] = -d * e2[..., None] + np.sum(r, axis=-1, dtype=F)
+        return logp.astype(F), g.astype(F)

@@ -371,6 +371,88 @@ def test_fullsize_dense_config2_65536x1024():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# rows larger than a warp's registers (1024 < D <= 18432): CTA-per-chain kernels, incl. BASELINE config 5's target
+# ---------------------------------------------------------------------------------------------------------
+def big_problem(kind, D, seed=41):
+    rs = np.random.default_rng(seed)
+    if kind == "diag":
+        s = np.exp(rs.uniform(-0.5, 0.5, D))
+        return T.DiagGaussian(s), otargets.DiagGaussian(s)
+    if kind == "funnel":
+        return T.Funnel(D), otargets.Funnel(D)
+    x, bits = T.HierLogit.synthetic_data(D - 4, seed=1)
+    return T.HierLogit(x, bits), otargets.HierLogit(x, bits)
+
+
+@pytest.mark.parametrize("kind, D, C", [("diag", 2048, 40), ("funnel", 1500, 24), ("hier", 1504, 24), ("hier", 10000, 6)])
+def test_big_rows_match_oracle(kind, D, C):
+    tgt, otgt = big_problem(kind, D)
+    rs = np.random.default_rng(5)
+    q = (0.3 * rs.standard_normal((C, D))).astype(F)
+    imm = np.exp(rs.uniform(-0.3, 0.3, D)).astype(F)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    om = ohmc.Metric(imm)
+    dq = tf(q)
+    logp, g = eng.init_state(dq)
+    lp0, g0 = otgt(q)
+    close(npy(g), g0, rtol=1e-5)
+    close(npy(logp), lp0, rtol=1e-5, scale=np.max(np.abs(lp0)) + 1)
+    keys = oprng.split(oprng.key(2), C)
+    p_ref = om.sample_momentum(keys, D)
+    close(npy(eng.sample_momentum(tk(keys))), p_ref, rtol=3e-6)
+    close(npy(eng.energy(tf(p_ref), logp)), -lp0 + om.kinetic_energy(p_ref), rtol=1e-5, scale=np.max(np.abs(lp0)) + D)
+    dp = tf(p_ref)
+    eps = F(0.01)
+    eng.leapfrog_(dq, dp, logp, g, float(eps), 5)
+    q1, p1, lp1, g1 = ohmc.static_integration(otgt, om, q, p_ref, lp0, g0, eps, 5)
+    close(npy(dq), q1, rtol=1e-5)
+    close(npy(dp), p1, rtol=2e-5)
+    close(npy(g), g1, rtol=2e-5)
+    close(npy(logp), lp1, rtol=1e-5, scale=np.max(np.abs(lp1)) + 1)
+    # one whole transition, teacher-forced
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, eps, om, 6)
+    st = bj.hmc.init(tf(q), tgt)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), st, tgt, float(eps), tf(imm), 6)
+    torch.cuda.synchronize()
+    close(npy(info.proposal.position), oinfo.proposal[0], rtol=1e-5)
+    close(npy(info.energy), oinfo.energy, rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + D)
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    tie = np.abs(u - oinfo.acceptance_rate) < 1e-3
+    acc = npy(info.is_accepted)
+    assert ((acc == oinfo.is_accepted) | tie).all()
+    same = acc == oinfo.is_accepted
+    close(npy(new.position)[same], onew.position[same], rtol=1e-5)
+    with pytest.raises(bj.BjxError, match="dim <= 1024"):
+        bj.nuts.build_kernel()(tk(keys), st, tgt, 0.01, tf(imm), 3)
+
+
+def test_fullsize_config5_hier_logit_10000d():
+    # BASELINE config 5 target/shape per chain (D = 10000); 8192 chains here (the config shards 1M chains over 8 GPUs).
+    # Properties: reversibility and energy conservation of the integrator; stationarity-free sanity of accept stats.
+    C, D, L = 8192, 10000, 20
+    x, bits = T.HierLogit.synthetic_data(D - 4, seed=1)
+    tgt = T.HierLogit(x, bits)
+    imm = torch.ones(D, device=DEV)
+    q0 = torch.zeros(C, D, device=DEV)
+    st = bj.hmc.init(q0, tgt)
+    eng = _engine.get_engine(q0, tgt)
+    eng.set_metric(imm)
+    p0 = eng.sample_momentum(bj.random.split(bj.random.key(3, DEV), C))
+    q, p, logp, g = q0.clone(), p0.clone(), st.logdensity.clone(), st.logdensity_grad.clone()
+    e0 = eng.energy(p, logp)
+    eng.leapfrog_(q, p, logp, g, 0.02, L)
+    e1 = eng.energy(p, logp)
+    assert float((e1 - e0).abs().max()) < 0.05 * float(e0.abs().mean())
+    p.neg_()
+    eng.leapfrog_(q, p, logp, g, 0.02, L)
+    assert float((q - q0).abs().max()) < 1e-3
+    new, info = bj.hmc.build_kernel()(bj.random.key(4, DEV), st, tgt, 0.02, imm, L)
+    assert 0.3 < float(info.acceptance_rate.mean()) <= 1.0
+    assert float(new.logdensity.mean()) > float(st.logdensity.mean())       # moves uphill from the origin
+
+
+# ---------------------------------------------------------------------------------------------------------
 # NUTS
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("step_size, diverge, turn, doublings",

@@ -34,9 +34,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from blackjax_b200 import _lib
     # bjx_target_desc: 2 x int32, 3 pointers, float (+pad); bjx_info: 14 pointers
-    assert C.sizeof(_lib.TargetDesc) == 40
+    assert C.sizeof(_lib.TargetDesc) == 64
     assert C.sizeof(_lib.Info) == 14 * 8
-    assert C.sizeof(_lib.Config) == 16 + 8 + 8 + 40
+    assert C.sizeof(_lib.Config) == 16 + 8 + 8 + 64
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
