@@ -90,6 +90,14 @@ class Engine:
         check(lib().bjx_set_metric(self.h, kind, ptr(imm)), self.h)
         return imm
 
+    def set_integrator(self, coefficients):
+        """integrators.py:62-152 coefficient table (tuple of floats); cached per engine."""
+        coef = tuple(float(c) for c in coefficients)
+        if getattr(self, "_coef", (0.5, 1.0, 0.5)) != coef:
+            arr = (C.c_float * len(coef))(*coef)
+            check(lib().bjx_set_integrator(self.h, arr, len(coef)), self.h)
+            self._coef = coef
+
     def mass_matrix_sqrt(self):
         out = C.c_void_p()
         check(lib().bjx_get_mass_matrix_sqrt(self.h, C.byref(out)), self.h)

@@ -131,6 +131,9 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   for (int m = 0; m < 3; ++m) { h->dense_mat_s[m] = nullptr; h->dense_mat_src[m] = nullptr; h->dense_mat_ver[m] = 0; }
   h->dense_version = 1;
   h->dense_bytes_built = 0;
+  h->ncoef = 3;
+  h->coef[0] = 0.5f; h->coef[1] = 1.0f; h->coef[2] = 0.5f;
+  h->general_integrator = false;
   int rc = validate_target(h, cfg->target, cfg->dim);
   if (rc) {
     g_err = h->err;
@@ -165,6 +168,18 @@ extern "C" int bjx_set_target(bjx_handle_t h, const bjx_target_desc* t) {
   if (rc) return rc;
   h->cfg.target = *t;
   h->dense_version++;
+  return 0;
+}
+
+// integrators.py:62-152,321-369: palindromic coefficient table (host array, odd length 3..11)
+extern "C" int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int32_t n) {
+  if (!h || !coefficients) return fail(h, BJX_E_INVALID, "null argument");
+  if (n < 3 || n > 11 || (n % 2) == 0) return fail(h, BJX_E_INVALID, "integrator needs an odd number (3..11) of coefficients");
+  for (int i = 0; i < n; ++i)
+    if (coefficients[i] != coefficients[n - 1 - i]) return fail(h, BJX_E_INVALID, "integrator coefficients must be palindromic");
+  h->ncoef = n;
+  for (int i = 0; i < n; ++i) h->coef[i] = coefficients[i];
+  h->general_integrator = !(n == 3 && coefficients[0] == 0.5f && coefficients[1] == 1.0f);
   return 0;
 }
 
@@ -254,11 +269,14 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.eps = eps;
   P.eps_dev = eps_dev;
   P.div_thr = h->cfg.divergence_threshold;
+  P.ncoef = h->ncoef;
+  for (int i = 0; i < 11; ++i) P.coef[i] = i < h->ncoef ? h->coef[i] : 0.f;
   return P;
 }
 
 static int dispatch(bjx_handle_t h, int kernel_id, bool target_dependent, LaunchArgs& a) {
   a.stream = h->stream;
+  a.general_integrator = h->general_integrator;
   const bool dm = h->metric_small_dense;
   int rc;
   const int tk = target_dependent ? h->cfg.target.kind : (int)BJX_TARGET_FUNNEL;
@@ -322,6 +340,8 @@ extern "C" int bjx_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, flo
   int rc = check_ready(h, true, ptrs, 3);
   if (rc) return rc;
   if (!logp || n_steps < 0) return fail(h, BJX_E_INVALID, "bad argument");
+  if ((use_dense_path(h) || use_big_path(h)) && h->general_integrator)
+    return fail(h, BJX_E_UNSUPPORTED, "only velocity Verlet is built for dim > 1024 / the tensor-core dense path");
   if (use_dense_path(h)) return bjx_dense_leapfrog(h, q, p, logp, grad, step_size, step_size_dev, n_steps);
   if (use_big_path(h)) return bjx_big_leapfrog(h, q, p, logp, grad, step_size, step_size_dev, n_steps);
   LaunchArgs a{};
@@ -402,6 +422,8 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
   if (!keys || !logp_in || !logp_out || L < 0) return fail(h, BJX_E_INVALID, "bad argument");
   if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  if ((use_dense_path(h) || use_big_path(h)) && h->general_integrator)
+    return fail(h, BJX_E_UNSUPPORTED, "only velocity Verlet is built for dim > 1024 / the tensor-core dense path");
   if (use_dense_path(h))
     return bjx_dense_hmc_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev, L,
                               make_info(info));

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) k_sample_momentum(Params P, const ui
 
 // ---- static_integration of velocity_verlet (trajectory.py:136-167, integrators.py:62-152) ----------
 // n_steps == 1 is the HBM-roofline kernel: reads q,p,g and writes q,p,g = 24*D bytes per chain.
-template <class R, int TK, bool DM>
+template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_leapfrog(Params P, float* __restrict__ q_io, float* __restrict__ p_io,
                                                        float* __restrict__ logp_io, float* __restrict__ g_io,
                                                        int n_steps) {
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(kThreads) k_leapfrog(Params P, float* __restri
   c.init(P, chain, lane, sm);
   const float eps = P.eps_dev ? P.eps_dev[chain] : P.eps;
   float logp = 0.f;
-  for (int i = 0; i + 1 < n_steps; ++i) c.template leapfrog<false>(P, q, p, g, logp, eps);
-  if (n_steps > 0) c.template leapfrog<true>(P, q, p, g, logp, eps);
+  for (int i = 0; i + 1 < n_steps; ++i) c.template step<GEN, false>(P, q, p, g, logp, eps);
+  if (n_steps > 0) c.template step<GEN, true>(P, q, p, g, logp, eps);
   R::store(q, q_io + roff, P.D, lane);
   R::store(p, p_io + roff, P.D, lane);
   R::store(g, g_io + roff, P.D, lane);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) k_is_turning(Params P, const float* 
 // key split -> momentum draw -> L leapfrogs -> energies -> Metropolis accept -> select.
 // HBM traffic per transition: read q,g (8D) + conditional write q,g (8D); the L leapfrogs never
 // touch HBM.
-template <class R, int TK, bool DM>
+template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uint32_t* __restrict__ keys,
                                                              const float* q_in, const float* logp_in, const float* g_in,
                                                              float* q_out, float* logp_out, float* g_out, int L,
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   const float e0 = -logp0 + c.kinetic(P, p);    // hmc.py:159
   const float eps = P.eps_dev ? P.eps_dev[chain] : P.eps;
   float logp = logp0;
-  for (int i = 0; i + 1 < L; ++i) c.template leapfrog<false>(P, q, p, g, logp, eps);  // trajectory.py:165
-  if (L > 0) c.template leapfrog<true>(P, q, p, g, logp, eps);
+  for (int i = 0; i + 1 < L; ++i) c.template step<GEN, false>(P, q, p, g, logp, eps);  // trajectory.py:165
+  if (L > 0) c.template step<GEN, true>(P, q, p, g, logp, eps);
 #pragma unroll
   for (int s = 0; s < R::NS; ++s) p[s] = -1.0f * p[s];              // flip_momentum hmc.py:158
   const float e1 = -logp + c.kinetic(P, p);                         // hmc.py:160
@@ -304,7 +304,7 @@ __device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const P
 // (proposal.py:118-143) and the iterative U-turn checkpoints (termination.py:56-104), then update the
 // proposal (biased progressive sampling, proposal.py:146-176), merge the trajectories and test the
 // full-trajectory U-turn.  Chains that keep expanding are appended to list_out.
-template <class R, int TK, bool DM>
+template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d, int max_doublings,
                                                             const int* __restrict__ list_in, int n_in,
                                                             int* __restrict__ list_out, int* counter_out,
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
   int n = 0;
   const int n_leaves = 1 << d;
   for (int i = 0; i < n_leaves; ++i) {
-    c.leapfrog(P, q, p, g, logp, eps);
+    c.template step<GEN, true>(P, q, p, g, logp, eps);
     const float e_new = -logp + c.kinetic(P, p);
     const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
     const float slpa_new = fminf(w_new, 0.f);

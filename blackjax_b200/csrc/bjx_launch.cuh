@@ -29,6 +29,7 @@ struct LaunchArgs {
   const float *pl, *pr, *ps;
   uint8_t* out_u8;
   float* e_out;
+  bool general_integrator;  // coefficient table other than velocity Verlet
   cudaStream_t stream;
 };
 
@@ -61,15 +62,26 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       k_init_state<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.q_in, a.logp_out, a.g_out);
       return 0;
     case K_LEAPFROG:
-      k_leapfrog<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
+      if (a.general_integrator)
+        k_leapfrog<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
+      else
+        k_leapfrog<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
       return 0;
     case K_HMC:
-      k_hmc_transition<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
-                                                              a.logp_out, a.g_out, a.n, a.info);
+      if (a.general_integrator)
+        k_hmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                      a.logp_out, a.g_out, a.n, a.info);
+      else
+        k_hmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                       a.logp_out, a.g_out, a.n, a.info);
       return 0;
     case K_NUTS_DOUBLING:
-      k_nuts_doubling<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in, a.list_out,
-                                                           a.counter, a.q_out, a.logp_out, a.g_out);
+      if (a.general_integrator)
+        k_nuts_doubling<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in,
+                                                                     a.list_out, a.counter, a.q_out, a.logp_out, a.g_out);
+      else
+        k_nuts_doubling<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in,
+                                                                      a.list_out, a.counter, a.q_out, a.logp_out, a.g_out);
       return 0;
     default:
       break;

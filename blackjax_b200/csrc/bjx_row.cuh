@@ -39,6 +39,9 @@ struct Params {
   float eps;
   const float* eps_dev;    // [C] or nullptr
   float div_thr;
+  // palindromic two-stage integrator coefficients (integrators.py:62-152); velocity Verlet = {0.5, 1, 0.5}
+  int ncoef;
+  float coef[11];
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -328,6 +331,35 @@ struct Ctx {
     }
     value_and_grad<WANT_LOGP>(P, q, g, logp);
     Vec<R::NS>::axpy(p, eh, g);
+  }
+
+  // generalized_two_stage_integrator (integrators.py:104-150) for an arbitrary palindromic coefficient table
+  // (mclachlan / yoshida / omelyan, integrators.py:335-369): even entries kick the momentum, odd entries drift
+  // the position and re-evaluate the gradient; the last kick skips the kinetic gradient.
+  template <bool WANT_LOGP = true>
+  __device__ __forceinline__ void integrate_general(const Params& P, float (&q)[R::NS], float (&p)[R::NS],
+                                                    float (&g)[R::NS], float& logp, float eps) {
+    for (int i = 0; i + 1 < P.ncoef; ++i) {
+      const float a = eps * P.coef[i];
+      if ((i & 1) == 0) {
+        Vec<R::NS>::axpy(p, a, g);
+      } else {
+        float v[R::NS];
+        velocity(P, p, v);  // kinetic_grad of the momentum just updated (integrators.py:242)
+        Vec<R::NS>::axpy(q, a, v);
+        if (WANT_LOGP || i + 2 < P.ncoef) value_and_grad<true>(P, q, g, logp);
+        else value_and_grad<false>(P, q, g, logp);
+      }
+    }
+    Vec<R::NS>::axpy(p, eps * P.coef[P.ncoef - 1], g);
+  }
+
+  // one integrator step: velocity Verlet fast path or the general coefficient table
+  template <bool GEN, bool WANT_LOGP = true>
+  __device__ __forceinline__ void step(const Params& P, float (&q)[R::NS], float (&p)[R::NS], float (&g)[R::NS],
+                                       float& logp, float eps) {
+    if constexpr (GEN) integrate_general<WANT_LOGP>(P, q, p, g, logp, eps);
+    else leapfrog<WANT_LOGP>(P, q, p, g, logp, eps);
   }
 
   // metric.sample_momentum  metrics.py:260-261 -> util.py:89-91: p = mass_matrix_sqrt (.) normal(key,(D,))

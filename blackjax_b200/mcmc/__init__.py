@@ -1,1 +1,1 @@
-from . import hmc, nuts  # noqa: F401
+from . import hmc, integrators, nuts  # noqa: F401

@@ -16,7 +16,8 @@ from ..base import build_sampling_algorithm
 
 __all__ = ["HMCState", "HMCInfo", "init", "build_kernel", "as_top_level_api"]
 
-velocity_verlet = "velocity_verlet"  # the only integrator built so far (integrators.py:321-322)
+from . import integrators
+from .integrators import velocity_verlet
 
 
 class HMCState(NamedTuple):
@@ -67,14 +68,14 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000,
                  full_info: bool = False, inplace: bool = False):
     """blackjax/mcmc/hmc.py:251-314.  ``inplace=True`` overwrites the input state's tensors (no
     allocation; the returned state aliases the input)."""
-    if integrator != velocity_verlet:
-        raise NotImplementedError("only velocity_verlet is built (SURVEY.md section 8f item 2)")
+    coefficients = integrators.as_coefficients(integrator)
     if build_proposal is not None:
         raise NotImplementedError("custom proposals are not supported by the fused transition kernel")
 
     def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps):
         q, logp, g = state
         eng = get_engine(q, logdensity_fn, divergence_threshold=divergence_threshold)
+        eng.set_integrator(coefficients)
         if eng._imm_key is not inverse_mass_matrix:
             eng.set_metric(inverse_mass_matrix)
             eng._imm_key = inverse_mass_matrix

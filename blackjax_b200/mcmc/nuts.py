@@ -7,8 +7,9 @@ import torch
 
 from .._engine import get_engine
 from ..base import build_sampling_algorithm
-from . import hmc
-from .hmc import HMCState, IntegratorState, per_chain_keys, velocity_verlet
+from . import hmc, integrators
+from .hmc import HMCState, IntegratorState, per_chain_keys
+from .integrators import velocity_verlet
 
 __all__ = ["NUTSInfo", "init", "build_kernel", "as_top_level_api"]
 
@@ -33,14 +34,14 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: int = 1000, f
                  inplace: bool = False, max_tree_depth: int = 10):
     """blackjax/mcmc/nuts.py:77-147.  ``max_tree_depth`` sizes the checkpoint workspace (upper bound for
     ``max_num_doublings``)."""
-    if integrator != velocity_verlet:
-        raise NotImplementedError("only velocity_verlet is built (SURVEY.md section 8f item 2)")
+    coefficients = integrators.as_coefficients(integrator)
 
     def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, max_num_doublings: int = 10,
                _momentum=None, _key_integrator=None):
         q, logp, g = state
         eng = get_engine(q, logdensity_fn, max_tree_depth=max(max_tree_depth, max_num_doublings),
                          divergence_threshold=divergence_threshold)
+        eng.set_integrator(coefficients)
         if eng._imm_key is not inverse_mass_matrix:
             eng.set_metric(inverse_mass_matrix)
             eng._imm_key = inverse_mass_matrix

@@ -102,6 +102,9 @@ int bjx_create(const bjx_config* cfg, bjx_handle_t* out);
 int bjx_destroy(bjx_handle_t h);
 const char* bjx_last_error(bjx_handle_t h); /* h may be NULL: last global error */
 int bjx_set_target(bjx_handle_t h, const bjx_target_desc* target);
+/* Palindromic two-stage integrator (integrators.py:62-152): host array of n coefficients, n odd in 3..11.
+ * {0.5, 1, 0.5} = velocity_verlet (default, :321-322); mclachlan :335-340, yoshida :351-357, omelyan :363-369. */
+int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int32_t n);
 int bjx_synchronize(bjx_handle_t h);
 
 /* metrics.default_metric / gaussian_euclidean (metrics.py:180-218,221-346): precomputes

@@ -24,6 +24,9 @@ _b1 = 0.1931833275037836
 MCLACHLAN = (_b1, 0.5, 1 - 2 * _b1, 0.5, _b1)                        # integrators.py:335-340
 _b1y, _a1y = 0.11888010966548, 0.29619504261126
 YOSHIDA = (_b1y, _a1y, 0.5 - _b1y, 1 - 2 * _a1y, 0.5 - _b1y, _a1y, _b1y)  # integrators.py:351-357
+_b1o, _a1o, _b2o, _a2o = 0.08398315262876693, 0.2539785108410595, 0.6822365335719091, -0.03230286765269967
+_b3o, _a3o = 0.5 - _b1o - _b2o, 1 - 2 * (_a1o + _a2o)
+OMELYAN = (_b1o, _a1o, _b2o, _a2o, _b3o, _a3o, _b3o, _a2o, _b2o, _a1o, _b1o)  # integrators.py:363-369
 
 
 # XLA:CPU compiles with llvm::FPOpFusion::Fast, so `x + (eps*coef)*grad` lowers to ONE fused multiply-add

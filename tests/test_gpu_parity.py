@@ -371,6 +371,59 @@ def test_fullsize_dense_config2_65536x1024():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# the other palindromic integrators (coefficient tables, integrators.py:335-369)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mclachlan", "yoshida", "omelyan"])
+@pytest.mark.parametrize("kind, D", [("diag", 100), ("funnel", 64), ("dense", 6)])
+def test_general_integrators_match_oracle(name, kind, D):
+    from blackjax_b200.mcmc import integrators as I
+    coef = getattr(I, name)
+    ocoef = getattr(ohmc, name.upper())
+    assert tuple(F(c) for c in coef) == tuple(F(c) for c in ocoef)
+    rs = np.random.default_rng(6)
+    tgt, otgt = make_target(kind, D, rs)
+    C = 21
+    imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    q = (0.3 * rs.standard_normal((C, D))).astype(F)
+    p = rs.standard_normal((C, D)).astype(F)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    eng.set_integrator(coef)
+    dq, dp = tf(q), tf(p)
+    logp, g = eng.init_state(dq)
+    eng.leapfrog_(dq, dp, logp, g, 0.1, 4)
+    lp0, g0 = otgt(q)
+    q1, p1, lp1, g1 = ohmc.static_integration(otgt, ohmc.Metric(imm), q, p, lp0, g0, F(0.1), 4, ocoef)
+    close(npy(dq), q1)
+    close(npy(dp), p1)
+    close(npy(g), g1)
+    close(npy(logp), lp1, rtol=1e-5, scale=np.max(np.abs(lp1)) + 1)
+    # whole transitions through the public API
+    keys = oprng.split(oprng.key(8), C)
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, F(0.1), imm, 5, coefficients=ocoef)
+    new, info = bj.hmc.build_kernel(integrator=coef, full_info=True)(tk(keys), bj.hmc.init(tf(q), tgt), tgt, 0.1, tf(imm), 5)
+    close(npy(info.proposal.position), oinfo.proposal[0])
+    close(npy(info.acceptance_rate), oinfo.acceptance_rate, rtol=1e-4, scale=1.0)
+    if kind != "dense":
+        onew, oinfo = onuts.nuts_kernel(keys, ohmc.init(q, otgt), otgt, F(0.2), imm, 6, coefficients=ocoef)
+        new, info = bj.nuts.build_kernel(integrator=name)(tk(keys), bj.nuts.init(tf(q), tgt), tgt, 0.2, tf(imm), 6)
+        same = npy(info.num_integration_steps) == oinfo.num_integration_steps
+        assert same.mean() >= 0.9
+        close(npy(new.position)[same], onew.position[same], rtol=1e-4)
+    eng.set_integrator(I.velocity_verlet)
+
+
+def test_integrator_validation():
+    from blackjax_b200.mcmc import integrators as I
+    with pytest.raises(ValueError):
+        I.as_coefficients((0.5, 1.0))
+    with pytest.raises(ValueError):
+        I.as_coefficients((0.3, 1.0, 0.5))
+    with pytest.raises(ValueError):
+        bj.hmc.build_kernel(integrator="leapfrogz")
+
+
+# ---------------------------------------------------------------------------------------------------------
 # rows larger than a warp's registers (1024 < D <= 18432): CTA-per-chain kernels, incl. BASELINE config 5's target
 # ---------------------------------------------------------------------------------------------------------
 def big_problem(kind, D, seed=41):

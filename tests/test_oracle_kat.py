@@ -66,7 +66,7 @@ def test_velocity_verlet_mvn_golden():
     assert abs(float(e0[0] - e1[0])) < 1e-4          # reference precision for velocity_verlet
 
 
-@pytest.mark.parametrize("coeffs", [hmc.VELOCITY_VERLET, hmc.MCLACHLAN, hmc.YOSHIDA])
+@pytest.mark.parametrize("coeffs", [hmc.VELOCITY_VERLET, hmc.MCLACHLAN, hmc.YOSHIDA, hmc.OMELYAN])
 def test_integrators_analytic(coeffs):
     # free fall: U = g*x, q(1)=0.5?  reference examples use harmonic oscillator & free fall
     t = targets.StdNormal(1)                         # harmonic oscillator: logp = -x^2/2
