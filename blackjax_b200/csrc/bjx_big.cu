@@ -16,7 +16,8 @@ using namespace bjx;
 
 namespace bjx {
 
-constexpr int kBigThreads = 256;
+constexpr int kBigThreads = 512;  // one CTA per SM (shared-memory bound): 16 warps hide the SFU / L2 latency
+constexpr int kBigWarps = kBigThreads / 32;
 
 struct BigParams {
   int C, D;
@@ -37,7 +38,7 @@ struct BigParams {
 
 // block-wide sum of up to NV values per thread (result valid in all threads)
 template <int NV>
-__device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[NV*8]*/) {
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[NV*kBigWarps]*/) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -47,14 +48,14 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[NV*8]*/)
   __syncthreads();  // protect red from the previous use
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) red[k * 8 + wid] = v[k];
+    for (int k = 0; k < NV; ++k) red[k * kBigWarps + wid] = v[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kBigThreads / 32; ++w) s += red[k * 8 + w];
+    for (int w = 0; w < kBigWarps; ++w) s += red[k * kBigWarps + w];
     v[k] = s;
   }
 }
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_momentum(BigParams P, const
 
 __global__ void __launch_bounds__(kBigThreads) k_big_energy(BigParams P, const float* __restrict__ p_in,
                                                             const float* __restrict__ logp, float* __restrict__ e) {
-  __shared__ float red[8];
+  __shared__ float red[kBigWarps];
   const int c = blockIdx.x;
   const float* imm = P.imm + (size_t)c * P.imm_stride;
   float acc[1] = {0.f};
@@ -306,7 +307,7 @@ static int big_smem(bjx_handle_t h, K kernel, size_t bytes) {
 
 #define BIG_DISPATCH(KERNEL, ROWS, ...)                                                                   \
   do {                                                                                                    \
-    const size_t smem_ = ((size_t)(ROWS)*h->cfg.dim + 64) * sizeof(float);                                \
+    const size_t smem_ = ((size_t)(ROWS)*h->cfg.dim + 5 * kBigWarps) * sizeof(float);                                \
     int rc_ = 0;                                                                                          \
     switch (h->cfg.target.kind) {                                                                         \
       case BJX_TARGET_DIAG_GAUSSIAN:                                                                      \

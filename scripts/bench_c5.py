@@ -13,7 +13,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 T_ = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-D, L, eps = 10000, 20, 0.02
+D, L, eps = 10000, 20, 0.01
 x, bits = bj.targets.HierLogit.synthetic_data(D - 4, seed=1)
 tgt = bj.targets.HierLogit(x, bits)
 imm = torch.ones(D, device=dev)

@@ -482,7 +482,9 @@ def test_big_rows_match_oracle(kind, D, C):
 
 def test_fullsize_config5_hier_logit_10000d():
     # BASELINE config 5 target/shape per chain (D = 10000); 8192 chains here (the config shards 1M chains over 8 GPUs).
-    # Properties: reversibility and energy conservation of the integrator; stationarity-free sanity of accept stats.
+    # Properties: reversibility and energy conservation of the integrator; sanity of the accept statistics.
+    # (eps = 0.01: mu and log_tau see a curvature ~ G = 9996 from the origin, so velocity Verlet with an identity
+    #  mass matrix is only stable for eps < 2/sqrt(G) = 0.02 -- the step SURVEY 8d pencilled in sits ON that limit.)
     C, D, L = 8192, 10000, 20
     x, bits = T.HierLogit.synthetic_data(D - 4, seed=1)
     tgt = T.HierLogit(x, bits)
@@ -494,13 +496,13 @@ def test_fullsize_config5_hier_logit_10000d():
     p0 = eng.sample_momentum(bj.random.split(bj.random.key(3, DEV), C))
     q, p, logp, g = q0.clone(), p0.clone(), st.logdensity.clone(), st.logdensity_grad.clone()
     e0 = eng.energy(p, logp)
-    eng.leapfrog_(q, p, logp, g, 0.02, L)
+    eng.leapfrog_(q, p, logp, g, 0.01, L)
     e1 = eng.energy(p, logp)
     assert float((e1 - e0).abs().max()) < 0.05 * float(e0.abs().mean())
     p.neg_()
-    eng.leapfrog_(q, p, logp, g, 0.02, L)
+    eng.leapfrog_(q, p, logp, g, 0.01, L)
     assert float((q - q0).abs().max()) < 1e-3
-    new, info = bj.hmc.build_kernel()(bj.random.key(4, DEV), st, tgt, 0.02, imm, L)
+    new, info = bj.hmc.build_kernel()(bj.random.key(4, DEV), st, tgt, 0.01, imm, L)
     assert 0.3 < float(info.acceptance_rate.mean()) <= 1.0
     assert float(new.logdensity.mean()) > float(st.logdensity.mean())       # moves uphill from the origin
 
