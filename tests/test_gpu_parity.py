@@ -480,31 +480,40 @@ def test_big_rows_match_oracle(kind, D, C):
         bj.nuts.build_kernel()(tk(keys), st, tgt, 0.01, tf(imm), 3)
 
 
+def hier_logit_typical_start(C, D, device, seed=0):
+    """A start in the typical set (the data-generating values + N(0, 0.7^2) group effects).  The origin is NOT usable:
+    with every alpha_g == mu the log_tau gradient is -G, tau collapses and the centred model's funnel makes any
+    fixed step size unstable -- the start/step SURVEY 8d pencilled in (q0 = 0, eps = 0.02) gives acceptance 0."""
+    g_ = torch.Generator(device=device).manual_seed(seed)
+    q0 = torch.empty(C, D, device=device)
+    q0[:, 0], q0[:, 1], q0[:, 2], q0[:, 3] = 0.5, float(np.log(0.7)), 1.0, -0.5
+    q0[:, 4:] = 0.5 + 0.7 * torch.randn(C, D - 4, device=device, generator=g_)
+    return q0
+
+
 def test_fullsize_config5_hier_logit_10000d():
     # BASELINE config 5 target/shape per chain (D = 10000); 8192 chains here (the config shards 1M chains over 8 GPUs).
     # Properties: reversibility and energy conservation of the integrator; sanity of the accept statistics.
-    # (eps = 0.01: mu and log_tau see a curvature ~ G = 9996 from the origin, so velocity Verlet with an identity
-    #  mass matrix is only stable for eps < 2/sqrt(G) = 0.02 -- the step SURVEY 8d pencilled in sits ON that limit.)
-    C, D, L = 8192, 10000, 20
+    C, D, L, eps = 8192, 10000, 20, 0.005
     x, bits = T.HierLogit.synthetic_data(D - 4, seed=1)
     tgt = T.HierLogit(x, bits)
     imm = torch.ones(D, device=DEV)
-    q0 = torch.zeros(C, D, device=DEV)
+    q0 = hier_logit_typical_start(C, D, DEV)
     st = bj.hmc.init(q0, tgt)
     eng = _engine.get_engine(q0, tgt)
     eng.set_metric(imm)
     p0 = eng.sample_momentum(bj.random.split(bj.random.key(3, DEV), C))
     q, p, logp, g = q0.clone(), p0.clone(), st.logdensity.clone(), st.logdensity_grad.clone()
     e0 = eng.energy(p, logp)
-    eng.leapfrog_(q, p, logp, g, 0.01, L)
+    eng.leapfrog_(q, p, logp, g, eps, L)
     e1 = eng.energy(p, logp)
-    assert float((e1 - e0).abs().max()) < 0.05 * float(e0.abs().mean())
+    assert float((e1 - e0).abs().max()) < 5.0              # O(eps^2) energy error on energies of order 1e4
     p.neg_()
-    eng.leapfrog_(q, p, logp, g, 0.01, L)
+    eng.leapfrog_(q, p, logp, g, eps, L)
     assert float((q - q0).abs().max()) < 1e-3
-    new, info = bj.hmc.build_kernel()(bj.random.key(4, DEV), st, tgt, 0.01, imm, L)
+    new, info = bj.hmc.build_kernel()(bj.random.key(4, DEV), st, tgt, eps, imm, L)
     assert 0.3 < float(info.acceptance_rate.mean()) <= 1.0
-    assert float(new.logdensity.mean()) > float(st.logdensity.mean())       # moves uphill from the origin
+    assert bool(info.is_accepted.any())
 
 
 # ---------------------------------------------------------------------------------------------------------
