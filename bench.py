@@ -264,9 +264,9 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # our kernels per step: k_prng_split + (diag) k_hmc_transition | (dense) normal, 2L+3 GEMMs, L axpy, L grad_kick,
-    # 2 energy, accept
-    launches = K * (2 if not dense else 1 + 1 + (2 * L + 3) + 2 * L + 2 + 1)
+    # our kernels per step: k_prng_split + (diag) k_hmc_transition | (dense) normal draw, 2L+3 x (operand split + GEMM),
+    # first half kick, L grad_kick, 2 energy, accept
+    launches = K * (2 if not dense else 1 + 1 + 2 * (2 * L + 3) + 1 + L + 2 + 1)
     acc_mean = float(info.acceptance_rate.mean())
     clocks = sampler.stop() if rank == 0 else None
 
