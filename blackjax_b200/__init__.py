@@ -5,15 +5,24 @@
 SamplingAlgorithm(init, step)`` surface (blackjax/__init__.py:70-80,104-112), natively batched over
 chains and executed by hand-written sm_100a CUDA kernels through the C ABI in ``include/bjx.h``.
 """
+import functools as _functools
+
 from . import random, targets, util  # noqa: F401
 from ._lib import BjxError  # noqa: F401
 from .adaptation.window_adaptation import build_schedule, window_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, GenerateSamplingAPI, SamplingAlgorithm  # noqa: F401
+from . import mcmc  # noqa: F401
 from .mcmc import hmc as _hmc
 from .mcmc import nuts as _nuts
 from .util import run_inference_algorithm  # noqa: F401
 
 hmc = GenerateSamplingAPI(_hmc.as_top_level_api, _hmc.init, _hmc.build_kernel)     # blackjax/__init__.py:111
 nuts = GenerateSamplingAPI(_nuts.as_top_level_api, _nuts.init, _nuts.build_kernel)  # blackjax/__init__.py:112
+mhmc = GenerateSamplingAPI(                                                          # blackjax/__init__.py:145-151
+    _functools.partial(_hmc.as_top_level_api, build_proposal=_hmc.multinomial_hmc_proposal),
+    _hmc.init,
+    _functools.partial(_hmc.build_kernel, build_proposal=_hmc.multinomial_hmc_proposal),
+)
+multinomial_hmc = mhmc  # backward-compatible alias (:152)
 
 __version__ = "0.1.0"

@@ -153,7 +153,8 @@ class Engine:
         return info
 
     # -- transitions -----------------------------------------------------------------------------------
-    def hmc_step(self, keys, q, logp, g, step_size, num_integration_steps, out=None, info_fields=None):
+    def hmc_step(self, keys, q, logp, g, step_size, num_integration_steps, out=None, info_fields=None,
+                 multinomial=False):
         keys = as_keys(keys, self.C, self.device)
         q = _f32(q, (self.C, self.D), "position")
         g = _f32(g, (self.C, self.D), "logdensity_grad")
@@ -161,8 +162,9 @@ class Engine:
         qo, lo, go = out if out is not None else (torch.empty_like(q), torch.empty_like(logp), torch.empty_like(g))
         eps, eps_dev = self._eps(step_size)
         info = self._info(info_fields or {})
-        check(lib().bjx_hmc_step(self.h, ptr(keys), ptr(q), ptr(logp), ptr(g), ptr(qo), ptr(lo), ptr(go), eps,
-                                 ptr(eps_dev), int(num_integration_steps), C.byref(info)), self.h)
+        fn = lib().bjx_mhmc_step if multinomial else lib().bjx_hmc_step
+        check(fn(self.h, ptr(keys), ptr(q), ptr(logp), ptr(g), ptr(qo), ptr(lo), ptr(go), eps,
+                 ptr(eps_dev), int(num_integration_steps), C.byref(info)), self.h)
         return qo, lo, go
 
     def nuts_step(self, keys, q, logp, g, step_size, max_num_doublings, out=None, info_fields=None,

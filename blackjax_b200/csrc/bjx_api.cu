@@ -444,6 +444,28 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
   return dispatch(h, K_HMC, true, a);
 }
 
+// hmc.build_kernel(build_proposal=multinomial_hmc_proposal) / blackjax.mhmc (hmc.py:181-248, __init__.py:145-151)
+extern "C" int bjx_mhmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                             const float* grad_in, float* q_out, float* logp_out, float* grad_out, float step_size,
+                             const float* step_size_dev, int32_t L, const bjx_info* info) {
+  const void* ptrs[] = {q_in, grad_in, q_out, grad_out};
+  int rc = check_ready(h, true, ptrs, 4);
+  if (rc) return rc;
+  if (!keys || !logp_in || !logp_out || L < 1) return fail(h, BJX_E_INVALID, "bad argument");
+  if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
+    return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
+  if (use_dense_path(h) || h->sc == SC_BIG)
+    return fail(h, BJX_E_UNSUPPORTED, "multinomial HMC is built for dim <= 1024 (dense metrics: dim <= 128)");
+  LaunchArgs a{};
+  a.P = make_params(h, step_size, step_size_dev);
+  a.keys = keys;
+  a.q_in = q_in; a.logp_in = logp_in; a.g_in = grad_in;
+  a.q_out = q_out; a.logp_out = logp_out; a.g_out = grad_out;
+  a.n = L;
+  a.info = make_info(info);
+  return dispatch(h, K_MHMC, true, a);
+}
+
 // ---- NUTS workspace -------------------------------------------------------------------------------------
 static int ensure_ws(bjx_handle_t h) {
   const int depth = h->cfg.max_tree_depth;

@@ -167,6 +167,67 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   }
 }
 
+// ---- multinomial HMC (hmc.py:181-248 + trajectory.py:170-232 static_progressive_integration) ---------------
+// Same trajectory as k_hmc_transition, but every leaf competes through progressive uniform sampling
+// (proposal.py:118-143) with step key fold_in(key_integrator, i); there is no Metropolis rejection.  The
+// running proposal lives in the output buffers (it is rewritten ~log L times), the moving state in registers.
+template <class R, int TK, bool DM, bool GEN>
+__global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const uint32_t* __restrict__ keys,
+                                                              const float* q_in, const float* logp_in, const float* g_in,
+                                                              float* q_out, float* logp_out, float* g_out, int L,
+                                                              InfoPtrs info) {
+  BJX_WARP_PROLOGUE();
+  Ctx<R, TK, DM> c;
+  float q[R::NS], p[R::NS], g[R::NS];
+  R::load(q, q_in + roff, P.D, lane);
+  R::load(g, g_in + roff, P.D, lane);
+  c.init(P, chain, lane, sm);
+  const Key rng{keys[2 * chain], keys[2 * chain + 1]};
+  const Key key_integrator = fold_in(rng, 1u);   // hmc.py:299
+  c.sample_momentum(P, chain, fold_in(rng, 0u), p);
+  if (info.momentum) R::store(p, info.momentum + roff, P.D, lane);
+  const float logp0 = logp_in[chain];
+  const float h0 = -logp0 + c.kinetic(P, p);     // trajectory.py:211
+  if (q_out != q_in) {                           // init_proposal = the initial state (:212)
+    R::store(q, q_out + roff, P.D, lane);
+    R::store(g, g_out + roff, P.D, lane);
+  }
+  if (info.proposal_momentum) R::store(p, info.proposal_momentum + roff, P.D, lane);
+  const float eps = P.eps_dev ? P.eps_dev[chain] : P.eps;
+  float logp = logp0, prop_logp = logp0, prop_energy = h0;
+  float weight = 0.f, slpa = -__int_as_float(0x7f800000);
+  bool any_div = false;
+  for (int i = 0; i < L; ++i) {
+    c.template step<GEN, true>(P, q, p, g, logp, eps);
+    const float e_new = -logp + c.kinetic(P, p);
+    const float w_new = safe_energy_diff(h0, e_new);          // proposal.py:94-98
+    any_div = any_div || ((-w_new) > P.div_thr);              // trajectory.py:220-221
+    const float p_accept = expit_f(w_new - weight);           // proposal.py:122
+    const bool take = uniform01(fold_in(key_integrator, (uint32_t)i)) < p_accept;  // trajectory.py:216
+    if (take) {
+      R::store(q, q_out + roff, P.D, lane);
+      R::store(g, g_out + roff, P.D, lane);
+      if (info.proposal_momentum) R::store(p, info.proposal_momentum + roff, P.D, lane);
+      prop_logp = logp;
+      prop_energy = e_new;
+    }
+    weight = logaddexp_f(weight, w_new);
+    slpa = logaddexp_f(slpa, fminf(w_new, 0.f));
+  }
+  if (info.proposal_position && info.proposal_position != q_out) {  // HMCInfo.proposal = the selected state
+    R::load(q, q_out + roff, P.D, lane);
+    R::store(q, info.proposal_position + roff, P.D, lane);
+  }
+  if (lane == 0) {
+    logp_out[chain] = prop_logp;
+    if (info.acceptance_rate) info.acceptance_rate[chain] = expf(slpa) / (float)L;  // hmc.py:232
+    if (info.is_accepted) info.is_accepted[chain] = 1;
+    if (info.is_divergent) info.is_divergent[chain] = any_div;
+    if (info.energy) info.energy[chain] = prop_energy;
+    if (info.num_integration_steps) info.num_integration_steps[chain] = L;
+  }
+}
+
 // =====================================================================================================
 // NUTS (nuts.py:223-321, trajectory.py:273-393,616-725, termination.py:31-106)
 //

@@ -7,7 +7,7 @@
 namespace bjx {
 
 enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_BIG, SC_NONE };  // SC_BIG: CTA-per-chain (bjx_big.cu)
-enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING };
+enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING, K_MHMC };
 
 struct LaunchArgs {
   Params P;
@@ -74,6 +74,14 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       else
         k_hmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
                                                                        a.logp_out, a.g_out, a.n, a.info);
+      return 0;
+    case K_MHMC:
+      if (a.general_integrator)
+        k_mhmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                       a.logp_out, a.g_out, a.n, a.info);
+      else
+        k_mhmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                        a.logp_out, a.g_out, a.n, a.info);
       return 0;
     case K_NUTS_DOUBLING:
       if (a.general_integrator)

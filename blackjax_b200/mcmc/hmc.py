@@ -14,7 +14,13 @@ from .. import random as bjx_random
 from .._engine import get_engine
 from ..base import build_sampling_algorithm
 
-__all__ = ["HMCState", "HMCInfo", "init", "build_kernel", "as_top_level_api"]
+__all__ = ["HMCState", "HMCInfo", "init", "build_kernel", "as_top_level_api", "hmc_proposal",
+           "multinomial_hmc_proposal"]
+
+# proposal selectors for build_kernel(build_proposal=...): the endpoint proposal of hmc.py:115-178 (default) and the
+# multinomial proposal of hmc.py:181-248; each maps to one fused transition kernel
+hmc_proposal = "hmc_proposal"
+multinomial_hmc_proposal = "multinomial_hmc_proposal"
 
 from . import integrators
 from .integrators import velocity_verlet
@@ -69,8 +75,10 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000,
     """blackjax/mcmc/hmc.py:251-314.  ``inplace=True`` overwrites the input state's tensors (no
     allocation; the returned state aliases the input)."""
     coefficients = integrators.as_coefficients(integrator)
-    if build_proposal is not None:
-        raise NotImplementedError("custom proposals are not supported by the fused transition kernel")
+    if build_proposal not in (None, hmc_proposal, multinomial_hmc_proposal):
+        raise NotImplementedError("build_proposal must be hmc.hmc_proposal or hmc.multinomial_hmc_proposal "
+                                  "(each is one fused transition kernel)")
+    multinomial = build_proposal == multinomial_hmc_proposal
 
     def kernel(rng_key, state, logdensity_fn, step_size, inverse_mass_matrix, num_integration_steps):
         q, logp, g = state
@@ -89,7 +97,8 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000,
             fields.update(momentum=torch.empty_like(q), proposal_position=torch.empty_like(q),
                           proposal_momentum=torch.empty_like(q))
         out = (q, logp, g) if inplace else None
-        qo, lo, go = eng.hmc_step(keys, q, logp, g, step_size, num_integration_steps, out=out, info_fields=fields)
+        qo, lo, go = eng.hmc_step(keys, q, logp, g, step_size, num_integration_steps, out=out, info_fields=fields,
+                                  multinomial=multinomial)
         proposal = None
         if full_info:
             proposal = IntegratorState(fields["proposal_position"], fields["proposal_momentum"], None, None)

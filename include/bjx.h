@@ -139,6 +139,13 @@ int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const 
                  const float* grad_in, float* q_out, float* logp_out, float* grad_out,
                  float step_size, const float* step_size_dev, int32_t num_integration_steps,
                  const bjx_info* info);
+/* Multinomial HMC: hmc.build_kernel(build_proposal=multinomial_hmc_proposal) = blackjax.mhmc (hmc.py:181-248,
+ * trajectory.py:170-232, blackjax/__init__.py:145-151).  Same arguments as bjx_hmc_step; is_accepted is always 1,
+ * acceptance_rate = exp(sum_log_p_accept) / L, proposal_* = the selected trajectory state. */
+int bjx_mhmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
+                  const float* grad_in, float* q_out, float* logp_out, float* grad_out,
+                  float step_size, const float* step_size_dev, int32_t num_integration_steps,
+                  const bjx_info* info);
 /* nuts.build_kernel(...).kernel (nuts.py:113-145) with iterative_nuts_proposal (nuts.py:223-321).
  * Tree doubling is driven from the host: one launch per doubling over the chains still expanding; each
  * warp integrates its chain's whole sub-tree (up to 2^d leapfrog leaves) inside the launch.

@@ -167,3 +167,48 @@ def hmc_kernel(keys, state, target, step_size, inverse_mass_matrix, num_integrat
                    np.where(a, g1, g0).astype(F))
     info = HMCInfo(p0, p_acc, acc, is_div, e1, (q1, p1, logp1, g1), int(num_integration_steps))
     return new, info
+
+
+def mhmc_kernel(keys, state, target, step_size, inverse_mass_matrix, num_integration_steps,
+                divergence_threshold=1000.0, coefficients=VELOCITY_VERLET):
+    """Multinomial HMC transition (hmc.py:181-248 multinomial_hmc_proposal + trajectory.py:170-232
+    static_progressive_integration + proposal.py:118-143 progressive_uniform_sampling) for every chain."""
+    from .nuts import expit, logaddexp
+    metric = inverse_mass_matrix if isinstance(inverse_mass_matrix, Metric) else Metric(inverse_mass_matrix)
+    q0, logp0, g0 = state
+    C, D = q0.shape
+    ks = prng.split(keys, 2)                                         # hmc.py:299
+    key_momentum, key_integrator = ks[:, 0], ks[:, 1]
+    p0 = metric.sample_momentum(key_momentum, D)
+    eps = np.asarray(step_size, F)
+    if eps.ndim == 1:
+        eps = eps[:, None]
+    h0 = (-logp0 + metric.kinetic_energy(p0)).astype(F)              # trajectory.py:211
+    prop = dict(q=q0.copy(), p=p0.copy(), g=g0.copy(), logp=logp0.copy(), energy=h0.copy(),
+                weight=np.zeros(C, F), slpa=np.full(C, -np.inf, F))  # :212
+    q, p, logp, g = q0, p0, logp0, g0
+    any_div = np.zeros(C, bool)
+    for i in range(int(num_integration_steps)):
+        step_key = prng.fold_in(key_integrator, i)                   # :216
+        q, p, logp, g = integrator_step(target, metric, q, p, g, eps, coefficients)
+        e_new = (-logp + metric.kinetic_energy(p)).astype(F)
+        w_new = safe_energy_diff(h0, e_new)                          # proposal.py:94-98
+        slpa_new = np.minimum(w_new, F(0.0)).astype(F)
+        any_div |= (-w_new) > F(divergence_threshold)                # :220-221
+        with np.errstate(invalid="ignore"):
+            p_accept = expit(w_new - prop["weight"])                 # proposal.py:122
+        acc = prng.uniform(step_key) < p_accept
+        a = acc[:, None]
+        prop["q"] = np.where(a, q, prop["q"]).astype(F)
+        prop["p"] = np.where(a, p, prop["p"]).astype(F)
+        prop["g"] = np.where(a, g, prop["g"]).astype(F)
+        prop["logp"] = np.where(acc, logp, prop["logp"]).astype(F)
+        prop["energy"] = np.where(acc, e_new, prop["energy"]).astype(F)
+        prop["weight"] = logaddexp(prop["weight"], w_new)
+        prop["slpa"] = logaddexp(prop["slpa"], slpa_new)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        acc_rate = (np.exp(prop["slpa"]).astype(F) / F(num_integration_steps)).astype(F)   # hmc.py:232
+    new = HMCState(prop["q"], prop["logp"], prop["g"])
+    info = HMCInfo(p0, acc_rate, np.ones(C, bool), any_div, prop["energy"],
+                   (prop["q"], prop["p"], prop["logp"], prop["g"]), int(num_integration_steps))
+    return new, info

@@ -371,6 +371,57 @@ def test_fullsize_dense_config2_65536x1024():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# multinomial HMC (blackjax.mhmc; hmc.py:181-248, trajectory.py:170-232)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind, D, C, L, eps, imm_kind", [
+    ("std", 100, 96, 10, 0.2, "ones"), ("diag", 516, 40, 12, 0.08, "diag"), ("funnel", 64, 64, 16, 0.1, "ones"),
+    ("banana", 2, 64, 10, 0.1, "dense"), ("std", 1, 32, 100, 1000.0, "ones")])
+def test_multinomial_hmc_matches_oracle(kind, D, C, L, eps, imm_kind):
+    rs = np.random.default_rng(12)
+    tgt, otgt = make_target(kind, D, rs)
+    if imm_kind == "ones":
+        imm = np.ones(D, F)
+    elif imm_kind == "diag":
+        imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    else:
+        A = rs.standard_normal((D, D))
+        imm = (A @ A.T / D + np.eye(D)).astype(F)
+    q = (0.5 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(14), C)
+    onew, oinfo = ohmc.mhmc_kernel(keys, ohmc.init(q, otgt), otgt, F(eps), imm, L)
+    kernel = bj.mhmc.build_kernel(full_info=True)
+    new, info = kernel(tk(keys), bj.mhmc.init(tf(q), tgt), tgt, float(eps), tf(imm), L)
+    torch.cuda.synchronize()
+    assert bool(info.is_accepted.all())
+    assert (npy(info.is_divergent) == oinfo.is_divergent).all()
+    # the multinomial selection index must agree (same uniforms); chains whose draw sits on a tie may differ
+    same = np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1)
+    assert same.mean() >= 0.95
+    close(npy(info.acceptance_rate)[same], oinfo.acceptance_rate[same], rtol=1e-4, scale=1.0)
+    fin = np.isfinite(oinfo.energy) & same
+    close(npy(info.energy)[fin], oinfo.energy[fin], rtol=1e-5, scale=np.max(np.abs(oinfo.energy[fin])) + 1)
+    close(npy(new.logdensity_grad)[same], onew.logdensity_grad[same], rtol=1e-4)
+    close(npy(info.proposal.momentum)[same], oinfo.proposal[1][same], rtol=1e-4)
+    assert torch.equal(info.proposal.position, new.position)
+
+
+def test_mhmc_api_and_sampling():
+    # tests/mcmc/test_multinomial_hmc.py:21-55,95-152
+    assert bj.multinomial_hmc is bj.mhmc
+    tgt = T.StdNormal(1)
+    alg = bj.mhmc(tgt, 0.5, torch.ones(1, device=DEV), 20)
+    st = alg.init(torch.zeros(4096, 1, device=DEV))
+    keys = bj.random.split(bj.random.key(0, DEV), 60)
+    for t in range(60):
+        st, info = alg.step(keys[t], st)
+    assert abs(float(st.position.mean())) < 0.3 and abs(float(st.position.std()) - 1.0) < 0.3
+    explicit = bj.hmc.build_kernel(build_proposal=bj.mcmc.hmc.multinomial_hmc_proposal)
+    a, _ = explicit(keys[0], st, tgt, 0.5, torch.ones(1, device=DEV), 20)
+    b, _ = bj.mhmc.build_kernel()(keys[0], st, tgt, 0.5, torch.ones(1, device=DEV), 20)
+    assert torch.equal(a.position, b.position)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # the other palindromic integrators (coefficient tables, integrators.py:335-369)
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["mclachlan", "yoshida", "omelyan"])

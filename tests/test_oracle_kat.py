@@ -260,3 +260,23 @@ def test_univariate_normal_hmc_and_nuts():
         d = np.concatenate(draws)
         assert abs(d.mean() - 1.0) < 0.1, name
         assert abs(d.var() - 4.0) < 0.4, name
+
+
+# ---- tests/mcmc/test_multinomial_hmc.py:36-80 (statistical + diagnostics) --------------------------------------
+def test_multinomial_hmc_oracle():
+    t = targets.StdNormal(1)
+    C = 128
+    st = hmc.init(np.zeros((C, 1), F), t)
+    draws = []
+    keys = prng.split(prng.key(0), 120)
+    for i in range(120):
+        st, info = hmc.mhmc_kernel(prng.split(keys[i], C), st, t, F(0.5), np.ones(1, F), 20)
+        assert info.is_accepted.all()
+        if i >= 20:
+            draws.append(st.position[:, 0].copy())
+    d = np.concatenate(draws)
+    assert abs(d.mean()) < 0.3 and abs(d.std() - 1.0) < 0.3                      # :54-55
+    _, info = hmc.mhmc_kernel(prng.split(prng.key(1), 4), hmc.init(np.ones((4, 1), F), t), t, F(1000.0), np.ones(1, F), 100)
+    assert info.is_divergent.all()                                               # :57-68
+    _, info = hmc.mhmc_kernel(prng.split(prng.key(2), 4), hmc.init(np.zeros((4, 1), F), t), t, F(0.1), np.ones(1, F), 10)
+    assert (info.acceptance_rate > 0.5).all()                                    # :70-80
