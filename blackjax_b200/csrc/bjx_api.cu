@@ -537,26 +537,37 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   rc = dispatch(h, K_NUTS_INIT, false, a);
   if (rc) return rc;
 
-  // Host-driven tree doubling (trajectory.py:616-725): one launch per doubling over the chains that are
-  // still expanding.  counters[d+1] = number of chains that continue after doubling d; their indices are
-  // compacted into list_a/list_b (ping-pong).  One pinned-memory readback per doubling.
+  // Host-driven tree doubling (trajectory.py:616-725).  The first kFusedDoublings doublings run in ONE launch over
+  // all chains (every chain needs them and their cost is the fixed per-doubling row traffic); after that each
+  // doubling is its own launch over the chains still expanding, whose indices the previous launch compacted into
+  // list_a/list_b (ping-pong).  counters[k] = number of chains that continue after launch k; one pinned-memory
+  // readback per launch.
+  const int kFusedDoublings = 4;
+  const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
+  const size_t dm_bytes = (h->metric_small_dense || h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
+                              ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
+  a.ckpt_smem = (ckpt_bytes + dm_bytes <= 40 * 1024) ? 1 : 0;  // stay under the 48 KB default dynamic-smem limit
   int n_active = C;
   const int* list_in = nullptr;
   int64_t launches = 0;
   int depth_reached = 0;
-  for (int d = 0; d < max_num_doublings && n_active > 0; ++d) {
-    int* list_out = (d & 1) ? h->ws.list_b : h->ws.list_a;
+  int d = 0;
+  while (d < max_num_doublings && n_active > 0) {
+    const int d_end = (d == 0) ? (max_num_doublings < kFusedDoublings ? max_num_doublings : kFusedDoublings) : d + 1;
+    int* list_out = (launches & 1) ? h->ws.list_b : h->ws.list_a;
     a.depth = d;
+    a.depth_end = d_end;
     a.list_in = list_in;
     a.n_in = n_active;
     a.list_out = list_out;
-    a.counter = h->ws.counters + d + 1;
+    a.counter = h->ws.counters + launches + 1;
     rc = dispatch(h, K_NUTS_DOUBLING, true, a);
     if (rc) return rc;
     ++launches;
-    depth_reached = d + 1;
-    if (d + 1 < max_num_doublings) {
-      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + d + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    depth_reached = d_end;
+    d = d_end;
+    if (d < max_num_doublings) {
+      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + launches, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       BJX_CUDA(cudaStreamSynchronize(h->stream));
       n_active = h->h_flag[0];
       list_in = list_out;

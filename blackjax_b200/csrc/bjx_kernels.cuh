@@ -360,110 +360,127 @@ __device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const P
   }
 }
 
-// One tree doubling for every chain still expanding (trajectory.py:642-717): draw the direction, integrate
-// the sub-tree of up to 2^d leaves (trajectory.py:318-372) with progressive uniform sampling
-// (proposal.py:118-143) and the iterative U-turn checkpoints (termination.py:56-104), then update the
+// Tree doublings [d_begin, d_end) for every chain still expanding (trajectory.py:642-717).  Per doubling: draw
+// the direction, integrate the sub-tree of up to 2^d leaves (trajectory.py:318-372) with progressive uniform
+// sampling (proposal.py:118-143) and the iterative U-turn checkpoints (termination.py:56-104), then update the
 // proposal (biased progressive sampling, proposal.py:146-176), merge the trajectories and test the
-// full-trajectory U-turn.  Chains that keep expanding are appended to list_out.
+// full-trajectory U-turn.  The host fuses the first few doublings (every chain runs them and their cost is the
+// fixed per-doubling row traffic) into one launch and gives each deep doubling its own launch over the compacted
+// list of chains that still expand; chains that want doubling d_end are appended to list_out.
+// Checkpoints live in shared memory when depth x D is small enough (ckpt_smem), else in the global workspace.
 template <class R, int TK, bool DM, bool GEN>
-__global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d, int max_doublings,
+__global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d_begin, int d_end, int max_doublings,
                                                             const int* __restrict__ list_in, int n_in,
                                                             int* __restrict__ list_out, int* counter_out,
-                                                            float* q_out, float* logp_out, float* g_out) {
+                                                            float* q_out, float* logp_out, float* g_out, int ckpt_smem) {
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  extern __shared__ float bjx_smem[];
-  float* sm = bjx_smem + (size_t)(threadIdx.x >> 5) * P.D;
+  const int wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * kWarpsPerBlock + wib;
+  extern __shared__ __align__(16) float bjx_smem[];
+  float* sm = bjx_smem + (size_t)wib * P.D;  // small dense matvec slice (first kWarpsPerBlock*D floats when used)
   if (w >= n_in) return;
   const int chain = list_in ? list_in[w] : w;
   const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK, DM> c;
-
-  // ---- begin: direction and keys of this doubling (trajectory.py:645-655) --------------------------------
-  const Key ki{ws.key_int[2 * chain], ws.key_int[2 * chain + 1]};
-  const Key sub = fold_in(ki, (uint32_t)d);
-  const Key tk = fold_in(sub, 1u), pk = fold_in(sub, 2u);
-  const int dir = (uniform01(fold_in(sub, 0u)) < 0.5f) ? 1 : -1;
-  float* eq = dir > 0 ? ws.right_q : ws.left_q;
-  float* ep = dir > 0 ? ws.right_p : ws.left_p;
-  float* eg = dir > 0 ? ws.right_g : ws.left_g;
-  float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
-  R::load(q, eq + roff, P.D, lane);
-  R::load(p, ep + roff, P.D, lane);
-  R::load(g, eg + roff, P.D, lane);
   c.init(P, chain, lane, sm);
-  const float eps = (float)dir * (P.eps_dev ? P.eps_dev[chain] : P.eps);  // direction * step_size  :323
+  const Key ki{ws.key_int[2 * chain], ws.key_int[2 * chain + 1]};
+  const float eps_c = P.eps_dev ? P.eps_dev[chain] : P.eps;
   const float h0 = ws.h0[chain];
-  const size_t coff = (size_t)chain * ws.max_depth * P.D;
   const float ninf = -__int_as_float(0x7f800000);
-
-  // ---- the sub-tree (trajectory.py:318-372) ---------------------------------------------------------------
-  float sub_weight = ninf, sub_slpa = ninf, sub_logp = 0.f, sub_energy = 0.f, logp = 0.f;
-  bool sub_div = false, sub_term = false;
-  int n = 0;
-  const int n_leaves = 1 << d;
-  for (int i = 0; i < n_leaves; ++i) {
-    c.template step<GEN, true>(P, q, p, g, logp, eps);
-    const float e_new = -logp + c.kinetic(P, p);
-    const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
-    const float slpa_new = fminf(w_new, 0.f);
-    const bool is_div = (-w_new) > P.div_thr;         // :325
-    bool take;
-    if (i == 0) {  // :329-334 the first leaf is taken unconditionally
-#pragma unroll
-      for (int s = 0; s < R::NS; ++s) ps[s] = p[s];
-      take = true;
-      sub_weight = w_new;
-      sub_slpa = slpa_new;
-    } else {  // :335-338 append + progressive uniform sampling
-#pragma unroll
-      for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
-      const float p_accept = expit_f(w_new - sub_weight);
-      take = uniform01(fold_in(tk, (uint32_t)i)) < p_accept;
-      sub_weight = logaddexp_f(sub_weight, w_new);
-      sub_slpa = logaddexp_f(sub_slpa, slpa_new);
-    }
-    if (take) {
-      R::store(q, ws.sub_prop_q + roff, P.D, lane);
-      R::store(g, ws.sub_prop_g + roff, P.D, lane);
-      sub_logp = logp;
-      sub_energy = e_new;
-    }
-    n = i + 1;
-    // termination.py:75-84 checkpoint index range of leaf i
-    const int idx_max = __popc((unsigned)i >> 1);
-    const int idx_min = idx_max - __popc((~(unsigned)i & ((unsigned)i + 1u)) - 1u) + 1;
-    if ((i & 1) == 0) {  // termination.py:66-72
-      R::store(p, ws.ckpt_p + coff + (size_t)idx_max * P.D, P.D, lane);
-      R::store(ps, ws.ckpt_sum + coff + (size_t)idx_max * P.D, P.D, lane);
-    }
-    bool turning = false;
-    for (int k = idx_max; k >= idx_min && !turning; --k)  // termination.py:96-103
-      turning = turning_vs_checkpoint<R, TK, DM>(c, P, ws.ckpt_p + coff + (size_t)k * P.D,
-                                                 ws.ckpt_sum + coff + (size_t)k * P.D, p, ps, lane);
-    sub_div = is_div;
-    sub_term = turning;
-    if (is_div || turning) break;
+  // checkpoint rows: [depth][D] momentum and [depth][D] momentum sums
+  float* ck_p;
+  float* ck_s;
+  if (ckpt_smem) {
+    float* base = bjx_smem + (size_t)((DM || TK == TK_DENSE) ? kWarpsPerBlock * P.D : 0) +
+                  (size_t)wib * 2 * ws.max_depth * P.D;
+    ck_p = base;
+    ck_s = base + (size_t)ws.max_depth * P.D;
+  } else {
+    ck_p = ws.ckpt_p + (size_t)chain * ws.max_depth * P.D;
+    ck_s = ws.ckpt_sum + (size_t)chain * ws.max_depth * P.D;
   }
-  // the last leaf is the new endpoint of the merged trajectory (trajectory.py:376-385,697-704)
-  R::store(q, eq + roff, P.D, lane);
-  R::store(p, ep + roff, P.D, lane);
-  R::store(g, eg + roff, P.D, lane);
+  float prop_weight = ws.prop_weight[chain], prop_slpa = ws.prop_slpa[chain];
+  int n_states = ws.n_states[chain];
+  bool run_next = true;
+  int d = d_begin;
+  for (; d < d_end && run_next; ++d) {
+    // ---- begin: direction and keys of this doubling (trajectory.py:645-655) ------------------------------
+    const Key sub = fold_in(ki, (uint32_t)d);
+    const Key tk = fold_in(sub, 1u), pk = fold_in(sub, 2u);
+    const int dir = (uniform01(fold_in(sub, 0u)) < 0.5f) ? 1 : -1;
+    float* eq = dir > 0 ? ws.right_q : ws.left_q;
+    float* ep = dir > 0 ? ws.right_p : ws.left_p;
+    float* eg = dir > 0 ? ws.right_g : ws.left_g;
+    float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
+    R::load(q, eq + roff, P.D, lane);
+    R::load(p, ep + roff, P.D, lane);
+    R::load(g, eg + roff, P.D, lane);
+    const float eps = (float)dir * eps_c;  // direction * step_size  :323
 
-  // ---- end of the doubling (trajectory.py:672-717) ---------------------------------------------------------
-  const bool bad = sub_div || sub_term;
-  const float pw = ws.prop_weight[chain];
-  const float new_slpa = logaddexp_f(ws.prop_slpa[chain], sub_slpa);
-  bool take2 = false;
-  if (!bad) take2 = uniform01(pk) < clip_max1(expf(sub_weight - pw));  // proposal.py:155-156
-  if (take2) {
-    float t[R::NS];
-    R::load(t, ws.sub_prop_q + roff, P.D, lane);
-    R::store(t, q_out + roff, P.D, lane);
-    R::load(t, ws.sub_prop_g + roff, P.D, lane);
-    R::store(t, g_out + roff, P.D, lane);
-  }
-  {
+    // ---- the sub-tree (trajectory.py:318-372) ----------------------------------------------------------------
+    float sub_weight = ninf, sub_slpa = ninf, sub_logp = 0.f, sub_energy = 0.f, logp = 0.f;
+    bool sub_div = false, sub_term = false;
+    int n = 0;
+    const int n_leaves = 1 << d;
+    for (int i = 0; i < n_leaves; ++i) {
+      c.template step<GEN, true>(P, q, p, g, logp, eps);
+      const float e_new = -logp + c.kinetic(P, p);
+      const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
+      const float slpa_new = fminf(w_new, 0.f);
+      const bool is_div = (-w_new) > P.div_thr;         // :325
+      bool take;
+      if (i == 0) {  // :329-334 the first leaf is taken unconditionally
+#pragma unroll
+        for (int s = 0; s < R::NS; ++s) ps[s] = p[s];
+        take = true;
+        sub_weight = w_new;
+        sub_slpa = slpa_new;
+      } else {  // :335-338 append + progressive uniform sampling
+#pragma unroll
+        for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
+        const float p_accept = expit_f(w_new - sub_weight);
+        take = uniform01(fold_in(tk, (uint32_t)i)) < p_accept;
+        sub_weight = logaddexp_f(sub_weight, w_new);
+        sub_slpa = logaddexp_f(sub_slpa, slpa_new);
+      }
+      if (take) {
+        R::store(q, ws.sub_prop_q + roff, P.D, lane);
+        R::store(g, ws.sub_prop_g + roff, P.D, lane);
+        sub_logp = logp;
+        sub_energy = e_new;
+      }
+      n = i + 1;
+      // termination.py:75-84 checkpoint index range of leaf i
+      const int idx_max = __popc((unsigned)i >> 1);
+      const int idx_min = idx_max - __popc((~(unsigned)i & ((unsigned)i + 1u)) - 1u) + 1;
+      if ((i & 1) == 0) {  // termination.py:66-72
+        R::store_generic(p, ck_p + (size_t)idx_max * P.D, P.D, lane);
+        R::store_generic(ps, ck_s + (size_t)idx_max * P.D, P.D, lane);
+        if (ckpt_smem) __syncwarp();
+      }
+      bool turning = false;
+      for (int k = idx_max; k >= idx_min && !turning; --k)  // termination.py:96-103
+        turning = turning_vs_checkpoint<R, TK, DM>(c, P, ck_p + (size_t)k * P.D, ck_s + (size_t)k * P.D, p, ps, lane);
+      sub_div = is_div;
+      sub_term = turning;
+      if (is_div || turning) break;
+    }
+    // the last leaf is the new endpoint of the merged trajectory (trajectory.py:376-385,697-704)
+    R::store(q, eq + roff, P.D, lane);
+    R::store(p, ep + roff, P.D, lane);
+    R::store(g, eg + roff, P.D, lane);
+
+    // ---- end of the doubling (trajectory.py:672-717) -----------------------------------------------------------
+    const bool bad = sub_div || sub_term;
+    bool take2 = false;
+    if (!bad) take2 = uniform01(pk) < clip_max1(expf(sub_weight - prop_weight));  // proposal.py:155-156
+    if (take2) {
+      float t[R::NS];
+      R::load(t, ws.sub_prop_q + roff, P.D, lane);
+      R::store(t, q_out + roff, P.D, lane);
+      R::load(t, ws.sub_prop_g + roff, P.D, lane);
+      R::store(t, g_out + roff, P.D, lane);
+    }
     float t[R::NS];
     R::load(t, ws.psum + roff, P.D, lane);
 #pragma unroll
@@ -473,21 +490,26 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     // :706-710 is_turning(p_left, p_right, p_sum)
     const bool turning = (dir > 0) ? c.is_turning(P, t, p, ps) : c.is_turning(P, p, t, ps);
     const bool is_turn = sub_term || turning;  // :715
-    const bool run_next = (d + 1 < max_doublings) && !sub_div && !is_turn;
+    run_next = (d + 1 < max_doublings) && !sub_div && !is_turn;
+    if (!bad) prop_weight = logaddexp_f(prop_weight, sub_weight);
+    prop_slpa = logaddexp_f(prop_slpa, sub_slpa);
+    n_states += n;
     if (lane == 0) {
       if (dir > 0) ws.right_logp[chain] = logp; else ws.left_logp[chain] = logp;
       if (take2) {
         logp_out[chain] = sub_logp;
         ws.prop_energy[chain] = sub_energy;
       }
-      if (!bad) ws.prop_weight[chain] = logaddexp_f(pw, sub_weight);
-      ws.prop_slpa[chain] = new_slpa;
-      ws.n_states[chain] += n;
-      ws.step[chain] = d + 1;
       ws.is_div[chain] = sub_div;
       ws.is_turn[chain] = is_turn;
-      if (run_next) list_out[atomicAdd(counter_out, 1)] = chain;
     }
+  }
+  if (lane == 0) {
+    ws.prop_weight[chain] = prop_weight;
+    ws.prop_slpa[chain] = prop_slpa;
+    ws.n_states[chain] = n_states;
+    ws.step[chain] = d;
+    if (run_next && d < max_doublings) list_out[atomicAdd(counter_out, 1)] = chain;
   }
 }
 

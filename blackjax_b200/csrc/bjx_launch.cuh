@@ -18,7 +18,9 @@ struct LaunchArgs {
   float *q_out, *logp_out, *g_out;
   float* p_io;
   int n;  // n_steps | L | max_doublings
-  int depth;            // current doubling
+  int depth;            // first doubling of this launch
+  int depth_end;        // one past the last doubling of this launch
+  int ckpt_smem;        // checkpoints in shared memory
   const int* list_in;   // compacted chain indices (nullptr = identity)
   int n_in;             // number of warps to launch (0 = all chains)
   int* list_out;
@@ -55,7 +57,8 @@ template <class R, int TK, bool DM>
 static int launch_one(int kernel_id, const LaunchArgs& a) {
   const int n_rows = (kernel_id == K_NUTS_DOUBLING) ? a.n_in : a.P.C;
   const dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
-  const size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
+  size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
+  if (kernel_id == K_NUTS_DOUBLING && a.ckpt_smem) smem += sizeof(float) * kWarpsPerBlock * 2 * a.ws.max_depth * a.P.D;
   cudaStream_t st = a.stream;
   switch (kernel_id) {
     case K_INIT:
@@ -85,11 +88,13 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       return 0;
     case K_NUTS_DOUBLING:
       if (a.general_integrator)
-        k_nuts_doubling<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in,
-                                                                     a.list_out, a.counter, a.q_out, a.logp_out, a.g_out);
+        k_nuts_doubling<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
+                                                                     a.n_in, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                     a.g_out, a.ckpt_smem);
       else
-        k_nuts_doubling<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.n, a.list_in, a.n_in,
-                                                                      a.list_out, a.counter, a.q_out, a.logp_out, a.g_out);
+        k_nuts_doubling<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
+                                                                      a.n_in, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                      a.g_out, a.ckpt_smem);
       return 0;
     default:
       break;

@@ -196,6 +196,39 @@ struct Row {
       }
     }
   }
+  // plain (generic-address) store: the destination may be shared memory (NUTS checkpoints)
+  __device__ static __forceinline__ void store_generic(const float (&x)[NS], float* row, int D, int lane) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        if (e < D) *reinterpret_cast<float4*>(row + e) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int e = s * 32 + lane;
+        if (e < D) row[e] = x[s];
+      }
+    }
+  }
+  __device__ static __forceinline__ void load_generic(float (&x)[NS], const float* row, int D, int lane) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int j = 0; j < NS / 4; ++j) {
+        const int e = (j * 32 + lane) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < D) t = *reinterpret_cast<const float4*>(row + e);
+        x[4 * j + 0] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int e = s * 32 + lane;
+        x[s] = (e < D) ? row[e] : 0.f;
+      }
+    }
+  }
   __device__ static __forceinline__ float dot(const float (&a)[NS], const float (&b)[NS]) {
     return warp_sum(Vec<NS>::dot_partial(a, b));
   }
