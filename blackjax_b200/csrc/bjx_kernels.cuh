@@ -311,13 +311,14 @@ __global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, con
 // is_turning(ckpt_p, p, p_sum - ckpt_sum + ckpt_p) against one checkpoint row (termination.py:96-103,
 // metrics.py:272-304), streaming the checkpoint through registers a slot at a time.
 template <class R, int TK, bool DM>
-__device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const Params& P, const float* __restrict__ cp_row,
-                                                      const float* __restrict__ cs_row, const float (&p)[R::NS],
+__device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const Params& P, const float* cp_row,
+                                                      const float* cs_row, const float (&p)[R::NS],
                                                       const float (&ps)[R::NS], int lane) {
+  // cp_row / cs_row are GENERIC addresses (shared memory or the global workspace): plain loads only
   if constexpr (DM) {
     float cp[R::NS], cs[R::NS];
-    R::load(cp, cp_row, P.D, lane);
-    R::load(cs, cs_row, P.D, lane);
+    R::load_generic(cp, cp_row, P.D, lane);
+    R::load_generic(cs, cs_row, P.D, lane);
 #pragma unroll
     for (int s = 0; s < R::NS; ++s) cs[s] = ps[s] - cs[s] + cp[s];
     return c.is_turning(P, cp, p, cs);
