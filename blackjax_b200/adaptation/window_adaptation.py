@@ -81,22 +81,29 @@ def _da_update(s, acceptance_rate, target, t0=10, gamma=0.05, kappa=0.75):
     return _DA(log_x.item(), log_x_avg.item(), step + 1, avg_error.item(), s.mu)
 
 
-def cgl_merge_blocks(blocks):
-    """Chan-Golub-LeVeque merge of per-GPU blocks [G, 2+2D] -> (sum_accept, n, mean[D], M2[D])
-    (metric_buffers.py:334-393), sequential in rank order so every rank computes identical bits."""
-    D = (blocks.shape[1] - 2) // 2
+def _cross(delta, dense):
+    return torch.outer(delta, delta) if dense else delta * delta
+
+
+def cgl_merge_blocks(blocks, dim=None):
+    """Chan-Golub-LeVeque merge of per-GPU blocks [G, 2+2D] (diagonal M2) or [G, 2+D+D*D] (dense M2, pass ``dim``)
+    -> (sum_accept, n, mean[D], M2)  (metric_buffers.py:334-393), sequential in rank order so every rank computes
+    identical bits."""
+    dense = dim is not None and blocks.shape[1] == 2 + dim + dim * dim and dim > 1
+    D = dim if dim is not None else (blocks.shape[1] - 2) // 2
+    shape = (D, D) if dense else (D,)
     acc = blocks[0, 0].clone()
     n = blocks[0, 1].clone()
     mean = blocks[0, 2:2 + D].clone()
-    m2 = blocks[0, 2 + D:].clone()
+    m2 = blocks[0, 2 + D:].reshape(shape).clone()
     for gidx in range(1, blocks.shape[0]):
         nb = blocks[gidx, 1]
         mb = blocks[gidx, 2:2 + D]
-        m2b = blocks[gidx, 2 + D:]
+        m2b = blocks[gidx, 2 + D:].reshape(shape)
         n_ab = n + nb
         delta = mb - mean
         mean = mean + delta * (nb / n_ab)
-        m2 = m2 + m2b + delta * delta * (n * nb / n_ab)
+        m2 = m2 + m2b + _cross(delta, dense) * (n * nb / n_ab)
         n = n_ab
         acc = acc + blocks[gidx, 0]
     return acc, n, mean, m2
@@ -120,8 +127,10 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
     """blackjax/adaptation/window_adaptation.py:296-444.  ``algorithm`` is ``blackjax_b200.hmc`` or
     ``blackjax_b200.nuts``; ``extra_parameters`` go to the kernel (``num_integration_steps`` /
     ``max_num_doublings``).  Returns an :class:`AdaptationAlgorithm` with ``run(rng_key, position, num_steps)``."""
-    if not is_mass_matrix_diagonal:
-        raise NotImplementedError("dense window adaptation (welford_dense) is not built yet (SURVEY.md section 8a a21)")
+    dense = not is_mass_matrix_diagonal
+    if dense and not shared:
+        raise NotImplementedError("dense (welford_dense) adaptation is built for the chain-pooled mode: pass shared=True "
+                                  "(a per-chain dense metric would need [C, D, D] mass matrices in the kernels)")
     mcmc_kernel = algorithm.build_kernel()
 
     def run(rng_key, position, num_steps: int = 1000):
@@ -142,15 +151,19 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
             step_keys = bjx_random.split(rng_key.to(dev), num_steps)
             da = _da_init(initial_step_size)
             eps = _f32(initial_step_size)
-            imm = torch.ones(D, dtype=torch.float32, device=dev)
-            w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(D, device=dev)
-            stats = torch.empty(2 + 2 * D, dtype=torch.float32, device=dev)
+            if dense and D > 128:
+                raise NotImplementedError("dense window adaptation is built for dim <= 128")
+            m2_shape = (D, D) if dense else (D,)
+            imm = torch.eye(D, dtype=torch.float32, device=dev) if dense else torch.ones(D, dtype=torch.float32, device=dev)
+            w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(m2_shape, device=dev)
+            stats = torch.empty(2 + D + (D * D if dense else D), dtype=torch.float32, device=dev)
+            pooled = lib().bjx_pooled_stats_dense if dense else lib().bjx_pooled_stats
             for t, (stage, window_end) in enumerate(schedule):
                 ck = bjx_random.split(step_keys[t], C * world)[rank * C:(rank + 1) * C]
                 state, info = mcmc_kernel(ck, state, logdensity_fn, eps, imm, **extra_parameters)
-                check(lib().bjx_pooled_stats(eng.h, ptr(state.position), ptr(info.acceptance_rate), ptr(stats)), eng.h)
+                check(pooled(eng.h, ptr(state.position), ptr(info.acceptance_rate), ptr(stats)), eng.h)
                 blocks = _allgather_stats(stats, process_group)
-                acc_sum, n_b, mean_b, m2_b = cgl_merge_blocks(blocks)
+                acc_sum, n_b, mean_b, m2_b = cgl_merge_blocks(blocks, D)
                 if stage == 1:  # CGL-merge this step's pooled block into the window accumulator
                     if w_n == 0.0:
                         w_n, w_mean, w_m2 = float(n_b), mean_b, m2_b
@@ -159,14 +172,16 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
                         n_ab = w_n + nb
                         delta = mean_b - w_mean
                         w_mean = w_mean + delta * (nb / n_ab)
-                        w_m2 = w_m2 + m2_b + delta * delta * (w_n * nb / n_ab)
+                        w_m2 = w_m2 + m2_b + _cross(delta, dense) * (w_n * nb / n_ab)
                         w_n = n_ab
                 da = _da_update(da, (acc_sum / n_b).item(), target_acceptance_rate)
                 eps = _f32(math.exp(da.log_step))
                 if window_end:  # mass_matrix.py:335-357 + staged_adaptation.py:233-249
                     cov = w_m2 / (w_n - 1.0)
-                    imm = ((w_n / (w_n + 5.0)) * cov + (5.0 / (w_n + 5.0)) * 1e-3).to(torch.float32).contiguous()
-                    w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+                    reg = (5.0 / (w_n + 5.0)) * 1e-3
+                    imm = (w_n / (w_n + 5.0)) * cov + (reg * torch.eye(D, device=dev) if dense else reg)
+                    imm = imm.to(torch.float32).contiguous()
+                    w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(m2_shape, device=dev)
                     da = _da_init(_f32(math.exp(da.log_step_avg)))
                     eps = _f32(math.exp(da.log_step))
                 history.append(eps)

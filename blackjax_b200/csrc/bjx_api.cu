@@ -686,3 +686,19 @@ extern "C" int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acc
   BJX_CHECK_LAUNCH("k_pooled_stats");
   return 0;
 }
+
+extern "C" int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acc, float* out) {
+  if (!h || !q || !acc || !out) return fail(h, BJX_E_INVALID, "null argument");
+  if (h->cfg.dim > 128) return fail(h, BJX_E_UNSUPPORTED, "dense pooled moments are built for dim <= 128 (dense NUTS/HMC warp path)");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t need = pooled_dense_scratch_floats(h->cfg.dim) * sizeof(float);
+  if (h->dense_bytes < need) {  // reuse the dense-path block as scratch (dim <= 128 never uses it otherwise)
+    if (h->dense_block) BJX_CUDA(cudaFree(h->dense_block));
+    h->dense_block = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->dense_block, need));
+    h->dense_bytes = need;
+  }
+  launch_pooled_stats_dense(h->cfg.n_chains, h->cfg.dim, q, acc, out, h->dense_block, h->stream);
+  BJX_CHECK_LAUNCH("k_pooled_stats_dense");
+  return 0;
+}

@@ -192,6 +192,49 @@ __global__ void k_pooled_accept(int C, const float* __restrict__ acc, float* __r
     out[1] = (float)C;
   }
 }
+// Dense pooled second moment: M2[i,j] = sum_c (x_ci - mean_i)(x_cj - mean_j)  (metric_buffers.py:396-420, dense
+// branch `centered.T @ centered`).  Two deterministic stages: Z chain slices -> partial [Z, D, D], then the sum.
+constexpr int kM2Slices = 32;
+__global__ void k_pooled_m2_partial(int C, int D, const float* __restrict__ x, const float* __restrict__ mean,
+                                    float* __restrict__ partial) {
+  __shared__ float xi[32][17], xj[32][17];
+  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * 16, j0 = blockIdx.y * 16, z = blockIdx.z;
+  const int per = (C + kM2Slices - 1) / kM2Slices;
+  const int c0 = z * per, c1 = min(C, c0 + per);
+  float acc = 0.f;
+  for (int cb = c0; cb < c1; cb += 32) {
+    for (int t = threadIdx.x; t < 32 * 16; t += 256) {
+      const int cc = cb + t / 16, k = t % 16;
+      const bool ok = cc < c1;
+      xi[t / 16][k] = (ok && i0 + k < D) ? x[(size_t)cc * D + i0 + k] - mean[i0 + k] : 0.f;
+      xj[t / 16][k] = (ok && j0 + k < D) ? x[(size_t)cc * D + j0 + k] - mean[j0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc = fmaf(xi[r][ti], xj[r][tj], acc);
+    __syncthreads();
+  }
+  if (i0 + ti < D && j0 + tj < D) partial[((size_t)z * D + i0 + ti) * D + j0 + tj] = acc;
+}
+__global__ void k_pooled_m2_sum(int D, const float* __restrict__ partial, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= D * D) return;
+  float s = 0.f;
+  for (int z = 0; z < kM2Slices; ++z) s += partial[(size_t)z * D * D + t];
+  out[t] = s;
+}
+// out = (sum acc, C, mean[D], M2[D,D]); scratch >= kM2Slices*D*D floats
+void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, float* out, float* scratch, cudaStream_t s) {
+  k_pooled_accept<<<1, 1024, 0, s>>>(C, acc, out);
+  k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, x, scratch);  // scratch[2:2+D] = mean (diag M2 unused)
+  cudaMemcpyAsync(out + 2, scratch + 2, sizeof(float) * D, cudaMemcpyDeviceToDevice, s);
+  float* partial = scratch + 2 + 2 * (size_t)D;
+  k_pooled_m2_partial<<<dim3((D + 15) / 16, (D + 15) / 16, kM2Slices), 256, 0, s>>>(C, D, x, out + 2, partial);
+  k_pooled_m2_sum<<<(D * D + 255) / 256, 256, 0, s>>>(D, partial, out + 2 + D);
+}
+size_t pooled_dense_scratch_floats(int D) { return 2 + 2 * (size_t)D + (size_t)kM2Slices * D * D; }
+
 void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s) {
   k_pooled_accept<<<1, 1024, 0, s>>>(C, acc, out);
   k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, x, out);

@@ -184,6 +184,9 @@ int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t count, flo
  * stats_out float32 [2 + 2*D] = (sum acceptance_rate, n_chains, mean[D], M2[D]).
  * The blocks of all GPUs are exchanged with ONE all-gather and CGL-merged on every rank. */
 int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
+/* Dense variant (welford_dense recipe; metric_buffers.py:396-420 `centered.T @ centered`), dim <= 128:
+ * stats_out float32 [2 + D + D*D] = (sum acceptance_rate, n_chains, mean[D], M2[D,D]). */
+int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
 
 #ifdef __cplusplus
 }

@@ -787,6 +787,77 @@ def test_window_adaptation_shared_matches_oracle_and_recovers_scales():
     np.testing.assert_allclose(np.array(hist[:20]), ohist[:20], rtol=2e-3)
 
 
+def test_window_adaptation_shared_dense_recovers_covariance():
+    # welford_dense recipe, chain-pooled (staged_adaptation.py:906-966 with a dense metric core): the adapted dense
+    # inverse mass matrix must recover the target covariance; the oracle run tracks it.
+    D, C, T_ = 6, 512, 150
+    from test_oracle_kat import COV6
+    cov = COV6
+    tgt, otgt = T.DenseGaussian(np.linalg.inv(cov)), otargets.DenseGaussian(np.linalg.inv(cov))
+    rs = np.random.default_rng(11)
+    q = rs.standard_normal((C, D)).astype(F)
+    okern = lambda k, s, t, e, m, **kw: onuts.nuts_kernel(k, s, t, e, m, 6)
+    ost, oeps, oimm, ohist = oadapt.window_adaptation_run(okern, otgt, oprng.key(6), q, T_, shared=True,
+                                                          is_mass_matrix_diagonal=False)
+    warm = bj.window_adaptation(bj.nuts, tgt, is_mass_matrix_diagonal=False, shared=True, max_num_doublings=6)
+    (st, params), hist = warm.run(bj.random.key(6, DEV), tf(q), T_)
+    imm = npy(params["inverse_mass_matrix"])
+    assert imm.shape == (D, D)
+    np.testing.assert_allclose(imm, cov, rtol=0.25, atol=0.25)
+    np.testing.assert_allclose(imm, oimm, rtol=0.15, atol=0.15)
+    assert abs(params["step_size"] / float(oeps) - 1) < 0.15
+    np.testing.assert_allclose(np.array(hist[:10]), ohist[:10], rtol=5e-3)
+    # the pooled dense block itself, against numpy
+    from blackjax_b200._lib import check, lib, ptr
+    eng = _engine.get_engine(st.position, tgt, max_tree_depth=6)
+    out = torch.empty(2 + D + D * D, device=DEV)
+    acc = torch.rand(C, device=DEV)
+    check(lib().bjx_pooled_stats_dense(eng.h, ptr(st.position), ptr(acc), ptr(out)), eng.h)
+    x = npy(st.position).astype(np.float64)
+    o = npy(out)
+    close(o[2:2 + D], x.mean(0), rtol=1e-5)
+    close(o[2 + D:].reshape(D, D), (x - x.mean(0)).T @ (x - x.mean(0)), rtol=1e-4)
+    with pytest.raises(NotImplementedError):
+        bj.window_adaptation(bj.nuts, tgt, is_mass_matrix_diagonal=False)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# free-running chains, compared distributionally (tests/mcmc/test_sampling.py:1343-1471: multi-chain MCSE test on a
+# correlated 2-D normal, HMC & NUTS, diagonal & dense mass matrix)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["hmc", "nuts", "mhmc"])
+@pytest.mark.parametrize("dense_metric", [False, True])
+def test_multichain_moments_correlated_normal(algo, dense_metric):
+    cov = np.array([[1.0, 0.6 * np.sqrt(2.0)], [0.6 * np.sqrt(2.0), 2.0]])       # corr 0.6, variances (1, 2)
+    tgt = T.DenseGaussian(np.linalg.inv(cov))
+    C, T_ = 4096, 250
+    imm = tf(cov.astype(F)) if dense_metric else tf(np.array([1.0, 2.0], F))
+    if algo == "hmc":
+        alg = bj.hmc(tgt, 0.45, imm, 12)
+    elif algo == "mhmc":
+        alg = bj.mhmc(tgt, 0.45, imm, 12)
+    else:
+        alg = bj.nuts(tgt, 0.45, imm)
+    st = alg.init(torch.zeros(C, 2, device=DEV))
+    keys = bj.random.split(bj.random.key(8456, DEV), T_)
+    s1 = torch.zeros(2, dtype=torch.float64, device=DEV)
+    s2 = torch.zeros(2, 2, dtype=torch.float64, device=DEV)
+    n = 0
+    for t in range(T_):
+        st, info = alg.step(keys[t], st)
+        if t >= 50:
+            x = st.position.double()
+            s1 += x.sum(0)
+            s2 += x.T @ x
+            n += C
+    mean = (s1 / n).cpu().numpy()
+    c = (s2 / n).cpu().numpy() - np.outer(mean, mean)
+    # 4096 chains x 200 kept draws; autocorrelation leaves an effective sample size well above 1e5
+    assert np.all(np.abs(mean) < 0.02), mean
+    np.testing.assert_allclose(np.diag(c), [1.0, 2.0], rtol=0.03)
+    assert abs(c[0, 1] / np.sqrt(c[0, 0] * c[1, 1]) - 0.6) < 0.02
+
+
 # ---------------------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     from blackjax_b200 import _lib
     lib = _lib.lib()
     declared = _declared_symbols()
-    assert len(declared) >= 31
+    assert len(declared) >= 32
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/bjx.h but not exported by libbjx.so"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared      # the ctypes binding covers the whole header
@@ -127,6 +127,21 @@ def test_cgl_merge_blocks_matches_oracle():
     for b, x in zip(blocks[1:], xs[1:]):
         w = oa.cgl_merge(w, oa.Welford(b[2:2 + D].astype(np.float32), b[2 + D:].astype(np.float32), len(x)))
     np.testing.assert_allclose(m2.numpy(), w.m2, rtol=1e-5)
+
+
+def test_cgl_merge_blocks_dense_matches_numpy():
+    from blackjax_b200.adaptation.window_adaptation import cgl_merge_blocks
+    rs = np.random.default_rng(2)
+    D, G = 5, 3
+    xs = [rs.standard_normal((40 + 7 * g, D)) @ rs.standard_normal((D, D)) for g in range(G)]
+    blocks = []
+    for x in xs:
+        m = x.mean(0)
+        blocks.append(np.concatenate([[1.0], [len(x)], m, ((x - m).T @ (x - m)).ravel()]))
+    acc, n, mean, m2 = cgl_merge_blocks(torch.tensor(np.stack(blocks), dtype=torch.float32), D)
+    allx = np.concatenate(xs)
+    assert m2.shape == (D, D) and float(n) == len(allx)
+    np.testing.assert_allclose(m2.numpy(), (allx - allx.mean(0)).T @ (allx - allx.mean(0)), rtol=1e-4, atol=1e-3)
 
 
 _GLOO_WORKER = r"""
