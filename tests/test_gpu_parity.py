@@ -822,6 +822,43 @@ def test_window_adaptation_shared_dense_recovers_covariance():
 
 
 # ---------------------------------------------------------------------------------------------------------
+# committed golden fixtures (tests/golden/hmc_nuts_golden.npz, generated by the oracle -- see make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+def test_device_matches_committed_golden():
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hmc_nuts_golden.npz"))
+    # A: HMC config-1 shape
+    tgt = T.StdNormal(100)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(G["A_keys"]), bj.hmc.init(tf(G["A_q"]), tgt), tgt, 0.2,
+                                                    torch.ones(100, device=DEV), 10)
+    assert (npy(info.is_accepted) == G["A_accepted"]).all()
+    close(npy(new.position), G["A_pos"])
+    close(npy(info.energy), G["A_energy"], rtol=1e-5, scale=np.max(np.abs(G["A_energy"])))
+    close(npy(info.acceptance_rate), G["A_acc"], rtol=1e-4, scale=1.0)
+    close(npy(info.momentum), G["A_momentum"], rtol=3e-6)
+    # B: NUTS funnel
+    tgt = T.Funnel(16)
+    new, info = bj.nuts.build_kernel(max_tree_depth=8)(tk(G["B_keys"]), bj.nuts.init(tf(G["B_q"]), tgt), tgt, 0.2,
+                                                       torch.ones(16, device=DEV), 8)
+    assert (npy(info.num_integration_steps) == G["B_n"]).all()
+    assert (npy(info.num_trajectory_expansions) == G["B_depth"]).all()
+    assert (npy(info.is_turning) == G["B_turn"]).all() and (npy(info.is_divergent) == G["B_div"]).all()
+    close(npy(new.position), G["B_pos"], rtol=1e-4)
+    close(npy(info.acceptance_rate), G["B_acc"], rtol=1e-4, scale=1.0)
+    # C: multinomial HMC
+    tgt = T.DiagGaussian(G["C_scale"])
+    new, info = bj.mhmc.build_kernel()(tk(G["C_keys"]), bj.mhmc.init(tf(G["C_q"]), tgt), tgt, 0.15, tf(G["C_imm"]), 7)
+    close(npy(new.position), G["C_pos"], rtol=1e-4)
+    close(npy(info.acceptance_rate), G["C_acc"], rtol=1e-4, scale=1.0)
+    # D: NUTS, dense metric, banana
+    tgt = T.Banana()
+    new, info = bj.nuts.build_kernel(max_tree_depth=6)(tk(G["D_keys"]), bj.nuts.init(tf(G["D_q"]), tgt), tgt, 0.1,
+                                                       tf(G["D_imm"]), 6)
+    assert (npy(info.num_integration_steps) == G["D_n"]).all()
+    close(npy(new.position), G["D_pos"], rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # free-running chains, compared distributionally (tests/mcmc/test_sampling.py:1343-1471: multi-chain MCSE test on a
 # correlated 2-D normal, HMC & NUTS, diagonal & dense mass matrix)
 # ---------------------------------------------------------------------------------------------------------

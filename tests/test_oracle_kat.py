@@ -280,3 +280,22 @@ def test_multinomial_hmc_oracle():
     assert info.is_divergent.all()                                               # :57-68
     _, info = hmc.mhmc_kernel(prng.split(prng.key(2), 4), hmc.init(np.zeros((4, 1), F), t), t, F(0.1), np.ones(1, F), 10)
     assert (info.acceptance_rate > 0.5).all()                                    # :70-80
+
+
+# ---- committed golden fixtures (tests/golden/, generated by the oracle: see make_golden.py) -----------------------
+def test_oracle_reproduces_committed_golden():
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    fresh = mg.cases()
+    stored = np.load(os.path.join(here, "golden", "hmc_nuts_golden.npz"))
+    assert sorted(fresh) == sorted(stored.files)
+    for k in stored.files:
+        a, b = fresh[k], stored[k]
+        if a.dtype.kind in "iub":
+            assert np.array_equal(a, b), k
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6, err_msg=k)   # BLAS/libm may differ across hosts
