@@ -403,6 +403,28 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
   float prop_weight = ws.prop_weight[chain], prop_slpa = ws.prop_slpa[chain];
   int n_states = ws.n_states[chain];
   bool run_next = true;
+  // Rows of up to 8 slots per lane: BOTH trajectory endpoints and the trajectory momentum sum stay in registers
+  // across the doublings of this launch (the "moving" endpoint is the one the current doubling extends, the "fixed"
+  // one only contributes its momentum to the U-turn test); larger rows re-load the moving endpoint per doubling.
+  constexpr bool RES = (R::NS <= 8);
+  constexpr int NF = RES ? R::NS : 1;
+  float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
+  float fq[NF], fp[NF], fg[NF], tsum[NF];
+  bool mov_right = true;
+  if constexpr (RES) {
+    R::load(q, ws.right_q + roff, P.D, lane);
+    R::load(p, ws.right_p + roff, P.D, lane);
+    R::load(g, ws.right_g + roff, P.D, lane);
+    R::load(fq, ws.left_q + roff, P.D, lane);
+    R::load(fp, ws.left_p + roff, P.D, lane);
+    R::load(fg, ws.left_g + roff, P.D, lane);
+    R::load(tsum, ws.psum + roff, P.D, lane);
+  }
+  float logp_mov = 0.f, logp_fix = 0.f;
+  if (RES) {
+    logp_mov = ws.right_logp[chain];
+    logp_fix = ws.left_logp[chain];
+  }
   int d = d_begin;
   for (; d < d_end && run_next; ++d) {
     // ---- begin: direction and keys of this doubling (trajectory.py:645-655) ------------------------------
@@ -412,10 +434,22 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     float* eq = dir > 0 ? ws.right_q : ws.left_q;
     float* ep = dir > 0 ? ws.right_p : ws.left_p;
     float* eg = dir > 0 ? ws.right_g : ws.left_g;
-    float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
-    R::load(q, eq + roff, P.D, lane);
-    R::load(p, ep + roff, P.D, lane);
-    R::load(g, eg + roff, P.D, lane);
+    if constexpr (RES) {
+      if ((dir > 0) != mov_right) {  // the other endpoint becomes the moving one: swap roles
+#pragma unroll
+        for (int s = 0; s < R::NS; ++s) {
+          float t0 = q[s]; q[s] = fq[s]; fq[s] = t0;
+          float t1 = p[s]; p[s] = fp[s]; fp[s] = t1;
+          float t2 = g[s]; g[s] = fg[s]; fg[s] = t2;
+        }
+        const float tl = logp_mov; logp_mov = logp_fix; logp_fix = tl;
+        mov_right = !mov_right;
+      }
+    } else {
+      R::load(q, eq + roff, P.D, lane);
+      R::load(p, ep + roff, P.D, lane);
+      R::load(g, eg + roff, P.D, lane);
+    }
     const float eps = (float)dir * eps_c;  // direction * step_size  :323
 
     // ---- the sub-tree (trajectory.py:318-372) ----------------------------------------------------------------
@@ -457,7 +491,6 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
       if ((i & 1) == 0) {  // termination.py:66-72
         R::store_generic(p, ck_p + (size_t)idx_max * P.D, P.D, lane);
         R::store_generic(ps, ck_s + (size_t)idx_max * P.D, P.D, lane);
-        if (ckpt_smem) __syncwarp();
       }
       bool turning = false;
       for (int k = idx_max; k >= idx_min && !turning; --k)  // termination.py:96-103
@@ -467,9 +500,13 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
       if (is_div || turning) break;
     }
     // the last leaf is the new endpoint of the merged trajectory (trajectory.py:376-385,697-704)
-    R::store(q, eq + roff, P.D, lane);
-    R::store(p, ep + roff, P.D, lane);
-    R::store(g, eg + roff, P.D, lane);
+    if constexpr (RES) {
+      logp_mov = logp;
+    } else {
+      R::store(q, eq + roff, P.D, lane);
+      R::store(p, ep + roff, P.D, lane);
+      R::store(g, eg + roff, P.D, lane);
+    }
 
     // ---- end of the doubling (trajectory.py:672-717) -----------------------------------------------------------
     const bool bad = sub_div || sub_term;
@@ -482,21 +519,30 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
       R::load(t, ws.sub_prop_g + roff, P.D, lane);
       R::store(t, g_out + roff, P.D, lane);
     }
-    float t[R::NS];
-    R::load(t, ws.psum + roff, P.D, lane);
+    bool turning;
+    if constexpr (RES) {
 #pragma unroll
-    for (int s = 0; s < R::NS; ++s) ps[s] = t[s] + ps[s];  // merge_trajectories  trajectory.py:102-125
-    R::store(ps, ws.psum + roff, P.D, lane);
-    R::load(t, (dir > 0 ? ws.left_p : ws.right_p) + roff, P.D, lane);  // the endpoint that did not move
-    // :706-710 is_turning(p_left, p_right, p_sum)
-    const bool turning = (dir > 0) ? c.is_turning(P, t, p, ps) : c.is_turning(P, p, t, ps);
+      for (int s = 0; s < R::NS; ++s) tsum[s] = tsum[s] + ps[s];  // merge_trajectories  trajectory.py:102-125
+      // :706-710 is_turning(p_left, p_right, p_sum)
+      turning = (dir > 0) ? c.is_turning(P, fp, p, tsum) : c.is_turning(P, p, fp, tsum);
+    } else {
+      float t[R::NS];
+      R::load(t, ws.psum + roff, P.D, lane);
+#pragma unroll
+      for (int s = 0; s < R::NS; ++s) ps[s] = t[s] + ps[s];
+      R::store(ps, ws.psum + roff, P.D, lane);
+      R::load(t, (dir > 0 ? ws.left_p : ws.right_p) + roff, P.D, lane);  // the endpoint that did not move
+      turning = (dir > 0) ? c.is_turning(P, t, p, ps) : c.is_turning(P, p, t, ps);
+    }
     const bool is_turn = sub_term || turning;  // :715
     run_next = (d + 1 < max_doublings) && !sub_div && !is_turn;
     if (!bad) prop_weight = logaddexp_f(prop_weight, sub_weight);
     prop_slpa = logaddexp_f(prop_slpa, sub_slpa);
     n_states += n;
     if (lane == 0) {
-      if (dir > 0) ws.right_logp[chain] = logp; else ws.left_logp[chain] = logp;
+      if (!RES) {
+        if (dir > 0) ws.right_logp[chain] = logp; else ws.left_logp[chain] = logp;
+      }
       if (take2) {
         logp_out[chain] = sub_logp;
         ws.prop_energy[chain] = sub_energy;
@@ -505,7 +551,20 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
       ws.is_turn[chain] = is_turn;
     }
   }
+  if constexpr (RES) {  // write the trajectory back once
+    R::store(q, (mov_right ? ws.right_q : ws.left_q) + roff, P.D, lane);
+    R::store(p, (mov_right ? ws.right_p : ws.left_p) + roff, P.D, lane);
+    R::store(g, (mov_right ? ws.right_g : ws.left_g) + roff, P.D, lane);
+    R::store(fq, (mov_right ? ws.left_q : ws.right_q) + roff, P.D, lane);
+    R::store(fp, (mov_right ? ws.left_p : ws.right_p) + roff, P.D, lane);
+    R::store(fg, (mov_right ? ws.left_g : ws.right_g) + roff, P.D, lane);
+    R::store(tsum, ws.psum + roff, P.D, lane);
+  }
   if (lane == 0) {
+    if (RES) {
+      ws.right_logp[chain] = mov_right ? logp_mov : logp_fix;
+      ws.left_logp[chain] = mov_right ? logp_fix : logp_mov;
+    }
     ws.prop_weight[chain] = prop_weight;
     ws.prop_slpa[chain] = prop_slpa;
     ws.n_states[chain] = n_states;
