@@ -392,10 +392,11 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
   float* ck_p;
   float* ck_s;
   if (ckpt_smem) {
+    // a sub-tree of 2^d leaves touches checkpoint rows 0..d-1, so this launch needs d_end rows per warp
     float* base = bjx_smem + (size_t)((DM || TK == TK_DENSE) ? kWarpsPerBlock * P.D : 0) +
-                  (size_t)wib * 2 * ws.max_depth * P.D;
+                  (size_t)wib * 2 * d_end * P.D;
     ck_p = base;
-    ck_s = base + (size_t)ws.max_depth * P.D;
+    ck_s = base + (size_t)d_end * P.D;
   } else {
     ck_p = ws.ckpt_p + (size_t)chain * ws.max_depth * P.D;
     ck_s = ws.ckpt_sum + (size_t)chain * ws.max_depth * P.D;
@@ -458,6 +459,9 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     int n = 0;
     const int n_leaves = 1 << d;
     for (int i = 0; i < n_leaves; ++i) {
+      // the multinomial draw of this leaf (trajectory.py:321 fold_in(rng_key, i)) is pure integer work with no
+      // dependence on the dynamics: issued first so its two threefry chains overlap the leapfrog's FP latency
+      const float u_leaf = uniform01(fold_in(tk, (uint32_t)i));
       c.template step<GEN, true>(P, q, p, g, logp, eps);
       const float e_new = -logp + c.kinetic(P, p);
       const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
 #pragma unroll
         for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
         const float p_accept = expit_f(w_new - sub_weight);
-        take = uniform01(fold_in(tk, (uint32_t)i)) < p_accept;
+        take = u_leaf < p_accept;
         sub_weight = logaddexp_f(sub_weight, w_new);
         sub_slpa = logaddexp_f(sub_slpa, slpa_new);
       }

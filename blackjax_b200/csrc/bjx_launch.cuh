@@ -58,7 +58,7 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
   const int n_rows = (kernel_id == K_NUTS_DOUBLING) ? a.n_in : a.P.C;
   const dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
   size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
-  if (kernel_id == K_NUTS_DOUBLING && a.ckpt_smem) smem += sizeof(float) * kWarpsPerBlock * 2 * a.ws.max_depth * a.P.D;
+  if (kernel_id == K_NUTS_DOUBLING && a.ckpt_smem) smem += sizeof(float) * kWarpsPerBlock * 2 * a.depth_end * a.P.D;
   cudaStream_t st = a.stream;
   switch (kernel_id) {
     case K_INIT:
