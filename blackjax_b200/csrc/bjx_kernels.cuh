@@ -197,13 +197,17 @@ __global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const ui
   float logp = logp0, prop_logp = logp0, prop_energy = h0;
   float weight = 0.f, slpa = -__int_as_float(0x7f800000);
   bool any_div = false;
+  float u_batch = 0.f;
   for (int i = 0; i < L; ++i) {
+    // step key fold_in(rng_key, i) (trajectory.py:216): lane l draws the uniform of step i+l, one pass per 32 steps
+    if ((i & 31) == 0) u_batch = uniform01(fold_in(key_integrator, (uint32_t)(i + lane)));
+    const float u_step = __shfl_sync(0xffffffffu, u_batch, i & 31);
     c.template step<GEN, true>(P, q, p, g, logp, eps);
     const float e_new = -logp + c.kinetic(P, p);
     const float w_new = safe_energy_diff(h0, e_new);          // proposal.py:94-98
     any_div = any_div || ((-w_new) > P.div_thr);              // trajectory.py:220-221
     const float p_accept = expit_f(w_new - weight);           // proposal.py:122
-    const bool take = uniform01(fold_in(key_integrator, (uint32_t)i)) < p_accept;  // trajectory.py:216
+    const bool take = u_step < p_accept;
     if (take) {
       R::store(q, q_out + roff, P.D, lane);
       R::store(g, g_out + roff, P.D, lane);
@@ -211,8 +215,9 @@ __global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const ui
       prop_logp = logp;
       prop_energy = e_new;
     }
-    weight = logaddexp_f(weight, w_new);
-    slpa = logaddexp_f(slpa, fminf(w_new, 0.f));
+    const float la = logaddexp_f(lane == 0 ? weight : slpa, lane == 0 ? w_new : fminf(w_new, 0.f));
+    weight = __shfl_sync(0xffffffffu, la, 0);
+    slpa = __shfl_sync(0xffffffffu, la, 1);
   }
   if (info.proposal_position && info.proposal_position != q_out) {  // HMCInfo.proposal = the selected state
     R::load(q, q_out + roff, P.D, lane);
@@ -458,10 +463,12 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     bool sub_div = false, sub_term = false;
     int n = 0;
     const int n_leaves = 1 << d;
+    float u_batch = 0.f;
     for (int i = 0; i < n_leaves; ++i) {
-      // the multinomial draw of this leaf (trajectory.py:321 fold_in(rng_key, i)) is pure integer work with no
-      // dependence on the dynamics: issued first so its two threefry chains overlap the leapfrog's FP latency
-      const float u_leaf = uniform01(fold_in(tk, (uint32_t)i));
+      // The multinomial draw of leaf i is uniform(fold_in(rng_key, i)) (trajectory.py:321): two threefry blocks of
+      // warp-uniform integer work.  Lane l evaluates the draw of leaf i+l instead, so one pass serves 32 leaves.
+      if ((i & 31) == 0) u_batch = uniform01(fold_in(tk, (uint32_t)(i + lane)));
+      const float u_leaf = __shfl_sync(0xffffffffu, u_batch, i & 31);
       c.template step<GEN, true>(P, q, p, g, logp, eps);
       const float e_new = -logp + c.kinetic(P, p);
       const float w_new = safe_energy_diff(h0, e_new);  // proposal.py:94-98
@@ -479,8 +486,10 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
         for (int s = 0; s < R::NS; ++s) ps[s] = ps[s] + p[s];
         const float p_accept = expit_f(w_new - sub_weight);
         take = u_leaf < p_accept;
-        sub_weight = logaddexp_f(sub_weight, w_new);
-        sub_slpa = logaddexp_f(sub_slpa, slpa_new);
+        // the two logaddexp updates (proposal.py:124-127) in one SIMD evaluation: lane 0 weight, other lanes slpa
+        const float la = logaddexp_f(lane == 0 ? sub_weight : sub_slpa, lane == 0 ? w_new : slpa_new);
+        sub_weight = __shfl_sync(0xffffffffu, la, 0);
+        sub_slpa = __shfl_sync(0xffffffffu, la, 1);
       }
       if (take) {
         R::store(q, ws.sub_prop_q + roff, P.D, lane);
