@@ -239,12 +239,14 @@ def main():
     else:
         tgt, imm = diag_tgt, diag_imm
         q0 = torch.randn(C, D, device=dev, generator=gen) * torch.from_numpy(s.astype(np.float32)).to(dev)
-    kernel = bj.hmc.build_kernel(inplace=True)
+    # one step key per transition; chain c of this rank uses split(step_key, C_global)[rank*C + c], derived inside the
+    # transition kernel (bjx_set_key_mode), so results do not depend on the GPU count
+    kernel = bj.hmc.build_kernel(inplace=True, chain_offset=rank * C)
     state = bj.hmc.init(q0.clone(), tgt)
     step_keys = bj.random.split(bj.random.key(0, dev), W + K + 1)
 
-    def chain_keys(t):  # split(step_key, C_global)[rank shard]  -- one launch of k_prng_split
-        return bj.random.split(step_keys[t], C * world)[rank * C:(rank + 1) * C]
+    def chain_keys(t):
+        return step_keys[t]
 
     def barrier():
         if dist is not None:
@@ -264,9 +266,9 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # our kernels per step: k_prng_split + (diag) k_hmc_transition | (dense) normal draw, 2L+3 x (operand split + GEMM),
+    # our kernels per step: (diag) k_hmc_transition | (dense) normal draw, 2L+3 x (operand split + GEMM),
     # first half kick, L grad_kick, 2 energy, accept
-    launches = K * (2 if not dense else 1 + 1 + 2 * (2 * L + 3) + 1 + L + 2 + 1)
+    launches = K * (1 if not dense else 1 + 2 * (2 * L + 3) + 1 + L + 2 + 1)
     acc_mean = float(info.acceptance_rate.mean())
     clocks = sampler.stop() if rank == 0 else None
 
@@ -274,7 +276,7 @@ def main():
     eng = _engine.get_engine(state.position, tgt)
     ms_gemm = 0.0
     if dense:  # the dominant kernel of the dense workload: v = M^-1 p for all chains = one [C,D]x[D,D] tensor-core GEMM
-        pv = eng.sample_momentum(chain_keys(W + K))
+        pv = eng.sample_momentum(chain_keys(W + K), chain_offset=rank * C)
         for _ in range(3):
             vv = eng.velocity(pv)
         torch.cuda.synchronize()
@@ -291,7 +293,7 @@ def main():
     qd = torch.randn(C, D, device=dev, generator=gen)
     deng = _engine.Engine(dev, C, D, diag_tgt)
     deng.set_metric(diag_imm)
-    p = deng.sample_momentum(chain_keys(W + K))
+    p = deng.sample_momentum(chain_keys(W + K), chain_offset=rank * C)
     lp1, g1 = deng.init_state(qd)
     q1 = qd
     for _ in range(3):
@@ -312,11 +314,11 @@ def main():
     q_host.copy_(state.position)
     out_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
     acc_host = torch.empty(C, dtype=torch.float32).pin_memory()
-    key_host = torch.empty(C, 2, dtype=torch.int32).pin_memory()
+    key_host = torch.empty(2, dtype=torch.int32).pin_memory()
     key_host.copy_(chain_keys(0).view(torch.int32))
     q_dev = torch.empty(C, D, device=dev)
-    k_dev = torch.empty(C, 2, dtype=torch.int32, device=dev)
-    kernel_e2e = bj.hmc.build_kernel(inplace=True)
+    k_dev = torch.empty(2, dtype=torch.int32, device=dev)
+    kernel_e2e = bj.hmc.build_kernel(inplace=True, chain_offset=rank * C)
     K_e2e = max(1, min(K, 10))
 
     def e2e_step():
@@ -390,7 +392,7 @@ def main():
                        "l2": "inputs larger than L2 (q,g = 2 x %.0f MB per GPU)" % (C * D * 4 / 1e6),
                        "mean_acceptance": acc_mean},
             "roofline": roofline, **extra,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + C * 8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + 8,
                     "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": K_e2e, "ms_per_step": ms_e2e / K_e2e},
             "gpu_launches": launches,
             "clocks": clocks,

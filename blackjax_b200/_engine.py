@@ -23,14 +23,14 @@ def _f32(t, shape=None, name="array"):
 
 
 def as_keys(keys, n, device):
-    """uint32 [n,2] raw threefry keys on ``device`` (accepts uint32/int32 tensors)."""
+    """uint32 [n,2] per-chain keys, or ONE key uint32 [2] (per-chain keys are then derived in-kernel), on ``device``."""
     if not isinstance(keys, torch.Tensor):
         raise TypeError("rng_key must be a torch tensor of raw uint32 key data")
     if keys.dtype not in (torch.uint32, torch.int32):
         raise TypeError(f"rng_key must be uint32 (or int32 bit patterns), got {keys.dtype}")
     keys = keys.to(device).contiguous()
-    if tuple(keys.shape) != (n, 2):
-        raise ValueError(f"rng_key has shape {tuple(keys.shape)}, expected ({n}, 2)")
+    if tuple(keys.shape) not in ((n, 2), (2,)):
+        raise ValueError(f"rng_key has shape {tuple(keys.shape)}, expected ({n}, 2) or (2,)")
     return keys
 
 
@@ -90,6 +90,13 @@ class Engine:
         check(lib().bjx_set_metric(self.h, kind, ptr(imm)), self.h)
         return imm
 
+    def _key_mode(self, keys, chain_offset=0):
+        """Select per-chain keys [C,2] or a shared step key [2] (+ global chain offset) for the next transition."""
+        mode = (1 if keys.ndim == 1 else 0, int(chain_offset))
+        if getattr(self, "_keymode", (0, 0)) != mode:
+            check(lib().bjx_set_key_mode(self.h, mode[0], mode[1]), self.h)
+            self._keymode = mode
+
     def set_integrator(self, coefficients):
         """integrators.py:62-152 coefficient table (tuple of floats); cached per engine."""
         coef = tuple(float(c) for c in coefficients)
@@ -111,8 +118,9 @@ class Engine:
         check(lib().bjx_init_state(self.h, ptr(q), ptr(logp), ptr(g)), self.h)
         return logp, g
 
-    def sample_momentum(self, keys):
+    def sample_momentum(self, keys, chain_offset=0):
         keys = as_keys(keys, self.C, self.device)
+        self._key_mode(keys, chain_offset)
         p = torch.empty(self.C, self.D, dtype=torch.float32, device=self.device)
         check(lib().bjx_sample_momentum(self.h, ptr(keys), ptr(p)), self.h)
         return p
@@ -154,8 +162,9 @@ class Engine:
 
     # -- transitions -----------------------------------------------------------------------------------
     def hmc_step(self, keys, q, logp, g, step_size, num_integration_steps, out=None, info_fields=None,
-                 multinomial=False):
+                 multinomial=False, chain_offset=0):
         keys = as_keys(keys, self.C, self.device)
+        self._key_mode(keys, chain_offset)
         q = _f32(q, (self.C, self.D), "position")
         g = _f32(g, (self.C, self.D), "logdensity_grad")
         logp = _f32(logp, (self.C,), "logdensity")
@@ -168,7 +177,7 @@ class Engine:
         return qo, lo, go
 
     def nuts_step(self, keys, q, logp, g, step_size, max_num_doublings, out=None, info_fields=None,
-                  momentum=None, key_integrator=None):
+                  momentum=None, key_integrator=None, chain_offset=0):
         if max_num_doublings > self.max_tree_depth:
             raise ValueError("max_num_doublings exceeds the engine's max_tree_depth")
         q = _f32(q, (self.C, self.D), "position")
@@ -180,6 +189,7 @@ class Engine:
             keys = None
         else:
             keys = as_keys(keys, self.C, self.device)
+            self._key_mode(keys, chain_offset)
         qo, lo, go = out if out is not None else (torch.empty_like(q), torch.empty_like(logp), torch.empty_like(g))
         eps, eps_dev = self._eps(step_size)
         info = self._info(info_fields or {})

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "bjx_last_error": (C.c_char_p, [C.c_void_p]),
     "bjx_set_target": (C.c_int, [C.c_void_p, C.POINTER(TargetDesc)]),
     "bjx_set_integrator": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
+    "bjx_set_key_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
     "bjx_synchronize": (C.c_int, [C.c_void_p]),
     "bjx_set_metric": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
     "bjx_get_mass_matrix_sqrt": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

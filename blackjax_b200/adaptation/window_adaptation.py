@@ -131,8 +131,6 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
     if dense and not shared:
         raise NotImplementedError("dense (welford_dense) adaptation is built for the chain-pooled mode: pass shared=True "
                                   "(a per-chain dense metric would need [C, D, D] mass matrices in the kernels)")
-    mcmc_kernel = algorithm.build_kernel()
-
     def run(rng_key, position, num_steps: int = 1000):
         from .._engine import get_engine
         position = position.contiguous()
@@ -142,12 +140,14 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
         eng = get_engine(position, logdensity_fn, max_tree_depth=extra_parameters.get("max_num_doublings", 10))
         schedule = build_schedule(num_steps)
         history = []
+        import torch.distributed as dist
+        world, rank = 1, 0
+        if shared and dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        # shared mode: one step key per warm-up step; chain c of this rank uses split(step_key, C_global)[rank*C + c]
+        # (staged_adaptation.py:920), derived inside the transition kernel
+        mcmc_kernel = algorithm.build_kernel(chain_offset=rank * C)
         if shared:
-            # keys: split(rng_key, num_steps); per step split(step_key, C_global) and take this rank's slice
-            import torch.distributed as dist
-            world, rank = 1, 0
-            if dist.is_available() and dist.is_initialized():
-                world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
             step_keys = bjx_random.split(rng_key.to(dev), num_steps)
             da = _da_init(initial_step_size)
             eps = _f32(initial_step_size)
@@ -159,8 +159,7 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
             stats = torch.empty(2 + D + (D * D if dense else D), dtype=torch.float32, device=dev)
             pooled = lib().bjx_pooled_stats_dense if dense else lib().bjx_pooled_stats
             for t, (stage, window_end) in enumerate(schedule):
-                ck = bjx_random.split(step_keys[t], C * world)[rank * C:(rank + 1) * C]
-                state, info = mcmc_kernel(ck, state, logdensity_fn, eps, imm, **extra_parameters)
+                state, info = mcmc_kernel(step_keys[t], state, logdensity_fn, eps, imm, **extra_parameters)
                 check(pooled(eng.h, ptr(state.position), ptr(info.acceptance_rate), ptr(stats)), eng.h)
                 blocks = _allgather_stats(stats, process_group)
                 acc_sum, n_b, mean_b, m2_b = cgl_merge_blocks(blocks, D)

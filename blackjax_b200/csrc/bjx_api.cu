@@ -134,6 +134,8 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->ncoef = 3;
   h->coef[0] = 0.5f; h->coef[1] = 1.0f; h->coef[2] = 0.5f;
   h->general_integrator = false;
+  h->key_shared = 0;
+  h->chain_offset = 0;
   int rc = validate_target(h, cfg->target, cfg->dim);
   if (rc) {
     g_err = h->err;
@@ -180,6 +182,15 @@ extern "C" int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int
   h->ncoef = n;
   for (int i = 0; i < n; ++i) h->coef[i] = coefficients[i];
   h->general_integrator = !(n == 3 && coefficients[0] == 0.5f && coefficients[1] == 1.0f);
+  return 0;
+}
+
+// Key source of the transition kernels: 0 = `keys` holds one key per chain [C,2]; 1 = `keys` holds ONE step key [2] and
+// chain c uses split(step_key, n_global)[chain_offset + c] (util.py:203 / staged_adaptation.py:920 step-major schedule).
+extern "C" int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_t chain_offset) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  h->key_shared = shared_step_key ? 1 : 0;
+  h->chain_offset = chain_offset;
   return 0;
 }
 
@@ -269,6 +280,8 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.eps = eps;
   P.eps_dev = eps_dev;
   P.div_thr = h->cfg.divergence_threshold;
+  P.key_shared = h->key_shared;
+  P.chain_offset = h->chain_offset;
   P.ncoef = h->ncoef;
   for (int i = 0; i < 11; ++i) P.coef[i] = i < h->ncoef ? h->coef[i] : 0.f;
   return P;

@@ -34,6 +34,8 @@ struct BigParams {
   float eps;
   const float* eps_dev;
   float div_thr;
+  int key_shared;
+  uint32_t chain_offset;
 };
 
 // block-wide sum of up to NV values per thread (result valid in all threads)
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_init(BigParams P, const flo
 __global__ void __launch_bounds__(kBigThreads) k_big_momentum(BigParams P, const uint32_t* __restrict__ keys,
                                                               float* __restrict__ p_out) {
   const int c = blockIdx.x;
-  const Key k{keys[2 * c], keys[2 * c + 1]};
+  const Key k = P.key_shared ? fold_in(Key{keys[0], keys[1]}, P.chain_offset + (uint32_t)c) : Key{keys[2 * c], keys[2 * c + 1]};
   const float* ms = P.msqrt + (size_t)c * P.imm_stride;
   for (int i = threadIdx.x; i < P.D; i += kBigThreads) p_out[(size_t)c * P.D + i] = __ldg(ms + i) * normal_at(k, (uint32_t)i);
 }
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_hmc(BigParams P, const uint
   const size_t ro = (size_t)c * P.D;
   big_load(q, q_in + ro, P.D);
   big_load(g, g_in + ro, P.D);
-  const Key rng{keys[2 * c], keys[2 * c + 1]};
+  const Key rng = P.key_shared ? fold_in(Key{keys[0], keys[1]}, P.chain_offset + (uint32_t)c) : Key{keys[2 * c], keys[2 * c + 1]};
   const Key km = fold_in(rng, 0u), ki = fold_in(rng, 1u);  // hmc.py:299
   const float* imm = P.imm + (size_t)c * P.imm_stride;
   const float* ms = P.msqrt + (size_t)c * P.imm_stride;
@@ -295,6 +297,8 @@ static BigParams big_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.eps = eps;
   P.eps_dev = eps_dev;
   P.div_thr = h->cfg.divergence_threshold;
+  P.key_shared = h->key_shared;
+  P.chain_offset = h->chain_offset;
   return P;
 }
 

@@ -63,14 +63,15 @@ __global__ void k_rows_split3(long long R, int K, const float* __restrict__ x, u
 }
 
 // z[c, i] = normal(key_c, (D,))[i] with key_c = split(rng_key_c, 2)[0] when split_first (hmc.py:299,302 -> util.py:89-91)
-__global__ void k_dense_normal(int C, int D, const uint32_t* __restrict__ keys, float* __restrict__ z, bool split_first) {
+__global__ void k_dense_normal(int C, int D, const uint32_t* __restrict__ keys, float* __restrict__ z, bool split_first,
+                               int key_shared, uint32_t chain_offset) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n4 = (long long)C * D / 4;
   if (t >= n4) return;
   const long long e = t * 4;
   const int c = (int)(e / D);
   const uint32_t i = (uint32_t)(e % D);
-  Key km{keys[2 * c], keys[2 * c + 1]};
+  Key km = key_shared ? fold_in(Key{keys[0], keys[1]}, chain_offset + (uint32_t)c) : Key{keys[2 * c], keys[2 * c + 1]};
   if (split_first) km = fold_in(km, 0u);
   float4 o;
   o.x = normal_at(km, i);
@@ -176,10 +177,11 @@ __global__ void k_rows_accept(int C, int D, const uint32_t* __restrict__ keys, c
                               const float* __restrict__ e1, float div_thr, const float* __restrict__ qw,
                               const float* __restrict__ gw, const float* __restrict__ lw, const float* q_in,
                               const float* g_in, const float* l_in, float* q_out, float* g_out, float* l_out, int L,
-                              InfoPtrs info) {
+                              InfoPtrs info, int key_shared, uint32_t chain_offset) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (c >= C) return;
-  const Key ki = fold_in(Key{keys[2 * c], keys[2 * c + 1]}, 1u);
+  const Key rk = key_shared ? fold_in(Key{keys[0], keys[1]}, chain_offset + (uint32_t)c) : Key{keys[2 * c], keys[2 * c + 1]};
+  const Key ki = fold_in(rk, 1u);
   float delta = e0[c] - e1[c];
   if (isnan(delta)) delta = -__int_as_float(0x7f800000);
   const bool is_div = (-delta) > div_thr;
@@ -330,7 +332,8 @@ int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out
   if (rc) return rc;
   const int C = h->cfg.n_chains, D = h->cfg.dim;
   float* z = (h->metric_kind == BJX_METRIC_DENSE) ? w.v : p_out;
-  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z, split_first);
+  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z, split_first, h->key_shared,
+                                                                    h->chain_offset);
   DN_LAUNCH("k_dense_normal");
   if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, z, MAT_MSQRT, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
   const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
@@ -416,7 +419,8 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
     DN_LAUNCH("k_rows_axpy");
   }
   k_rows_accept<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, keys, w.e0, w.e1, h->cfg.divergence_threshold, w.q, w.g,
-                                                          w.lw, q_in, g_in, logp_in, q_out, g_out, logp_out, L, info);
+                                                          w.lw, q_in, g_in, logp_in, q_out, g_out, logp_out, L, info, h->key_shared,
+                                                          h->chain_offset);
   DN_LAUNCH("k_rows_accept");
   return 0;
 }

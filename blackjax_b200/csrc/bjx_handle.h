@@ -33,6 +33,8 @@ struct bjx_handle_s {
   int ncoef;            // integrator coefficient table (integrators.py:321-369); {0.5, 1, 0.5} = velocity Verlet
   float coef[11];
   bool general_integrator;
+  int key_shared;          // see bjx_set_key_mode
+  uint32_t chain_offset;
   std::string err;
 };
 

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kThreads) k_sample_momentum(Params P, const ui
   Ctx<R, TK_FUNNEL, DM> c;  // target-independent
   c.init(P, chain, lane, sm);
   float p[R::NS];
-  Key k{keys[2 * chain], keys[2 * chain + 1]};
+  const Key k = chain_key(P, keys, chain);
   c.sample_momentum(P, chain, k, p);
   R::store(p, p_out + roff, P.D, lane);
 }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   R::load(q, q_in + roff, P.D, lane);
   R::load(g, g_in + roff, P.D, lane);
   c.init(P, chain, lane, sm);
-  const Key rng{keys[2 * chain], keys[2 * chain + 1]};
+  const Key rng = chain_key(P, keys, chain);
   const Key key_momentum = fold_in(rng, 0u);    // jax.random.split(rng_key, 2)  hmc.py:299
   const Key key_integrator = fold_in(rng, 1u);
   c.sample_momentum(P, chain, key_momentum, p);  // hmc.py:302
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const ui
   R::load(q, q_in + roff, P.D, lane);
   R::load(g, g_in + roff, P.D, lane);
   c.init(P, chain, lane, sm);
-  const Key rng{keys[2 * chain], keys[2 * chain + 1]};
+  const Key rng = chain_key(P, keys, chain);
   const Key key_integrator = fold_in(rng, 1u);   // hmc.py:299
   c.sample_momentum(P, chain, fold_in(rng, 0u), p);
   if (info.momentum) R::store(p, info.momentum + roff, P.D, lane);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, con
     key_integrator = Key{keyint_override[2 * chain], keyint_override[2 * chain + 1]};
     R::load(p, mom_override + roff, P.D, lane);
   } else {
-    const Key rng{keys[2 * chain], keys[2 * chain + 1]};
+    const Key rng = chain_key(P, keys, chain);
     key_integrator = fold_in(rng, 1u);
     c.sample_momentum(P, chain, fold_in(rng, 0u), p);
   }

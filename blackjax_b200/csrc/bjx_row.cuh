@@ -39,6 +39,12 @@ struct Params {
   float eps;
   const float* eps_dev;    // [C] or nullptr
   float div_thr;
+  // PRNG key source: per-chain keys [C,2] (key_shared == 0) or ONE step key [2] from which chain c derives
+  // split(step_key, n_global)[chain_offset + c] = fold_in(step_key, chain_offset + c) in-kernel (key_shared == 1):
+  // the reference's step-major schedule (howto_sample_multiple_chains.md:116-129) without a separate split launch,
+  // and invariant to how the chains are sharded over GPUs.
+  int key_shared;
+  uint32_t chain_offset;
   // palindromic two-stage integrator coefficients (integrators.py:62-152); velocity Verlet = {0.5, 1, 0.5}
   int ncoef;
   float coef[11];
@@ -426,6 +432,11 @@ struct Ctx {
     return (dl <= 0.f) || (dr <= 0.f);
   }
 };
+
+__device__ __forceinline__ Key chain_key(const Params& P, const uint32_t* __restrict__ keys, int chain) {
+  if (P.key_shared) return fold_in(Key{keys[0], keys[1]}, P.chain_offset + (uint32_t)chain);
+  return Key{keys[2 * chain], keys[2 * chain + 1]};
+}
 
 __device__ __forceinline__ float safe_energy_diff(float e0, float e1) {  // proposal.py:45-48
   const float d = e0 - e1;

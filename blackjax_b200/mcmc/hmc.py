@@ -65,15 +65,16 @@ def init(position, logdensity_fn):
 
 
 def per_chain_keys(rng_key, n_chains, device):
-    if rng_key.ndim == 1:
-        return bjx_random.split(rng_key.to(device), n_chains)
+    """A single key [2] is passed through: chain c then uses split(rng_key, n_global)[chain_offset + c], derived inside
+    the transition kernel (bjx_set_key_mode) -- same bits as an explicit ``split`` + per-chain keys."""
     return rng_key
 
 
 def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000, build_proposal=None,
-                 full_info: bool = False, inplace: bool = False):
+                 full_info: bool = False, inplace: bool = False, chain_offset: int = 0):
     """blackjax/mcmc/hmc.py:251-314.  ``inplace=True`` overwrites the input state's tensors (no
-    allocation; the returned state aliases the input)."""
+    allocation; the returned state aliases the input).  ``chain_offset``: global index of this process's first chain
+    when one shared ``rng_key`` is split across GPUs."""
     coefficients = integrators.as_coefficients(integrator)
     if build_proposal not in (None, hmc_proposal, multinomial_hmc_proposal):
         raise NotImplementedError("build_proposal must be hmc.hmc_proposal or hmc.multinomial_hmc_proposal "
@@ -98,7 +99,7 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000,
                           proposal_momentum=torch.empty_like(q))
         out = (q, logp, g) if inplace else None
         qo, lo, go = eng.hmc_step(keys, q, logp, g, step_size, num_integration_steps, out=out, info_fields=fields,
-                                  multinomial=multinomial)
+                                  multinomial=multinomial, chain_offset=chain_offset)
         proposal = None
         if full_info:
             proposal = IntegratorState(fields["proposal_position"], fields["proposal_momentum"], None, None)

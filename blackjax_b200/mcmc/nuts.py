@@ -31,7 +31,7 @@ class NUTSInfo(NamedTuple):
 
 
 def build_kernel(integrator=velocity_verlet, divergence_threshold: int = 1000, full_info: bool = False,
-                 inplace: bool = False, max_tree_depth: int = 10):
+                 inplace: bool = False, max_tree_depth: int = 10, chain_offset: int = 0):
     """blackjax/mcmc/nuts.py:77-147.  ``max_tree_depth`` sizes the checkpoint workspace (upper bound for
     ``max_num_doublings``)."""
     coefficients = integrators.as_coefficients(integrator)
@@ -58,7 +58,7 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: int = 1000, f
                 fields[k] = torch.empty_like(q)
         out = (q, logp, g) if inplace else None
         qo, lo, go = eng.nuts_step(keys, q, logp, g, step_size, max_num_doublings, out=out, info_fields=fields,
-                                   momentum=_momentum, key_integrator=_key_integrator)
+                                   momentum=_momentum, key_integrator=_key_integrator, chain_offset=chain_offset)
         left = right = None
         if full_info:
             left = IntegratorState(fields["left_position"], fields["left_momentum"], None, None)

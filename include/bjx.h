@@ -105,6 +105,12 @@ int bjx_set_target(bjx_handle_t h, const bjx_target_desc* target);
 /* Palindromic two-stage integrator (integrators.py:62-152): host array of n coefficients, n odd in 3..11.
  * {0.5, 1, 0.5} = velocity_verlet (default, :321-322); mclachlan :335-340, yoshida :351-357, omelyan :363-369. */
 int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int32_t n);
+/* Key source for bjx_sample_momentum / bjx_hmc_step / bjx_mhmc_step / bjx_nuts_step: shared_step_key = 0 (default):
+ * `keys` is uint32 [n_chains, 2], one rng_key per chain.  shared_step_key = 1: `keys` is ONE key uint32 [2] and
+ * chain c uses jax.random.split(key, n_global)[chain_offset + c] (= fold_in(key, chain_offset + c)), derived inside the
+ * kernel -- the reference's step-major schedule (docs/examples/howto_sample_multiple_chains.md:116-129), independent
+ * of how the chains are sharded over GPUs (chain_offset = first global chain of this handle). */
+int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_t chain_offset);
 int bjx_synchronize(bjx_handle_t h);
 
 /* metrics.default_metric / gaussian_euclidean (metrics.py:180-218,221-346): precomputes

@@ -249,6 +249,24 @@ def test_hmc_transition_matches_oracle(kind, D, C, L, eps, imm_kind, pce):
     run_hmc_case(kind, D, C, L, eps, imm_kind, pce)
 
 
+@pytest.mark.parametrize("algo", ["hmc", "nuts", "mhmc"])
+def test_shared_step_key_equals_explicit_split(algo):
+    # a single key [2] == jax.random.split(key, C_global) per-chain keys; chain_offset selects this process's shard
+    tgt = T.Funnel(32)
+    C, Cg, off = 96, 256, 100
+    q = 0.1 * torch.randn(C, 32, device=DEV)
+    imm = torch.ones(32, device=DEV)
+    key = bj.random.key(31, DEV)
+    explicit = bj.random.split(key, Cg)[off:off + C]
+    mod = {"hmc": bj.hmc, "nuts": bj.nuts, "mhmc": bj.mhmc}[algo]
+    args = (0.1, imm) if algo == "nuts" else (0.1, imm, 7)
+    a, ia = mod.build_kernel()(explicit, mod.init(q.clone(), tgt), tgt, *args)
+    b, ib = mod.build_kernel(chain_offset=off)(key, mod.init(q.clone(), tgt), tgt, *args)
+    assert torch.equal(a.position, b.position) and torch.equal(ia.acceptance_rate, ib.acceptance_rate)
+    c, _ = mod.build_kernel(chain_offset=0)(key, mod.init(q.clone(), tgt), tgt, *args)
+    assert not torch.equal(a.position, c.position)
+
+
 def test_hmc_inplace_and_out_of_place_agree():
     tgt = T.StdNormal(64)
     q = torch.randn(128, 64, device=DEV)
