@@ -136,6 +136,8 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->general_integrator = false;
   h->key_shared = 0;
   h->chain_offset = 0;
+  h->sample_keys = nullptr;
+  h->sample_keys_cap = 0;
   int rc = validate_target(h, cfg->target, cfg->dim);
   if (rc) {
     g_err = h->err;
@@ -159,6 +161,7 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->ws_block) cudaFree(h->ws_block);
   if (h->dense_block) cudaFree(h->dense_block);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
+  if (h->sample_keys) cudaFree(h->sample_keys);
   if (h->h_flag) cudaFreeHost(h->h_flag);
   delete h;
   return 0;
@@ -477,6 +480,44 @@ extern "C" int bjx_mhmc_step(bjx_handle_t h, const uint32_t* keys, const float* 
   a.n = L;
   a.info = make_info(info);
   return dispatch(h, K_MHMC, true, a);
+}
+
+// run_inference_algorithm (blackjax/util.py:150-213) for HMC / multinomial HMC, natively: keys = split(rng_key,
+// num_steps) (util.py:203) on the device, then num_steps transitions enqueued back to back with NO host
+// synchronisation; per-chain keys come from the step key inside the kernel (bjx_set_key_mode's chain_offset is
+// honoured).  history (optional) receives the positions after every `thin`-th transition.
+extern "C" int bjx_hmc_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* logp, float* grad, float step_size,
+                              const float* step_size_dev, int32_t L, int32_t num_steps, int32_t multinomial,
+                              float* history, int32_t thin, float* acceptance_history) {
+  if (!h || !rng_key || num_steps < 0 || thin < 1) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  if (num_steps == 0) return 0;
+  if ((size_t)num_steps > h->sample_keys_cap) {
+    if (h->sample_keys) BJX_CUDA(cudaFree(h->sample_keys));
+    h->sample_keys = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->sample_keys, (size_t)num_steps * 2 * sizeof(uint32_t)));
+    h->sample_keys_cap = (size_t)num_steps;
+  }
+  launch_prng_split(rng_key, 1, num_steps, h->sample_keys, h->stream);
+  BJX_CHECK_LAUNCH("k_prng_split");
+  const int saved_mode = h->key_shared;
+  h->key_shared = 1;
+  const size_t row_bytes = (size_t)h->cfg.n_chains * h->cfg.dim * sizeof(float);
+  int rc = 0;
+  for (int t = 0; t < num_steps && rc == 0; ++t) {
+    bjx_info info{};
+    info.acceptance_rate = acceptance_history ? acceptance_history + (size_t)t * h->cfg.n_chains : nullptr;
+    const uint32_t* key_t = h->sample_keys + 2 * (size_t)t;
+    rc = multinomial ? bjx_mhmc_step(h, key_t, q, logp, grad, q, logp, grad, step_size, step_size_dev, L, &info)
+                     : bjx_hmc_step(h, key_t, q, logp, grad, q, logp, grad, step_size, step_size_dev, L, &info);
+    if (rc == 0 && history && ((t + 1) % thin) == 0) {
+      cudaError_t e = cudaMemcpyAsync(history + (size_t)((t + 1) / thin - 1) * h->cfg.n_chains * h->cfg.dim, q, row_bytes,
+                                      cudaMemcpyDeviceToDevice, h->stream);
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "cudaMemcpyAsync(history)");
+    }
+  }
+  h->key_shared = saved_mode;
+  return rc;
 }
 
 // ---- NUTS workspace -------------------------------------------------------------------------------------

@@ -35,6 +35,8 @@ struct bjx_handle_s {
   bool general_integrator;
   int key_shared;          // see bjx_set_key_mode
   uint32_t chain_offset;
+  uint32_t* sample_keys;   // [num_steps, 2] step keys of bjx_hmc_sample
+  size_t sample_keys_cap;
   std::string err;
 };
 

@@ -152,6 +152,14 @@ int bjx_mhmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   const float* grad_in, float* q_out, float* logp_out, float* grad_out,
                   float step_size, const float* step_size_dev, int32_t num_integration_steps,
                   const bjx_info* info);
+/* blackjax.util.run_inference_algorithm (util.py:150-213) for HMC (multinomial = 0) / multinomial HMC (1), run
+ * natively: step keys = jax.random.split(rng_key, num_steps) (util.py:203), num_steps in-place transitions enqueued back
+ * to back without host synchronisation; chain c of step t uses split(step_key_t, n_global)[chain_offset + c].
+ * rng_key: ONE key uint32 [2] (device).  history (optional): float32 [num_steps / thin, C, D], the positions after every
+ * thin-th transition; acceptance_history (optional): float32 [num_steps, C]. */
+int bjx_hmc_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* logp, float* grad, float step_size,
+                   const float* step_size_dev, int32_t num_integration_steps, int32_t num_steps, int32_t multinomial,
+                   float* history, int32_t thin, float* acceptance_history);
 /* nuts.build_kernel(...).kernel (nuts.py:113-145) with iterative_nuts_proposal (nuts.py:223-321).
  * Tree doubling is driven from the host: one launch per doubling over the chains still expanding; each
  * warp integrates its chain's whole sub-tree (up to 2^d leapfrog leaves) inside the launch.

@@ -267,6 +267,25 @@ def test_shared_step_key_equals_explicit_split(algo):
     assert not torch.equal(a.position, c.position)
 
 
+@pytest.mark.parametrize("multinomial", [False, True])
+def test_native_sampler_equals_python_loop(multinomial):
+    # bjx_hmc_sample == run_inference_algorithm's loop (util.py:200-211): same keys, same draws, history and all
+    tgt = T.DiagGaussian(np.logspace(-0.3, 0.3, 40))
+    C, T_ = 300, 12
+    imm = torch.ones(40, device=DEV)
+    st0 = bj.hmc.init(torch.randn(C, 40, device=DEV), tgt)
+    key = bj.random.key(77, DEV)
+    alg = (bj.mhmc if multinomial else bj.hmc)(tgt, 0.2, imm, 9)
+    st, hist = bj.run_inference_algorithm(key, alg, T_, initial_state=st0, transform=lambda s, i: (s.position, i.acceptance_rate))
+    fin, positions, acc = bj.sample_hmc_native(key, st0, tgt, 0.2, imm, 9, T_, multinomial=multinomial)
+    assert torch.equal(fin.position, st.position) and torch.equal(fin.logdensity_grad, st.logdensity_grad)
+    assert torch.equal(positions[-1], st.position) and torch.equal(positions[3], hist[3][0])
+    assert torch.equal(acc[5], hist[5][1])
+    fin2, pos2, _ = bj.sample_hmc_native(key, st0, tgt, 0.2, imm, 9, T_, multinomial=multinomial, thin=4)
+    assert pos2.shape[0] == 3 and torch.equal(pos2[0], positions[3]) and torch.equal(pos2[2], positions[11])
+    assert torch.equal(st0.position, st0.position.clone())      # input state untouched (native path works on a copy)
+
+
 def test_hmc_inplace_and_out_of_place_agree():
     tgt = T.StdNormal(64)
     q = torch.randn(128, 64, device=DEV)
