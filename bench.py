@@ -359,8 +359,14 @@ def main():
         bytes_1step = 24.0 * C * D
         achieved = bytes_1step / (ms_1step * 1e-3) / 1e9
         ms_step = ms_total / K
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        # (profiles/r01_ncu_diag_hmc.md, profiles/r01_ncu_gemm_dense.md); only meaningful at the captured shape
+        at_captured_shape = (C, D) == (65536, 1024)
+        traffic_leapfrog = (805.4e6 + 747.7e6) if at_captured_shape else None
+        traffic_gemm = (903.3e6 + 247.4e6) if at_captured_shape else None
         hbm_roofline = {"bound": "hbm", "kernel": "k_leapfrog (diag metric, 1 step/launch, 24*D B per chain)",
-                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic_leapfrog, "traffic_source": "ncu --set full, profiles/r01_ncu_diag_hmc.md",
                         "peak_source": peak_src, "avg_launch_ms": ms_1step, "launches_timed": n1}
         if dense:
             tpeak = float(peaks.get("bf16_tflops", 1590.0))
@@ -368,7 +374,9 @@ def main():
             roofline = {"bound": "tensor", "kernel": "v = M^-1 p for all chains: k_rows_split3 + tcgen05 bf16 GEMM [C,6D]x[6D,D] "
                         "(float32-accurate: 6 bf16 products per float32 product)", "achieved": tf_achieved, "peak": tpeak,
                         "unit": "TFLOP/s",
-                        "frac": tf_achieved / tpeak, "traffic": None,
+                        "frac": tf_achieved / tpeak, "traffic": traffic_gemm,
+                        "traffic_source": "ncu --set full of the GEMM kernel alone, profiles/r01_ncu_gemm_dense.md "
+                                          "(the split kernel adds 268 MB read + 805 MB written)",
                         "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
                                         else "fallback 1590 TFLOP/s"),
                         "avg_launch_ms": ms_gemm, "launches_timed": 20,
