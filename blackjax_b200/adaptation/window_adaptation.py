@@ -24,30 +24,33 @@ from .._lib import check, lib, ptr
 from ..base import AdaptationAlgorithm, AdaptationResults
 
 
-def build_schedule(num_steps, initial_buffer_size=75, final_buffer_size=50, first_window_size=25):
-    """blackjax/adaptation/staged_adaptation.py:315-405: list of (stage, is_middle_window_end)."""
-    schedule = []
+def slow_windows(num_steps, initial_buffer_size=75, final_buffer_size=50, first_window_size=25):
+    """Half-open [start, end) ranges of the slow (mass-matrix) windows of Stan's warm-up: windows double in size until
+    the next doubled window would not fit before the final fast buffer, and the last one absorbs the remainder
+    (same arithmetic as blackjax/adaptation/staged_adaptation.py:357-395)."""
     if num_steps < 20:
-        schedule += [(0, False)] * num_steps
-    else:
-        if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
-            initial_buffer_size = int(0.15 * num_steps)
-            final_buffer_size = int(0.1 * num_steps)
-            first_window_size = num_steps - initial_buffer_size - final_buffer_size
-        schedule += [(0, False)] * initial_buffer_size
-        final_buffer_start = num_steps - final_buffer_size
-        next_window_size = first_window_size
-        next_window_start = initial_buffer_size
-        while next_window_start < final_buffer_start:
-            current_start, current_size = next_window_start, next_window_size
-            if 3 * current_size <= final_buffer_start - current_start:
-                next_window_size = 2 * current_size
-            else:
-                current_size = final_buffer_start - current_start
-            next_window_start = current_start + current_size
-            schedule += [(1, False)] * (next_window_start - 1 - current_start)
-            schedule.append((1, True))
-        schedule += [(0, False)] * (num_steps - final_buffer_start)
+        return []
+    if initial_buffer_size + first_window_size + final_buffer_size > num_steps:
+        initial_buffer_size = int(0.15 * num_steps)
+        final_buffer_size = int(0.1 * num_steps)
+        first_window_size = num_steps - initial_buffer_size - final_buffer_size
+    stop = num_steps - final_buffer_size
+    windows, start, size = [], initial_buffer_size, first_window_size
+    while start < stop:
+        room = stop - start
+        end = start + size if 3 * size <= room else stop
+        windows.append((start, end))
+        start, size = end, 2 * size
+    return windows
+
+
+def build_schedule(num_steps, initial_buffer_size=75, final_buffer_size=50, first_window_size=25):
+    """Per-step (stage, is_middle_window_end) pairs, stage 0 = fast (step size only), 1 = slow (step size + mass
+    matrix); the last step of every slow window carries True (blackjax/adaptation/staged_adaptation.py:315-405)."""
+    schedule = [(0, False)] * num_steps
+    for start, end in slow_windows(num_steps, initial_buffer_size, final_buffer_size, first_window_size):
+        for t in range(start, end):
+            schedule[t] = (1, t == end - 1)
     return schedule
 
 
