@@ -409,10 +409,10 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
   float prop_weight = ws.prop_weight[chain], prop_slpa = ws.prop_slpa[chain];
   int n_states = ws.n_states[chain];
   bool run_next = true;
-  // Rows of up to 16 slots per lane: BOTH trajectory endpoints and the trajectory momentum sum stay in registers
+  // Rows of up to 8 slots per lane: BOTH trajectory endpoints and the trajectory momentum sum stay in registers
   // across the doublings of this launch (the "moving" endpoint is the one the current doubling extends, the "fixed"
   // one only contributes its momentum to the U-turn test); larger rows re-load the moving endpoint per doubling.
-  constexpr bool RES = (R::NS <= 16);
+  constexpr bool RES = (R::NS <= 8);
   constexpr int NF = RES ? R::NS : 1;
   float q[R::NS], p[R::NS], g[R::NS], ps[R::NS];
   float fq[NF], fp[NF], fg[NF], tsum[NF];
