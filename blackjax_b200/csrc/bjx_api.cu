@@ -131,6 +131,7 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   for (int m = 0; m < 3; ++m) { h->dense_mat_s[m] = nullptr; h->dense_mat_src[m] = nullptr; h->dense_mat_ver[m] = 0; }
   h->dense_version = 1;
   h->dense_bytes_built = 0;
+  h->dense_streams_ready = false;
   h->ncoef = 3;
   h->coef[0] = 0.5f; h->coef[1] = 1.0f; h->coef[2] = 0.5f;
   h->general_integrator = false;
@@ -162,6 +163,10 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->dense_block) cudaFree(h->dense_block);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->sample_keys) cudaFree(h->sample_keys);
+  if (h->dense_streams_ready) {
+    for (int k = 0; k < 2; ++k) { cudaStreamDestroy(h->dense_stream[k]); cudaEventDestroy(h->dense_join[k]); }
+    cudaEventDestroy(h->dense_fork);
+  }
   if (h->h_flag) cudaFreeHost(h->h_flag);
   delete h;
   return 0;

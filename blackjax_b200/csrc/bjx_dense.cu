@@ -228,6 +228,17 @@ struct DenseWs {
 };
 enum { MAT_IMM = 0, MAT_MSQRT = 1, MAT_PREC = 2 };
 
+// The chain batch is processed as kParts independent slices on separate streams: the GEMMs are tensor-bound and
+// the split / kick / energy row kernels are HBM-bound, so while one slice's GEMM occupies the MMA pipes the other
+// slice's row kernels stream through HBM (chains never interact, so the slices share nothing but the constant
+// matrices).  Slices fork from and join back into the handle's stream with events.
+constexpr int kParts = 2;
+struct Part {
+  int c0, n;          // chains [c0, c0 + n)
+  cudaStream_t st;
+  void* gws;          // CUTLASS workspace of this slice
+};
+
 static int dense_ws(bjx_handle_t h, DenseWs& w) {
   const size_t C = h->cfg.n_chains, D = h->cfg.dim;
   const size_t row = ((C * D * sizeof(float)) + 255) & ~(size_t)255, vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
@@ -240,12 +251,20 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
     DN_CUDA(cudaMalloc((void**)&h->dense_block, need));
     h->dense_bytes = need;
   }
-  const size_t gw = gemm_workspace_bytes((int)C, (int)D, (int)(6 * D));
-  if (gw > h->gemm_ws_bytes) {
+  const size_t gw = ((gemm_workspace_bytes((int)C, (int)D, (int)(6 * D)) + 255) & ~(size_t)255) + 256;
+  if (kParts * gw > h->gemm_ws_bytes) {
     if (h->gemm_ws) DN_CUDA(cudaFree(h->gemm_ws));
     h->gemm_ws = nullptr;
-    DN_CUDA(cudaMalloc(&h->gemm_ws, gw));
-    h->gemm_ws_bytes = gw;
+    DN_CUDA(cudaMalloc(&h->gemm_ws, kParts * gw));
+    h->gemm_ws_bytes = kParts * gw;
+  }
+  if (!h->dense_streams_ready) {
+    for (int k = 0; k < kParts; ++k) {
+      DN_CUDA(cudaStreamCreateWithFlags(&h->dense_stream[k], cudaStreamNonBlocking));
+      DN_CUDA(cudaEventCreateWithFlags(&h->dense_join[k], cudaEventDisableTiming));
+    }
+    DN_CUDA(cudaEventCreateWithFlags(&h->dense_fork, cudaEventDisableTiming));
+    h->dense_streams_ready = true;
   }
   char* b = (char*)h->dense_block;
   w.p = (float*)b; w.v = (float*)(b + row); w.q = (float*)(b + 2 * row); w.g = (float*)(b + 3 * row);
@@ -271,40 +290,72 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
   return 0;
 }
 
-// Y = alpha * X . A^T + beta * Cin with A one of the handle's constant matrices (float32-accurate, see bjx_gemm.cu)
-static int gemm(bjx_handle_t h, DenseWs& w, const float* X, int mat, float* Y, const float* Cin, float alpha, float beta) {
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
-  k_rows_split3<false><<<g4((long long)C * D / 4), 256, 0, h->stream>>>((long long)C, D, X, w.xs);
+// Run fn(part) for every slice: fork from the handle's stream, one stream per slice, join back.
+template <class F>
+static int for_parts(bjx_handle_t h, F fn) {
+  const int C = h->cfg.n_chains;
+  const int parts = (C >= 8192) ? kParts : 1;
+  const size_t gw = h->gemm_ws_bytes / kParts;
+  if (parts == 1) {
+    Part pt{0, C, h->stream, h->gemm_ws};
+    return fn(pt);
+  }
+  DN_CUDA(cudaEventRecord(h->dense_fork, h->stream));
+  int rc = 0;
+  for (int k = 0; k < parts; ++k) {
+    const int c0 = (int)((long long)C * k / parts) & ~7, c1 = (k + 1 == parts) ? C : ((int)((long long)C * (k + 1) / parts) & ~7);
+    Part pt{c0, c1 - c0, h->dense_stream[k], (char*)h->gemm_ws + k * gw};
+    DN_CUDA(cudaStreamWaitEvent(pt.st, h->dense_fork, 0));
+    if (rc == 0) rc = fn(pt);
+    DN_CUDA(cudaEventRecord(h->dense_join[k], pt.st));
+    DN_CUDA(cudaStreamWaitEvent(h->stream, h->dense_join[k], 0));
+  }
+  return rc;
+}
+
+// Y = alpha * X . A^T + beta * Cin for the slice, A one of the handle's constant matrices (float32-accurate, bjx_gemm.cu).
+// X, Y, Cin are FULL [C,D] arrays; the slice's rows are addressed here.
+static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int mat, float* Y, const float* Cin, float alpha,
+                float beta) {
+  const int D = h->cfg.dim;
+  const size_t ro = (size_t)pt.c0 * D;
+  uint16_t* xs = w.xs + (size_t)pt.c0 * 6 * D;
+  k_rows_split3<false><<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>((long long)pt.n, D, X + ro, xs);
   DN_LAUNCH("k_rows_split3");
-  const int rc = gemm_split(w.xs, h->dense_mat_s[mat], Y, Cin, alpha, beta, C, D, 6 * D, h->gemm_ws, h->stream);
+  const int rc = gemm_split(xs, h->dense_mat_s[mat], Y + ro, Cin ? Cin + ro : nullptr, alpha, beta, pt.n, D, 6 * D, pt.gws, pt.st);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
   DN_LAUNCH("gemm");
   return 0;
 }
 
 // v = M^-1 p
-static int dense_velocity(bjx_handle_t h, DenseWs& w, const float* p, float* v) {
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
-  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, p, MAT_IMM, v, nullptr, 1.f, 0.f);
-  const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
-  k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->imm, stride, p, v);
+static int dense_velocity(bjx_handle_t h, DenseWs& w, const Part& pt, const float* p, float* v) {
+  const int D = h->cfg.dim;
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, pt, p, MAT_IMM, v, nullptr, 1.f, 0.f);
+  const bool per_chain = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN);
+  const size_t ro = (size_t)pt.c0 * D;
+  k_rows_scale<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, h->imm + (per_chain ? ro : 0), per_chain ? D : 0,
+                                                              p + ro, v + ro);
   DN_LAUNCH("k_rows_scale");
   return 0;
 }
 
-// g, logp = value_and_grad(q); optionally p += eh * g.  aux: [C,D] scratch for P q.
-static int dense_grad(bjx_handle_t h, DenseWs& w, const float* q, float* aux, float* p, float eps, const float* eps_dev,
-                      float* g, float* logp, int kicks = 1) {
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
+// g, logp = value_and_grad(q); optionally p += eh * g (once or twice).  aux: [C,D] scratch for P q.
+static int dense_grad(bjx_handle_t h, DenseWs& w, const Part& pt, const float* q, float* aux, float* p, float eps,
+                      const float* eps_dev, float* g, float* logp, int kicks = 1) {
+  const int D = h->cfg.dim;
   const bjx_target_desc& t = h->cfg.target;
+  const size_t ro = (size_t)pt.c0 * D;
+  const float* ed = eps_dev ? eps_dev + pt.c0 : nullptr;
+  float* pp = p ? p + ro : nullptr;
   if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
-    int rc = gemm(h, w, q, MAT_PREC, aux, nullptr, 1.f, 0.f);
+    int rc = gemm(h, w, pt, q, MAT_PREC, aux, nullptr, 1.f, 0.f);
     if (rc) return rc;
-    k_rows_grad_kick<2><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, aux, nullptr, nullptr, t.logp_offset, p, eps,
-                                                                 eps_dev, g, logp, kicks);
+    k_rows_grad_kick<2><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, aux + ro, nullptr, nullptr, t.logp_offset,
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks);
   } else if (t.kind == BJX_TARGET_DIAG_GAUSSIAN) {
-    k_rows_grad_kick<0><<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, q, nullptr, t.inv_var, t.mean, t.logp_offset, p,
-                                                                 eps, eps_dev, g, logp, kicks);
+    k_rows_grad_kick<0><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, nullptr, t.inv_var, t.mean, t.logp_offset,
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks);
   } else {
     return bjx_fail(h, BJX_E_UNSUPPORTED, "large-D dense path supports DENSE_GAUSSIAN and DIAG_GAUSSIAN targets");
   }
@@ -312,72 +363,88 @@ static int dense_grad(bjx_handle_t h, DenseWs& w, const float* q, float* aux, fl
   return 0;
 }
 
+static int dense_momentum(bjx_handle_t h, DenseWs& w, const Part& pt, const uint32_t* keys, float* p_out, bool split_first) {
+  const int D = h->cfg.dim;
+  const size_t ro = (size_t)pt.c0 * D;
+  const bool dense_m = (h->metric_kind == BJX_METRIC_DENSE);
+  float* z = dense_m ? w.v : p_out;
+  const uint32_t* kp = h->key_shared ? keys : keys + 2 * (size_t)pt.c0;
+  k_dense_normal<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, kp, z + ro, split_first, h->key_shared,
+                                                                h->chain_offset + (uint32_t)pt.c0);
+  DN_LAUNCH("k_dense_normal");
+  if (dense_m) return gemm(h, w, pt, z, MAT_MSQRT, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
+  const bool per_chain = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN);
+  k_rows_scale<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, h->msqrt + (per_chain ? ro : 0), per_chain ? D : 0,
+                                                              z + ro, p_out + ro);
+  DN_LAUNCH("k_rows_scale");
+  return 0;
+}
+
+static int dense_energy(bjx_handle_t h, DenseWs& w, const Part& pt, const float* p, const float* logp, float* e_out) {
+  const int D = h->cfg.dim;
+  int rc = dense_velocity(h, w, pt, p, w.v);
+  if (rc) return rc;
+  const size_t ro = (size_t)pt.c0 * D;
+  k_rows_energy<<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, w.v + ro, p + ro, logp + pt.c0, e_out + pt.c0, 1.f);
+  DN_LAUNCH("k_rows_energy");
+  return 0;
+}
+
+// n velocity-Verlet steps in place (integrators.py:104-150)
+static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, const Part& pt, float* q, float* p, float* logp, float* g,
+                               float eps, const float* eps_dev, int n_steps) {
+  const int D = h->cfg.dim;
+  const long long n4 = (long long)pt.n * D / 4;
+  const size_t ro = (size_t)pt.c0 * D;
+  const float* ed = eps_dev ? eps_dev + pt.c0 : nullptr;
+  if (n_steps > 0) {
+    k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, p + ro, g + ro, eps, ed, 0.5f);  // first half kick p += (eps/2) g
+    DN_LAUNCH("k_rows_axpy");
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    int rc;
+    if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
+      rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
+      if (rc) return rc;
+    } else {
+      rc = dense_velocity(h, w, pt, p, w.v);
+      if (rc) return rc;
+      k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, q + ro, w.v + ro, eps, ed, 1.0f);
+      DN_LAUNCH("k_rows_axpy");
+    }
+    // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick when one follows
+    rc = dense_grad(h, w, pt, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int bjx_dense_velocity(bjx_handle_t h, const float* p, float* v) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  return dense_velocity(h, w, p, v);
+  return for_parts(h, [&](const Part& pt) { return dense_velocity(h, w, pt, p, v); });
 }
 
 int bjx_dense_init_state(bjx_handle_t h, const float* q, float* logp_out, float* grad_out) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  return dense_grad(h, w, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out);
+  return for_parts(h, [&](const Part& pt) { return dense_grad(h, w, pt, q, w.v, nullptr, 0.f, nullptr, grad_out, logp_out); });
 }
 
 int bjx_dense_sample_momentum(bjx_handle_t h, const uint32_t* keys, float* p_out, bool split_first) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
-  float* z = (h->metric_kind == BJX_METRIC_DENSE) ? w.v : p_out;
-  k_dense_normal<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, keys, z, split_first, h->key_shared,
-                                                                    h->chain_offset);
-  DN_LAUNCH("k_dense_normal");
-  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, z, MAT_MSQRT, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
-  const long long stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? D : 0;
-  k_rows_scale<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, h->msqrt, stride, z, p_out);
-  DN_LAUNCH("k_rows_scale");
-  return 0;
+  return for_parts(h, [&](const Part& pt) { return dense_momentum(h, w, pt, keys, p_out, split_first); });
 }
 
 int bjx_dense_energy(bjx_handle_t h, const float* p, const float* logp, float* e_out) {
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  rc = dense_velocity(h, w, p, w.v);
-  if (rc) return rc;
-  k_rows_energy<<<grow(h->cfg.n_chains), kRowWarps * 32, 0, h->stream>>>(h->cfg.n_chains, h->cfg.dim, w.v, p, logp, e_out, 1.f);
-  DN_LAUNCH("k_rows_energy");
-  return 0;
-}
-
-// n velocity-Verlet steps in place (integrators.py:104-150)
-static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, float* q, float* p, float* logp, float* g, float eps,
-                               const float* eps_dev, int n_steps) {
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
-  const long long n4 = (long long)C * D / 4;
-  if (n_steps > 0) {
-    k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, p, g, eps, eps_dev, 0.5f);  // first half kick p += (eps/2) g
-    DN_LAUNCH("k_rows_axpy");
-  }
-  for (int s = 0; s < n_steps; ++s) {
-    int rc;
-    if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
-      rc = gemm(h, w, p, MAT_IMM, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
-      if (rc) return rc;
-    } else {
-      rc = dense_velocity(h, w, p, w.v);
-      if (rc) return rc;
-      k_rows_axpy<<<g4(n4), 256, 0, h->stream>>>(C, D, q, w.v, eps, eps_dev, 1.0f);
-      DN_LAUNCH("k_rows_axpy");
-    }
-    // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick when one follows
-    rc = dense_grad(h, w, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
-    if (rc) return rc;
-  }
-  return 0;
+  return for_parts(h, [&](const Part& pt) { return dense_energy(h, w, pt, p, logp, e_out); });
 }
 
 int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev,
@@ -385,7 +452,47 @@ int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  return dense_leapfrog_core(h, w, q, p, logp, g, eps, eps_dev, n_steps);
+  return for_parts(h, [&](const Part& pt) { return dense_leapfrog_core(h, w, pt, q, p, logp, g, eps, eps_dev, n_steps); });
+}
+
+static int dense_hmc_part(bjx_handle_t h, DenseWs& w, const Part& pt, const uint32_t* keys, const float* q_in,
+                          const float* logp_in, const float* g_in, float* q_out, float* logp_out, float* g_out, float eps,
+                          const float* eps_dev, int L, const InfoPtrs& info) {
+  const int D = h->cfg.dim;
+  const size_t ro = (size_t)pt.c0 * D;
+  const size_t bytes = (size_t)pt.n * D * sizeof(float);
+  int rc = dense_momentum(h, w, pt, keys, w.p, true);  // hmc.py:299-302
+  if (rc) return rc;
+  if (info.momentum) DN_CUDA(cudaMemcpyAsync(info.momentum + ro, w.p + ro, bytes, cudaMemcpyDeviceToDevice, pt.st));
+  rc = dense_energy(h, w, pt, w.p, logp_in, w.e0);  // hmc.py:159
+  if (rc) return rc;
+  DN_CUDA(cudaMemcpyAsync(w.q + ro, q_in + ro, bytes, cudaMemcpyDeviceToDevice, pt.st));
+  DN_CUDA(cudaMemcpyAsync(w.g + ro, g_in + ro, bytes, cudaMemcpyDeviceToDevice, pt.st));
+  DN_CUDA(cudaMemcpyAsync(w.lw + pt.c0, logp_in + pt.c0, (size_t)pt.n * sizeof(float), cudaMemcpyDeviceToDevice, pt.st));
+  rc = dense_leapfrog_core(h, w, pt, w.q, w.p, w.lw, w.g, eps, eps_dev, L);  // trajectory.py:165
+  if (rc) return rc;
+  // kinetic energy of the (flipped) end momentum: (-p)^T M^-1 (-p) = p^T M^-1 p   (hmc.py:158-160)
+  rc = dense_energy(h, w, pt, w.p, w.lw, w.e1);
+  if (rc) return rc;
+  if (info.proposal_position) DN_CUDA(cudaMemcpyAsync(info.proposal_position + ro, w.q + ro, bytes, cudaMemcpyDeviceToDevice, pt.st));
+  if (info.proposal_momentum) {  // flipped momentum (hmc.py:158)
+    DN_CUDA(cudaMemsetAsync(info.proposal_momentum + ro, 0, bytes, pt.st));
+    k_rows_axpy<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, info.proposal_momentum + ro, w.p + ro, -1.0f, nullptr, 1.0f);
+    DN_LAUNCH("k_rows_axpy");
+  }
+  InfoPtrs ip = info;  // per-chain outputs of this slice
+  if (ip.acceptance_rate) ip.acceptance_rate += pt.c0;
+  if (ip.is_accepted) ip.is_accepted += pt.c0;
+  if (ip.is_divergent) ip.is_divergent += pt.c0;
+  if (ip.energy) ip.energy += pt.c0;
+  if (ip.num_integration_steps) ip.num_integration_steps += pt.c0;
+  const uint32_t* kp = h->key_shared ? keys : keys + 2 * (size_t)pt.c0;
+  k_rows_accept<<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, kp, w.e0 + pt.c0, w.e1 + pt.c0, h->cfg.divergence_threshold,
+                                                         w.q + ro, w.g + ro, w.lw + pt.c0, q_in + ro, g_in + ro, logp_in + pt.c0,
+                                                         q_out + ro, g_out + ro, logp_out + pt.c0, L, ip, h->key_shared,
+                                                         h->chain_offset + (uint32_t)pt.c0);
+  DN_LAUNCH("k_rows_accept");
+  return 0;
 }
 
 int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
@@ -394,33 +501,7 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
   DenseWs w;
   int rc = dense_ws(h, w);
   if (rc) return rc;
-  const int C = h->cfg.n_chains, D = h->cfg.dim;
-  const size_t bytes = (size_t)C * D * sizeof(float);
-  rc = bjx_dense_sample_momentum(h, keys, w.p, true);  // hmc.py:299-302
-  if (rc) return rc;
-  if (info.momentum) DN_CUDA(cudaMemcpyAsync(info.momentum, w.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  rc = dense_velocity(h, w, w.p, w.v);
-  if (rc) return rc;
-  k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, logp_in, w.e0, 1.f);  // hmc.py:159
-  DN_LAUNCH("k_rows_energy");
-  DN_CUDA(cudaMemcpyAsync(w.q, q_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  DN_CUDA(cudaMemcpyAsync(w.g, g_in, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  DN_CUDA(cudaMemcpyAsync(w.lw, logp_in, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-  rc = dense_leapfrog_core(h, w, w.q, w.p, w.lw, w.g, eps, eps_dev, L);  // trajectory.py:165
-  if (rc) return rc;
-  rc = dense_velocity(h, w, w.p, w.v);  // kinetic energy of the (flipped) end momentum: (-p)^T M^-1 (-p) = p^T M^-1 p
-  if (rc) return rc;
-  k_rows_energy<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, w.v, w.p, w.lw, w.e1, 1.f);  // hmc.py:160
-  DN_LAUNCH("k_rows_energy");
-  if (info.proposal_position) DN_CUDA(cudaMemcpyAsync(info.proposal_position, w.q, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  if (info.proposal_momentum) {  // flipped momentum (hmc.py:158)
-    DN_CUDA(cudaMemsetAsync(info.proposal_momentum, 0, bytes, h->stream));
-    k_rows_axpy<<<g4((long long)C * D / 4), 256, 0, h->stream>>>(C, D, info.proposal_momentum, w.p, -1.0f, nullptr, 1.0f);
-    DN_LAUNCH("k_rows_axpy");
-  }
-  k_rows_accept<<<grow(C), kRowWarps * 32, 0, h->stream>>>(C, D, keys, w.e0, w.e1, h->cfg.divergence_threshold, w.q, w.g,
-                                                          w.lw, q_in, g_in, logp_in, q_out, g_out, logp_out, L, info, h->key_shared,
-                                                          h->chain_offset);
-  DN_LAUNCH("k_rows_accept");
-  return 0;
+  return for_parts(h, [&](const Part& pt) {
+    return dense_hmc_part(h, w, pt, keys, q_in, logp_in, g_in, q_out, logp_out, g_out, eps, eps_dev, L, info);
+  });
 }

@@ -344,7 +344,8 @@ def test_dense_path_building_blocks(D, C, metric, target):
     close(npy(logp), lp1, rtol=2e-5, scale=np.max(np.abs(lp1)) + 1)
 
 
-@pytest.mark.parametrize("D, C, L, pce", [(256, 96, 6, False), (384, 40, 4, True)])
+@pytest.mark.parametrize("D, C, L, pce", [(256, 96, 6, False), (384, 40, 4, True), (256, 8203, 3, False),
+                                          (256, 8200, 2, True)])     # >= 8192 chains: two slices on two streams
 def test_dense_hmc_transition_matches_oracle(D, C, L, pce):
     tgt, otgt, imm, q = dense_problem(D, C)
     keys = oprng.split(oprng.key(17), C)
