@@ -132,6 +132,7 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->dense_version = 1;
   h->dense_bytes_built = 0;
   h->dense_streams_ready = false;
+  h->dense_stagger_armed = false;
   h->ncoef = 3;
   h->coef[0] = 0.5f; h->coef[1] = 1.0f; h->coef[2] = 0.5f;
   h->general_integrator = false;
@@ -166,6 +167,7 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->dense_streams_ready) {
     for (int k = 0; k < 2; ++k) { cudaStreamDestroy(h->dense_stream[k]); cudaEventDestroy(h->dense_join[k]); }
     cudaEventDestroy(h->dense_fork);
+    cudaEventDestroy(h->dense_stagger);
   }
   if (h->h_flag) cudaFreeHost(h->h_flag);
   delete h;

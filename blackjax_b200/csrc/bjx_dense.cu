@@ -237,6 +237,7 @@ struct Part {
   int c0, n;          // chains [c0, c0 + n)
   cudaStream_t st;
   void* gws;          // CUTLASS workspace of this slice
+  int index;
 };
 
 static int dense_ws(bjx_handle_t h, DenseWs& w) {
@@ -264,6 +265,7 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
       DN_CUDA(cudaEventCreateWithFlags(&h->dense_join[k], cudaEventDisableTiming));
     }
     DN_CUDA(cudaEventCreateWithFlags(&h->dense_fork, cudaEventDisableTiming));
+    DN_CUDA(cudaEventCreateWithFlags(&h->dense_stagger, cudaEventDisableTiming));
     h->dense_streams_ready = true;
   }
   char* b = (char*)h->dense_block;
@@ -297,15 +299,19 @@ static int for_parts(bjx_handle_t h, F fn) {
   const int parts = (C >= 8192) ? kParts : 1;
   const size_t gw = h->gemm_ws_bytes / kParts;
   if (parts == 1) {
-    Part pt{0, C, h->stream, h->gemm_ws};
+    Part pt{0, C, h->stream, h->gemm_ws, -1};
     return fn(pt);
   }
   DN_CUDA(cudaEventRecord(h->dense_fork, h->stream));
   int rc = 0;
+  h->dense_stagger_armed = true;  // slice 0 records dense_stagger once its first operand split is enqueued
   for (int k = 0; k < parts; ++k) {
     const int c0 = (int)((long long)C * k / parts) & ~7, c1 = (k + 1 == parts) ? C : ((int)((long long)C * (k + 1) / parts) & ~7);
-    Part pt{c0, c1 - c0, h->dense_stream[k], (char*)h->gemm_ws + k * gw};
+    Part pt{c0, c1 - c0, h->dense_stream[k], (char*)h->gemm_ws + k * gw, k};
     DN_CUDA(cudaStreamWaitEvent(pt.st, h->dense_fork, 0));
+    // phase offset: slice 1 starts when slice 0 reaches its first GEMM, so that from then on one slice's tensor-bound
+    // GEMM runs beside the other slice's HBM-bound row kernels instead of both slices doing the same thing at once
+    if (k > 0 && !h->dense_stagger_armed) DN_CUDA(cudaStreamWaitEvent(pt.st, h->dense_stagger, 0));
     if (rc == 0) rc = fn(pt);
     DN_CUDA(cudaEventRecord(h->dense_join[k], pt.st));
     DN_CUDA(cudaStreamWaitEvent(h->stream, h->dense_join[k], 0));
@@ -322,6 +328,10 @@ static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int 
   uint16_t* xs = w.xs + (size_t)pt.c0 * 6 * D;
   k_rows_split3<false><<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>((long long)pt.n, D, X + ro, xs);
   DN_LAUNCH("k_rows_split3");
+  if (pt.index == 0 && h->dense_stagger_armed) {
+    DN_CUDA(cudaEventRecord(h->dense_stagger, pt.st));
+    h->dense_stagger_armed = false;
+  }
   const int rc = gemm_split(xs, h->dense_mat_s[mat], Y + ro, Cin ? Cin + ro : nullptr, alpha, beta, pt.n, D, 6 * D, pt.gws, pt.st);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
   DN_LAUNCH("gemm");

@@ -31,7 +31,8 @@ struct bjx_handle_s {
   unsigned dense_version;        // bumped by bjx_set_metric / bjx_set_target (contents may change behind the same pointer)
   size_t dense_bytes_built;
   cudaStream_t dense_stream[2];  // chain slices of the dense path run on their own streams (bjx_dense.cu)
-  cudaEvent_t dense_fork, dense_join[2];
+  cudaEvent_t dense_fork, dense_join[2], dense_stagger;
+  bool dense_stagger_armed;
   bool dense_streams_ready;
   int ncoef;            // integrator coefficient table (integrators.py:321-369); {0.5, 1, 0.5} = velocity Verlet
   float coef[11];
