@@ -126,7 +126,7 @@ __global__ void k_rows_energy(int C, int D, const float* __restrict__ v, const f
 }
 
 // Gradient + second half kick for one leapfrog, streaming the row:
-//   TARGET 2 (dense Gaussian): aux = P q from the GEMM; g = -aux; logp = -1/2 q.aux + offset
+//   TARGET 2 (dense Gaussian): g = -P q was written by the GEMM epilogue (alpha = -1); logp = 1/2 q.g + offset
 //   TARGET 0 (diag Gaussian) : g = -(q - mean) / s^2;      logp = -1/2 sum (q-mean)^2/s^2 + offset
 //   then (if p != null) p += (eps_c * 0.5) * g                                  (integrators.py:134-141)
 //   and, when another leapfrog follows (kicks == 2), that step's first half kick p += (eps_c * 0.5) * g
@@ -135,7 +135,8 @@ template <int TARGET>
 __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, const float* __restrict__ aux,
                                  const float* __restrict__ inv_var, const float* __restrict__ mean, float offset,
                                  float* __restrict__ p, float eps, const float* __restrict__ eps_dev,
-                                 float* __restrict__ g_out, float* __restrict__ logp_out, int kicks) {
+                                 float* __restrict__ g_out, float* __restrict__ logp_out, int kicks,
+                                 uint16_t* __restrict__ p_split /* [C,6D] bf16 planes of the new p, or null */) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   const size_t ro = (size_t)c * D;
@@ -145,8 +146,7 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
     const float4 qv = __ldcs(reinterpret_cast<const float4*>(q + ro) + i);
     float4 gv;
     if (TARGET == 2) {
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(aux + ro) + i);
-      gv = make_float4(-a.x, -a.y, -a.z, -a.w);
+      gv = __ldcs(reinterpret_cast<const float4*>(aux + ro) + i);  // aux == g_out: already the gradient
       acc = fmaf(qv.x, gv.x, acc); acc = fmaf(qv.y, gv.y, acc); acc = fmaf(qv.z, gv.z, acc); acc = fmaf(qv.w, gv.w, acc);
     } else {
       const float4 w = __ldg(reinterpret_cast<const float4*>(inv_var) + i);
@@ -158,7 +158,7 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
       gv = make_float4(d.x * -w.x, d.y * -w.y, d.z * -w.z, d.w * -w.w);
       acc = fmaf(d.x, gv.x, acc); acc = fmaf(d.y, gv.y, acc); acc = fmaf(d.z, gv.z, acc); acc = fmaf(d.w, gv.w, acc);
     }
-    __stcs(reinterpret_cast<float4*>(g_out + ro) + i, gv);
+    if (TARGET != 2) __stcs(reinterpret_cast<float4*>(g_out + ro) + i, gv);
     if (p) {
       float4 pv = __ldcs(reinterpret_cast<const float4*>(p + ro) + i);
       pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
@@ -166,6 +166,21 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
         pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
       }
       __stcs(reinterpret_cast<float4*>(p + ro) + i, pv);
+      if (p_split) {  // the operand planes of the next M^-1 p product, written while p is in registers
+        uint16_t p1[4], p2[4], p3[4];
+        split3(pv.x, p1[0], p2[0], p3[0]);
+        split3(pv.y, p1[1], p2[1], p3[1]);
+        split3(pv.z, p1[2], p2[2], p3[2]);
+        split3(pv.w, p1[3], p2[3], p3[3]);
+        const uint2 u1 = pack4(p1), u2 = pack4(p2), u3 = pack4(p3);
+        uint16_t* row = p_split + (size_t)c * 6 * D + 4 * i;
+        *reinterpret_cast<uint2*>(row) = u1;
+        *reinterpret_cast<uint2*>(row + (size_t)D) = u2;
+        *reinterpret_cast<uint2*>(row + (size_t)2 * D) = u3;
+        *reinterpret_cast<uint2*>(row + (size_t)3 * D) = u1;
+        *reinterpret_cast<uint2*>(row + (size_t)4 * D) = u2;
+        *reinterpret_cast<uint2*>(row + (size_t)5 * D) = u1;
+      }
     }
   }
   acc = wsum(acc);
@@ -322,12 +337,14 @@ static int for_parts(bjx_handle_t h, F fn) {
 // Y = alpha * X . A^T + beta * Cin for the slice, A one of the handle's constant matrices (float32-accurate, bjx_gemm.cu).
 // X, Y, Cin are FULL [C,D] arrays; the slice's rows are addressed here.
 static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int mat, float* Y, const float* Cin, float alpha,
-                float beta) {
+                float beta, bool presplit = false) {
   const int D = h->cfg.dim;
   const size_t ro = (size_t)pt.c0 * D;
   uint16_t* xs = w.xs + (size_t)pt.c0 * 6 * D;
-  k_rows_split3<false><<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>((long long)pt.n, D, X + ro, xs);
-  DN_LAUNCH("k_rows_split3");
+  if (!presplit) {  // (presplit: the producer of X already wrote its operand planes into w.xs)
+    k_rows_split3<false><<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>((long long)pt.n, D, X + ro, xs);
+    DN_LAUNCH("k_rows_split3");
+  }
   if (pt.index == 0 && h->dense_stagger_armed) {
     DN_CUDA(cudaEventRecord(h->dense_stagger, pt.st));
     h->dense_stagger_armed = false;
@@ -352,20 +369,22 @@ static int dense_velocity(bjx_handle_t h, DenseWs& w, const Part& pt, const floa
 
 // g, logp = value_and_grad(q); optionally p += eh * g (once or twice).  aux: [C,D] scratch for P q.
 static int dense_grad(bjx_handle_t h, DenseWs& w, const Part& pt, const float* q, float* aux, float* p, float eps,
-                      const float* eps_dev, float* g, float* logp, int kicks = 1) {
+                      const float* eps_dev, float* g, float* logp, int kicks = 1, bool split_p = false) {
   const int D = h->cfg.dim;
   const bjx_target_desc& t = h->cfg.target;
   const size_t ro = (size_t)pt.c0 * D;
   const float* ed = eps_dev ? eps_dev + pt.c0 : nullptr;
   float* pp = p ? p + ro : nullptr;
+  uint16_t* ps = (split_p && pp) ? w.xs + (size_t)pt.c0 * 6 * D : nullptr;
+  (void)aux;
   if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
-    int rc = gemm(h, w, pt, q, MAT_PREC, aux, nullptr, 1.f, 0.f);
+    int rc = gemm(h, w, pt, q, MAT_PREC, g, nullptr, -1.f, 0.f);  // g = -(q P): the sign rides on the GEMM epilogue
     if (rc) return rc;
-    k_rows_grad_kick<2><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, aux + ro, nullptr, nullptr, t.logp_offset,
-                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks);
+    k_rows_grad_kick<2><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, g + ro, nullptr, nullptr, t.logp_offset,
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps);
   } else if (t.kind == BJX_TARGET_DIAG_GAUSSIAN) {
     k_rows_grad_kick<0><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, nullptr, t.inv_var, t.mean, t.logp_offset,
-                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks);
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps);
   } else {
     return bjx_fail(h, BJX_E_UNSUPPORTED, "large-D dense path supports DENSE_GAUSSIAN and DIAG_GAUSSIAN targets");
   }
@@ -411,19 +430,25 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, const Part& pt, float
     k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, p + ro, g + ro, eps, ed, 0.5f);  // first half kick p += (eps/2) g
     DN_LAUNCH("k_rows_axpy");
   }
+  const bool dense_m = (h->metric_kind == BJX_METRIC_DENSE);
   for (int s = 0; s < n_steps; ++s) {
     int rc;
-    if (h->metric_kind == BJX_METRIC_DENSE && !eps_dev) {
-      rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps * 1.0f, 1.f);  // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
+    const bool presplit = dense_m && s > 0;  // the previous step's kick kernel left split(p) in w.xs
+    if (dense_m && !eps_dev) {
+      // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
+      rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps * 1.0f, 1.f, presplit);
       if (rc) return rc;
     } else {
-      rc = dense_velocity(h, w, pt, p, w.v);
+      if (dense_m) rc = gemm(h, w, pt, p, MAT_IMM, w.v, nullptr, 1.f, 0.f, presplit);
+      else rc = dense_velocity(h, w, pt, p, w.v);
       if (rc) return rc;
       k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, q + ro, w.v + ro, eps, ed, 1.0f);
       DN_LAUNCH("k_rows_axpy");
     }
-    // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick when one follows
-    rc = dense_grad(h, w, pt, q, w.v, p, eps, eps_dev, g, logp, (s + 1 < n_steps) ? 2 : 1);
+    // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick -- and, with a dense metric, the
+    // operand planes of that step's M^-1 p product -- when one follows
+    const bool more = (s + 1 < n_steps);
+    rc = dense_grad(h, w, pt, q, w.v, p, eps, eps_dev, g, logp, more ? 2 : 1, more && dense_m);
     if (rc) return rc;
   }
   return 0;
