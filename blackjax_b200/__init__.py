@@ -7,7 +7,7 @@ chains and executed by hand-written sm_100a CUDA kernels through the C ABI in ``
 """
 import functools as _functools
 
-from . import random, targets, util  # noqa: F401
+from . import diagnostics, random, targets, util  # noqa: F401
 from ._lib import BjxError  # noqa: F401
 from .adaptation.window_adaptation import build_schedule, window_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, GenerateSamplingAPI, SamplingAlgorithm  # noqa: F401

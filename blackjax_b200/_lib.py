@@ -76,6 +76,7 @@ _SIGNATURES = {
     "bjx_welford_final": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p]),
     "bjx_pooled_stats": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_pooled_stats_dense": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
+    "bjx_potential_scale_reduction": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -763,3 +763,16 @@ extern "C" int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const floa
   BJX_CHECK_LAUNCH("k_pooled_stats_dense");
   return 0;
 }
+
+// blackjax.diagnostics.potential_scale_reduction (diagnostics.py:39-89) for a history [T, C, D] (chain axis 1, sample
+// axis 0): rhat_out [D].  scratch: device buffer of at least 2*C*D + 4 + 4*D floats.
+extern "C" int bjx_potential_scale_reduction(bjx_handle_t h, const float* history, int32_t num_samples, float* rhat_out,
+                                             float* scratch) {
+  if (!h || !history || !rhat_out || !scratch) return fail(h, BJX_E_INVALID, "null argument");
+  if (num_samples < 2 || h->cfg.n_chains < 2)
+    return fail(h, BJX_E_INVALID, "potential_scale_reduction as implemented only works for two or more chains (and draws)");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_rhat(num_samples, h->cfg.n_chains, h->cfg.dim, history, rhat_out, scratch, h->stream);
+  BJX_CHECK_LAUNCH("k_rhat");
+  return 0;
+}

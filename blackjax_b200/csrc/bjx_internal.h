@@ -14,4 +14,5 @@ void launch_welford_final(long long n, float* mean, float* m2, int count, float*
 void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s);
 void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, float* out, float* scratch, cudaStream_t s);
 size_t pooled_dense_scratch_floats(int D);
+void launch_rhat(int T, int C, int D, const float* hist, float* rhat, float* scratch, cudaStream_t s);
 }  // namespace bjx

@@ -235,6 +235,45 @@ void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, f
 }
 size_t pooled_dense_scratch_floats(int D) { return 2 + 2 * (size_t)D + (size_t)kM2Slices * D * D; }
 
+// ---- potential scale reduction (blackjax/diagnostics.py:39-89) over a device-resident history [T, C, D] ---------
+// stage 1: per (chain, dim) sample mean and unbiased variance over the T draws (coalesced along D);
+// stage 2 (k_pooled_colstats twice): across-chain mean / sum of squared deviations of those two [C,D] arrays.
+__global__ void k_chain_moments(int T, long long CD, const float* __restrict__ hist, float* __restrict__ mean,
+                                float* __restrict__ var) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= CD) return;
+  float m = 0.f, m2 = 0.f;
+  for (int i = 0; i < T; ++i) {  // Welford over the draws
+    const float x = __ldcs(hist + (size_t)i * CD + t);
+    const float d = x - m;
+    m += d / (float)(i + 1);
+    m2 = fmaf(d, x - m, m2);
+  }
+  mean[t] = m;
+  var[t] = m2 / (float)(T - 1);
+}
+__global__ void k_rhat_finish(int T, int C, int D, const float* __restrict__ stats_mean, const float* __restrict__ stats_var,
+                              float* __restrict__ rhat) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  // stats_* = (unused, C, mean over chains [D], sum sq. dev. over chains [D]) as written by k_pooled_colstats
+  const float between = (float)T * (stats_mean[2 + D + d] / (float)(C - 1));  // num_samples * var(per-chain means, ddof=1)
+  const float within = stats_var[2 + d];                                         // mean of the per-chain variances
+  const float est = (float)(T - 1) / (float)T * within + between / (float)T;
+  rhat[d] = sqrtf(est / within);
+}
+// scratch: 2*C*D + 2*(2+2D) floats
+void launch_rhat(int T, int C, int D, const float* hist, float* rhat, float* scratch, cudaStream_t s) {
+  float* mean = scratch;
+  float* var = scratch + (size_t)C * D;
+  float* st_m = var + (size_t)C * D;
+  float* st_v = st_m + 2 + 2 * (size_t)D;
+  k_chain_moments<<<grid1d((long long)C * D), 256, 0, s>>>(T, (long long)C * D, hist, mean, var);
+  k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, mean, st_m);
+  k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, var, st_v);
+  k_rhat_finish<<<(D + 255) / 256, 256, 0, s>>>(T, C, D, st_m, st_v, rhat);
+}
+
 void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s) {
   k_pooled_accept<<<1, 1024, 0, s>>>(C, acc, out);
   k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, x, out);

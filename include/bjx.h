@@ -202,6 +202,12 @@ int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acceptance_rat
  * stats_out float32 [2 + D + D*D] = (sum acceptance_rate, n_chains, mean[D], M2[D,D]). */
 int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
 
+/* ---- diagnostics on a device-resident history ---------------------------------------------- */
+/* blackjax.diagnostics.potential_scale_reduction (diagnostics.py:39-89): history float32 [num_samples, C, D] as written
+ * by bjx_hmc_sample; rhat_out float32 [D]; scratch: at least 2*C*D + 4 + 4*D floats (device). */
+int bjx_potential_scale_reduction(bjx_handle_t h, const float* history, int32_t num_samples, float* rhat_out,
+                                  float* scratch);
+
 #ifdef __cplusplus
 }
 #endif

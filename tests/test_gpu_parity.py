@@ -286,6 +286,21 @@ def test_native_sampler_equals_python_loop(multinomial):
     assert torch.equal(st0.position, st0.position.clone())      # input state untouched (native path works on a copy)
 
 
+def test_potential_scale_reduction_on_device_history():
+    from oracle import diagnostics as odiag
+    tgt = T.DiagGaussian(np.logspace(-0.3, 0.3, 24))
+    C, T_ = 64, 200
+    imm = torch.ones(24, device=DEV)
+    st0 = bj.hmc.init(torch.randn(C, 24, device=DEV), tgt)
+    _, hist, _ = bj.sample_hmc_native(bj.random.key(5, DEV), st0, tgt, 0.3, imm, 8, T_)
+    rhat = npy(bj.diagnostics.potential_scale_reduction(hist, tgt))
+    ref = odiag.potential_scale_reduction(npy(hist), chain_axis=1, sample_axis=0)
+    np.testing.assert_allclose(rhat, ref, rtol=2e-5)
+    assert np.all(rhat < 1.05)                       # the chains start in the typical set and mix
+    hist[:, : C // 2] += 3.0                         # shift half the chains: R-hat must flag it
+    assert np.all(npy(bj.diagnostics.potential_scale_reduction(hist, tgt)) > 1.5)
+
+
 def test_hmc_inplace_and_out_of_place_agree():
     tgt = T.StdNormal(64)
     q = torch.randn(128, 64, device=DEV)

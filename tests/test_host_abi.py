@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     from blackjax_b200 import _lib
     lib = _lib.lib()
     declared = _declared_symbols()
-    assert len(declared) >= 34
+    assert len(declared) >= 35
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/bjx.h but not exported by libbjx.so"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared      # the ctypes binding covers the whole header

@@ -299,3 +299,24 @@ def test_oracle_reproduces_committed_golden():
             assert np.array_equal(a, b), k
         else:
             np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6, err_msg=k)   # BLAS/libm may differ across hosts
+
+
+def test_hier_logit_oracle_gradient_matches_finite_differences():
+    # BASELINE config 5 target (builder-defined): the hand-derived gradient against central differences in float64
+    from blackjax_b200.targets import HierLogit
+    x, bits = HierLogit.synthetic_data(12, seed=1)
+    t = targets.HierLogit(x, bits)
+    y = ((bits[:, None] >> np.arange(8, dtype=np.uint8)) & 1).astype(np.float64)
+
+    def logp64(q):
+        mu, lt, b0, b1, a = q[0], q[1], q[2], q[3], q[4:]
+        eta = a[:, None] + b0 * x[:, :, 0] + b1 * x[:, :, 1]
+        ll = np.sum(y * eta - np.logaddexp(0.0, eta))
+        return (-0.005 * mu ** 2 - 0.5 * lt ** 2 - 0.08 * (b0 ** 2 + b1 ** 2)
+                + np.sum(-0.5 * (a - mu) ** 2 * np.exp(-2 * lt) - lt) + ll)
+
+    q = np.random.default_rng(0).standard_normal(16) * 0.3
+    lp, g = t(q[None].astype(F))
+    fd = np.array([(logp64(q + 1e-6 * e) - logp64(q - 1e-6 * e)) / 2e-6 for e in np.eye(16)])
+    np.testing.assert_allclose(g[0], fd, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(lp[0], logp64(q.astype(F).astype(np.float64)), rtol=1e-5)
