@@ -298,7 +298,7 @@ def test_potential_scale_reduction_on_device_history():
     np.testing.assert_allclose(rhat, ref, rtol=2e-5)
     assert np.all(rhat < 1.05)                       # the chains start in the typical set and mix
     hist[:, : C // 2] += 3.0                         # shift half the chains: R-hat must flag it
-    assert np.all(npy(bj.diagnostics.potential_scale_reduction(hist, tgt)) > 1.5)
+    assert np.all(npy(bj.diagnostics.potential_scale_reduction(hist, tgt)) > 1.2)
 
 
 def test_hmc_inplace_and_out_of_place_agree():
