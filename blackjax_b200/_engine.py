@@ -7,7 +7,12 @@ import torch
 from . import _lib
 from ._lib import check, lib, ptr
 
-_ENGINES = {}
+import collections
+
+# Engines own device workspaces (NUTS: (9 + 2*depth) rows of [C,D]; dense path: 4 rows + operand planes), so the cache is a
+# small LRU: the least recently used engine is destroyed (its handle freed) when a new shape/target comes in.
+_ENGINES = collections.OrderedDict()
+_MAX_ENGINES = 8
 
 
 def _f32(t, shape=None, name="array"):
@@ -58,11 +63,15 @@ class Engine:
         self._imm = None      # keeps the caller's inverse mass matrix alive
         self._imm_key = None
 
+    def close(self):
+        """Destroy the libbjx handle (synchronises its stream and frees its workspaces)."""
+        if getattr(self, "h", None):
+            lib().bjx_destroy(self.h)
+            self.h = None
+
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                lib().bjx_destroy(self.h)
-                self.h = None
+            self.close()
         except Exception:
             pass
 
@@ -223,4 +232,9 @@ def get_engine(position, target, max_tree_depth=10, divergence_threshold=1000.0)
             raise ValueError(f"position has dim {position.shape[1]} but the target has dim {target.dim}")
         eng = Engine(dev, position.shape[0], position.shape[1], target, max_tree_depth, divergence_threshold, stream)
         _ENGINES[key] = eng
+        while len(_ENGINES) > _MAX_ENGINES:
+            _, old = _ENGINES.popitem(last=False)
+            old.close()
+    else:
+        _ENGINES.move_to_end(key)
     return eng

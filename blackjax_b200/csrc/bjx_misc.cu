@@ -224,13 +224,17 @@ __global__ void k_pooled_m2_sum(int D, const float* __restrict__ partial, float*
   for (int z = 0; z < kM2Slices; ++z) s += partial[(size_t)z * D * D + t];
   out[t] = s;
 }
+__global__ void k_copy_f32(int n, const float* __restrict__ src, float* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = src[t];
+}
 // out = (sum acc, C, mean[D], M2[D,D]); scratch >= kM2Slices*D*D floats
 void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, float* out, float* scratch, cudaStream_t s) {
   k_pooled_accept<<<1, 1024, 0, s>>>(C, acc, out);
   k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, x, scratch);  // scratch[2:2+D] = mean (diag M2 unused)
-  cudaMemcpyAsync(out + 2, scratch + 2, sizeof(float) * D, cudaMemcpyDeviceToDevice, s);
   float* partial = scratch + 2 + 2 * (size_t)D;
-  k_pooled_m2_partial<<<dim3((D + 15) / 16, (D + 15) / 16, kM2Slices), 256, 0, s>>>(C, D, x, out + 2, partial);
+  k_pooled_m2_partial<<<dim3((D + 15) / 16, (D + 15) / 16, kM2Slices), 256, 0, s>>>(C, D, x, scratch + 2, partial);
+  k_copy_f32<<<(D + 255) / 256, 256, 0, s>>>(D, scratch + 2, out + 2);
   k_pooled_m2_sum<<<(D * D + 255) / 256, 256, 0, s>>>(D, partial, out + 2 + D);
 }
 size_t pooled_dense_scratch_floats(int D) { return 2 + 2 * (size_t)D + (size_t)kM2Slices * D * D; }
