@@ -603,7 +603,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   // doubling is its own launch over the chains still expanding, whose indices the previous launch compacted into
   // list_a/list_b (ping-pong).  counters[k] = number of chains that continue after launch k; one pinned-memory
   // readback per launch.
-  const int kFusedDoublings = 4;
+  const int kFusedDoublings = 4;  // (the kernel's lane-parallel key schedule handles up to 10 doublings per launch)
   const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
   const size_t dm_bytes = (h->metric_small_dense || h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
                               ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;

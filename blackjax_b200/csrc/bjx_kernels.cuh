@@ -431,12 +431,25 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     logp_mov = ws.right_logp[chain];
     logp_fix = ws.left_logp[chain];
   }
+  // ---- key schedule of the doublings of this launch (trajectory.py:645-650), lane-parallel ------------------
+  // Doubling d needs subkey = fold_in(rng_key, d), then (direction_key, trajectory_key, proposal_key) =
+  // split(subkey, 3) and two scalar uniforms.  All of it is warp-uniform integer work, so lane j evaluates the
+  // subkey of doubling d_begin + j, lane 3j + r the r-th split child of doubling j, and the same lanes their
+  // uniform: three threefry passes per LAUNCH instead of six blocks per doubling (the host keeps
+  // d_end - d_begin <= 10, i.e. at most 30 busy lanes).
+  const int nd = d_end - d_begin;
+  const Key sub_l = fold_in(ki, (uint32_t)(d_begin + (lane < nd ? lane : 0)));
+  const int kj = (lane < 3 * nd) ? lane / 3 : 0, kr = lane % 3;
+  const Key sub_j{__shfl_sync(0xffffffffu, sub_l.a, kj), __shfl_sync(0xffffffffu, sub_l.b, kj)};
+  const Key k3 = fold_in(sub_j, (uint32_t)kr);   // r = 0 direction key, 1 trajectory key, 2 proposal key
+  const float u3 = uniform01(k3);                 // meaningful in the direction / proposal lanes
   int d = d_begin;
   for (; d < d_end && run_next; ++d) {
     // ---- begin: direction and keys of this doubling (trajectory.py:645-655) ------------------------------
-    const Key sub = fold_in(ki, (uint32_t)d);
-    const Key tk = fold_in(sub, 1u), pk = fold_in(sub, 2u);
-    const int dir = (uniform01(fold_in(sub, 0u)) < 0.5f) ? 1 : -1;
+    const int kl = 3 * (d - d_begin);
+    const Key tk{__shfl_sync(0xffffffffu, k3.a, kl + 1), __shfl_sync(0xffffffffu, k3.b, kl + 1)};
+    const float u_prop = __shfl_sync(0xffffffffu, u3, kl + 2);
+    const int dir = (__shfl_sync(0xffffffffu, u3, kl) < 0.5f) ? 1 : -1;
     float* eq = dir > 0 ? ws.right_q : ws.left_q;
     float* ep = dir > 0 ? ws.right_p : ws.left_p;
     float* eg = dir > 0 ? ws.right_g : ws.left_g;
@@ -524,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     // ---- end of the doubling (trajectory.py:672-717) -----------------------------------------------------------
     const bool bad = sub_div || sub_term;
     bool take2 = false;
-    if (!bad) take2 = uniform01(pk) < clip_max1(expf(sub_weight - prop_weight));  // proposal.py:155-156
+    if (!bad) take2 = u_prop < clip_max1(expf(sub_weight - prop_weight));  // proposal.py:155-156
     if (take2) {
       float t[R::NS];
       R::load(t, ws.sub_prop_q + roff, P.D, lane);
