@@ -7,16 +7,16 @@
 
 #include "bjx_handle.h"
 #include "bjx_internal.h"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "bjx_prng.cuh"
 
 using namespace bjx;
 
 namespace bjx {
-size_t gemm_workspace_bytes(int M, int N, int K6);
-int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, float alpha, float beta, int M, int N, int K6,
-               void* workspace, cudaStream_t stream);
+size_t gemm_workspace_bytes(int M, int N, int K3);
+int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, const float* row_alpha, float beta, int M, int N,
+               int K3, void* workspace, cudaStream_t stream);
 
 constexpr int kRowWarps = 8;
 
@@ -26,40 +26,100 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-// ---- float32 -> 3 x bfloat16 operand split (see bjx_gemm.cu) ------------------------------------------------
-__device__ __forceinline__ void split3(float x, uint16_t& b1, uint16_t& b2, uint16_t& b3) {
-  const __nv_bfloat16 h1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(h1);
-  const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(h2);
-  const __nv_bfloat16 h3 = __float2bfloat16_rn(r2);
-  b1 = __bfloat16_as_ushort(h1);
-  b2 = __bfloat16_as_ushort(h2);
-  b3 = __bfloat16_as_ushort(h3);
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- float32 -> 2 x binary16 operand split (see bjx_gemm.cu) ------------------------------------------------
+// The power of two 2^s that lifts amax into [2^13, 2^14): high enough in binary16's range that the second term
+// x2 = x - fp16(x) (~2^-11 |x|) of every element that matters stays a normal number, with two binades of headroom
+// below 65504.  Zero / non-finite maxima leave the row unscaled (their NaN/inf propagate like the reference's).
+__device__ __forceinline__ float pow2_lift(float amax) {
+  if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+  int s = 13 - ((int)((__float_as_uint(amax) >> 23) & 0xffu) - 127);
+  s = s < -126 ? -126 : (s > 126 ? 126 : s);
+  return __uint_as_float((uint32_t)(s + 127) << 23);
+}
+__device__ __forceinline__ void split2(float x, uint16_t& h1, uint16_t& h2) {
+  const __half a = __float2half_rn(x);
+  const __half b = __float2half_rn(x - __half2float(a));
+  h1 = __half_as_ushort(a);
+  h2 = __half_as_ushort(b);
 }
 __device__ __forceinline__ uint2 pack4(const uint16_t (&v)[4]) {
   return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
 }
-// rows: X [R, K] float32 -> X' [R, 6K] bf16.  MATRIX=false (activations): planes (x1,x2,x3,x1,x2,x1);
-// MATRIX=true (constant matrices): planes (a1,a1,a1,a2,a2,a3); plane j of row r starts at r*6K + j*K.
-template <bool MATRIX>
-__global__ void k_rows_split3(long long R, int K, const float* __restrict__ x, uint16_t* __restrict__ xs) {
+// Plane stride: K rounded up to 8 halves so that every row of planes is 16-byte aligned for TMA; the pad columns
+// are zeroed once at allocation and never written (zero x zero adds nothing to the product).
+__host__ __device__ __forceinline__ int plane_stride(int K) { return (K + 7) & ~7; }
+// the (x1, x2, x1) planes of four consecutive elements of an activation row, scaled by sc
+__device__ __forceinline__ void store_planes(uint16_t* row, int KP, int k, float4 v, float sc) {
+  uint16_t p1[4], p2[4];
+  split2(v.x * sc, p1[0], p2[0]);
+  split2(v.y * sc, p1[1], p2[1]);
+  split2(v.z * sc, p1[2], p2[2]);
+  split2(v.w * sc, p1[3], p2[3]);
+  const uint2 u1 = pack4(p1), u2 = pack4(p2);
+  *reinterpret_cast<uint2*>(row + k) = u1;
+  *reinterpret_cast<uint2*>(row + (size_t)KP + k) = u2;
+  *reinterpret_cast<uint2*>(row + (size_t)2 * KP + k) = u1;
+}
+
+// Activation rows, one warp per row: X [R, K] float32 -> X' [R, 3K] fp16 planes (x1, x2, x1) of 2^s_r x, and the
+// per-row epilogue factor of the product that consumes them: row_alpha[r] = alpha_r * 2^-s_r * 2^-s_A
+// (alpha_r = alpha_dev[r] * alpha, or alpha), with 2^-s_A the constant matrix's unscale factor.
+__global__ void k_rows_split2(int R, int K, const float* __restrict__ x, uint16_t* __restrict__ xs, float alpha,
+                              const float* __restrict__ alpha_dev, const float* __restrict__ mat_unscale,
+                              float* __restrict__ row_alpha) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)r * K);
+  float amax = 0.f;
+  for (int i = lane; i < K / 4; i += 32) {
+    const float4 v = xr[i];
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  const float sc = pow2_lift(wmax(amax));
+  const int KP = plane_stride(K);
+  uint16_t* row = xs + (size_t)r * 3 * KP;
+  for (int i = lane; i < K / 4; i += 32) store_planes(row, KP, 4 * i, xr[i], sc);  // second read: L1/L2
+  if (lane == 0) row_alpha[r] = (alpha_dev ? alpha_dev[r] * alpha : alpha) * (1.0f / sc) * mat_unscale[0];
+}
+
+// max |x| of a constant matrix into *out (float bits; non-negative floats order like ints); *out zeroed beforehand
+__global__ void k_absmax(long long n4, const float* __restrict__ x, float* out) {
+  float m = 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[t];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = wmax(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+// Constant matrices: A [R, K] float32 -> A' [R, 3K] fp16 planes (a1, a1, a2) of 2^s_A a; *unscale = 2^-s_A
+__global__ void k_matrix_split2(long long R, int K, const float* __restrict__ x, uint16_t* __restrict__ xs,
+                                const float* __restrict__ amax, float* __restrict__ unscale) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float sc = pow2_lift(amax[0]);
+  if (t == 0) unscale[0] = 1.0f / sc;
   if (t >= R * K / 4) return;
   const long long e = t * 4;
   const long long r = e / K;
   const int k = (int)(e % K);
-  const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + t);
-  uint16_t p1[4], p2[4], p3[4];
-  split3(v.x, p1[0], p2[0], p3[0]);
-  split3(v.y, p1[1], p2[1], p3[1]);
-  split3(v.z, p1[2], p2[2], p3[2]);
-  split3(v.w, p1[3], p2[3], p3[3]);
-  const uint2 u1 = pack4(p1), u2 = pack4(p2), u3 = pack4(p3);
-  uint16_t* row = xs + r * 6 * K + k;
-  auto st = [&](int j, uint2 u) { *reinterpret_cast<uint2*>(row + (size_t)j * K) = u; };
-  if (MATRIX) { st(0, u1); st(1, u1); st(2, u1); st(3, u2); st(4, u2); st(5, u3); }
-  else        { st(0, u1); st(1, u2); st(2, u3); st(3, u1); st(4, u2); st(5, u1); }
+  const float4 v = reinterpret_cast<const float4*>(x)[t];
+  uint16_t p1[4], p2[4];
+  split2(v.x * sc, p1[0], p2[0]);
+  split2(v.y * sc, p1[1], p2[1]);
+  split2(v.z * sc, p1[2], p2[2]);
+  split2(v.w * sc, p1[3], p2[3]);
+  const uint2 u1 = pack4(p1), u2 = pack4(p2);
+  const int KP = plane_stride(K);
+  uint16_t* row = xs + r * 3 * KP + k;
+  *reinterpret_cast<uint2*>(row) = u1;
+  *reinterpret_cast<uint2*>(row + (size_t)KP) = u1;
+  *reinterpret_cast<uint2*>(row + (size_t)2 * KP) = u2;
 }
 
 // z[c, i] = normal(key_c, (D,))[i] with key_c = split(rng_key_c, 2)[0] when split_first (hmc.py:299,302 -> util.py:89-91)
@@ -136,12 +196,14 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
                                  const float* __restrict__ inv_var, const float* __restrict__ mean, float offset,
                                  float* __restrict__ p, float eps, const float* __restrict__ eps_dev,
                                  float* __restrict__ g_out, float* __restrict__ logp_out, int kicks,
-                                 uint16_t* __restrict__ p_split /* [C,6D] bf16 planes of the new p, or null */) {
+                                 uint16_t* __restrict__ p_split /* [C,3D] fp16 planes of the new p, or null */,
+                                 float* __restrict__ row_alpha, const float* __restrict__ mat_unscale) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (c >= C) return;
   const size_t ro = (size_t)c * D;
-  const float eh = (eps_dev ? eps_dev[c] : eps) * 0.5f;
-  float acc = 0.f;
+  const float eps_c = eps_dev ? eps_dev[c] : eps;
+  const float eh = eps_c * 0.5f;
+  float acc = 0.f, amax = 0.f;
   for (int i = lane; i < D / 4; i += 32) {
     const float4 qv = __ldcs(reinterpret_cast<const float4*>(q + ro) + i);
     float4 gv;
@@ -165,23 +227,22 @@ __global__ void k_rows_grad_kick(int C, int D, const float* __restrict__ q, cons
       if (kicks == 2) {
         pv.x = fmaf(eh, gv.x, pv.x); pv.y = fmaf(eh, gv.y, pv.y); pv.z = fmaf(eh, gv.z, pv.z); pv.w = fmaf(eh, gv.w, pv.w);
       }
-      __stcs(reinterpret_cast<float4*>(p + ro) + i, pv);
-      if (p_split) {  // the operand planes of the next M^-1 p product, written while p is in registers
-        uint16_t p1[4], p2[4], p3[4];
-        split3(pv.x, p1[0], p2[0], p3[0]);
-        split3(pv.y, p1[1], p2[1], p3[1]);
-        split3(pv.z, p1[2], p2[2], p3[2]);
-        split3(pv.w, p1[3], p2[3], p3[3]);
-        const uint2 u1 = pack4(p1), u2 = pack4(p2), u3 = pack4(p3);
-        uint16_t* row = p_split + (size_t)c * 6 * D + 4 * i;
-        *reinterpret_cast<uint2*>(row) = u1;
-        *reinterpret_cast<uint2*>(row + (size_t)D) = u2;
-        *reinterpret_cast<uint2*>(row + (size_t)2 * D) = u3;
-        *reinterpret_cast<uint2*>(row + (size_t)3 * D) = u1;
-        *reinterpret_cast<uint2*>(row + (size_t)4 * D) = u2;
-        *reinterpret_cast<uint2*>(row + (size_t)5 * D) = u1;
+      if (p_split) {
+        reinterpret_cast<float4*>(p + ro)[i] = pv;  // re-read below: keep it cached
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(pv.x), fabsf(pv.y))), fmaxf(fabsf(pv.z), fabsf(pv.w)));
+      } else {
+        __stcs(reinterpret_cast<float4*>(p + ro) + i, pv);
       }
     }
+  }
+  if (p_split) {
+    // the operand planes of the next step's M^-1 p product (and its per-row epilogue factor eps_c * 1.0 * 2^-s),
+    // written while the row is hot: each lane re-reads exactly the elements it stored above
+    const float sc = pow2_lift(wmax(amax));
+    const int KP = plane_stride(D);
+    uint16_t* row = p_split + (size_t)c * 3 * KP;
+    for (int i = lane; i < D / 4; i += 32) store_planes(row, KP, 4 * i, reinterpret_cast<const float4*>(p + ro)[i], sc);
+    if (lane == 0) row_alpha[c] = (eps_c * 1.0f) * (1.0f / sc) * mat_unscale[0];
   }
   acc = wsum(acc);
   if (lane == 0) logp_out[c] = 0.5f * acc + offset;
@@ -239,7 +300,10 @@ static inline dim3 grow(int C) { return dim3((C + kRowWarps - 1) / kRowWarps); }
 
 struct DenseWs {
   float *p, *v, *q, *g, *lw, *e0, *e1;
-  uint16_t* xs;  // [C, 6D] bf16 split activations
+  float* alpha;      // [C] per-row epilogue factors of the product whose operand planes sit in xs
+  uint16_t* xs;      // [C, 3D] fp16 split activations
+  float* mat_max;    // [3] max |a| of the constant matrices
+  float* mat_unscale;  // [3] 2^-s_A
 };
 enum { MAT_IMM = 0, MAT_MSQRT = 1, MAT_PREC = 2 };
 
@@ -258,16 +322,17 @@ struct Part {
 static int dense_ws(bjx_handle_t h, DenseWs& w) {
   const size_t C = h->cfg.n_chains, D = h->cfg.dim;
   const size_t row = ((C * D * sizeof(float)) + 255) & ~(size_t)255, vec = ((C * sizeof(float)) + 255) & ~(size_t)255;
-  const size_t xsb = ((C * 6 * D * sizeof(uint16_t)) + 255) & ~(size_t)255;
-  const size_t mat = ((D * 6 * D * sizeof(uint16_t)) + 255) & ~(size_t)255;
-  const size_t need = 4 * row + 3 * vec + xsb + 3 * mat;
+  const size_t KP = plane_stride((int)D);
+  const size_t xsb = ((C * 3 * KP * sizeof(uint16_t)) + 255) & ~(size_t)255;
+  const size_t mat = ((D * 3 * KP * sizeof(uint16_t)) + 255) & ~(size_t)255;
+  const size_t need = 4 * row + 4 * vec + xsb + 3 * mat + 256;
   if (h->dense_bytes < need) {
     if (h->dense_block) DN_CUDA(cudaFree(h->dense_block));
     h->dense_block = nullptr;
     DN_CUDA(cudaMalloc((void**)&h->dense_block, need));
     h->dense_bytes = need;
   }
-  const size_t gw = ((gemm_workspace_bytes((int)C, (int)D, (int)(6 * D)) + 255) & ~(size_t)255) + 256;
+  const size_t gw = ((gemm_workspace_bytes((int)C, (int)D, (int)(3 * KP)) + 255) & ~(size_t)255) + 256;
   if (kParts * gw > h->gemm_ws_bytes) {
     if (h->gemm_ws) DN_CUDA(cudaFree(h->gemm_ws));
     h->gemm_ws = nullptr;
@@ -286,9 +351,13 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
   char* b = (char*)h->dense_block;
   w.p = (float*)b; w.v = (float*)(b + row); w.q = (float*)(b + 2 * row); w.g = (float*)(b + 3 * row);
   w.lw = (float*)(b + 4 * row); w.e0 = (float*)(b + 4 * row + vec); w.e1 = (float*)(b + 4 * row + 2 * vec);
-  w.xs = (uint16_t*)(b + 4 * row + 3 * vec);
-  for (int m = 0; m < 3; ++m) h->dense_mat_s[m] = (uint16_t*)(b + 4 * row + 3 * vec + xsb + m * mat);
-  if (h->dense_bytes_built != need) {  // fresh block: every split matrix must be rebuilt
+  w.alpha = (float*)(b + 4 * row + 3 * vec);
+  w.xs = (uint16_t*)(b + 4 * row + 4 * vec);
+  for (int m = 0; m < 3; ++m) h->dense_mat_s[m] = (uint16_t*)(b + 4 * row + 4 * vec + xsb + m * mat);
+  w.mat_max = (float*)(b + 4 * row + 4 * vec + xsb + 3 * mat);
+  w.mat_unscale = w.mat_max + 4;
+  if (h->dense_bytes_built != need) {  // fresh block: zero the plane pads, every split matrix must be rebuilt
+    DN_CUDA(cudaMemsetAsync(w.xs, 0, xsb + 3 * mat, h->stream));
     for (int m = 0; m < 3; ++m) h->dense_mat_src[m] = nullptr;
     h->dense_bytes_built = need;
   }
@@ -298,8 +367,12 @@ static int dense_ws(bjx_handle_t h, DenseWs& w) {
                          h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN ? h->cfg.target.precision : nullptr};
   for (int m = 0; m < 3; ++m) {
     if (src[m] && (h->dense_mat_src[m] != src[m] || h->dense_mat_ver[m] != h->dense_version)) {
-      k_rows_split3<true><<<g4((long long)D * D / 4), 256, 0, h->stream>>>((long long)D, (int)D, src[m], h->dense_mat_s[m]);
-      DN_LAUNCH("k_rows_split3<matrix>");
+      DN_CUDA(cudaMemsetAsync(w.mat_max + m, 0, sizeof(float), h->stream));
+      k_absmax<<<148, 256, 0, h->stream>>>((long long)D * D / 4, src[m], w.mat_max + m);
+      DN_LAUNCH("k_absmax");
+      k_matrix_split2<<<g4((long long)D * D / 4), 256, 0, h->stream>>>((long long)D, (int)D, src[m], h->dense_mat_s[m],
+                                                                      w.mat_max + m, w.mat_unscale + m);
+      DN_LAUNCH("k_matrix_split2");
       h->dense_mat_src[m] = src[m];
       h->dense_mat_ver[m] = h->dense_version;
     }
@@ -334,22 +407,26 @@ static int for_parts(bjx_handle_t h, F fn) {
   return rc;
 }
 
-// Y = alpha * X . A^T + beta * Cin for the slice, A one of the handle's constant matrices (float32-accurate, bjx_gemm.cu).
-// X, Y, Cin are FULL [C,D] arrays; the slice's rows are addressed here.
+// Y[c,:] = alpha_c * (X . A^T)[c,:] + beta * Cin[c,:] for the slice, alpha_c = alpha * alpha_dev[c] (or alpha), A one of the
+// handle's constant matrices (float32-accurate, bjx_gemm.cu).  X, Y, Cin, alpha_dev are FULL [C,D] / [C] arrays; the
+// slice's rows are addressed here.  presplit: the producer of X already wrote its operand planes and w.alpha.
 static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int mat, float* Y, const float* Cin, float alpha,
-                float beta, bool presplit = false) {
+                const float* alpha_dev, float beta, bool presplit = false) {
   const int D = h->cfg.dim;
   const size_t ro = (size_t)pt.c0 * D;
-  uint16_t* xs = w.xs + (size_t)pt.c0 * 6 * D;
-  if (!presplit) {  // (presplit: the producer of X already wrote its operand planes into w.xs)
-    k_rows_split3<false><<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>((long long)pt.n, D, X + ro, xs);
-    DN_LAUNCH("k_rows_split3");
+  const int KP = plane_stride(D);
+  uint16_t* xs = w.xs + (size_t)pt.c0 * 3 * KP;
+  if (!presplit) {
+    k_rows_split2<<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, X + ro, xs, alpha, alpha_dev ? alpha_dev + pt.c0 : nullptr,
+                                                          w.mat_unscale + mat, w.alpha + pt.c0);
+    DN_LAUNCH("k_rows_split2");
   }
   if (pt.index == 0 && h->dense_stagger_armed) {
     DN_CUDA(cudaEventRecord(h->dense_stagger, pt.st));
     h->dense_stagger_armed = false;
   }
-  const int rc = gemm_split(xs, h->dense_mat_s[mat], Y + ro, Cin ? Cin + ro : nullptr, alpha, beta, pt.n, D, 6 * D, pt.gws, pt.st);
+  const int rc = gemm_split(xs, h->dense_mat_s[mat], Y + ro, Cin ? Cin + ro : nullptr, w.alpha + pt.c0, beta, pt.n, D, 3 * KP,
+                            pt.gws, pt.st);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
   DN_LAUNCH("gemm");
   return 0;
@@ -358,7 +435,7 @@ static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int 
 // v = M^-1 p
 static int dense_velocity(bjx_handle_t h, DenseWs& w, const Part& pt, const float* p, float* v) {
   const int D = h->cfg.dim;
-  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, pt, p, MAT_IMM, v, nullptr, 1.f, 0.f);
+  if (h->metric_kind == BJX_METRIC_DENSE) return gemm(h, w, pt, p, MAT_IMM, v, nullptr, 1.f, nullptr, 0.f);
   const bool per_chain = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN);
   const size_t ro = (size_t)pt.c0 * D;
   k_rows_scale<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, h->imm + (per_chain ? ro : 0), per_chain ? D : 0,
@@ -375,16 +452,18 @@ static int dense_grad(bjx_handle_t h, DenseWs& w, const Part& pt, const float* q
   const size_t ro = (size_t)pt.c0 * D;
   const float* ed = eps_dev ? eps_dev + pt.c0 : nullptr;
   float* pp = p ? p + ro : nullptr;
-  uint16_t* ps = (split_p && pp) ? w.xs + (size_t)pt.c0 * 6 * D : nullptr;
+  uint16_t* ps = (split_p && pp) ? w.xs + (size_t)pt.c0 * 3 * plane_stride(D) : nullptr;
   (void)aux;
   if (t.kind == BJX_TARGET_DENSE_GAUSSIAN) {
-    int rc = gemm(h, w, pt, q, MAT_PREC, g, nullptr, -1.f, 0.f);  // g = -(q P): the sign rides on the GEMM epilogue
+    int rc = gemm(h, w, pt, q, MAT_PREC, g, nullptr, -1.f, nullptr, 0.f);  // g = -(q P): the sign rides on the GEMM epilogue
     if (rc) return rc;
     k_rows_grad_kick<2><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, g + ro, nullptr, nullptr, t.logp_offset,
-                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps);
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps, w.alpha + pt.c0,
+                                                                w.mat_unscale + MAT_IMM);
   } else if (t.kind == BJX_TARGET_DIAG_GAUSSIAN) {
     k_rows_grad_kick<0><<<grow(pt.n), kRowWarps * 32, 0, pt.st>>>(pt.n, D, q + ro, nullptr, t.inv_var, t.mean, t.logp_offset,
-                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps);
+                                                                pp, eps, ed, g + ro, logp + pt.c0, kicks, ps, w.alpha + pt.c0,
+                                                                w.mat_unscale + MAT_IMM);
   } else {
     return bjx_fail(h, BJX_E_UNSUPPORTED, "large-D dense path supports DENSE_GAUSSIAN and DIAG_GAUSSIAN targets");
   }
@@ -401,7 +480,7 @@ static int dense_momentum(bjx_handle_t h, DenseWs& w, const Part& pt, const uint
   k_dense_normal<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, kp, z + ro, split_first, h->key_shared,
                                                                 h->chain_offset + (uint32_t)pt.c0);
   DN_LAUNCH("k_dense_normal");
-  if (dense_m) return gemm(h, w, pt, z, MAT_MSQRT, p_out, nullptr, 1.f, 0.f);  // p = L^-T z
+  if (dense_m) return gemm(h, w, pt, z, MAT_MSQRT, p_out, nullptr, 1.f, nullptr, 0.f);  // p = L^-T z
   const bool per_chain = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN);
   k_rows_scale<<<g4((long long)pt.n * D / 4), 256, 0, pt.st>>>(pt.n, D, h->msqrt + (per_chain ? ro : 0), per_chain ? D : 0,
                                                               z + ro, p_out + ro);
@@ -434,13 +513,12 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, const Part& pt, float
   for (int s = 0; s < n_steps; ++s) {
     int rc;
     const bool presplit = dense_m && s > 0;  // the previous step's kick kernel left split(p) in w.xs
-    if (dense_m && !eps_dev) {
-      // q = q + eps * (p M^-1): axpy fused in the GEMM epilogue
-      rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps * 1.0f, 1.f, presplit);
+    if (dense_m) {
+      // q = q + (eps_c * 1.0) * (p M^-1): the axpy rides on the GEMM epilogue's per-row factor
+      rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps_dev ? 1.0f : eps * 1.0f, eps_dev, 1.f, presplit);
       if (rc) return rc;
     } else {
-      if (dense_m) rc = gemm(h, w, pt, p, MAT_IMM, w.v, nullptr, 1.f, 0.f, presplit);
-      else rc = dense_velocity(h, w, pt, p, w.v);
+      rc = dense_velocity(h, w, pt, p, w.v);
       if (rc) return rc;
       k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, q + ro, w.v + ro, eps, ed, 1.0f);
       DN_LAUNCH("k_rows_axpy");

@@ -25,7 +25,7 @@ struct bjx_handle_s {
   size_t dense_bytes;
   void* gemm_ws;
   size_t gemm_ws_bytes;
-  uint16_t* dense_mat_s[3];      // bf16-split copies of M^-1, L^-T, target precision ([D, 6D] each)
+  uint16_t* dense_mat_s[3];      // fp16-split copies of M^-1, L^-T, target precision ([D, 3D] each)
   const float* dense_mat_src[3]; // the float32 matrices they were built from
   unsigned dense_mat_ver[3];
   unsigned dense_version;        // bumped by bjx_set_metric / bjx_set_target (contents may change behind the same pointer)
