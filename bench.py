@@ -371,8 +371,8 @@ def main():
         if dense:
             tpeak = float(peaks.get("bf16_tflops", 1590.0))
             tf_achieved = 2.0 * C * D * D / (ms_gemm * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "v = M^-1 p for all chains: k_rows_split3 + tcgen05 bf16 GEMM [C,6D]x[6D,D] "
-                        "(float32-accurate: 6 bf16 products per float32 product)", "achieved": tf_achieved, "peak": tpeak,
+            roofline = {"bound": "tensor", "kernel": "v = M^-1 p for all chains: k_rows_split2 + tcgen05 fp16 GEMM [C,3D]x[3D,D] "
+                        "(float32-accurate: 3 fp16 products per float32 product, rows scaled by powers of two)", "achieved": tf_achieved, "peak": tpeak,
                         "unit": "TFLOP/s",
                         "frac": tf_achieved / tpeak, "traffic": traffic_gemm,
                         "traffic_source": "ncu --set full of the GEMM kernel alone, profiles/r01_ncu_gemm_dense.md "
@@ -380,8 +380,8 @@ def main():
                         "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
                                         else "fallback 1590 TFLOP/s"),
                         "avg_launch_ms": ms_gemm, "launches_timed": 20,
-                        "note": "algorithmic float32 flops 2*C*D^2 per call; the hardware executes 6x that in bf16 MMAs; "
-                                "the timed call includes the operand-split kernel",
+                        "note": "algorithmic float32 flops 2*C*D^2 per call; the hardware executes 3x that in fp16 MMAs "
+                                "(ceiling frac = 1/3); the timed call includes the operand-split kernel",
                         "gemms_per_step": 2 * L + 3, "gemm_share_of_step": (2 * L + 3) * ms_gemm / ms_step}
             extra = {"roofline_hbm_leapfrog": hbm_roofline}
         else:

@@ -16,7 +16,7 @@ using namespace bjx;
 namespace bjx {
 size_t gemm_workspace_bytes(int M, int N, int K3);
 int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, const float* row_alpha, float beta, int M, int N,
-               int K3, void* workspace, cudaStream_t stream);
+               int K3, void* workspace, cudaStream_t stream, bool double_kick);
 
 constexpr int kRowWarps = 8;
 
@@ -410,8 +410,9 @@ static int for_parts(bjx_handle_t h, F fn) {
 // Y[c,:] = alpha_c * (X . A^T)[c,:] + beta * Cin[c,:] for the slice, alpha_c = alpha * alpha_dev[c] (or alpha), A one of the
 // handle's constant matrices (float32-accurate, bjx_gemm.cu).  X, Y, Cin, alpha_dev are FULL [C,D] / [C] arrays; the
 // slice's rows are addressed here.  presplit: the producer of X already wrote its operand planes and w.alpha.
+// double_kick: Y = alpha_c acc + (alpha_c acc + Cin) instead (the two half kicks between consecutive leapfrog steps).
 static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int mat, float* Y, const float* Cin, float alpha,
-                const float* alpha_dev, float beta, bool presplit = false) {
+                const float* alpha_dev, float beta, bool presplit = false, bool double_kick = false) {
   const int D = h->cfg.dim;
   const size_t ro = (size_t)pt.c0 * D;
   const int KP = plane_stride(D);
@@ -426,7 +427,7 @@ static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int 
     h->dense_stagger_armed = false;
   }
   const int rc = gemm_split(xs, h->dense_mat_s[mat], Y + ro, Cin ? Cin + ro : nullptr, w.alpha + pt.c0, beta, pt.n, D, 3 * KP,
-                            pt.gws, pt.st);
+                            pt.gws, pt.st, double_kick);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core GEMM failed (cutlass status " + std::to_string(rc) + ")");
   DN_LAUNCH("gemm");
   return 0;
@@ -510,9 +511,10 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, const Part& pt, float
     DN_LAUNCH("k_rows_axpy");
   }
   const bool dense_m = (h->metric_kind == BJX_METRIC_DENSE);
+  bool p_presplit = false;
   for (int s = 0; s < n_steps; ++s) {
     int rc;
-    const bool presplit = dense_m && s > 0;  // the previous step's kick kernel left split(p) in w.xs
+    const bool presplit = p_presplit;  // the previous step's kick kernel left split(p) in w.xs
     if (dense_m) {
       // q = q + (eps_c * 1.0) * (p M^-1): the axpy rides on the GEMM epilogue's per-row factor
       rc = gemm(h, w, pt, p, MAT_IMM, q, q, eps_dev ? 1.0f : eps * 1.0f, eps_dev, 1.f, presplit);
@@ -523,11 +525,22 @@ static int dense_leapfrog_core(bjx_handle_t h, DenseWs& w, const Part& pt, float
       k_rows_axpy<<<g4(n4), 256, 0, pt.st>>>(pt.n, D, q + ro, w.v + ro, eps, ed, 1.0f);
       DN_LAUNCH("k_rows_axpy");
     }
+    const bool more = (s + 1 < n_steps);
+    if (more && dense_m && h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN) {
+      // Between two steps neither g nor logp is observable, only p += (eps_c/2) g twice (this step's second half kick
+      // and the next step's first, integrators.py:134-141,235-239) with g = -(q P): both FMAs ride on the epilogue of
+      // the gradient product, per-row factor -(eps_c * 0.5) (bit-identical to kicking with the stored gradient, since
+      // the row scales are powers of two).  The next iteration splits the new p itself.
+      rc = gemm(h, w, pt, q, MAT_PREC, p, p, eps_dev ? -0.5f : -(eps * 0.5f), eps_dev, 1.f, false, true);
+      if (rc) return rc;
+      p_presplit = false;
+      continue;
+    }
     // g, logp at the new q; p += (eps/2) g; plus the next step's first half kick -- and, with a dense metric, the
     // operand planes of that step's M^-1 p product -- when one follows
-    const bool more = (s + 1 < n_steps);
     rc = dense_grad(h, w, pt, q, w.v, p, eps, eps_dev, g, logp, more ? 2 : 1, more && dense_m);
     if (rc) return rc;
+    p_presplit = more && dense_m;
   }
   return 0;
 }

@@ -33,6 +33,64 @@
 
 #include "bjx_internal.h"
 
+// ---- a second epilogue: the two half kicks of consecutive leapfrog steps on the gradient product ---------------
+//   D = alpha[row] * acc + (alpha[row] * acc + C)        (two separately rounded FMAs, integrators.py:134-141,235-239)
+// Defined like the library's own fused operations: an operation tag plus the FusionCallbacks specialisation that
+// maps it onto an epilogue visitor tree (the sm100 TMA epilogue forwards to the sm90 callbacks).
+namespace cutlass::epilogue::fusion {
+
+template <class ElementOutput_, class ElementCompute_, class ElementSource_ = ElementOutput_,
+          class ElementScalar_ = ElementCompute_, FloatRoundStyle RoundStyle_ = FloatRoundStyle::round_to_nearest>
+struct PerRowDoubleAxpy : LinearCombination<ElementOutput_, ElementCompute_, ElementSource_, ElementScalar_, RoundStyle_> {
+  static constexpr bool IsPerRowScaleSupported = true;
+};
+
+template <class CtaTileShapeMNK, class ElementOutput, class ElementCompute, class ElementSource, class ElementScalar,
+          FloatRoundStyle RoundStyle>
+using Sm90PerRowDoubleAxpy =
+    Sm90EVT<Sm90Compute<homogeneous_multiply_add, ElementOutput, ElementCompute, RoundStyle>,  // alpha * acc + (...)
+            Sm90ColBroadcast<0, CtaTileShapeMNK, ElementScalar, ElementCompute, Stride<bool, _0, int64_t>, 1>,
+            Sm90AccFetch,
+            Sm90EVT<Sm90Compute<homogeneous_multiply_add, ElementCompute, ElementCompute, RoundStyle>,  // alpha * acc + C
+                    Sm90ColBroadcast<0, CtaTileShapeMNK, ElementScalar, ElementCompute, Stride<bool, _0, int64_t>, 1>,
+                    Sm90AccFetch,
+                    Sm90SrcFetch<ElementSource>>>;
+
+template <int StagesC, int StagesD, int FragmentSize, bool ReuseSmemC, bool DelayTmaStore, class ElementOutput,
+          class ElementCompute, class ElementSource, class ElementScalar, FloatRoundStyle RoundStyle, class CtaTileShapeMNK,
+          class EpilogueTile>
+struct FusionCallbacks<epilogue::Sm90TmaWarpSpecialized<StagesC, StagesD, FragmentSize, ReuseSmemC, DelayTmaStore>,
+                       fusion::PerRowDoubleAxpy<ElementOutput, ElementCompute, ElementSource, ElementScalar, RoundStyle>,
+                       CtaTileShapeMNK, EpilogueTile>
+    : Sm90PerRowDoubleAxpy<CtaTileShapeMNK, ElementOutput, ElementCompute, ElementSource, ElementScalar, RoundStyle> {
+  using Impl = Sm90PerRowDoubleAxpy<CtaTileShapeMNK, ElementOutput, ElementCompute, ElementSource, ElementScalar, RoundStyle>;
+  using Operation = fusion::PerRowDoubleAxpy<ElementOutput, ElementCompute, ElementSource, ElementScalar, RoundStyle>;
+
+  struct Arguments {
+    ElementScalar const* alpha_ptr = nullptr;  // [M] per-row factors
+
+    operator typename Impl::Arguments() const {
+      using StrideAlpha = Stride<bool, _0, int64_t>;
+      const StrideAlpha dAlpha = {bool(1), _0{}, 0};
+      return {
+          {alpha_ptr, ElementScalar(0), dAlpha},  // leaf: alpha
+          {},                                     // leaf: acc
+          {
+              {alpha_ptr, ElementScalar(0), dAlpha},  // leaf: alpha
+              {},                                     // leaf: acc
+              {},                                     // leaf: C
+              {}                                      // multiply_add
+          },
+          {}  // multiply_add
+      };
+    }
+  };
+
+  using Impl::Impl;
+};
+
+}  // namespace cutlass::epilogue::fusion
+
 namespace bjx {
 
 using namespace cute;
@@ -56,45 +114,51 @@ using ClusterShape = Shape<_2, _1, _1>;
 using FusionOp = cutlass::epilogue::fusion::PerRowLinCombPerRowBiasEltAct<cutlass::epilogue::thread::Identity, ElementC,
                                                                          ElementAcc, float, ElementC, float, 1, 1>;
 
-using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
-    cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, kAlignC, ElementC,
-    LayoutC, kAlignC, cutlass::epilogue::collective::EpilogueScheduleAuto, FusionOp>::CollectiveOp;
+using FusionKick = cutlass::epilogue::fusion::PerRowDoubleAxpy<ElementC, ElementAcc, ElementC, float>;
 
-using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlignAB, ElementB, LayoutB, kAlignAB,
-    ElementAcc, MmaTileShape, ClusterShape,
-    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+template <class Fusion>
+struct GemmOf {
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
+      cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, kAlignC, ElementC,
+      LayoutC, kAlignC, cutlass::epilogue::collective::EpilogueScheduleAuto, Fusion>::CollectiveOp;
 
-using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
-using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlignAB, ElementB, LayoutB, kAlignAB,
+      ElementAcc, MmaTileShape, ClusterShape,
+      cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+};
+using Gemm = GemmOf<FusionOp>::Gemm;          // Y = alpha_row * acc + beta * Cin
+using GemmKick = GemmOf<FusionKick>::Gemm;    // Y = alpha_row * acc + (alpha_row * acc + Cin)
 
 size_t gemm_workspace_bytes(int M, int N, int K3) {
   typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K3, 1}};
-  return Gemm::get_workspace_size(args);
+  typename GemmKick::Arguments args2{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K3, 1}};
+  const size_t a = Gemm::get_workspace_size(args), b = GemmKick::get_workspace_size(args2);
+  return a > b ? a : b;
 }
 
-// Y[m,:] = row_alpha[m] * (X'.A'^T)[m,:] + beta * Cin[m,:] with X' [M, K3] fp16, A' [N, K3] fp16 (both K'-contiguous),
-// Y/Cin [M, N] float, row_alpha [M] float (device).
-// returns 0 on success, a positive code (stage*100 + cutlass::Status) otherwise
-int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, const float* row_alpha, float beta, int M, int N,
-               int K3, void* workspace, cudaStream_t stream) {
-  using StrideA = typename Gemm::GemmKernel::StrideA;
-  using StrideB = typename Gemm::GemmKernel::StrideB;
-  using StrideC = typename Gemm::GemmKernel::StrideC;
-  using StrideD = typename Gemm::GemmKernel::StrideD;
+template <class G, class SetFusion>
+static int run_gemm(const void* Xs, const void* As, float* Y, const float* Cin, int M, int N, int K3, void* workspace,
+                    cudaStream_t stream, SetFusion set_fusion) {
+  using StrideA = typename G::GemmKernel::StrideA;
+  using StrideB = typename G::GemmKernel::StrideB;
+  using StrideC = typename G::GemmKernel::StrideC;
+  using StrideD = typename G::GemmKernel::StrideD;
   StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K3, 1));
   StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K3, 1));
   StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, make_shape(M, N, 1));
   StrideD sd = cutlass::make_cute_packed_stride(StrideD{}, make_shape(M, N, 1));
-  typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
-                                {M, N, K3, 1},
-                                {reinterpret_cast<const ElementA*>(Xs), sa, reinterpret_cast<const ElementB*>(As), sb},
-                                {{}, Cin ? Cin : Y, sc, Y, sd}};
-  args.epilogue.thread.alpha_ptr = row_alpha;
-  args.epilogue.thread.beta = beta;
-  Gemm gemm;
+  typename G::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
+                             {M, N, K3, 1},
+                             {reinterpret_cast<const ElementA*>(Xs), sa, reinterpret_cast<const ElementB*>(As), sb},
+                             {{}, Cin ? Cin : Y, sc, Y, sd}};
+  set_fusion(args.epilogue.thread);
+  G gemm;
   cutlass::Status st = gemm.can_implement(args);
   if (st != cutlass::Status::kSuccess) return 100 + (int)st;
   st = gemm.initialize(args, workspace, stream);
@@ -102,6 +166,20 @@ int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, const
   st = gemm.run(stream);
   if (st != cutlass::Status::kSuccess) return 300 + (int)st;
   return 0;
+}
+
+// X' [M, K3] fp16, A' [N, K3] fp16 (both K'-contiguous), Y/Cin [M, N] float, row_alpha [M] float (device).
+//   double_kick == false:  Y[m,:] = row_alpha[m] * (X'.A'^T)[m,:] + beta * Cin[m,:]
+//   double_kick == true :  Y[m,:] = row_alpha[m] * acc + (row_alpha[m] * acc + Cin[m,:])      (beta ignored)
+// returns 0 on success, a positive code (stage*100 + cutlass::Status) otherwise
+int gemm_split(const void* Xs, const void* As, float* Y, const float* Cin, const float* row_alpha, float beta, int M, int N,
+               int K3, void* workspace, cudaStream_t stream, bool double_kick) {
+  if (double_kick)
+    return run_gemm<GemmKick>(Xs, As, Y, Cin, M, N, K3, workspace, stream, [&](auto& f) { f.alpha_ptr = row_alpha; });
+  return run_gemm<Gemm>(Xs, As, Y, Cin, M, N, K3, workspace, stream, [&](auto& f) {
+    f.alpha_ptr = row_alpha;
+    f.beta = beta;
+  });
 }
 
 }  // namespace bjx
