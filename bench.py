@@ -266,9 +266,9 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # our kernels per step: (diag) k_hmc_transition | (dense) normal draw, 2L+3 x (operand split + GEMM),
-    # first half kick, L grad_kick, 2 energy, accept
-    launches = K * (1 if not dense else 1 + 2 * (2 * L + 3) + 1 + L + 2 + 1)
+    # our kernels per step: (diag) k_hmc_transition | (dense, per chain slice; two slices on two streams from 8192
+    # chains) normal draw, 2L+3 x (operand split + GEMM), first half kick, the closing grad_kick, 2 energy, accept
+    launches = K * (1 if not dense else (2 if C >= 8192 else 1) * (1 + 2 * (2 * L + 3) + 1 + 1 + 2 + 1))
     acc_mean = float(info.acceptance_rate.mean())
     clocks = sampler.stop() if rank == 0 else None
 
@@ -363,7 +363,7 @@ def main():
         # (profiles/r01_ncu_diag_hmc.md, profiles/r01_ncu_gemm_dense.md); only meaningful at the captured shape
         at_captured_shape = (C, D) == (65536, 1024)
         traffic_leapfrog = (805.4e6 + 747.7e6) if at_captured_shape else None
-        traffic_gemm = (903.3e6 + 247.4e6) if at_captured_shape else None
+        traffic_gemm = 2 * (351.0e6 + 100.8e6) if at_captured_shape else None  # two 32768-chain slice launches per call
         hbm_roofline = {"bound": "hbm", "kernel": "k_leapfrog (diag metric, 1 step/launch, 24*D B per chain)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic_leapfrog, "traffic_source": "ncu --set full, profiles/r01_ncu_diag_hmc.md",
@@ -376,7 +376,7 @@ def main():
                         "unit": "TFLOP/s",
                         "frac": tf_achieved / tpeak, "traffic": traffic_gemm,
                         "traffic_source": "ncu --set full of the GEMM kernel alone, profiles/r01_ncu_gemm_dense.md "
-                                          "(the split kernel adds 268 MB read + 805 MB written)",
+                                          "(two slice launches; the split kernel adds 2 x (136 MB read + 148 MB written))",
                         "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
                                         else "fallback 1590 TFLOP/s"),
                         "avg_launch_ms": ms_gemm, "launches_timed": 20,
