@@ -14,6 +14,7 @@ from .base import AdaptationAlgorithm, AdaptationResults, GenerateSamplingAPI, S
 from . import mcmc  # noqa: F401
 from .mcmc import hmc as _hmc
 from .mcmc import nuts as _nuts
+from .mcmc import dynamic_hmc as _dynamic_hmc
 from .util import run_inference_algorithm, sample_hmc_native  # noqa: F401
 
 hmc = GenerateSamplingAPI(_hmc.as_top_level_api, _hmc.init, _hmc.build_kernel)     # blackjax/__init__.py:111
@@ -24,5 +25,12 @@ mhmc = GenerateSamplingAPI(                                                     
     _functools.partial(_hmc.build_kernel, build_proposal=_hmc.multinomial_hmc_proposal),
 )
 multinomial_hmc = mhmc  # backward-compatible alias (:152)
+dhmc = GenerateSamplingAPI(_dynamic_hmc.as_top_level_api, _dynamic_hmc.init, _dynamic_hmc.build_kernel)  # :117
+dynamic_hmc = dhmc  # backward-compatible alias (:118)
+dmhmc = GenerateSamplingAPI(                                                         # blackjax/__init__.py:154-162
+    _functools.partial(_dynamic_hmc.as_top_level_api, build_proposal=_hmc.multinomial_hmc_proposal),
+    _dynamic_hmc.init,
+    _functools.partial(_dynamic_hmc.build_kernel, build_proposal=_hmc.multinomial_hmc_proposal),
+)
 
 __version__ = "0.1.0"

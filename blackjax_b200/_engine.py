@@ -181,8 +181,20 @@ class Engine:
         eps, eps_dev = self._eps(step_size)
         info = self._info(info_fields or {})
         fn = lib().bjx_mhmc_step if multinomial else lib().bjx_hmc_step
-        check(fn(self.h, ptr(keys), ptr(q), ptr(logp), ptr(g), ptr(qo), ptr(lo), ptr(go), eps,
-                 ptr(eps_dev), int(num_integration_steps), C.byref(info)), self.h)
+        steps_dev = None
+        if isinstance(num_integration_steps, torch.Tensor):  # dynamic HMC: one trajectory length per chain
+            steps_dev = num_integration_steps.to(device=self.device, dtype=torch.int32).contiguous()
+            if steps_dev.shape != (self.C,):
+                raise ValueError(f"per-chain num_integration_steps must have shape ({self.C},)")
+            num_integration_steps = 1
+        check(lib().bjx_set_integration_steps(self.h, ptr(steps_dev)), self.h)
+        try:
+            check(fn(self.h, ptr(keys), ptr(q), ptr(logp), ptr(g), ptr(qo), ptr(lo), ptr(go), eps,
+                     ptr(eps_dev), int(num_integration_steps), C.byref(info)), self.h)
+        finally:
+            if steps_dev is not None:
+                check(lib().bjx_set_integration_steps(self.h, None), self.h)
+                self._steps_keepalive = steps_dev  # the launch is asynchronous: keep the array until the next call
         return qo, lo, go
 
     def nuts_step(self, keys, q, logp, g, step_size, max_num_doublings, out=None, info_fields=None,

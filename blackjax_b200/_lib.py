@@ -45,6 +45,7 @@ _SIGNATURES = {
     "bjx_set_target": (C.c_int, [C.c_void_p, C.POINTER(TargetDesc)]),
     "bjx_set_integrator": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "bjx_set_key_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
+    "bjx_set_integration_steps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bjx_synchronize": (C.c_int, [C.c_void_p]),
     "bjx_set_metric": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
     "bjx_get_mass_matrix_sqrt": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -68,6 +69,7 @@ _SIGNATURES = {
     "bjx_prng_random_bits": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f32p]),
     "bjx_prng_uniform": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f32p]),
     "bjx_prng_normal": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f32p]),
+    "bjx_prng_randint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "bjx_da_init": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_da_update": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_float, _f32p]),
     "bjx_da_reset": (C.c_int, [C.c_void_p, _f32p, _f32p]),
@@ -77,6 +79,8 @@ _SIGNATURES = {
     "bjx_pooled_stats": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_pooled_stats_dense": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_potential_scale_reduction": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
+    "bjx_ess_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "bjx_effective_sample_size": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

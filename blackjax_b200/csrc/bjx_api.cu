@@ -137,6 +137,7 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->coef[0] = 0.5f; h->coef[1] = 1.0f; h->coef[2] = 0.5f;
   h->general_integrator = false;
   h->key_shared = 0;
+  h->steps_dev = nullptr;
   h->chain_offset = 0;
   h->sample_keys = nullptr;
   h->sample_keys_cap = 0;
@@ -201,6 +202,14 @@ extern "C" int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_
   if (!h) return fail(h, BJX_E_INVALID, "null handle");
   h->key_shared = shared_step_key ? 1 : 0;
   h->chain_offset = chain_offset;
+  return 0;
+}
+
+// Dynamic HMC (blackjax/mcmc/dynamic_hmc.py:109-120): per-chain numbers of integration steps int32 [C] (device) for the
+// following bjx_hmc_step / bjx_mhmc_step calls, whose scalar L is then ignored; NULL restores the scalar.
+extern "C" int bjx_set_integration_steps(bjx_handle_t h, const int32_t* steps_dev) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  h->steps_dev = steps_dev;
   return 0;
 }
 
@@ -292,6 +301,7 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.div_thr = h->cfg.divergence_threshold;
   P.key_shared = h->key_shared;
   P.chain_offset = h->chain_offset;
+  P.steps_dev = h->steps_dev;
   P.ncoef = h->ncoef;
   for (int i = 0; i < 11; ++i) P.coef[i] = i < h->ncoef ? h->coef[i] : 0.f;
   return P;
@@ -447,6 +457,8 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
   if ((use_dense_path(h) || use_big_path(h)) && h->general_integrator)
     return fail(h, BJX_E_UNSUPPORTED, "only velocity Verlet is built for dim > 1024 / the tensor-core dense path");
+  if ((use_dense_path(h) || use_big_path(h)) && h->steps_dev)
+    return fail(h, BJX_E_UNSUPPORTED, "per-chain integration steps need dim <= 1024 and the row-resident kernels");
   if (use_dense_path(h))
     return bjx_dense_hmc_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev, L,
                               make_info(info));
@@ -689,6 +701,16 @@ extern "C" int bjx_prng_uniform(bjx_handle_t h, const uint32_t* keys, int64_t n_
   BJX_CHECK_LAUNCH("k_prng_draw");
   return 0;
 }
+// jax.random.randint(key, shape, minval, maxval) int32 (jax/_src/random.py _randint: two 32-bit draws from split(key),
+// combined modulo the span with the 2^32 % span multiplier)
+extern "C" int bjx_prng_randint(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, int32_t minval,
+                                int32_t maxval, int32_t* out) {
+  BJX_PRNG_PROLOGUE();
+  if (per_key < 0 || per_key > 0xFFFFFFFFll) return fail(h, BJX_E_INVALID, "bad per_key");
+  launch_prng_randint(keys, n_keys, per_key, minval, maxval, out, pstream);
+  BJX_CHECK_LAUNCH("k_prng_randint");
+  return 0;
+}
 extern "C" int bjx_prng_normal(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out) {
   BJX_PRNG_PROLOGUE();
   if (per_key < 0 || per_key > 0xFFFFFFFFll) return fail(h, BJX_E_INVALID, "bad per_key");
@@ -774,5 +796,21 @@ extern "C" int bjx_potential_scale_reduction(bjx_handle_t h, const float* histor
   BJX_CUDA(cudaSetDevice(h->cfg.device));
   launch_rhat(num_samples, h->cfg.n_chains, h->cfg.dim, history, rhat_out, scratch, h->stream);
   BJX_CHECK_LAUNCH("k_rhat");
+  return 0;
+}
+
+// blackjax.diagnostics.effective_sample_size (diagnostics.py:159-305) for a history [T, C, D] (chain axis 1, sample axis
+// 0): ess_out [D].  scratch: 8-byte aligned device buffer of at least bjx_ess_scratch_floats(T, C, D) floats.
+extern "C" int64_t bjx_ess_scratch_floats(int32_t num_samples, int32_t n_chains, int32_t dim) {
+  return (int64_t)ess_scratch_floats(num_samples, n_chains, dim);
+}
+extern "C" int bjx_effective_sample_size(bjx_handle_t h, const float* history, int32_t num_samples, float* ess_out,
+                                         float* scratch) {
+  if (!h || !history || !ess_out || !scratch) return fail(h, BJX_E_INVALID, "null argument");
+  if (num_samples < 2) return fail(h, BJX_E_INVALID, "The input array must have at least 2 samples");
+  if ((reinterpret_cast<uintptr_t>(scratch) & 7u) != 0) return fail(h, BJX_E_INVALID, "scratch must be 8-byte aligned");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_ess(num_samples, h->cfg.n_chains, h->cfg.dim, history, ess_out, scratch, h->stream);
+  BJX_CHECK_LAUNCH("k_ess");
   return 0;
 }

@@ -15,4 +15,8 @@ void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* 
 void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, float* out, float* scratch, cudaStream_t s);
 size_t pooled_dense_scratch_floats(int D);
 void launch_rhat(int T, int C, int D, const float* hist, float* rhat, float* scratch, cudaStream_t s);
+void launch_prng_randint(const uint32_t* keys, long long n, long long per_key, int minval, int maxval, int* out,
+                         cudaStream_t s);
+size_t ess_scratch_floats(int T, int C, int D);
+void launch_ess(int T, int C, int D, const float* hist, float* ess, float* scratch, cudaStream_t s);
 }  // namespace bjx

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) k_is_turning(Params P, const float* 
 template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uint32_t* __restrict__ keys,
                                                              const float* q_in, const float* logp_in, const float* g_in,
-                                                             float* q_out, float* logp_out, float* g_out, int L,
+                                                             float* q_out, float* logp_out, float* g_out, int L_all,
                                                              InfoPtrs info) {
   BJX_WARP_PROLOGUE();
   Ctx<R, TK, DM> c;
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   R::load(q, q_in + roff, P.D, lane);
   R::load(g, g_in + roff, P.D, lane);
   c.init(P, chain, lane, sm);
+  const int L = P.steps_dev ? P.steps_dev[chain] : L_all;  // dynamic HMC: this chain's own trajectory length
   const Key rng = chain_key(P, keys, chain);
   const Key key_momentum = fold_in(rng, 0u);    // jax.random.split(rng_key, 2)  hmc.py:299
   const Key key_integrator = fold_in(rng, 1u);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
 template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const uint32_t* __restrict__ keys,
                                                               const float* q_in, const float* logp_in, const float* g_in,
-                                                              float* q_out, float* logp_out, float* g_out, int L,
+                                                              float* q_out, float* logp_out, float* g_out, int L_all,
                                                               InfoPtrs info) {
   BJX_WARP_PROLOGUE();
   Ctx<R, TK, DM> c;
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(kThreads) k_mhmc_transition(Params P, const ui
   R::load(q, q_in + roff, P.D, lane);
   R::load(g, g_in + roff, P.D, lane);
   c.init(P, chain, lane, sm);
+  const int L = P.steps_dev ? P.steps_dev[chain] : L_all;
   const Key rng = chain_key(P, keys, chain);
   const Key key_integrator = fold_in(rng, 1u);   // hmc.py:299
   c.sample_momentum(P, chain, fold_in(rng, 0u), p);

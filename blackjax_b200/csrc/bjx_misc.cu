@@ -33,6 +33,25 @@ __global__ void k_prng_draw(const uint32_t* __restrict__ keys, long long n_keys,
   if (MODE == 2) reinterpret_cast<float*>(out)[t] = normal_at(key, i);
 }
 
+// jax.random.randint for int32 (jax/_src/random.py _randint): k1, k2 = split(key); higher/lower = random_bits(k1/k2);
+// span = maxval - minval (1 when maxval <= minval); multiplier = ((2^16 % span)^2) % span = 2^32 % span;
+// offset = ((higher % span) * multiplier + lower % span) % span, all in uint32; result = minval + offset.
+__global__ void k_prng_randint(const uint32_t* __restrict__ keys, long long n_keys, long long per_key, int minval,
+                               int maxval, int* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_keys * per_key) return;
+  const long long k = t / per_key;
+  const uint32_t i = (uint32_t)(t % per_key);
+  const Key key{keys[2 * k], keys[2 * k + 1]};
+  const uint32_t hi = random_bits(fold_in(key, 0u), i), lo = random_bits(fold_in(key, 1u), i);
+  uint32_t span = (uint32_t)maxval - (uint32_t)minval;
+  if (maxval <= minval) span = 1u;
+  uint32_t mult = (1u << 16) % span;
+  mult = (mult * mult) % span;
+  const uint32_t off = ((hi % span) * mult + lo % span) % span;
+  out[t] = (int)((uint32_t)minval + off);
+}
+
 static inline dim3 grid1d(long long n, int b = 256) { return dim3((unsigned)((n + b - 1) / b)); }
 
 void launch_prng_split(const uint32_t* keys, long long n, int num, uint32_t* out, cudaStream_t s) {
@@ -40,6 +59,10 @@ void launch_prng_split(const uint32_t* keys, long long n, int num, uint32_t* out
 }
 void launch_prng_fold_in(const uint32_t* keys, long long n, uint32_t data, uint32_t* out, cudaStream_t s) {
   if (n > 0) k_prng_fold_in<<<grid1d(n), 256, 0, s>>>(keys, n, data, out);
+}
+void launch_prng_randint(const uint32_t* keys, long long n, long long per_key, int minval, int maxval, int* out,
+                         cudaStream_t s) {
+  if (n * per_key > 0) k_prng_randint<<<grid1d(n * per_key), 256, 0, s>>>(keys, n, per_key, minval, maxval, out);
 }
 void launch_prng_draw(int mode, const uint32_t* keys, long long n, long long per_key, void* out, cudaStream_t s) {
   if (n * per_key <= 0) return;
@@ -276,6 +299,152 @@ void launch_rhat(int T, int C, int D, const float* hist, float* rhat, float* scr
   k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, mean, st_m);
   k_pooled_colstats<<<dim3((D + 31) / 32), dim3(32, 8), 0, s>>>(C, D, var, st_v);
   k_rhat_finish<<<(D + 255) / 256, 256, 0, s>>>(T, C, D, st_m, st_v, rhat);
+}
+
+// ---- effective sample size (blackjax/diagnostics.py:159-305) over a device-resident history [T, C, D] -----------
+// stage 1: per (chain, dim) sample mean (:210) and "differs from its first draw anywhere" flag (:203-208)
+__global__ void k_ess_chain_mean(int T, int C, int D, const float* __restrict__ hist, float* __restrict__ mean,
+                                 int* __restrict__ has_var) {
+  const long long CD = (long long)C * D;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= CD) return;
+  const float x0 = hist[t];
+  double acc = 0.0;
+  bool varies = false;
+  for (int i = 0; i < T; ++i) {
+    const float x = __ldcs(hist + (size_t)i * CD + t);
+    acc += (double)x;
+    varies |= (x != x0);
+  }
+  mean[t] = (float)(acc / (double)T);
+  if (varies) atomicOr(has_var + (int)(t % D), 1);
+}
+
+// stage 2: acov[lag, d] += sum over chains and draws of (x[s] - m)(x[s + lag] - m)  -- the zero-padded (linear)
+// autocovariance the reference gets from its FFT (:212-221), evaluated directly.  A thread owns one (chain, dim) series
+// (32 consecutive dims per warp: coalesced), a block of 8 warps walks a chunk of chains, blockIdx.y picks a block of 32
+// lags; per 8 draws x 32 lags the inner product is 256 FMAs on 16 newly loaded values, all in registers.
+constexpr int kEssLags = 32;
+constexpr int kEssDraws = 8;
+constexpr int kEssWarps = 8;
+__global__ void __launch_bounds__(kEssWarps * 32) k_ess_autocov(int T, int C, int D, const float* __restrict__ hist,
+                                                               const float* __restrict__ mean, double* __restrict__ acov,
+                                                               int chains_per_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
+  const int lag0 = blockIdx.y * kEssLags;
+  const bool live = d < D;
+  const size_t CD = (size_t)C * D;
+  float acc[kEssLags];
+#pragma unroll
+  for (int l = 0; l < kEssLags; ++l) acc[l] = 0.f;
+  const int c_end = min(C, (int)(blockIdx.z + 1) * chains_per_block);
+  for (int c = blockIdx.z * chains_per_block + warp; c < c_end; c += kEssWarps) {
+    const float m = live ? mean[(size_t)c * D + d] : 0.f;
+    const float* series = hist + (size_t)c * D + (live ? d : 0);
+    auto at = [&](int s) -> float { return (live && s < T) ? series[(size_t)s * CD] - m : 0.f; };
+    // window w[i] = x[s + lag0 + i], i < kEssLags + kEssDraws; a[i] = x[s + i], i < kEssDraws
+    float a[kEssDraws], w[kEssLags + kEssDraws];
+#pragma unroll
+    for (int i = 0; i < kEssLags; ++i) w[i] = at(lag0 + i);
+    for (int s = 0; s < T - lag0; s += kEssDraws) {
+#pragma unroll
+      for (int i = 0; i < kEssDraws; ++i) {
+        a[i] = at(s + i);
+        w[kEssLags + i] = at(s + lag0 + kEssLags + i);
+      }
+#pragma unroll
+      for (int i = 0; i < kEssDraws; ++i) {
+#pragma unroll
+        for (int l = 0; l < kEssLags; ++l) acc[l] = fmaf(a[i], w[i + l], acc[l]);
+      }
+#pragma unroll
+      for (int i = 0; i < kEssLags; ++i) w[i] = w[i + kEssDraws];
+    }
+  }
+  __shared__ float red[kEssWarps][kEssLags][32];
+#pragma unroll
+  for (int l = 0; l < kEssLags; ++l) red[warp][l][lane] = acc[l];
+  __syncthreads();
+  for (int l = warp; l < kEssLags; l += kEssWarps) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kEssWarps; ++w) sum += red[w][l][lane];
+    if (live && lag0 + l < T) atomicAdd(acov + (size_t)(lag0 + l) * D + d, (double)sum);
+  }
+}
+
+// stage 3, one thread per dim: Geyer's initial positive / initial monotone sequences on the chain-averaged
+// autocorrelation (:222-301).  The reference builds arrays with scans and a scatter; here the pairs are regenerated on
+// the fly.  Its index max_t + 1 can be one past the last pair: JAX drops that scatter and clamps that gather.
+__global__ void k_ess_finish(int T, int C, int D, const float* __restrict__ mean, const int* __restrict__ has_var,
+                             const double* __restrict__ acov, float* __restrict__ ess) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const double norm = 1.0 / ((double)T * (double)C);
+  auto a = [&](int t) -> float { return (float)(acov[(size_t)t * D + d] * norm); };
+  const float Tf = (float)T;
+  const float var0 = a(0) * Tf / (Tf - 1.0f);                                      // :222-226
+  const bool degenerate = isfinite(var0) && (!has_var[d] || var0 <= 0.0f);         // :227-229
+  float wvar = var0 * (Tf - 1.0f) / Tf;                                            // :230
+  if (C > 1) {                                                                     // :231-237 var of the chain means, ddof=1
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < C; ++c) {
+      const double v = (double)mean[(size_t)c * D + d];
+      s1 += v;
+      s2 += v * v;
+    }
+    wvar += (float)((s2 - s1 * s1 / (double)C) / (double)(C - 1));
+  }
+  if (degenerate) wvar = 1.0f;                                                     // :238-240
+  const int K = (T - T % 2) / 2;                                                   // pairs (rho[2k], rho[2k+1])
+  auto rho = [&](int t) -> float { return t == 0 ? 1.0f : 1.0f - (var0 - a(t)) / wvar; };   // :243-253
+  int n_true = 0;                                                                  // :259-270 leading run of positive pairs
+  while (n_true < K && rho(2 * n_true) + rho(2 * n_true + 1) > 0.0f) ++n_true;
+  const int max_t = n_true > 0 ? n_true - 1 : 0;
+  const int idx = max_t + 1, idx_get = idx < K ? idx : K - 1;
+  const bool even_at_idx = rho(2 * idx_get) > 0.0f;                                // :273 (unmasked value)
+  float carry = 0.f, sum = 0.f, e_at = 0.f;
+  const int k_end = (idx + 1 < K) ? idx + 1 : K;                                   // every later pair is masked to zero
+  for (int k = 0; k < k_end; ++k) {
+    const bool mk = k < n_true;
+    const bool mk_even = (k == idx) ? even_at_idx : mk;                            // :273
+    float e = mk_even ? rho(2 * k) : 0.f;                                          // :274
+    float o = mk ? rho(2 * k + 1) : 0.f;                                           // :271
+    const float s = e + o;
+    if (k == 0) carry = s;                                                         // :282-285
+    const bool upd = s > carry;                                                    // :277-280
+    const float nxt = upd ? carry : s;
+    carry = nxt;
+    if (upd) e = o = nxt / 2.0f;                                                   // :287-288
+    sum += e + o;
+    if (k == idx_get) e_at = e;
+  }
+  const float ess_raw = (float)C * (float)T;                                       // :292
+  float tau = -1.0f + 2.0f * sum - e_at;                                           // :293-297
+  tau = fmaxf(tau, 1.0f / log10f(ess_raw));                                        // :299
+  ess[d] = degenerate ? 0.0f : ess_raw / tau;                                      // :300-301
+}
+
+size_t ess_scratch_floats(int T, int C, int D) { return 2 * (size_t)T * D + (size_t)C * D + (size_t)D + 8; }
+// scratch (8-byte aligned): acov double [T, D] | mean float [C, D] | has_var int [D]
+void launch_ess(int T, int C, int D, const float* hist, float* ess, float* scratch, cudaStream_t s) {
+  double* acov = reinterpret_cast<double*>(scratch);
+  float* mean = scratch + 2 * (size_t)T * D;
+  int* has_var = reinterpret_cast<int*>(mean + (size_t)C * D);
+  cudaMemsetAsync(acov, 0, sizeof(double) * (size_t)T * D, s);
+  cudaMemsetAsync(has_var, 0, sizeof(int) * (size_t)D, s);
+  k_ess_chain_mean<<<grid1d((long long)C * D), 256, 0, s>>>(T, C, D, hist, mean, has_var);
+  const int lag_blocks = (T + kEssLags - 1) / kEssLags;
+  // enough chain chunks to fill the GPU, few enough that the double atomics stay rare
+  const int d_blocks = (D + 31) / 32;
+  int chunks = (4 * 148 + d_blocks * lag_blocks - 1) / (d_blocks * lag_blocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  const int max_chunks = (C + kEssWarps - 1) / kEssWarps;
+  chunks = chunks > max_chunks ? max_chunks : chunks;
+  const int cpb = (C + chunks - 1) / chunks;
+  k_ess_autocov<<<dim3(d_blocks, lag_blocks, (C + cpb - 1) / cpb), kEssWarps * 32, 0, s>>>(T, C, D, hist, mean, acov, cpb);
+  k_ess_finish<<<(D + 127) / 128, 128, 0, s>>>(T, C, D, mean, has_var, acov, ess);
 }
 
 void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s) {

@@ -45,6 +45,8 @@ struct Params {
   // and invariant to how the chains are sharded over GPUs.
   int key_shared;
   uint32_t chain_offset;
+  // per-chain number of integration steps (dynamic HMC, mcmc/dynamic_hmc.py:109-120) or nullptr (the launch's scalar L)
+  const int* steps_dev;
   // palindromic two-stage integrator coefficients (integrators.py:62-152); velocity Verlet = {0.5, 1, 0.5}
   int ncoef;
   float coef[11];

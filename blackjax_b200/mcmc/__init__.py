@@ -1,1 +1,1 @@
-from . import hmc, integrators, nuts  # noqa: F401
+from . import dynamic_hmc, hmc, integrators, nuts  # noqa: F401

@@ -72,3 +72,15 @@ def uniform(keys, shape=()):
 def normal(keys, shape=()):
     """``jax.random.normal(key, shape)`` float32."""
     return _draw(lib().bjx_prng_normal, keys, shape, torch.float32)
+
+
+def randint(keys, shape, minval, maxval):
+    """``jax.random.randint(key, shape, minval, maxval)`` int32 in [minval, maxval)."""
+    k, n = _flat(keys)
+    per = 1
+    for s_ in shape:
+        per *= int(s_)
+    out = torch.empty(tuple(k.shape[:-1]) + tuple(shape), dtype=torch.int32, device=k.device)
+    with torch.cuda.device(k.device):
+        check(lib().bjx_prng_randint(None, ptr(k), n, per, int(minval), int(maxval), ptr(out)))
+    return out

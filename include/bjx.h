@@ -111,6 +111,10 @@ int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int32_t n);
  * kernel -- the reference's step-major schedule (docs/examples/howto_sample_multiple_chains.md:116-129), independent
  * of how the chains are sharded over GPUs (chain_offset = first global chain of this handle). */
 int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_t chain_offset);
+/* Dynamic HMC (blackjax/mcmc/dynamic_hmc.py:62-130): every chain integrates its own number of steps.  steps_dev: int32
+ * [n_chains] device array read by the following bjx_hmc_step / bjx_mhmc_step calls (their scalar L is then ignored);
+ * NULL restores the scalar.  The caller keeps the array alive until those calls have run.  dim <= 1024 only. */
+int bjx_set_integration_steps(bjx_handle_t h, const int32_t* steps_dev);
 int bjx_synchronize(bjx_handle_t h);
 
 /* metrics.default_metric / gaussian_euclidean (metrics.py:180-218,221-346): precomputes
@@ -180,6 +184,10 @@ int bjx_prng_fold_in(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, uint3
 int bjx_prng_random_bits(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, uint32_t* out);
 int bjx_prng_uniform(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out);
 int bjx_prng_normal(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, float* out);
+/* jax.random.randint(key, shape, minval, maxval) int32 -- dynamic_hmc's default integration_steps_fn
+ * (dynamic_hmc.py:66: randint(key, (), 1, 10)) */
+int bjx_prng_randint(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, int32_t minval, int32_t maxval,
+                     int32_t* out);
 
 /* ---- window adaptation (staged_adaptation.py:111-307) -------------------------------------------- */
 /* Per-chain dual averaging (optimizers/dual_averaging.py:87-129).  da_state float32 [C,5] =
@@ -207,6 +215,12 @@ int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acceptan
  * by bjx_hmc_sample; rhat_out float32 [D]; scratch: at least 2*C*D + 4 + 4*D floats (device). */
 int bjx_potential_scale_reduction(bjx_handle_t h, const float* history, int32_t num_samples, float* rhat_out,
                                   float* scratch);
+
+/* blackjax.diagnostics.effective_sample_size (diagnostics.py:159-305; Geyer initial positive + monotone sequences on
+ * the chain-averaged autocovariance), same history layout; ess_out float32 [D]; scratch: 8-byte aligned device buffer of
+ * at least bjx_ess_scratch_floats(num_samples, C, D) floats.  One chain is allowed (no between-chain term). */
+int64_t bjx_ess_scratch_floats(int32_t num_samples, int32_t n_chains, int32_t dim);
+int bjx_effective_sample_size(bjx_handle_t h, const float* history, int32_t num_samples, float* ess_out, float* scratch);
 
 #ifdef __cplusplus
 }

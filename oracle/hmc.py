@@ -169,6 +169,29 @@ def hmc_kernel(keys, state, target, step_size, inverse_mass_matrix, num_integrat
     return new, info
 
 
+def dynamic_hmc_kernel(keys, state, random_generator_arg, target, step_size, inverse_mass_matrix,
+                       divergence_threshold=1000.0, coefficients=VELOCITY_VERLET, multinomial=False):
+    """Dynamic HMC (blackjax/mcmc/dynamic_hmc.py:97-128) with the default ``integration_steps_fn =
+    randint(key, (), 1, 10)`` (:66) and ``next_random_arg_fn = split(key)[1]`` (:65): every chain draws its own number
+    of integration steps from its ``random_generator_arg`` and runs the static HMC kernel with it.  Restated chain by
+    chain (the step counts differ).  Returns (new_state, info, next_random_generator_arg, steps)."""
+    q0, logp0, g0 = state
+    C = q0.shape[0]
+    steps = prng.randint(random_generator_arg, (), 1, 10)                       # :109-111
+    base = mhmc_kernel if multinomial else hmc_kernel
+    eps = np.asarray(step_size, F)
+    news, infos = [], []
+    for c in range(C):
+        st = (q0[c:c + 1], logp0[c:c + 1], g0[c:c + 1])
+        new, info = base(keys[c:c + 1], st, target, eps[c:c + 1] if eps.ndim == 1 else eps, inverse_mass_matrix,
+                         int(steps[c]), divergence_threshold, coefficients)   # :113-120
+        news.append(new)
+        infos.append(info)
+    new = HMCState(*[np.concatenate([n[i] for n in news]) for i in range(3)])
+    nxt = prng.split(random_generator_arg, 2)[:, 1]                             # :121
+    return new, infos, nxt, steps
+
+
 def mhmc_kernel(keys, state, target, step_size, inverse_mass_matrix, num_integration_steps,
                 divergence_threshold=1000.0, coefficients=VELOCITY_VERLET):
     """Multinomial HMC transition (hmc.py:181-248 multinomial_hmc_proposal + trajectory.py:170-232

@@ -87,6 +87,24 @@ def uniform(keys, shape=(), minval=0.0, maxval=1.0):
     return np.maximum(lo, f * (hi - lo) + lo).astype(np.float32)
 
 
+def randint(keys, shape, minval, maxval):
+    """``jax.random.randint(key, shape, minval, maxval)`` int32 (jax/_src/random.py ``_randint``, restated from memory of
+    jax 0.10 -- PARITY UNPINNED like the rest of the PRNG spec): ``k1, k2 = split(key)``; two 32-bit draws; the 64-bit
+    value ``higher * 2**32 + lower`` is reduced modulo ``span = maxval - minval`` with the multiplier
+    ``2**32 % span`` computed as ``((2**16 % span) ** 2) % span``; all arithmetic wraps in uint32."""
+    keys = np.asarray(keys, _U32)
+    ks = split(keys, 2)
+    higher = random_bits(ks[..., 0, :], shape).astype(np.uint64)
+    lower = random_bits(ks[..., 1, :], shape).astype(np.uint64)
+    span = np.uint64((int(maxval) - int(minval)) & 0xFFFFFFFF) if maxval > minval else np.uint64(1)
+    m32 = np.uint64(0xFFFFFFFF)
+    mult = np.uint64(1 << 16) % span
+    mult = ((mult * mult) & m32) % span
+    off = ((((higher % span) * mult) & m32) + (lower % span)) & m32
+    off = off % span
+    return ((np.uint64(int(minval) & 0xFFFFFFFF) + off) & m32).astype(_U32).view(np.int32)
+
+
 def bernoulli(keys, p=np.float32(0.5)):
     """``jax.random.bernoulli(key, p)`` = uniform(key, shape(p)) < p (p: per-key scalar)."""
     p = np.asarray(p, np.float32)

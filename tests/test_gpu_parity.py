@@ -301,6 +301,47 @@ def test_potential_scale_reduction_on_device_history():
     assert np.all(npy(bj.diagnostics.potential_scale_reduction(hist, tgt)) > 1.2)
 
 
+@pytest.mark.parametrize("C, T_, D", [(64, 200, 24), (1, 501, 5), (7, 64, 132), (3, 33, 1)])
+def test_effective_sample_size_on_device_history(C, T_, D):
+    """blackjax/diagnostics.py:159-305 on the device vs the oracle, on autocorrelated draws (AR(1) per dim with a
+    different coefficient each, incl. anti-correlated ones) plus the degenerate columns of tests/test_diagnostics.py:91-116."""
+    from oracle import diagnostics as odiag
+    rs = np.random.default_rng(C * 1000 + T_)
+    phi = np.linspace(-0.6, 0.95, D)
+    x = np.zeros((T_, C, D), F)
+    e = rs.standard_normal((T_, C, D)).astype(F)
+    for t in range(1, T_):
+        x[t] = phi * x[t - 1] + e[t]
+    if D >= 5:
+        x[:, :, 1] = 0.0                                    # constant
+        x[:, :, 2] = np.arange(C, dtype=F)[None, :]         # constant per chain, different means
+        x[:, :, 3] = 1e-30 * e[:, :, 3]                      # numerically constant
+    tgt = T.StdNormal(D)
+    ess = npy(bj.diagnostics.effective_sample_size(tf(x), tgt))
+    ref = np.atleast_1d(odiag.effective_sample_size(x, chain_axis=1, sample_axis=0))
+    if D >= 5:
+        np.testing.assert_array_equal(ess[1:4], 0.0)
+        np.testing.assert_array_equal(ref[1:4], 0.0)
+    # the truncation points of Geyer's sequences are discontinuous in the autocorrelations: allow a few columns to land
+    # on the other side of a float32-level tie, require the rest to agree tightly
+    rel = np.abs(ess - ref) / np.maximum(np.abs(ref), 1e-30)
+    rel[ref == 0] = np.abs(ess[ref == 0])
+    assert np.mean(rel < 2e-3) >= 0.9, (ess, ref)
+    assert np.all(rel < 0.2), (ess, ref)
+
+
+def test_effective_sample_size_iid_and_hmc_history():
+    tgt = T.DiagGaussian(np.logspace(-0.3, 0.3, 24))
+    C, T_ = 256, 100
+    iid = torch.randn(T_, C, 24, device=DEV)
+    ess = npy(bj.diagnostics.effective_sample_size(iid, tgt))
+    np.testing.assert_allclose(ess, C * T_, rtol=0.1)
+    st0 = bj.hmc.init(torch.randn(C, 24, device=DEV), tgt)
+    _, hist, _ = bj.sample_hmc_native(bj.random.key(5, DEV), st0, tgt, 0.3, torch.ones(24, device=DEV), 8, T_)
+    ess = npy(bj.diagnostics.effective_sample_size(hist, tgt))
+    assert np.all(ess > 0.05 * C * T_) and np.all(np.isfinite(ess))
+
+
 def test_hmc_inplace_and_out_of_place_agree():
     tgt = T.StdNormal(64)
     q = torch.randn(128, 64, device=DEV)
@@ -472,6 +513,74 @@ def test_mhmc_api_and_sampling():
     a, _ = explicit(keys[0], st, tgt, 0.5, torch.ones(1, device=DEV), 20)
     b, _ = bj.mhmc.build_kernel()(keys[0], st, tgt, 0.5, torch.ones(1, device=DEV), 20)
     assert torch.equal(a.position, b.position)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8f item 4 (first piece): dynamic HMC -- per-chain random trajectory lengths (mcmc/dynamic_hmc.py)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape, lo, hi", [((), 1, 10), ((5,), 0, 100), ((3,), -7, 7), ((), 4, 4), ((2,), 0, 1 << 20)])
+def test_randint_bit_exact(shape, lo, hi):
+    keys = oprng.split(oprng.key(21), 257)
+    ref = oprng.randint(keys, shape, lo, hi)
+    out = bj.random.randint(tk(keys), shape, lo, hi).cpu().numpy()
+    assert out.dtype == np.int32 and out.shape == ref.shape
+    np.testing.assert_array_equal(out, ref)
+    assert out.min() >= lo and (out.max() < hi or hi <= lo)
+
+
+@pytest.mark.parametrize("kind, D, multinomial", [("std", 100, False), ("diag", 1024, False), ("funnel", 64, False),
+                                                  ("dense", 6, False), ("diag", 97, True)])
+def test_dynamic_hmc_matches_oracle(kind, D, multinomial):
+    rs = np.random.default_rng(31)
+    tgt, otgt = make_target(kind, D, rs)
+    C, eps = 48, 0.11
+    imm = np.exp(rs.uniform(-0.5, 0.5, D)).astype(F)
+    q = (0.4 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(8), C)
+    rga = oprng.split(oprng.key(9), C)
+    onew, oinfos, onext, osteps = ohmc.dynamic_hmc_kernel(keys, ohmc.init(q, otgt), rga, otgt, F(eps), imm,
+                                                          multinomial=multinomial)
+    alg = bj.dmhmc if multinomial else bj.dhmc
+    kernel = alg.build_kernel()
+    state = alg.init(tf(q), tgt, tk(rga))
+    new, info = kernel(tk(keys), state, tgt, float(eps), tf(imm))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(info.num_integration_steps.cpu().numpy(), osteps)     # bit-exact step counts
+    assert len(set(osteps.tolist())) > 3                                                # the chains really differ
+    np.testing.assert_array_equal(new.random_generator_arg.cpu().numpy().view(np.uint32), onext)
+    oacc = np.array([i.is_accepted[0] for i in oinfos])
+    orate = np.array([i.acceptance_rate[0] for i in oinfos])
+    if multinomial:
+        same = np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1)
+        assert same.mean() >= 0.9
+    else:
+        assert (npy(info.is_accepted) == oacc).all()
+        same = np.ones(C, bool)
+    close(npy(info.acceptance_rate)[same], orate[same], rtol=1e-4, scale=1.0)
+    close(npy(new.position)[same], onew.position[same], rtol=1e-5 if not multinomial else 1e-4)
+    close(npy(new.logdensity)[same], onew.logdensity[same], rtol=1e-5, scale=np.max(np.abs(onew.logdensity)) + 1)
+
+
+def test_dynamic_hmc_top_level_api_samples():
+    # tests/mcmc/test_sampling.py dynamic HMC usage: the step-count keys evolve, the sampler mixes
+    assert bj.dynamic_hmc is bj.dhmc
+    tgt = T.DiagGaussian(np.array([1.0, 2.0], F))
+    alg = bj.dhmc(tgt, 0.5, torch.ones(2, device=DEV))
+    st = alg.init(torch.zeros(8192, 2, device=DEV), bj.random.key(3, DEV))
+    assert st.random_generator_arg.shape == (8192, 2)
+    keys = bj.random.split(bj.random.key(0, DEV), 80)
+    for t in range(80):
+        prev = st.random_generator_arg
+        st, info = alg.step(keys[t], st)
+        assert not torch.equal(prev, st.random_generator_arg)
+    assert int(info.num_integration_steps.min()) >= 1 and int(info.num_integration_steps.max()) <= 9
+    std = st.position.std(0).cpu().numpy()
+    np.testing.assert_allclose(std, [1.0, 2.0], rtol=0.1)
+    with pytest.raises(bj.BjxError):                       # per-chain step counts are a row-kernel feature
+        big = T.DiagGaussian(np.ones(2048, F))
+        k = bj.dhmc.build_kernel()
+        s0 = bj.dhmc.init(torch.zeros(16, 2048, device=DEV), big, bj.random.split(bj.random.key(1, DEV), 16))
+        k(keys[0], s0, big, 0.1, torch.ones(2048, device=DEV))
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -84,6 +84,13 @@ def test_api_surface_mirrors_blackjax():
     assert isinstance(alg, bj.SamplingAlgorithm)
     assert list(inspect.signature(alg.step).parameters) == ["rng_key", "state"]
     assert bj.nuts.init is bj.hmc.init                     # blackjax/mcmc/nuts.py:33
+    # blackjax/__init__.py:117-118,154-162 and mcmc/dynamic_hmc.py:54-60,97-104
+    assert bj.dynamic_hmc is bj.dhmc and callable(bj.dmhmc.build_kernel)
+    assert list(inspect.signature(bj.dhmc.init).parameters) == ["position", "logdensity_fn", "random_generator_arg"]
+    assert list(inspect.signature(bj.dhmc.build_kernel()).parameters) == [
+        "rng_key", "state", "logdensity_fn", "step_size", "inverse_mass_matrix", "integration_steps_params"]
+    assert bj.mcmc.dynamic_hmc.DynamicHMCState._fields == ("position", "logdensity", "logdensity_grad",
+                                                           "random_generator_arg")
 
 
 def test_schedule_matches_reference_kat():

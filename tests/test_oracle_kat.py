@@ -320,3 +320,51 @@ def test_hier_logit_oracle_gradient_matches_finite_differences():
     fd = np.array([(logp64(q + 1e-6 * e) - logp64(q - 1e-6 * e)) / 2e-6 for e in np.eye(16)])
     np.testing.assert_allclose(g[0], fd, rtol=2e-4, atol=2e-4)
     np.testing.assert_allclose(lp[0], logp64(q.astype(F).astype(np.float64)), rtol=1e-5)
+
+
+# ---- tests/test_diagnostics.py:54-124 (effective sample size) -----------------------------------------------------
+@pytest.mark.parametrize("num_chains", [1, 2, 10])
+def test_ess_iid_draws_close_to_total(num_chains):
+    from oracle import diagnostics as odiag
+    x = np.random.default_rng(32).standard_normal((num_chains, 5000, 3))
+    ess = odiag.effective_sample_size(x)
+    assert ess.shape == (3,)
+    np.testing.assert_allclose(ess, num_chains * 5000, rtol=0.1)          # the reference allows rtol=10
+    # axis handling (tests/test_diagnostics.py:300-312)
+    np.testing.assert_allclose(odiag.effective_sample_size(np.moveaxis(x, 0, 1), chain_axis=1, sample_axis=0), ess)
+
+
+@pytest.mark.parametrize("num_chains", [1, 2])
+def test_ess_zero_for_numerically_degenerate_chains(num_chains):
+    from oracle import diagnostics as odiag
+    T_ = 2000
+    r = np.random.default_rng(32).standard_normal((num_chains, T_))
+    samples = np.stack([np.zeros((num_chains, T_)), np.broadcast_to(np.arange(num_chains)[:, None], (num_chains, T_)),
+                        1e-30 * r, r], axis=-1)
+    ess = odiag.effective_sample_size(samples)
+    np.testing.assert_array_equal(ess[:3], np.zeros(3))
+    assert ess[3] > 0
+
+
+def test_ess_antithetic_chain_exceeds_draw_count_and_ar1_matches_theory():
+    from oracle import diagnostics as odiag
+    assert odiag.effective_sample_size(np.tile(np.array([-1.0, 1.0]), 1000)[None, :]) > 2000
+    rs = np.random.default_rng(3)
+    phi, C, T_ = 0.9, 8, 4000
+    e = rs.standard_normal((C, T_))
+    x = np.zeros((C, T_))
+    for t in range(1, T_):
+        x[:, t] = phi * x[:, t - 1] + e[:, t]
+    np.testing.assert_allclose(odiag.effective_sample_size(x), C * T_ * (1 - phi) / (1 + phi), rtol=0.15)
+
+
+def test_randint_range_and_uniformity():
+    # jax.random.randint contract used by dynamic_hmc.py:66: int32 in [minval, maxval), (near) uniform
+    from oracle import prng as oprng
+    k = oprng.split(oprng.key(3), 20000)
+    r = oprng.randint(k, (), 1, 10)
+    assert r.dtype == np.int32 and r.min() == 1 and r.max() == 9
+    np.testing.assert_allclose(np.bincount(r)[1:] / len(r), 1 / 9, atol=0.01)
+    assert np.all(oprng.randint(k[:10], (4,), 5, 5) == 5)          # maxval <= minval returns minval
+    big = oprng.randint(k[:100], (3,), -(1 << 30), 1 << 30)
+    assert big.min() < -(1 << 28) and big.max() > (1 << 28)
