@@ -373,7 +373,8 @@ def dense_problem(D, C, seed=31, metric="dense", target="dense"):
 
 
 @pytest.mark.parametrize("D, C, metric, target", [(256, 100, "dense", "dense"), (512, 37, "dense", "dense"),
-                                                  (256, 64, "diag", "dense"), (256, 64, "dense", "diag")])
+                                                  (256, 64, "diag", "dense"), (256, 64, "dense", "diag"),
+                                                  (132, 21, "dense", "dense")])   # D % 8 != 0: padded operand planes
 def test_dense_path_building_blocks(D, C, metric, target):
     tgt, otgt, imm, q = dense_problem(D, C, metric=metric, target=target)
     eng = _engine.Engine(DEV, C, D, tgt)
@@ -400,8 +401,36 @@ def test_dense_path_building_blocks(D, C, metric, target):
     close(npy(logp), lp1, rtol=2e-5, scale=np.max(np.abs(lp1)) + 1)
 
 
+def test_dense_velocity_row_scaling_and_non_finite_rows():
+    """The fp16 operand split is only float32-accurate because every row is lifted by a power of two first
+    (bjx_dense.cu k_rows_split2): rows of magnitude 1e-6 ... 1e6 must all come out at float32 accuracy relative to
+    their own scale, matrices of any magnitude too, and a NaN / inf row must poison only itself."""
+    D, C = 256, 40
+    rs = np.random.default_rng(5)
+    for mat_scale in (1e-5, 1.0, 3e4):
+        A = rs.standard_normal((D, D))
+        imm = ((A @ A.T / D + np.eye(D)) * mat_scale).astype(F)
+        tgt = T.DiagGaussian(np.ones(D, F))
+        eng = _engine.Engine(DEV, C, D, tgt)
+        eng.set_metric(tf(imm))
+        p = rs.standard_normal((C, D)).astype(F)
+        p *= (10.0 ** rs.uniform(-6, 6, size=(C, 1))).astype(F)
+        p[3, 7] = np.nan
+        p[5, 0] = np.inf
+        v = npy(eng.velocity(tf(p)))
+        ok = np.ones(C, bool)
+        ok[[3, 5]] = False
+        ref = p[ok].astype(np.float64) @ imm.astype(np.float64)
+        err = np.abs(v[ok] - ref).max(axis=1) / np.abs(ref).max(axis=1)
+        assert err.max() < 3e-6, (mat_scale, err.max())
+        assert not np.isfinite(v[3]).any() or np.isnan(v[3]).any()
+        assert np.isnan(v[3]).all() and not np.isfinite(v[5]).all()
+        eng.close()
+
+
 @pytest.mark.parametrize("D, C, L, pce", [(256, 96, 6, False), (384, 40, 4, True), (256, 8203, 3, False),
-                                          (256, 8200, 2, True)])     # >= 8192 chains: two slices on two streams
+                                          (256, 8200, 2, True),      # >= 8192 chains: two slices on two streams
+                                          (132, 33, 5, True)])       # padded operand planes
 def test_dense_hmc_transition_matches_oracle(D, C, L, pce):
     tgt, otgt, imm, q = dense_problem(D, C)
     keys = oprng.split(oprng.key(17), C)
