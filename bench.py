@@ -19,6 +19,9 @@ import sys
 import threading
 import time
 
+# NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line, so send them to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
