@@ -106,6 +106,8 @@ constexpr int kAlignAB = 8;                     // 16-byte TMA alignment (fp16)
 constexpr int kAlignC = 4;                      // 16 bytes (float)
 
 // CTA pair (cta_group::2): a 256x256 accumulator tile shared by two SMs, operands split between them
+// (measured alternatives on config 2, ms per transition: 256x256x64 / cluster 2x1 48.9 -- this one; cluster 2x2 48.4-48.6;
+// 256x128x64 52.0; 256x256x128 51.0-52.5: the step is power-capped, tile shape moves it by noise except where it hurts)
 using MmaTileShape = Shape<_256, _256, _64>;
 using ClusterShape = Shape<_2, _1, _1>;
 
