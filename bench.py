@@ -155,13 +155,16 @@ def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
                 cport.hmc_step(0, inv_var, imm, keys, q, logp, g, eps, L)
             return time.perf_counter() - t0
 
-    probe_c = max(cores * (16 if wl.get("dense") else 4), 64)
+    # the dense twin works on blocks of 48 chains (its GEMM micro-kernel): keep every thread on whole blocks
+    gran = cores * (48 if wl.get("dense") else 1)
+    probe_c = max(gran if wl.get("dense") else cores * 4, 64)
     run(probe_c, 1)
     t = run(probe_c, 1)
     per_chain = t / probe_c
     n_steps = max(1, steps)
     Cs = int(min(wl["C"], max(probe_c, budget_s / max(per_chain * (n_steps + warmup), 1e-9))))
-    Cs = max(cores, (Cs // cores) * cores)
+    Cs = max(gran, (Cs // gran) * gran)
+    Cs = min(Cs, max(gran, (wl["C"] // gran) * gran)) if wl["C"] >= gran else wl["C"]
     if steps <= 1:  # cpu_baseline leg: fill the ~budget_s of CPU work with more transitions when all chains fit
         n_steps = int(max(1, min(200, budget_s / max(per_chain * Cs, 1e-9))))
     if warmup:

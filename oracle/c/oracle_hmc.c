@@ -182,30 +182,82 @@ long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const fl
 
 /* ------------------------------------------------------------------------------------------------------
  * Dense variant (BASELINE config 2): dense Gaussian target logp = -1/2 x^T P x, dense inverse mass matrix.
- * Chains are processed in blocks of BLK so every matrix row is reused BLK times from L1 (a small GEMM).
+ * Chains are processed in blocks of BLK through a register-blocked GEMM micro-kernel (the matrices are symmetric;
+ * L^-T is transposed once per call).
  * ------------------------------------------------------------------------------------------------------ */
-#define BLK 16
+#define BLK 48
 typedef struct {
   int c0, c1, D, L;
-  const float *prec, *imm, *msqrt;
+  const float *prec, *imm, *msqrt_t;
   const uint32_t* keys;
   float *q, *logp, *g, eps, *acc_rate;
   unsigned char* accepted;
 } djob_t;
 
-/* Y[b][i] = sum_j A[i][j] X[b][j]   (A row-major [D,D]) */
-static void matmul_blk(int nb, int D, const float* A, const float* X, float* Y) {
-  for (int i = 0; i < D; ++i) {
-    const float* row = A + (size_t)i * D;
+/* Y[b][i] = sum_j X[b][j] At[j][i]   (At row-major [D,D] = A^T; the symmetric matrices are passed as they are).
+ * A register-blocked GEMM micro-kernel: 6 chains x 16 outputs of accumulators, broadcast X, stream rows of At --
+ * what a compiled "vmap of linear_map" amounts to on a CPU (XLA:CPU hands the batched product to an Eigen GEMM). */
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+static void matmul_blk(int nb, int D, const float* At, const float* X, float* Y) {
+  const int D16 = D & ~15;
+  for (int i0 = 0; i0 < D16; i0 += 16) {
+    int b0 = 0;
+    for (; b0 + 6 <= nb; b0 += 6) {
+      __m256 c00 = _mm256_setzero_ps(), c01 = c00, c10 = c00, c11 = c00, c20 = c00, c21 = c00, c30 = c00, c31 = c00,
+             c40 = c00, c41 = c00, c50 = c00, c51 = c00;
+      const float* x0 = X + (size_t)b0 * D;
+      for (int j = 0; j < D; ++j) {
+        const __m256 a0 = _mm256_loadu_ps(At + (size_t)j * D + i0), a1 = _mm256_loadu_ps(At + (size_t)j * D + i0 + 8);
+        __m256 x;
+        x = _mm256_broadcast_ss(x0 + j);                 c00 = _mm256_fmadd_ps(x, a0, c00); c01 = _mm256_fmadd_ps(x, a1, c01);
+        x = _mm256_broadcast_ss(x0 + (size_t)D + j);     c10 = _mm256_fmadd_ps(x, a0, c10); c11 = _mm256_fmadd_ps(x, a1, c11);
+        x = _mm256_broadcast_ss(x0 + (size_t)2 * D + j); c20 = _mm256_fmadd_ps(x, a0, c20); c21 = _mm256_fmadd_ps(x, a1, c21);
+        x = _mm256_broadcast_ss(x0 + (size_t)3 * D + j); c30 = _mm256_fmadd_ps(x, a0, c30); c31 = _mm256_fmadd_ps(x, a1, c31);
+        x = _mm256_broadcast_ss(x0 + (size_t)4 * D + j); c40 = _mm256_fmadd_ps(x, a0, c40); c41 = _mm256_fmadd_ps(x, a1, c41);
+        x = _mm256_broadcast_ss(x0 + (size_t)5 * D + j); c50 = _mm256_fmadd_ps(x, a0, c50); c51 = _mm256_fmadd_ps(x, a1, c51);
+      }
+      float* y0 = Y + (size_t)b0 * D + i0;
+      _mm256_storeu_ps(y0, c00);                 _mm256_storeu_ps(y0 + 8, c01);
+      _mm256_storeu_ps(y0 + (size_t)D, c10);     _mm256_storeu_ps(y0 + (size_t)D + 8, c11);
+      _mm256_storeu_ps(y0 + (size_t)2 * D, c20); _mm256_storeu_ps(y0 + (size_t)2 * D + 8, c21);
+      _mm256_storeu_ps(y0 + (size_t)3 * D, c30); _mm256_storeu_ps(y0 + (size_t)3 * D + 8, c31);
+      _mm256_storeu_ps(y0 + (size_t)4 * D, c40); _mm256_storeu_ps(y0 + (size_t)4 * D + 8, c41);
+      _mm256_storeu_ps(y0 + (size_t)5 * D, c50); _mm256_storeu_ps(y0 + (size_t)5 * D + 8, c51);
+    }
+    for (; b0 < nb; ++b0) { /* leftover chains of the block */
+      __m256 c0 = _mm256_setzero_ps(), c1 = c0;
+      const float* x0 = X + (size_t)b0 * D;
+      for (int j = 0; j < D; ++j) {
+        const __m256 x = _mm256_broadcast_ss(x0 + j);
+        c0 = _mm256_fmadd_ps(x, _mm256_loadu_ps(At + (size_t)j * D + i0), c0);
+        c1 = _mm256_fmadd_ps(x, _mm256_loadu_ps(At + (size_t)j * D + i0 + 8), c1);
+      }
+      _mm256_storeu_ps(Y + (size_t)b0 * D + i0, c0);
+      _mm256_storeu_ps(Y + (size_t)b0 * D + i0 + 8, c1);
+    }
+  }
+  for (int i = D16; i < D; ++i) /* leftover outputs */
     for (int b = 0; b < nb; ++b) {
-      const float* x = X + (size_t)b * D;
       float acc = 0.f;
-#pragma omp simd reduction(+ : acc)
-      for (int j = 0; j < D; ++j) acc += row[j] * x[j];
+      for (int j = 0; j < D; ++j) acc += X[(size_t)b * D + j] * At[(size_t)j * D + i];
       Y[(size_t)b * D + i] = acc;
+    }
+}
+#else
+static void matmul_blk(int nb, int D, const float* At, const float* X, float* Y) {
+  for (int b = 0; b < nb; ++b) {
+    float* y = Y + (size_t)b * D;
+    for (int i = 0; i < D; ++i) y[i] = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float x = X[(size_t)b * D + j];
+      const float* row = At + (size_t)j * D;
+#pragma omp simd
+      for (int i = 0; i < D; ++i) y[i] += x * row[i];
     }
   }
 }
+#endif
 
 static void* dworker(void* arg) {
   djob_t* J = (djob_t*)arg;
@@ -227,7 +279,7 @@ static void* dworker(void* arg) {
       memcpy(g1 + (size_t)b * D, J->g + (size_t)c * D, sizeof(float) * D);
       lp[b] = J->logp[c];
     }
-    matmul_blk(nb, D, J->msqrt, z, p); /* p = L^-T z */
+    matmul_blk(nb, D, J->msqrt_t, z, p); /* p = L^-T z */
     matmul_blk(nb, D, J->imm, p, v);
     for (int b = 0; b < nb; ++b) {
       float k = 0.f;
@@ -285,14 +337,18 @@ long long oracle_hmc_dense_step(int C, int D, const float* prec, const float* im
   if (T < 1) T = 1;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * T);
   djob_t* jobs = (djob_t*)malloc(sizeof(djob_t) * T);
+  float* msqrt_t = (float*)malloc(sizeof(float) * (size_t)D * D); /* (L^-T)^T, so that p_i = sum_j z_j msqrt_t[j][i] */
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) msqrt_t[(size_t)j * D + i] = msqrt[(size_t)i * D + j];
   for (int t = 0; t < T; ++t) {
     int b0 = (int)((long long)nblk * t / T), b1 = (int)((long long)nblk * (t + 1) / T);
-    djob_t j = {b0 * BLK, b1 * BLK < C ? b1 * BLK : C, D, L, prec, imm, msqrt, keys, q, logp, g, eps, acc_rate, accepted};
+    djob_t j = {b0 * BLK, b1 * BLK < C ? b1 * BLK : C, D, L, prec, imm, msqrt_t, keys, q, logp, g, eps, acc_rate, accepted};
     jobs[t] = j;
     pthread_create(&th[t], NULL, dworker, &jobs[t]);
   }
   for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
   free(th);
   free(jobs);
+  free(msqrt_t);
   return (long long)C * L;
 }
