@@ -174,6 +174,18 @@ np.testing.assert_allclose(m2.numpy(), ((x_all - x_all.mean(0)) ** 2).sum(0), rt
 gathered = [torch.empty_like(m2) for _ in range(2)]
 dist.all_gather(gathered, m2)
 assert torch.equal(gathered[0], gathered[1])
+# dense mass-matrix adaptation: the block carries the full [D, D] matrix of co-moments (bjx_pooled_stats_dense layout)
+xc = x - m
+blockd = torch.tensor(np.concatenate([[a.sum()], [32.0], m, (xc.T @ xc).ravel()]), dtype=torch.float32)
+blocksd = _allgather_stats(blockd, None)
+accd, nd, meand, m2d = cgl_merge_blocks(blocksd, dim=D)
+assert blocksd.shape == (2, 2 + D + D * D) and m2d.shape == (D, D) and float(nd) == 64
+xa = x_all - x_all.mean(0)
+np.testing.assert_allclose(m2d.numpy(), xa.T @ xa, rtol=1e-4, atol=1e-3)
+np.testing.assert_allclose(meand.numpy(), x_all.mean(0), rtol=1e-5, atol=1e-6)
+gathered = [torch.empty_like(m2d) for _ in range(2)]
+dist.all_gather(gathered, m2d)
+assert torch.equal(gathered[0], gathered[1])
 dist.destroy_process_group()
 print("OK", rank)
 """
