@@ -368,3 +368,28 @@ def test_randint_range_and_uniformity():
     assert np.all(oprng.randint(k[:10], (4,), 5, 5) == 5)          # maxval <= minval returns minval
     big = oprng.randint(k[:100], (3,), -(1 << 30), 1 << 30)
     assert big.min() < -(1 << 28) and big.max() > (1 << 28)
+
+
+# ---- size-independent properties of the restated integrators (docs: integrators.py:62-152 are symplectic,
+#      time-reversible maps; tests/mcmc/test_integrators.py checks energy conservation of the same schemes) ----------
+@pytest.mark.parametrize("name", ["VELOCITY_VERLET", "MCLACHLAN", "YOSHIDA", "OMELYAN"])
+def test_integrators_are_time_reversible_and_conserve_energy(name):
+    from oracle import hmc as ohmc, targets as otargets
+    rs = np.random.default_rng(4)
+    D, C, L = 40, 16, 25
+    t = otargets.DiagGaussian(np.exp(rs.uniform(-0.5, 0.5, D)))
+    metric = ohmc.Metric(np.exp(rs.uniform(-0.3, 0.3, D)).astype(np.float32))
+    q0 = rs.standard_normal((C, D)).astype(np.float32)
+    p0 = rs.standard_normal((C, D)).astype(np.float32)
+    logp0, g0 = t(q0)
+    eps = np.float32(0.05)
+    coef = getattr(ohmc, name)
+    q1, p1, logp1, g1 = ohmc.static_integration(t, metric, q0, p0, logp0, g0, eps, L, coef)
+    # flip the momentum, integrate back, flip again: the start state comes back up to float32 rounding
+    q2, p2, _, _ = ohmc.static_integration(t, metric, q1, -p1, logp1, g1, eps, L, coef)
+    np.testing.assert_allclose(q2, q0, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(-p2, p0, rtol=0, atol=2e-4)
+    e0 = -logp0 + metric.kinetic_energy(p0)
+    e1 = -logp1 + metric.kinetic_energy(p1)
+    tol = 2e-2 if name == "VELOCITY_VERLET" else 5e-3          # second order vs the higher-order / tuned schemes
+    assert np.max(np.abs(e1 - e0)) < tol
