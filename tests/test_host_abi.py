@@ -225,3 +225,20 @@ def test_bench_reference_arm_contract():
         ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                               capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert ours.returncode != 0          # no silent CPU path
+
+
+def test_library_is_sm100a_with_tcgen05_and_packed_fp32_sass():
+    """Static evidence that the shipped library is Blackwell code, not a recompiled generic kernel: every cubin is
+    sm_100a, the dense path's GEMM issues tcgen05 MMAs on CTA pairs fed by TMA (UTCHMMA.2CTA, UTMALDG/UTMASTG, LDTM),
+    and the row kernels use the packed FP32 pipe (FFMA2 / FMUL2 / FADD2)."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "blackjax_b200", "libbjx.so")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    archs = {l.split("=")[1].strip() for l in sass.splitlines() if l.startswith("arch =")}
+    assert archs == {"sm_100a"}, archs
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "FFMA2", "FMUL2", "FADD2"):
+        assert mnemonic in sass, f"{mnemonic} missing from libbjx.so SASS"
+    assert "HMMA.16816" not in sass and "HGMMA" not in sass      # no mma.sync / wgmma-style fallbacks
