@@ -71,6 +71,7 @@ static inline float normal_at(uint32_t k0, uint32_t k1, uint32_t i) {
 static float value_and_grad(int kind, int D, const float* inv_var, const float* q, float* g) {
   if (kind == 0) {
     float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
     for (int i = 0; i < D; ++i) {
       float t = q[i] * inv_var[i];
       acc += q[i] * t;
@@ -79,6 +80,7 @@ static float value_and_grad(int kind, int D, const float* inv_var, const float* 
     return -0.5f * acc;
   }
   float y = q[0], ss = 0.f;
+#pragma omp simd reduction(+ : ss)
   for (int i = 1; i < D; ++i) ss += q[i] * q[i];
   float ey = expf(-y), n = (float)(D - 1), t = y / 3.0f;
   for (int i = 1; i < D; ++i) g[i] = -(ey * q[i]);
@@ -126,6 +128,7 @@ static void* worker(void* arg) {
       for (int i = 0; i < D; ++i) p[i] = p[i] + eh * g1[i];
     }
     float k1 = 0.f;
+#pragma omp simd reduction(+ : k1)
     for (int i = 0; i < D; ++i) {
       float pf = -1.0f * p[i];
       k1 += (imm[i] * pf) * pf;
