@@ -5,11 +5,11 @@ roofline of the vectorised leapfrog kernel and the CPU baseline timed beside it.
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N>1)
     python bench.py --impl reference --gpus N --steps K ...   # reference arm: CPU oracle twin
 
-A "step" is one HMC transition (L leapfrogs) over every chain of the workload.  `value` counts
-executed leapfrogs (C * L per step) with the chain state resident in HBM; `e2e` is the same metric
-through the public API with HOST buffers (pinned host -> device copy of the step's positions and keys,
-hmc.init, one step, device -> host copy of the new positions and acceptance rates, all inside the
-timed region).  See DESIGN.md section "Measurement".
+A "step" is one pass of the hot path over every chain of the workload: one HMC transition (L leapfrogs), one NUTS
+transition (config 3), or one complete 200-step window-adaptation warm-up (config 4).  `value` counts executed
+leapfrogs with the chain state resident in HBM; `e2e` is the same metric through the public API with HOST buffers
+(pinned host -> device copy of the step's positions and keys, init, one step, device -> host copy of the new positions
+and acceptance rates, all inside the timed region).  See DESIGN.md section "Measurement".
 """
 import argparse
 import json
@@ -38,6 +38,14 @@ WORKLOADS = {
     "hmc_diag_gaussian_65536x1024_L50": dict(C=65536, D=1024, L=50, eps=0.1, dense=False),
     # BASELINE configs[0]: the reference's own CPU-runnable case
     "hmc_iso_gaussian_1024x100_L10": dict(C=1024, D=100, L=10, eps=0.2, dense=False),
+    # BASELINE configs[2]: NUTS, Neal's funnel (D=128), 65536 chains, diag mass, max_tree_depth=10 (eps 0.1,
+    # q0 = 0.1 N(0,1)); a step is one NUTS transition, value counts the leapfrogs the trees actually executed
+    "nuts_funnel_65536x128": dict(C=65536, D=128, eps=0.1, nuts=True, depth=10),
+    # BASELINE configs[3]: NUTS + window adaptation (dual averaging + diagonal mass matrix, ONE step size / metric for all
+    # chains of all GPUs), 512-D Gaussian with std = logspace(-1,1), 32768 chains per GPU (262144 over 8), eps0 = 1.0,
+    # target 0.8; a step is one complete 200-step warm-up: per warm-up step one NUTS transition, the block statistics,
+    # ONE NCCL all-gather and the device-side merge / dual averaging
+    "nuts_window_adaptation_512": dict(C=32768, D=512, adapt=True, warmup_steps=200, depth=10),
 }
 DEFAULT_WORKLOAD = "hmc_dense_gaussian_65536x1024_L50"
 
@@ -169,27 +177,250 @@ def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
         n_steps = int(max(1, min(200, budget_s / max(per_chain * Cs, 1e-9))))
     if warmup:
         run(Cs, warmup)
-    t = run(Cs, n_steps)
+    # three repeats, median: worker threads are pinned (oracle/c/oracle_hmc.c) and the thread count follows the cgroup
+    # CPU quota, so the repeats agree to a few per cent instead of swinging with the box's scheduler
+    n_steps = max(1, n_steps // 3) if steps <= 1 else n_steps
+    ts = sorted(run(Cs, n_steps) for _ in range(3))
+    t = ts[1]
     rate = Cs * L * n_steps / t
-    return rate, cores, f"{Cs} of {wl['C']} chains x {D} dims x L={L}, {n_steps} transition(s), {t:.2f} s", t / n_steps * 1e3
+    extra = {"repeats_s": [round(x, 3) for x in ts]}
+    if wl.get("dense"):  # two D x D matvecs per leapfrog per chain
+        extra["gflops"] = round(4.0 * D * D * rate / 1e9, 1)
+    sample = f"{Cs} of {wl['C']} chains x {D} dims x L={L}, {n_steps} transition(s) x 3 repeats (median {t:.2f} s)"
+    return rate, cores, sample, t / n_steps * 1e3, extra
+
+
+def cpu_nuts_rate(wl, budget_s=12.0):
+    """leapfrog-steps/s of the restated numpy oracle (oracle/nuts.py, oracle/adaptation.py) on a bounded chain sample of
+    the NUTS workloads: one process, numpy's own threading (the port is vectorised over chains, not multi-threaded)."""
+    import numpy as np
+    from oracle import adaptation as oadapt, hmc as ohmc, nuts as onuts, prng, targets as otargets
+    D = wl["D"]
+    F = np.float32
+    rs = np.random.default_rng(0)
+    if wl.get("adapt"):
+        tgt = otargets.DiagGaussian(np.logspace(-1, 1, D))
+        Cs, T = 64, 12
+        q = rs.standard_normal((Cs, D)).astype(F)
+        count = {"n": 0}
+
+        def kernel(keys, state, target, eps, imm, **kw):
+            st, info = onuts.nuts_kernel(keys, state, target, eps, imm, wl["depth"])
+            count["n"] += int(info.num_integration_steps.sum())
+            return st, info
+        t0 = time.perf_counter()
+        oadapt.window_adaptation_run(kernel, tgt, prng.key(11), q, T, shared=True)
+        t = time.perf_counter() - t0
+        return count["n"] / t, 1, f"{Cs} of {wl['C']} chains x {D} dims, first {T} of {wl['warmup_steps']} warm-up steps ({t:.1f} s)", t * 1e3, {}
+    tgt = otargets.Funnel(D)
+    Cs = 256
+    q = (0.1 * rs.standard_normal((Cs, D))).astype(F)
+    st = ohmc.init(q, tgt)
+    keys = prng.split(prng.key(1), Cs)
+    imm = np.ones(D, F)
+    n, t0, reps = 0, time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s and reps < 20:
+        st, info = onuts.nuts_kernel(prng.split(prng.fold_in(prng.key(1), reps), Cs), st, tgt, F(wl["eps"]), imm, wl["depth"])
+        n += int(info.num_integration_steps.sum())
+        reps += 1
+    t = time.perf_counter() - t0
+    return n / t, 1, f"{Cs} of {wl['C']} chains x {D} dims, {reps} NUTS transition(s) ({t:.1f} s)", t / reps * 1e3, {}
+
+
+def cpu_rate(wl, budget_s, steps=1, warmup=0):
+    if wl.get("nuts") or wl.get("adapt"):
+        return cpu_nuts_rate(wl, budget_s)
+    return cpu_hmc_rate(wl, budget_s, steps, warmup)
 
 
 def run_reference(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, cores, sample, ms = cpu_hmc_rate(wl, budget_s=20.0, steps=args.steps, warmup=min(args.warmup, 1))
+    rate, cores, sample, ms, extra = cpu_rate(wl, budget_s=20.0, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl_name, "note": "restated oracle (C/pthreads twin of oracle/hmc.py), not JAX: "
-                   "blackjax needs jax 0.10.0 which cannot be installed in this image"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl_name, **{k: v for k, v in wl.items()},
+                   "note": "baseline/_ref (BlackJAX on JAX) was tried first and cannot be installed in this image (no jax / "
+                           "jaxlib wheel, no network); this arm times the restated oracle instead: the C/pthreads twin of "
+                           "oracle/hmc.py (HMC workloads) or the numpy oracle (NUTS workloads)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **extra},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel at its benchmark shape, from the committed
+    `ncu --set full` capture summaries (profiles/r02_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep of the
+    same command); None when no capture of that kernel is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        e = t.get(kernel_key)
+        return (float(e["dram_bytes"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
+    """BASELINE configs[2] (NUTS on the funnel) and configs[3] (NUTS + shared window adaptation).  value = leapfrogs the
+    trees actually executed (sum of num_integration_steps over chains, steps and ranks) / max-over-ranks CUDA-event time."""
+    import numpy as np
+    import torch
+
+    import blackjax_b200 as bj
+
+    C, D, depth = wl["C"], wl["D"], wl["depth"]
+    K, W = args.steps, args.warmup
+    adapt = bool(wl.get("adapt"))
+    n_gpus = world
+    key0 = bj.random.key(7, dev)
+    # global chain c starts at normal(split(key, C_global)[c]): the same chains whatever the GPU count
+    chain_keys = bj.random.split(key0, C * world)[rank * C:(rank + 1) * C]
+    if adapt:
+        tgt = bj.targets.DiagGaussian(np.logspace(-1, 1, D))
+        q0 = bj.random.normal(chain_keys, (D,))
+        T = wl["warmup_steps"]
+        warm = bj.window_adaptation(bj.nuts, tgt, shared=True, initial_step_size=1.0, target_acceptance_rate=0.8,
+                                    max_num_doublings=depth)
+    else:
+        tgt = bj.targets.Funnel(D)
+        q0 = 0.1 * bj.random.normal(chain_keys, (D,))
+        imm = torch.ones(D, device=dev)
+        kern = bj.nuts.build_kernel(inplace=True, chain_offset=rank * C, max_tree_depth=depth)
+    step_keys = bj.random.split(bj.random.key(0, dev), W + K + 16)
+    lf = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if adapt:
+        def one_step(t, count):
+            (st, params), hist = warm.run(step_keys[t], q0, T, _leapfrog_counter=count)
+            return st, params
+        state = None
+    else:
+        state = bj.nuts.init(q0.clone(), tgt)
+
+        def one_step(t, count):
+            nonlocal state
+            state, info = kern(step_keys[t], state, tgt, wl["eps"], imm, depth)
+            if count is not None:
+                count += info.num_integration_steps.sum()
+            return state, info
+    for t in range(W):
+        out = one_step(t, None)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(W, W + K):
+        out = one_step(t, lf)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if dist is not None:
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        ok = [c for c in allc if c and c.get("sm_mhz")]
+        if ok:
+            clocks = {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] for c in ok),
+                      "reasons": sorted(set(r for c in ok for r in c["reasons"])),
+                      "per_rank_sm_mhz": [c["sm_mhz"] for c in ok], "samples": sum(c.get("samples", 0) for c in ok)}
+
+    # ---- end to end with HOST buffers: positions in from pinned memory, one step, positions + a per-chain result out -----
+    q_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    q_host.copy_(q0 if adapt else state.position)
+    out_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+    acc_host = torch.empty(C, dtype=torch.float32).pin_memory()
+    q_dev = torch.empty(C, D, device=dev)
+    lf_e2e = torch.zeros(1, dtype=torch.int64, device=dev)
+    K_e2e = max(1, min(K, 5))
+
+    def e2e_step(t, count):
+        q_dev.copy_(q_host, non_blocking=True)
+        if adapt:
+            (st, params), hist = warm.run(step_keys[t], q_dev, T, _leapfrog_counter=count)
+            out_host.copy_(st.position, non_blocking=True)
+            acc_host.copy_(st.logdensity, non_blocking=True)
+        else:
+            st = bj.nuts.init(q_dev, tgt)
+            st, info = kern(step_keys[t], st, tgt, wl["eps"], imm, depth)
+            count += info.num_integration_steps.sum()
+            out_host.copy_(st.position, non_blocking=True)
+            acc_host.copy_(info.acceptance_rate, non_blocking=True)
+    e2e_step(0, lf_e2e)
+    lf_e2e.zero_()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for t in range(K_e2e):
+        e2e_step(W + t, lf_e2e)
+    g1.record()
+    barrier()
+    ms_e2e = g0.elapsed_time(g1)
+
+    tot = torch.tensor([float(lf.item()), float(lf_e2e.item())], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    n_lf, n_lf_e2e = float(tot[0]), float(tot[1])
+    ms_total, ms_e2e = float(times[0]), float(times[1])
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    value = n_lf / (ms_total * 1e-3)
+    transitions = K * (T if adapt else 1)
+    # SURVEY 8d: a NUTS leaf moves ~44*D bytes if every leapfrog round-tripped HBM (24*D leapfrog + p_sum + checkpoints)
+    achieved = 44.0 * D * value / 1e9
+    traffic, traffic_src = ncu_traffic("k_nuts_doubling_adapt512" if adapt else "k_nuts_doubling_funnel128")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "chains_per_gpu": C, "dims": D, "max_tree_depth": depth,
+                   "mass_matrix": "diag", "step": ("one %d-step window-adaptation warm-up (NUTS transition + block statistics "
+                                                   "+ one NCCL all-gather + device-side merge / dual averaging per warm-up step)" % T)
+                   if adapt else "one NUTS transition",
+                   "parallelism": (f"chains sharded x{n_gpus}; one NCCL all-gather of {(C // 4096) * (2 + 2 * D) * 4} bytes per rank "
+                                   "per warm-up step (bjx_allgather_stats)") if adapt
+                   else f"chains sharded x{n_gpus}, no data-path collective",
+                   "l2": "state arrays %.0f MB per GPU (workspace rows 9 + 2*depth); inputs exceed L2" % (C * D * 4 / 1e6),
+                   "mean_tree_size": n_lf / (n_gpus * C * transitions), "ms_per_transition": ms_total / transitions},
+        "roofline": {"bound": "hbm", "kernel": "k_nuts_doubling (tree doubling; rows register-resident inside a launch, so the kernel "
+                     "is bound by dependent-instruction latency / issue slots: ncu numbers in profiles/)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
+                     "note": "achieved = 44*D algorithmic bytes per executed leapfrog x leapfrogs/s over the whole timed step "
+                             "(init, doubling and finish launches included)",
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+        "e2e": {"value": n_lf_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + 8,
+                "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": K_e2e, "ms_per_step": ms_e2e / K_e2e},
+        "gpu_launches": K * ((T * 7 + 2) if adapt else 4),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and n_gpus == 1:
+        rate, cores, sample, _, extra_cpu = cpu_rate(wl, budget_s=12.0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "note": "restated numpy oracle, not JAX (no jax wheel in this image)", **extra_cpu}
+    print(json.dumps(line), flush=True)
+
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -229,6 +460,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
+    if wl.get("nuts") or wl.get("adapt"):
+        run_nuts_workload(args, wl, dev, dist, world, rank, local_rank)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     C, D, L, eps = wl["C"], wl["D"], wl["L"], wl["eps"]
     K, W = args.steps, args.warmup
@@ -263,8 +499,7 @@ def main():
     for t in range(W):
         state, info = kernel(chain_keys(t), state, tgt, eps, imm, L)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank samples its own GPU
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -273,29 +508,44 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    # our kernels per step: (diag) k_hmc_transition | (dense, per chain slice; two slices on two streams from 8192
-    # chains) normal draw, 2L+3 x (operand split + GEMM), first half kick, the closing grad_kick, 2 energy, accept
-    launches = K * (1 if not dense else (2 if C >= 8192 else 1) * (1 + 2 * (2 * L + 3) + 1 + 1 + 2 + 1))
+    # our kernels per step: (diag) k_hmc_transition | (dense) 2L+3 products (bjx::k_gemm_f16x3), 2L-1 window checks, normal
+    # draw, 2 exact operand splits, 2 energies, the opening and the closing row kernel, accept
+    launches = K * (1 if not dense else (4 * L + 10))
     acc_mean = float(info.acceptance_rate.mean())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if dist is not None:  # rank 0 reports the slowest GPU's median SM clock and the union of throttle reasons
+        all_clocks = [None] * world
+        dist.all_gather_object(all_clocks, clocks)
+        if rank == 0:
+            ok = [c for c in all_clocks if c and c.get("sm_mhz")]
+            if ok:
+                clocks = {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] for c in ok),
+                          "reasons": sorted(set(r for c in ok for r in c["reasons"])),
+                          "per_rank_sm_mhz": [c["sm_mhz"] for c in ok], "samples": sum(c.get("samples", 0) for c in ok)}
 
     # ---- the vectorised single-step leapfrog kernel: the HBM roofline the north star names -------------
     eng = _engine.get_engine(state.position, tgt)
     ms_gemm = 0.0
-    if dense:  # the dominant kernel of the dense workload: v = M^-1 p for all chains = one [C,D]x[D,D] tensor-core GEMM
+    n_prod = 0
+    if dense:
+        # The dominant kernel of the dense workload: bjx::k_gemm_f16x3 in its fused form (Cin + lincomb / double kick + Y +
+        # operand planes of Y), timed where it runs: inside a run of leapfrog steps on the engine's stream.  n_lf steps =
+        # 2 n_lf products (2 n_lf - 1 fused + the closing gradient product) + one opening and one closing row kernel +
+        # the 3 us window checks; the average below charges all of that to the products (conservative).
         pv = eng.sample_momentum(chain_keys(W + K), chain_offset=rank * C)
-        for _ in range(3):
-            vv = eng.velocity(pv)
+        qv, lv, gv = state.position.clone(), state.logdensity.clone(), state.logdensity_grad.clone()
+        n_lf = 20
+        eng.leapfrog_(qv, pv, lv, gv, 0.01, n_lf)
         torch.cuda.synchronize()
-        n_g = 20
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(n_g):
-            vv = eng.velocity(pv)
+        for _ in range(2):
+            eng.leapfrog_(qv, pv, lv, gv, 0.01, n_lf)
         f1.record()
         torch.cuda.synchronize()
-        ms_gemm = f0.elapsed_time(f1) / n_g
-        del pv, vv
+        n_prod = 2 * 2 * n_lf
+        ms_gemm = f0.elapsed_time(f1) / n_prod
+        del pv, qv, lv, gv
     # the vectorised one-step leapfrog kernel (diagonal metric) at the same chains x dims: the HBM roofline kernel
     qd = torch.randn(C, D, device=dev, generator=gen)
     deng = _engine.Engine(dev, C, D, diag_tgt)
@@ -374,39 +624,36 @@ def main():
     e2e_value = n_gpus * C * L * K_e2e / (ms_e2e * 1e-3)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         bytes_1step = 24.0 * C * D
         achieved = bytes_1step / (ms_1step * 1e-3) / 1e9
         ms_step = ms_total / K
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-        # (profiles/r01_ncu_diag_hmc.md, profiles/r01_ncu_gemm_dense.md); only meaningful at the captured shape
-        at_captured_shape = (C, D) == (65536, 1024)
-        traffic_leapfrog = (805.4e6 + 747.7e6) if at_captured_shape else None
-        traffic_gemm = 2 * (351.0e6 + 100.8e6) if at_captured_shape else None  # two 32768-chain slice launches per call
+        traffic_leapfrog, src_leapfrog = ncu_traffic("k_leapfrog_diag_65536x1024") if (C, D) == (65536, 1024) else (None, None)
+        traffic_gemm, src_gemm = ncu_traffic("k_gemm_f16x3_fused_65536x1024") if (C, D) == (65536, 1024) else (None, None)
         hbm_roofline = {"bound": "hbm", "kernel": "k_leapfrog (diag metric, 1 step/launch, 24*D B per chain)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic_leapfrog, "traffic_source": "ncu --set full, profiles/r01_ncu_diag_hmc.md",
+                        "traffic": traffic_leapfrog, "traffic_source": src_leapfrog,
                         "peak_source": peak_src, "avg_launch_ms": ms_1step, "launches_timed": n1}
         if dense:
-            tpeak = float(peaks.get("bf16_tflops", 1590.0))
+            burst = float(peaks.get("bf16_tflops", 1590.0))
+            tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             tf_achieved = 2.0 * C * D * D / (ms_gemm * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "v = M^-1 p for all chains: k_rows_split2 + tcgen05 fp16 GEMM [C,3D]x[3D,D] "
-                        "(float32-accurate: 3 fp16 products per float32 product, rows scaled by powers of two)", "achieved": tf_achieved, "peak": tpeak,
-                        "unit": "TFLOP/s",
-                        "frac": tf_achieved / tpeak, "traffic": traffic_gemm,
-                        "traffic_source": "ncu --set full of the GEMM kernel alone, profiles/r01_ncu_gemm_dense.md "
-                                          "(two slice launches; the split kernel adds 2 x (136 MB read + 148 MB written))",
-                        "peak_source": ("measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks
-                                        else "fallback 1590 TFLOP/s"),
-                        "avg_launch_ms": ms_gemm, "launches_timed": 20,
-                        "note": "algorithmic float32 flops 2*C*D^2 per call; the hardware executes 3x that in fp16 MMAs "
-                                "(ceiling frac = 1/3); the timed call includes the operand-split kernel",
+            roofline = {"bound": "tensor",
+                        "kernel": "bjx::k_gemm_f16x3, fused form (hand-written tcgen05.mma.cta_group::2 + TMA; epilogue: Cin, per-row "
+                                  "lincomb / double kick, Y, operand planes of Y for the next product); float32-accurate: 3 fp16 "
+                                  "products per float32 product (ceiling frac = 1/3)",
+                        "achieved": tf_achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": tf_achieved / tpeak,
+                        "frac_of_burst_peak": tf_achieved / burst, "burst_peak": burst,
+                        "traffic": traffic_gemm, "traffic_source": src_gemm,
+                        "algorithmic_bytes": 16.0 * C * D,
+                        "peak_source": ("measured sustained bf16 (MEASURED_PEAKS.json bf16_tflops_sustained): the kernel is timed inside "
+                                        "a run of leapfrog steps under the power cap" if "bf16_tflops_sustained" in peaks
+                                        else "fallback 1400 TFLOP/s sustained"),
+                        "avg_launch_ms": ms_gemm, "launches_timed": n_prod,
+                        "note": "algorithmic float32 flops 2*C*D^2 per launch; CUDA events on the engine's stream around 2 x 20 "
+                                "leapfrog steps = 80 products, row kernels and window checks of those steps charged to the products",
                         "gemms_per_step": 2 * L + 3, "gemm_share_of_step": (2 * L + 3) * ms_gemm / ms_step}
             extra = {"roofline_hbm_leapfrog": hbm_roofline}
         else:
@@ -433,9 +680,10 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and n_gpus == 1:
-            rate, cores, sample, _ = cpu_hmc_rate(wl, budget_s=12.0)
+            rate, cores, sample, _, extra_cpu = cpu_rate(wl, budget_s=12.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                    "note": "restated oracle (C/pthreads), not JAX"}
+                                    "note": "restated oracle (C/pthreads twin or numpy), not JAX (no jax wheel in this image)",
+                                    **extra_cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -10,7 +10,8 @@ from ._lib import check, lib, ptr
 import collections
 
 # Engines own device workspaces (NUTS: (9 + 2*depth) rows of [C,D]; dense path: 4 rows + operand planes), so the cache is a
-# small LRU: the least recently used engine is destroyed (its handle freed) when a new shape/target comes in.
+# small LRU: the least recently used engine leaves the cache when a new shape/target comes in and is destroyed (handle
+# and workspaces freed) as soon as nobody else holds it.
 _ENGINES = collections.OrderedDict()
 _MAX_ENGINES = 8
 
@@ -99,10 +100,24 @@ class Engine:
         check(lib().bjx_set_metric(self.h, kind, ptr(imm)), self.h)
         return imm
 
+    def ensure_metric(self, inverse_mass_matrix):
+        """Install the metric unless this exact tensor CONTENT is already installed: the cache key is (storage pointer,
+        shape, torch's in-place version counter), so an in-place update of the caller's tensor re-derives
+        mass_matrix_sqrt and the dense operand planes instead of silently keeping stale ones."""
+        imm = inverse_mass_matrix
+        key = ((imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device)) if isinstance(imm, torch.Tensor)
+               else None)
+        if key is None or key != self._imm_key:
+            installed = self.set_metric(imm)
+            # a converted copy (dtype / device / layout) is owned by the engine: key on the caller's tensor all the same
+            self._imm_key = key
+            return installed
+        return self._imm
+
     def _key_mode(self, keys, chain_offset=0):
         """Select per-chain keys [C,2] or a shared step key [2] (+ global chain offset) for the next transition."""
         mode = (1 if keys.ndim == 1 else 0, int(chain_offset))
-        if getattr(self, "_keymode", (0, 0)) != mode:
+        if getattr(self, "_keymode", None) != mode:
             check(lib().bjx_set_key_mode(self.h, mode[0], mode[1]), self.h)
             self._keymode = mode
 
@@ -217,6 +232,8 @@ class Engine:
         check(lib().bjx_nuts_step(self.h, ptr(keys), ptr(q), ptr(logp), ptr(g), ptr(qo), ptr(lo), ptr(go), eps,
                                   ptr(eps_dev), int(max_num_doublings), C.byref(info), ptr(momentum),
                                   ptr(key_integrator)), self.h)
+        if key_integrator is not None:
+            self._keymode = None  # per-call override: re-establish the key mode on the next ordinary call
         return qo, lo, go
 
     def nuts_last_stats(self):
@@ -245,8 +262,9 @@ def get_engine(position, target, max_tree_depth=10, divergence_threshold=1000.0)
         eng = Engine(dev, position.shape[0], position.shape[1], target, max_tree_depth, divergence_threshold, stream)
         _ENGINES[key] = eng
         while len(_ENGINES) > _MAX_ENGINES:
-            _, old = _ENGINES.popitem(last=False)
-            old.close()
+            # drop the least recently used engine from the cache only: callers may still hold it (its handle and
+            # workspaces are freed by Engine.__del__ once the last reference goes)
+            _ENGINES.popitem(last=False)
     else:
         _ENGINES.move_to_end(key)
     return eng

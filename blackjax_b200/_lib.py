@@ -78,6 +78,16 @@ _SIGNATURES = {
     "bjx_welford_final": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p]),
     "bjx_pooled_stats": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_pooled_stats_dense": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
+    "bjx_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "bjx_nccl_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bjx_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "bjx_allgather_stats": (C.c_int, [C.c_void_p, C.c_void_p, _f32p, C.c_int64, _f32p]),
+    "bjx_adapt_shared_state_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "bjx_adapt_shared_init": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, _f32p]),
+    "bjx_adapt_shared_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _f32p, _f32p, _f32p, C.c_int32, C.c_int32,
+                                          C.c_float, _f32p, _f32p, _f32p]),
+    "bjx_adapt_shared_final": (C.c_int, [C.c_void_p, _f32p, _f32p]),
+    "bjx_set_default_stream": (C.c_int, [C.c_void_p]),
     "bjx_potential_scale_reduction": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
     "bjx_ess_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "bjx_effective_sample_size": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),

@@ -134,7 +134,7 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
     if dense and not shared:
         raise NotImplementedError("dense (welford_dense) adaptation is built for the chain-pooled mode: pass shared=True "
                                   "(a per-chain dense metric would need [C, D, D] mass matrices in the kernels)")
-    def run(rng_key, position, num_steps: int = 1000):
+    def run(rng_key, position, num_steps: int = 1000, _leapfrog_counter=None):
         from .._engine import get_engine
         position = position.contiguous()
         C, D = position.shape
@@ -150,6 +150,33 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
         # shared mode: one step key per warm-up step; chain c of this rank uses split(step_key, C_global)[rank*C + c]
         # (staged_adaptation.py:920), derived inside the transition kernel
         mcmc_kernel = algorithm.build_kernel(chain_offset=rank * C)
+        if shared and not dense and position.is_cuda:
+            # ---- device-resident shared adaptation (libbjx bjx_adapt_shared_*): block statistics, ONE NCCL all-gather,
+            # merge + dual averaging + window bookkeeping on the device; no host round trip per warm-up step --------
+            from .._comm import nccl_comm
+            comm, n_ranks, rank = nccl_comm(dev, process_group)
+            mcmc_kernel = algorithm.build_kernel(chain_offset=rank * C)
+            step_keys = bjx_random.split(rng_key.to(dev), num_steps)
+            L = lib()
+            st = torch.empty(L.bjx_adapt_shared_state_floats(C, D, n_ranks), dtype=torch.float32, device=dev)
+            eps_c = torch.empty(C, dtype=torch.float32, device=dev)
+            imm = torch.empty(D, dtype=torch.float32, device=dev)
+            eps_hist = torch.empty(num_steps, dtype=torch.float32, device=dev)
+            check(L.bjx_adapt_shared_init(eng.h, ptr(st), float(initial_step_size), ptr(eps_c), ptr(imm)), eng.h)
+            eng._imm, eng._imm_key = imm, (imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device))
+            for t, (stage, window_end) in enumerate(schedule):
+                state, info = mcmc_kernel(step_keys[t], state, logdensity_fn, eps_c, imm, **extra_parameters)
+                if _leapfrog_counter is not None:  # bench.py: executed leapfrogs, accumulated on the device
+                    n_int = info.num_integration_steps
+                    _leapfrog_counter += (n_int.sum() if isinstance(n_int, torch.Tensor) else n_int * C)
+                check(L.bjx_adapt_shared_update(eng.h, comm, n_ranks, ptr(st), ptr(state.position),
+                                                ptr(info.acceptance_rate), int(stage), int(window_end),
+                                                float(target_acceptance_rate), ptr(eps_c), ptr(imm), ptr(eps_hist)), eng.h)
+            step = torch.empty(1, dtype=torch.float32, device=dev)
+            check(L.bjx_adapt_shared_final(eng.h, ptr(st), ptr(step)), eng.h)
+            step_size = float(step.item())   # the one host read of the warm-up
+            parameters = {"step_size": step_size, "inverse_mass_matrix": imm, **extra_parameters}
+            return AdaptationResults(state, parameters), eps_hist.cpu()
         if shared:
             step_keys = bjx_random.split(rng_key.to(dev), num_steps)
             da = _da_init(initial_step_size)

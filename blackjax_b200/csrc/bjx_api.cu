@@ -610,41 +610,42 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   rc = dispatch(h, K_NUTS_INIT, false, a);
   if (rc) return rc;
 
-  // Host-driven tree doubling (trajectory.py:616-725).  The first kFusedDoublings doublings run in ONE launch over
-  // all chains (every chain needs them and their cost is the fixed per-doubling row traffic); after that each
-  // doubling is its own launch over the chains still expanding, whose indices the previous launch compacted into
-  // list_a/list_b (ping-pong).  counters[k] = number of chains that continue after launch k; one pinned-memory
-  // readback per launch.
+  // Tree doubling (trajectory.py:616-725) in two launches and without a host round trip.  The first kFusedDoublings
+  // doublings run in ONE launch over all chains (every chain needs them and their cost is the fixed per-doubling row
+  // traffic) and compact the chains that keep expanding into list_a; the second launch takes each of those chains
+  // through ALL its remaining doublings (its row count is read on the device from counters[1], the grid covers every
+  // chain and surplus warps exit at once).  Chains never interact, so nothing forces them through the tree in lock step.
   const int kFusedDoublings = 4;  // (the kernel's lane-parallel key schedule handles up to 10 doublings per launch)
   const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
   const size_t dm_bytes = (h->metric_small_dense || h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
                               ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
   a.ckpt_smem = (ckpt_bytes + dm_bytes <= 40 * 1024) ? 1 : 0;  // stay under the 48 KB default dynamic-smem limit
-  int n_active = C;
-  const int* list_in = nullptr;
   int64_t launches = 0;
-  int depth_reached = 0;
-  int d = 0;
-  while (d < max_num_doublings && n_active > 0) {
-    const int d_end = (d == 0) ? (max_num_doublings < kFusedDoublings ? max_num_doublings : kFusedDoublings) : d + 1;
-    int* list_out = (launches & 1) ? h->ws.list_b : h->ws.list_a;
+  const int d_fused = max_num_doublings < kFusedDoublings ? max_num_doublings : kFusedDoublings;
+  if (max_num_doublings > 0) {
+    a.depth = 0;
+    a.depth_end = d_fused;
+    a.list_in = nullptr;
+    a.n_in = C;
+    a.n_in_dev = nullptr;
+    a.list_out = h->ws.list_a;
+    a.counter = h->ws.counters + 1;
+    rc = dispatch(h, K_NUTS_DOUBLING, true, a);
+    if (rc) return rc;
+    ++launches;
+  }
+  for (int d = d_fused; d < max_num_doublings; d += 10) {  // one launch unless max_tree_depth > 14
+    const int d_end = (max_num_doublings - d > 10) ? d + 10 : max_num_doublings;
     a.depth = d;
     a.depth_end = d_end;
-    a.list_in = list_in;
-    a.n_in = n_active;
-    a.list_out = list_out;
+    a.list_in = (launches & 1) ? h->ws.list_a : h->ws.list_b;
+    a.n_in = C;
+    a.n_in_dev = h->ws.counters + launches;
+    a.list_out = (launches & 1) ? h->ws.list_b : h->ws.list_a;
     a.counter = h->ws.counters + launches + 1;
     rc = dispatch(h, K_NUTS_DOUBLING, true, a);
     if (rc) return rc;
     ++launches;
-    depth_reached = d_end;
-    d = d_end;
-    if (d < max_num_doublings) {
-      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + launches, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      BJX_CUDA(cudaStreamSynchronize(h->stream));
-      n_active = h->h_flag[0];
-      list_in = list_out;
-    }
   }
   k_nuts_finish<<<(C + 255) / 256, 256, 0, h->stream>>>(C, h->ws, make_info(info));
   BJX_CHECK_LAUNCH("k_nuts_finish");
@@ -656,23 +657,36 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
     if (info->right_momentum) BJX_CUDA(cudaMemcpyAsync(info->right_momentum, h->ws.right_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
   }
   h->last_leaf_launches = launches;
-  h->last_depth = depth_reached;
+  h->last_depth = -1;  // known on the device only: bjx_nuts_last_stats reads it back on demand
   return 0;
 }
 
 extern "C" int bjx_nuts_last_stats(bjx_handle_t h, int64_t* leaf_launches, int64_t* depth_reached) {
   if (!h) return fail(h, BJX_E_INVALID, "null handle");
   if (leaf_launches) *leaf_launches = h->last_leaf_launches;
-  if (depth_reached) *depth_reached = h->last_depth;
+  if (depth_reached) {
+    if (h->last_depth < 0 && h->ws_block) {  // the one host round trip of the NUTS path, and only on request
+      BJX_CUDA(cudaMemcpyAsync(h->h_flag, h->ws.counters + 63, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      BJX_CUDA(cudaStreamSynchronize(h->stream));
+      h->last_depth = h->h_flag[0];
+    }
+    *depth_reached = h->last_depth;
+  }
   return 0;
 }
 
 // ---- PRNG ----------------------------------------------------------------------------------------------
-// h may be NULL: the call then runs on the current device's legacy default stream.
+// h may be NULL: the call then runs on the calling thread's registered stream (bjx_set_default_stream; the legacy
+// default stream until one is registered).
+static thread_local cudaStream_t t_default_stream = (cudaStream_t)0;
+extern "C" int bjx_set_default_stream(void* stream) {
+  t_default_stream = (cudaStream_t)stream;
+  return 0;
+}
 #define BJX_PRNG_PROLOGUE()                                                        \
   if (!keys || !out || n_keys < 0) return fail(h, BJX_E_INVALID, "bad argument");  \
   if (h) BJX_CUDA(cudaSetDevice(h->cfg.device));                                   \
-  cudaStream_t pstream = h ? h->stream : (cudaStream_t)0;
+  cudaStream_t pstream = h ? h->stream : t_default_stream;
 
 extern "C" int bjx_prng_split(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out) {
   BJX_PRNG_PROLOGUE();

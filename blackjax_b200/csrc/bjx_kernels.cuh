@@ -379,6 +379,7 @@ __device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const P
 template <class R, int TK, bool DM, bool GEN>
 __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d_begin, int d_end, int max_doublings,
                                                             const int* __restrict__ list_in, int n_in,
+                                                            const int* __restrict__ n_in_dev,
                                                             int* __restrict__ list_out, int* counter_out,
                                                             float* q_out, float* logp_out, float* g_out, int ckpt_smem) {
   const int lane = threadIdx.x & 31;
@@ -386,7 +387,9 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
   const int w = blockIdx.x * kWarpsPerBlock + wib;
   extern __shared__ __align__(16) float bjx_smem[];
   float* sm = bjx_smem + (size_t)wib * P.D;  // small dense matvec slice (first kWarpsPerBlock*D floats when used)
-  if (w >= n_in) return;
+  // n_in_dev: the row count was produced on the device by the previous launch (no host round trip); the grid then
+  // covers every chain and the surplus warps leave here
+  if (w >= (n_in_dev ? *n_in_dev : n_in)) return;
   const int chain = list_in ? list_in[w] : w;
   const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK, DM> c;
@@ -604,14 +607,21 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
 // nuts.py:303-319: acceptance_rate = exp(sum_log_p_accept) / num_states and the NUTSInfo scalars
 static __global__ void k_nuts_finish(int C, NutsWs ws, InfoPtrs info) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= C) return;
-  const int n = ws.n_states[chain];
-  if (info.acceptance_rate) info.acceptance_rate[chain] = expf(ws.prop_slpa[chain]) / (float)n;
-  if (info.is_divergent) info.is_divergent[chain] = ws.is_div[chain];
-  if (info.is_turning) info.is_turning[chain] = ws.is_turn[chain];
-  if (info.energy) info.energy[chain] = ws.prop_energy[chain];
-  if (info.num_integration_steps) info.num_integration_steps[chain] = n;
-  if (info.num_trajectory_expansions) info.num_trajectory_expansions[chain] = ws.step[chain];
+  int dmax = 0;
+  if (chain < C) {
+    const int n = ws.n_states[chain];
+    if (info.acceptance_rate) info.acceptance_rate[chain] = expf(ws.prop_slpa[chain]) / (float)n;
+    if (info.is_divergent) info.is_divergent[chain] = ws.is_div[chain];
+    if (info.is_turning) info.is_turning[chain] = ws.is_turn[chain];
+    if (info.energy) info.energy[chain] = ws.prop_energy[chain];
+    if (info.num_integration_steps) info.num_integration_steps[chain] = n;
+    if (info.num_trajectory_expansions) info.num_trajectory_expansions[chain] = ws.step[chain];
+    dmax = ws.step[chain];
+  }
+  // deepest tree of this transition (bjx_nuts_last_stats): one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(ws.counters + 63, dmax);
 }
 
 }  // namespace bjx

@@ -23,6 +23,7 @@ struct LaunchArgs {
   int ckpt_smem;        // checkpoints in shared memory
   const int* list_in;   // compacted chain indices (nullptr = identity)
   int n_in;             // number of warps to launch (0 = all chains)
+  const int* n_in_dev;  // device-side row count (then n_in is only the grid's upper bound)
   int* list_out;
   int* counter;
   const float* mom_override;
@@ -89,12 +90,12 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
     case K_NUTS_DOUBLING:
       if (a.general_integrator)
         k_nuts_doubling<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
-                                                                     a.n_in, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                     a.g_out, a.ckpt_smem);
+                                                                     a.n_in, a.n_in_dev, a.list_out, a.counter, a.q_out,
+                                                                     a.logp_out, a.g_out, a.ckpt_smem);
       else
         k_nuts_doubling<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
-                                                                      a.n_in, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                      a.g_out, a.ckpt_smem);
+                                                                      a.n_in, a.n_in_dev, a.list_out, a.counter, a.q_out,
+                                                                      a.logp_out, a.g_out, a.ckpt_smem);
       return 0;
     default:
       break;

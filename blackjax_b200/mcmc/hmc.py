@@ -64,12 +64,6 @@ def init(position, logdensity_fn):
     return HMCState(position, logp, grad)
 
 
-def per_chain_keys(rng_key, n_chains, device):
-    """A single key [2] is passed through: chain c then uses split(rng_key, n_global)[chain_offset + c], derived inside
-    the transition kernel (bjx_set_key_mode) -- same bits as an explicit ``split`` + per-chain keys."""
-    return rng_key
-
-
 def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000, build_proposal=None,
                  full_info: bool = False, inplace: bool = False, chain_offset: int = 0):
     """blackjax/mcmc/hmc.py:251-314.  ``inplace=True`` overwrites the input state's tensors (no
@@ -85,10 +79,8 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: float = 1000,
         q, logp, g = state
         eng = get_engine(q, logdensity_fn, divergence_threshold=divergence_threshold)
         eng.set_integrator(coefficients)
-        if eng._imm_key is not inverse_mass_matrix:
-            eng.set_metric(inverse_mass_matrix)
-            eng._imm_key = inverse_mass_matrix
-        keys = per_chain_keys(rng_key, eng.C, eng.device)
+        eng.ensure_metric(inverse_mass_matrix)
+        keys = rng_key  # one key [2]: chain c uses split(rng_key, n_global)[chain_offset + c], derived in-kernel
         C, dev = eng.C, eng.device
         fields = dict(acceptance_rate=torch.empty(C, dtype=torch.float32, device=dev),
                       is_accepted=torch.empty(C, dtype=torch.uint8, device=dev),

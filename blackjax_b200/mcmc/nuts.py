@@ -8,7 +8,7 @@ import torch
 from .._engine import get_engine
 from ..base import build_sampling_algorithm
 from . import hmc, integrators
-from .hmc import HMCState, IntegratorState, per_chain_keys
+from .hmc import HMCState, IntegratorState
 from .integrators import velocity_verlet
 
 __all__ = ["NUTSInfo", "init", "build_kernel", "as_top_level_api"]
@@ -42,10 +42,8 @@ def build_kernel(integrator=velocity_verlet, divergence_threshold: int = 1000, f
         eng = get_engine(q, logdensity_fn, max_tree_depth=max(max_tree_depth, max_num_doublings),
                          divergence_threshold=divergence_threshold)
         eng.set_integrator(coefficients)
-        if eng._imm_key is not inverse_mass_matrix:
-            eng.set_metric(inverse_mass_matrix)
-            eng._imm_key = inverse_mass_matrix
-        keys = None if _key_integrator is not None else per_chain_keys(rng_key, eng.C, eng.device)
+        eng.ensure_metric(inverse_mass_matrix)
+        keys = None if _key_integrator is not None else rng_key
         C, dev = eng.C, eng.device
         fields = dict(acceptance_rate=torch.empty(C, dtype=torch.float32, device=dev),
                       is_divergent=torch.empty(C, dtype=torch.uint8, device=dev),

@@ -22,6 +22,12 @@ def key(seed, device=None):
     return torch.tensor([0, s], dtype=torch.int32, device=_dev(device)).view(torch.uint32)
 
 
+def _on_current_stream(device):
+    """The handle-less PRNG entry points run on the stream registered here: torch's current stream of ``device``
+    (side streams do not synchronise with the legacy default stream)."""
+    check(lib().bjx_set_default_stream(torch.cuda.current_stream(device).cuda_stream))
+
+
 def _flat(keys):
     if keys.dtype not in (torch.uint32, torch.int32) or keys.shape[-1] != 2:
         raise TypeError("keys must be uint32[..., 2]")
@@ -36,6 +42,7 @@ def split(keys, num=2):
     k, n = _flat(keys)
     out = torch.empty(tuple(k.shape[:-1]) + (int(num), 2), dtype=torch.uint32, device=k.device)
     with torch.cuda.device(k.device):
+        _on_current_stream(k.device)
         check(lib().bjx_prng_split(None, ptr(k), n, int(num), ptr(out)))
     return out
 
@@ -45,6 +52,7 @@ def fold_in(keys, data):
     k, n = _flat(keys)
     out = torch.empty_like(k, dtype=torch.uint32)
     with torch.cuda.device(k.device):
+        _on_current_stream(k.device)
         check(lib().bjx_prng_fold_in(None, ptr(k), n, int(data) & 0xFFFFFFFF, ptr(out)))
     return out
 
@@ -56,6 +64,7 @@ def _draw(fn, keys, shape, dtype):
         per *= int(s)
     out = torch.empty(tuple(k.shape[:-1]) + tuple(shape), dtype=dtype, device=k.device)
     with torch.cuda.device(k.device):
+        _on_current_stream(k.device)
         check(fn(None, ptr(k), n, per, ptr(out)))
     return out
 
@@ -82,5 +91,6 @@ def randint(keys, shape, minval, maxval):
         per *= int(s_)
     out = torch.empty(tuple(k.shape[:-1]) + tuple(shape), dtype=torch.int32, device=k.device)
     with torch.cuda.device(k.device):
+        _on_current_stream(k.device)
         check(lib().bjx_prng_randint(None, ptr(k), n, per, int(minval), int(maxval), ptr(out)))
     return out

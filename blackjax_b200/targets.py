@@ -89,6 +89,12 @@ class DenseGaussian(Target):
         p = np.asarray(precision, np.float32)
         if p.ndim != 2 or p.shape[0] != p.shape[1]:
             raise ValueError("precision must be a square matrix")
+        # the kernels evaluate grad = -P x, which is the gradient of -1/2 x^T P x (what autodiff of the reference's
+        # logdensity gives: -1/2 (P + P^T) x) only for a symmetric P
+        asym = float(np.max(np.abs(p - p.T))) if p.size else 0.0
+        if asym > 1e-6 * max(float(np.max(np.abs(p))), 1e-30):
+            raise ValueError("precision must be symmetric (the fused value_and_grad computes -P x); "
+                             "pass 0.5 * (P + P.T) for a general quadratic form")
         self.precision = p
         self.dim = int(p.shape[0])
         self.logp_offset = float(logp_offset)

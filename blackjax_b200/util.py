@@ -15,9 +15,7 @@ def sample_hmc_native(rng_key, state, logdensity_fn, step_size, inverse_mass_mat
     from .mcmc.hmc import HMCState
     q, logp, g = (t.clone() for t in state)
     eng = get_engine(q, logdensity_fn)
-    if eng._imm_key is not inverse_mass_matrix:
-        eng.set_metric(inverse_mass_matrix)
-        eng._imm_key = inverse_mass_matrix
+    eng.ensure_metric(inverse_mass_matrix)
     key = rng_key.to(q.device).contiguous()
     if key.ndim != 1:
         raise ValueError("sample_hmc_native takes ONE rng_key of shape [2]")

@@ -11,8 +11,9 @@
  *  - State arrays are row-major float32 [n_chains, dim] (chain-major, dimension contiguous);
  *    per-chain scalars are [n_chains]; PRNG keys are uint32 [n_chains, 2] (raw threefry keys,
  *    i.e. jax.random.key_data layout).
- *  - Every call is asynchronous and ordered on the handle's stream, except bjx_nuts_step
- *    which synchronises the stream once per tree doubling (host-driven tree building).
+ *  - Every call is asynchronous and ordered on the handle's stream (bjx_nuts_step included: the tree doubling is
+ *    driven from host C++ as two launches whose row counts stay on the device); the only calls that wait for the
+ *    device are bjx_synchronize, bjx_destroy and bjx_nuts_last_stats.
  *  - Return value: 0 ok; <0 invalid argument / unsupported configuration (BJX_E_*);
  *    >0 a cudaError_t.  bjx_last_error(handle) returns the text.  No exceptions or
  *    callbacks cross this ABI.  A handle is not thread-safe; distinct handles are independent.
@@ -174,11 +175,13 @@ int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   float step_size, const float* step_size_dev, int32_t max_num_doublings,
                   const bjx_info* info, const float* momentum_override,
                   const uint32_t* key_integrator_override);
-/* doubling launches and doublings reached by the last bjx_nuts_step (host ints) */
+/* doubling launches and the deepest tree of the last bjx_nuts_step (host ints; reading the depth synchronises the stream) */
 int bjx_nuts_last_stats(bjx_handle_t h, int64_t* doubling_launches, int64_t* depth_reached);
 
 /* ---- PRNG (jax.random restated; keys raw uint32 pairs) ----------------------------------------- */
-/* h may be NULL for the PRNG entry points: current device, legacy default stream */
+/* h may be NULL for the PRNG entry points: current device, and the stream this thread registered with
+ * bjx_set_default_stream (a cudaStream_t; the legacy default stream until one is registered) */
+int bjx_set_default_stream(void* cuda_stream);
 int bjx_prng_split(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);
 int bjx_prng_fold_in(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, uint32_t data, uint32_t* out);
 int bjx_prng_random_bits(bjx_handle_t h, const uint32_t* keys, int64_t n_keys, int64_t per_key, uint32_t* out);
@@ -209,6 +212,39 @@ int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acceptance_rat
 /* Dense variant (welford_dense recipe; metric_buffers.py:396-420 `centered.T @ centered`), dim <= 128:
  * stats_out float32 [2 + D + D*D] = (sum acceptance_rate, n_chains, mean[D], M2[D,D]). */
 int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
+
+/* ---- shared (cross-chain, cross-GPU) window adaptation, device resident ------------------------------------------
+ * The reference's multi-chain path (staged_adaptation.py:153-171,906-966): ONE dual-averaging update per warm-up step
+ * on the mean acceptance rate of ALL chains and, in slow windows, the chain-pooled moment block merged into the window
+ * accumulator (metric_buffers.py:334-420); its cross-device collective is lax.psum over "chains" (eca.py:56-62).
+ * Here: each GPU reduces its chains in fixed blocks of BJX_STAT_BLOCK_CHAINS chains to (sum accept, n, mean[D], M2[D]),
+ * ONE NCCL all-gather exchanges the blocks, and every rank merges them in global chain order and applies the same
+ * update on the device -- results do not depend on the GPU count when chains_per_gpu % BJX_STAT_BLOCK_CHAINS == 0. */
+#define BJX_STAT_BLOCK_CHAINS 4096
+/* NCCL communicator helpers (libnccl.so.2 is bound at run time; single-GPU callers never need it).  A caller that
+ * already owns an ncclComm_t (e.g. an XLA / framework communicator) passes it to the calls below as is. */
+int bjx_nccl_unique_id(void* id128_out);                      /* ncclGetUniqueId: 128 bytes, on rank 0 */
+int bjx_nccl_comm_init_rank(const void* id128, int32_t n_ranks, int32_t rank, int32_t device, void** nccl_comm_out);
+int bjx_nccl_comm_destroy(void* nccl_comm);
+/* The collective of the path: all-gather `count` floats per rank into gathered[n_ranks * count] on the handle's stream.
+ * nccl_comm is an ncclComm_t (NULL: one rank, gathered = block). */
+int bjx_allgather_stats(bjx_handle_t h, void* nccl_comm, const float* block, int64_t count, float* gathered);
+/* Device state of the shared adaptation: bjx_adapt_shared_state_floats(...) floats (dual averaging, window accumulator,
+ * this rank's blocks and the gathered blocks). */
+int64_t bjx_adapt_shared_state_floats(int32_t n_chains_local, int32_t dim, int32_t n_ranks);
+/* step_size_chain_out [C] (every entry = initial_step_size: the array the transition kernels read as per-chain step
+ * sizes), imm_out [D] = ones (also installed as the handle's diagonal metric). */
+int bjx_adapt_shared_init(bjx_handle_t h, float* state, float initial_step_size, float* step_size_chain_out, float* imm_out);
+/* One warm-up step after the transition: block statistics of (q, acceptance_rate) -> all-gather -> merge, dual
+ * averaging, window bookkeeping (stage: 0 fast / 1 slow; window_end: last step of a slow window: imm rewritten,
+ * accumulator reset, dual averaging re-initialised, the handle's metric re-installed).  step_size_chain [C] is
+ * refilled with the new step size.  eps_history (nullable, device): the step size of warm-up step t lands in [t].
+ * Fully asynchronous on the handle's stream. */
+int bjx_adapt_shared_update(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, float* state, const float* q,
+                            const float* acceptance_rate, int32_t stage, int32_t window_end, float target_acceptance,
+                            float* step_size_chain, float* imm, float* eps_history);
+/* final step size exp(log_step_avg) (staged_adaptation.py:303) into step_size_out [1] (device) */
+int bjx_adapt_shared_final(bjx_handle_t h, const float* state, float* step_size_out);
 
 /* ---- diagnostics on a device-resident history ---------------------------------------------- */
 /* blackjax.diagnostics.potential_scale_reduction (diagnostics.py:39-89): history float32 [num_samples, C, D] as written

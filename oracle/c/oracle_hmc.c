@@ -11,11 +11,15 @@
  *
  * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=fast -pthread -shared -fPIC oracle_hmc.c -o liboracle_hmc.so -lm
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <sched.h>
+#include <stdio.h>
+#include <string.h>
 #include <unistd.h>
 
 static inline uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
@@ -154,9 +158,56 @@ static void* worker(void* arg) {
   return NULL;
 }
 
+/* CPUs this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota (a container that
+ * reports 128 online CPUs but is throttled to a few cores' worth of time runs faster with that many threads). */
+static int affinity_cpus(int* ids, int cap) {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n = 0;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0)
+    for (int c = 0; c < CPU_SETSIZE && n < cap; ++c)
+      if (CPU_ISSET(c, &set)) ids[n++] = c;
+  return n;
+}
+static double cgroup_cpu_quota(void) {
+  FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+  double q = 0.0;
+  if (f) {
+    char a[64];
+    long long period = 0;
+    if (fscanf(f, "%63s %lld", a, &period) == 2 && strcmp(a, "max") != 0 && period > 0) q = atof(a) / (double)period;
+    fclose(f);
+  } else { /* cgroup v1 */
+    FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+    FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+    long long quota = -1, period = 0;
+    if (fq && fp && fscanf(fq, "%lld", &quota) == 1 && fscanf(fp, "%lld", &period) == 1 && quota > 0 && period > 0)
+      q = (double)quota / (double)period;
+    if (fq) fclose(fq);
+    if (fp) fclose(fp);
+  }
+  return q; /* 0: unlimited */
+}
 int oracle_num_threads(void) {
-  long n = sysconf(_SC_NPROCESSORS_ONLN);
-  return n > 0 ? (int)n : 1;
+  int ids[CPU_SETSIZE];
+  int n = affinity_cpus(ids, CPU_SETSIZE);
+  if (n <= 0) {
+    long m = sysconf(_SC_NPROCESSORS_ONLN);
+    n = m > 0 ? (int)m : 1;
+  }
+  const double q = cgroup_cpu_quota();
+  if (q >= 1.0 && q < (double)n) n = (int)q;
+  return n > 0 ? n : 1;
+}
+/* pin worker t to the t-th CPU of the affinity mask (no migration between the timed repeats) */
+static void pin_thread(pthread_t th, int t) {
+  int ids[CPU_SETSIZE];
+  const int n = affinity_cpus(ids, CPU_SETSIZE);
+  if (n <= 0) return;
+  cpu_set_t one;
+  CPU_ZERO(&one);
+  CPU_SET(ids[t % n], &one);
+  pthread_setaffinity_np(th, sizeof(one), &one);
 }
 
 /* One HMC transition for chains [0, C): in-place on q, logp, g.  Returns the number of leapfrogs done. */
@@ -175,6 +226,7 @@ long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const fl
                q, logp, g, eps, acc_rate, accepted};
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
+    pin_thread(th[t], t);
   }
   for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
   free(th);
@@ -348,6 +400,7 @@ long long oracle_hmc_dense_step(int C, int D, const float* prec, const float* im
     djob_t j = {b0 * BLK, b1 * BLK < C ? b1 * BLK : C, D, L, prec, imm, msqrt_t, keys, q, logp, g, eps, acc_rate, accepted};
     jobs[t] = j;
     pthread_create(&th[t], NULL, dworker, &jobs[t]);
+    pin_thread(th[t], t);
   }
   for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
   free(th);

@@ -88,6 +88,16 @@ class Metric:
         tr = np.sum(self.velocity(p_right) * rho, axis=-1, dtype=F) <= 0
         return tl | tr
 
+    def turning_margin(self, p_left, p_right, p_sum):
+        """Test aid (not in the reference): how far the two U-turn dot products are from the decision boundary 0,
+        relative to the sum of the magnitudes of their terms -- a value near 0 marks a float tie."""
+        rho = p_sum - (p_right + p_left) / F(2.0)
+        out = np.full(np.shape(p_left)[:-1], np.inf)
+        for pe in (p_left, p_right):
+            t = (self.velocity(pe) * rho).astype(np.float64)
+            out = np.minimum(out, np.abs(t.sum(-1)) / np.maximum(np.abs(t).sum(-1), 1e-300))
+        return out
+
 
 def integrator_step(target, metric, q, p, g, eps, coefficients=VELOCITY_VERLET):
     """One palindromic two-stage step; eps is f32 scalar or [C,1] (signed)."""

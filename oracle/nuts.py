@@ -44,13 +44,16 @@ def leaf_idx_to_ckpt_idxs(n):
     return idx_max - num_subtrees + 1, idx_max
 
 
-def is_iterative_turning(metric, ckpt_p, ckpt_sum, idx_min, idx_max, p_sum, p):
-    """termination.py:86-104 for ONE chain (ckpt arrays [depth, D])."""
+def is_iterative_turning(metric, ckpt_p, ckpt_sum, idx_min, idx_max, p_sum, p, margin=None):
+    """termination.py:86-104 for ONE chain (ckpt arrays [depth, D]).  ``margin``: 1-element array, lowered to the
+    smallest relative distance of any evaluated U-turn product from its decision boundary (test aid)."""
     i = idx_max
     turning = False
     while i >= idx_min and not turning:
         sub = (p_sum - ckpt_sum[i] + ckpt_p[i]).astype(F)
         turning = bool(metric.is_turning(ckpt_p[i][None], p[None], sub[None])[0])
+        if margin is not None:
+            margin[0] = min(margin[0], float(metric.turning_margin(ckpt_p[i][None], p[None], sub[None])[0]))
         i -= 1
     return turning
 
@@ -72,8 +75,16 @@ def _sel(mask, a, b):
     return np.where(m, a, b).astype(np.asarray(a).dtype)
 
 
+def _lower(margins, mask, values):
+    """margins[mask] = min(margins[mask], values[mask]) (NaNs ignored)."""
+    if margins is None:
+        return
+    v = np.where(mask & np.isfinite(values), values, np.inf)
+    np.minimum(margins, v, out=margins)
+
+
 def subtree(target, metric, keys, q, p, logp, g, direction, ckpt_p, ckpt_sum, max_num_steps,
-            eps, h0, run, divergence_threshold=1000.0, coefficients=VELOCITY_VERLET):
+            eps, h0, run, divergence_threshold=1000.0, coefficients=VELOCITY_VERLET, margins=None):
     """dynamic_progressive_integration for all chains flagged ``run`` (bool[C]).
 
     Returns dict with the sub-tree's last leaf (q,p,logp,g), first leaf, momentum_sum,
@@ -105,6 +116,8 @@ def subtree(target, metric, keys, q, p, logp, g, direction, ckpt_p, ckpt_sum, ma
         w_new = safe_energy_diff(h0, e_new)                                  # proposal.py:94-98
         slpa_new = np.minimum(w_new, F(0.0)).astype(F)
         div_new = (-w_new) > F(divergence_threshold)                         # :325
+        with np.errstate(invalid="ignore"):
+            _lower(margins, act, np.abs(-w_new.astype(np.float64) - divergence_threshold) / divergence_threshold)
         if i == 0:                                                           # :329-334
             new_sum = np_.copy()
             acc = np.ones(C, bool)
@@ -113,7 +126,9 @@ def subtree(target, metric, keys, q, p, logp, g, direction, ckpt_p, ckpt_sum, ma
             new_sum = (p_sum + np_).astype(F)
             with np.errstate(invalid="ignore"):
                 p_accept = expit(w_new - prop["weight"])
-            acc = prng.uniform(pk) < p_accept
+            u_leaf = prng.uniform(pk)
+            acc = u_leaf < p_accept
+            _lower(margins, act, np.abs(u_leaf.astype(np.float64) - p_accept))
             w_tot = logaddexp(prop["weight"], w_new)
             slpa_tot = logaddexp(prop["slpa"], slpa_new)
         idx_min, idx_max = leaf_idx_to_ckpt_idxs(i)
@@ -122,8 +137,9 @@ def subtree(target, metric, keys, q, p, logp, g, direction, ckpt_p, ckpt_sum, ma
             if i % 2 == 0:                                                   # termination.py:66-72
                 ckpt_p[c, idx_max] = np_[c]
                 ckpt_sum[c, idx_max] = new_sum[c]
+            m1 = None if margins is None else margins[c:c + 1]
             turning[c] = is_iterative_turning(metric, ckpt_p[c], ckpt_sum[c], idx_min, idx_max,
-                                              new_sum[c], np_[c])
+                                              new_sum[c], np_[c], m1)
         # commit for active chains only
         for k, v in zip(range(4), (nq, np_, nlogp, ng)):
             cur[k] = _sel(act, v, cur[k])
@@ -147,8 +163,11 @@ def subtree(target, metric, keys, q, p, logp, g, direction, ckpt_p, ckpt_sum, ma
 
 def nuts_kernel(keys, state, target, step_size, inverse_mass_matrix, max_num_doublings=10,
                 divergence_threshold=1000.0, coefficients=VELOCITY_VERLET, momentum=None,
-                key_integrator=None):
-    """One NUTS transition for every chain.  keys uint32[C,2]."""
+                key_integrator=None, margins=None):
+    """One NUTS transition for every chain.  keys uint32[C,2].  ``margins`` (test aid): float64[C] initialised to inf,
+    lowered in place to each chain's smallest decision margin -- |u - p| of every multinomial / biased draw, the
+    relative distance of every U-turn product from 0 and of -delta from the divergence threshold; a chain whose
+    device result differs from this oracle by float rounding must show a margin near 0 (a tie)."""
     metric = inverse_mass_matrix if isinstance(inverse_mass_matrix, Metric) else Metric(inverse_mass_matrix)
     q0, logp0, g0 = (np.asarray(a, F) for a in state)
     C, D = q0.shape
@@ -183,13 +202,15 @@ def nuts_kernel(keys, state, target, step_size, inverse_mass_matrix, max_num_dou
         start = [_sel(fwd, r, l) for r, l in zip(right, left)]               # :651-655
         sub = subtree(target, metric, trajectory_key, start[0], start[1], start[2], start[3],
                       direction, ckpt_p, ckpt_sum, 2 ** d, eps, h0, run,
-                      divergence_threshold, coefficients)                    # :662-670
+                      divergence_threshold, coefficients, margins)           # :662-670
         sprop = sub["prop"]
         bad = sub["is_div"] | sub["has_term"]
         # :678-694 proposal update
         with np.errstate(invalid="ignore", over="ignore"):
             p_accept = np.minimum(np.exp((sprop["weight"] - prop["weight"]).astype(F)).astype(F), F(1.0))
-        acc = prng.uniform(proposal_key) < p_accept                          # proposal.py:155-156
+        u_prop = prng.uniform(proposal_key)
+        acc = u_prop < p_accept                                              # proposal.py:155-156
+        _lower(margins, run & ~bad, np.abs(u_prop.astype(np.float64) - p_accept))
         new_w = logaddexp(prop["weight"], sprop["weight"])
         new_slpa = logaddexp(prop["slpa"], sprop["slpa"])
         take = run & ~bad & acc
@@ -204,6 +225,8 @@ def nuts_kernel(keys, state, target, step_size, inverse_mass_matrix, max_num_dou
         p_sum = _sel(run, (p_sum + sub["p_sum"]).astype(F), p_sum)
         n_states = np.where(run, n_states + sub["n"], n_states).astype(np.int32)
         turning = metric.is_turning(left[1], right[1], p_sum)                # :706-710
+        if margins is not None:
+            _lower(margins, run, metric.turning_margin(left[1], right[1], p_sum))
         step = np.where(run, step + 1, step).astype(np.int32)
         is_div = np.where(run, sub["is_div"], is_div)
         is_turn = np.where(run, sub["has_term"] | turning, is_turn)          # :715

@@ -1,0 +1,285 @@
+"""GPU parity tests added in round 2 (ADVICE): the named configurations at their own shapes,
+teacher-forced shared adaptation, tie checks for every NUTS chain that disagrees with the oracle, stream and metric-cache
+hygiene, and the G = 1 vs G = 2 invariance of the sharded warm-up.  Everything goes through the C ABI (ctypes)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import blackjax_b200 as bj
+from blackjax_b200 import _engine, targets as T
+from blackjax_b200._lib import check, lib, ptr
+from oracle import adaptation as oadapt
+from oracle import hmc as ohmc
+from oracle import nuts as onuts
+from oracle import prng as oprng
+from oracle import targets as otargets
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tk(keys_np):
+    return torch.from_numpy(np.ascontiguousarray(keys_np).view(np.int32)).to(DEV).view(torch.uint32)
+
+
+def tf(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def close_elementwise(a, b, rtol, floor):
+    """|a - b| <= rtol * max(|b|, floor) for EVERY element: relative to the element itself, with an absolute floor that
+    is stated by the caller (the scale below which the quantity is noise for the comparison at hand)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    bound = rtol * np.maximum(np.abs(b), floor)
+    bad = np.abs(a - b) > bound
+    assert not bad.any(), (f"{bad.sum()} of {bad.size} elements off; worst |a-b|/max(|b|,floor) = "
+                           f"{np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)):.3e} (rtol {rtol:.1e}, floor {floor:.1e})")
+
+
+def max_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 2 at its own shape: 1024-D correlated Gaussian, dense mass matrix, 64-chain oracle subset
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L, tol_state, tol_energy", [(5, 2e-5, 2e-5), (50, 3e-4, 2e-4)])
+def test_config2_dense_1024_transition_vs_oracle(L, tol_state, tol_energy):
+    """Full HMC transition at config 2's matrices (Sigma = Q diag(logspace(-1,1)) Q^T, kappa = 100, M^-1 = Sigma, eps = 0.5)
+    against the float32 oracle from the same (state, key).  Stated tolerance of the path: 1e-5 per float32 product; what
+    a transition can hold is bounded by the products it chains: one tensor-core product is 6.4e-6 of max |y| at K = 1024
+    (profiles/r02_ncu_gemm_f16x3.md: the MMA's float32 accumulator truncates at each of the 192 accumulation steps; the
+    oracle's own SGEMM is ~1e-6), L = 5 chains 10 of them, L = 50 chains 100 at eps = 0.5, which is near the
+    stability limit of this target (the round-off of EITHER float32 implementation is amplified ~kappa^(1/2))."""
+    C, D = 64, 1024
+    cov, prec = otargets.correlated_gaussian(D, seed=0)
+    tgt, otgt = T.DenseGaussian(prec), otargets.DenseGaussian(prec)
+    rs = np.random.default_rng(4)
+    q = (0.1 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(23), C)
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, F(0.5), ohmc.Metric(cov), L)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), bj.hmc.init(tf(q), tgt), tgt, 0.5, tf(cov), L)
+    torch.cuda.synchronize()
+    e_mom = max_rel(npy(info.momentum), oinfo.momentum)
+    e_q = max_rel(npy(info.proposal.position), oinfo.proposal[0])
+    e_p = max_rel(npy(info.proposal.momentum), oinfo.proposal[1])
+    e_en = float(np.max(np.abs(npy(info.energy) - oinfo.energy)) / (np.max(np.abs(oinfo.energy)) + D))
+    print(f"config-2 shape, L={L}: momentum {e_mom:.2e}  proposal q {e_q:.2e} p {e_p:.2e}  energy {e_en:.2e}")
+    assert e_mom < 1e-5
+    assert e_q < tol_state and e_p < tol_state
+    assert e_en < tol_energy
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    acc = npy(info.is_accepted)
+    # a differing accept decision must sit on a tie: |u - p_accept| below the acceptance-rate error the energy error allows
+    tie = np.abs(u - oinfo.acceptance_rate) < 5 * tol_energy * (np.max(np.abs(oinfo.energy)) + D)
+    assert ((acc == oinfo.is_accepted) | tie).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 4's adaptation path: D = 512 shared warm-up, teacher-forced per step against oracle/adaptation.py
+# ---------------------------------------------------------------------------------------------------------
+def test_config4_shared_adaptation_teacher_forced_d512():
+    """Every warm-up step, the device update (bjx_adapt_shared_update: block statistics -> merge -> dual averaging ->
+    window bookkeeping) and the oracle (staged_adaptation.py:153-171,233-297 restated) are fed the SAME positions and
+    acceptance rates; step size after every step, inverse mass matrix at the window end and the final step size must
+    agree to 1e-5 relative (elementwise; the inverse mass matrix has no small elements: floor = its smallest entry)."""
+    D, C, T_ = 512, 8192, 150          # two statistic blocks; schedule: 75 fast, one 25-step slow window, 50 fast
+    scale = np.logspace(-1, 1, D)
+    tgt = T.DiagGaussian(scale)
+    rs = np.random.default_rng(12)
+    q = rs.standard_normal((C, D)).astype(F)
+    state = bj.nuts.init(tf(q), tgt)
+    eng = _engine.get_engine(state.position, tgt, max_tree_depth=6)
+    kernel = bj.nuts.build_kernel(max_tree_depth=6)
+    L_ = lib()
+    st = torch.empty(L_.bjx_adapt_shared_state_floats(C, D, 1), device=DEV)
+    eps_c = torch.empty(C, device=DEV)
+    imm = torch.empty(D, device=DEV)
+    hist = torch.empty(T_, device=DEV)
+    check(L_.bjx_adapt_shared_init(eng.h, ptr(st), 1.0, ptr(eps_c), ptr(imm)), eng.h)
+    eng._imm, eng._imm_key = imm, (imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device))
+    oda, owf, oimm = oadapt.da_init(1.0), oadapt.welford_init(D), np.ones(D, F)
+    step_keys = bj.random.split(bj.random.key(3, DEV), T_)
+    schedule = oadapt.build_schedule(T_)
+    assert any(w for _, w in schedule)
+    for t, (stage, wend) in enumerate(schedule):
+        state, info = kernel(step_keys[t], state, tgt, eps_c, imm, 6)
+        check(L_.bjx_adapt_shared_update(eng.h, None, 1, ptr(st), ptr(state.position), ptr(info.acceptance_rate),
+                                         int(stage), int(wend), 0.8, ptr(eps_c), ptr(imm), ptr(hist)), eng.h)
+        x, a = npy(state.position), npy(info.acceptance_rate)
+        if stage == 1:
+            mean_b = np.mean(x, axis=0, dtype=F)
+            cb = (x - mean_b).astype(F)
+            owf = oadapt.cgl_merge(owf, oadapt.Welford(mean_b, np.sum(cb * cb, axis=0, dtype=F), C))
+        oda = oadapt.da_update(oda, np.mean(a, dtype=F), 0.8)
+        oeps = np.exp(oda.log_step_size).astype(F)
+        if wend:
+            oimm = oadapt.welford_final(owf)
+            owf = oadapt.welford_init(D)
+            oda = oadapt.da_init(oadapt.da_final(oda))
+            oeps = np.exp(oda.log_step_size).astype(F)
+            close_elementwise(npy(imm), oimm, rtol=1e-5, floor=float(oimm.min()))
+        dev_eps = npy(eps_c)
+        assert (dev_eps == dev_eps[0]).all()                       # one step size for all chains
+        close_elementwise(dev_eps[:1], [oeps], rtol=1e-5, floor=1e-30)
+    close_elementwise(npy(hist)[-1:], [oeps], rtol=1e-5, floor=1e-30)
+    fin = torch.empty(1, device=DEV)
+    check(L_.bjx_adapt_shared_final(eng.h, ptr(st), ptr(fin)), eng.h)
+    close_elementwise(npy(fin), [oadapt.da_final(oda)], rtol=1e-5, floor=1e-30)
+    # the adapted metric tracks the target's variances (25 pooled draws x 8192 chains)
+    np.testing.assert_allclose(npy(imm), scale ** 2, rtol=0.25)
+
+
+def test_packaged_shared_warmup_equals_the_teacher_forced_loop_and_old_python_path():
+    """window_adaptation(shared=True).run is exactly the loop above (same bits), and the device-side merge / dual
+    averaging agrees with the host-side float32 restatement it replaced to 1e-5 on a free run of 60 steps."""
+    D, C, T_ = 64, 4096 + 1024, 60     # a full and a partial statistic block
+    scale = np.logspace(-0.5, 0.5, D)
+    tgt = T.DiagGaussian(scale)
+    q = np.random.default_rng(5).standard_normal((C, D)).astype(F)
+    warm = bj.window_adaptation(bj.hmc, tgt, shared=True, num_integration_steps=8)
+    (st, params), hist = warm.run(bj.random.key(9, DEV), tf(q), T_)
+    (st2, params2), hist2 = warm.run(bj.random.key(9, DEV), tf(q), T_)
+    assert torch.equal(st.position, st2.position) and params["step_size"] == params2["step_size"]
+    assert torch.equal(params["inverse_mass_matrix"], params2["inverse_mass_matrix"])
+    okern = lambda k, s, t, e, m, **kw: ohmc.hmc_kernel(k, s, t, e, m, 8)
+    ost, oeps, oimm, ohist = oadapt.window_adaptation_run(okern, otargets.DiagGaussian(scale), oprng.key(9), q, T_, shared=True)
+    np.testing.assert_allclose(np.asarray(hist)[:15], ohist[:15], rtol=2e-4)   # free-running: accept flips on ties later on
+    assert abs(params["step_size"] / float(oeps) - 1) < 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NUTS: every chain that disagrees with the oracle sits on a float tie
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind, D, C, depth, eps", [("funnel", 128, 1024, 10, 0.1), ("diag", 64, 512, 8, 0.3),
+                                                    ("std", 100, 512, 6, 0.4)])
+def test_nuts_disagreements_sit_on_ties(kind, D, C, depth, eps):
+    rs = np.random.default_rng(41)
+    if kind == "funnel":
+        tgt, otgt = T.Funnel(D), otargets.Funnel(D)
+        q = (0.1 * rs.standard_normal((C, D))).astype(F)
+    elif kind == "diag":
+        s = np.exp(rs.uniform(-1, 1, D))
+        tgt, otgt = T.DiagGaussian(s), otargets.DiagGaussian(s)
+        q = (rs.standard_normal((C, D)) * s).astype(F)
+    else:
+        tgt, otgt = T.StdNormal(D), otargets.StdNormal(D)
+        q = rs.standard_normal((C, D)).astype(F)
+    imm = np.ones(D, F)
+    keys = oprng.split(oprng.key(77), C)
+    margins = np.full(C, np.inf)
+    onew, oinfo = onuts.nuts_kernel(keys, ohmc.init(q, otgt), otgt, F(eps), imm, depth, margins=margins)
+    new, info = bj.nuts.build_kernel(max_tree_depth=depth)(tk(keys), bj.nuts.init(tf(q), tgt), tgt, eps, tf(imm), depth)
+    torch.cuda.synchronize()
+    same = ((npy(info.num_integration_steps) == oinfo.num_integration_steps)
+            & (npy(info.num_trajectory_expansions) == oinfo.num_trajectory_expansions)
+            & (npy(info.is_turning) == oinfo.is_turning) & (npy(info.is_divergent) == oinfo.is_divergent)
+            & np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1))
+    print(f"{kind} D={D}: {same.mean():.4f} of chains identical; margins of the others: {np.sort(margins[~same])[:6]}; "
+          f"max tree {oinfo.num_integration_steps.max()}")
+    assert same.mean() >= 0.97
+    # One transition integrates up to 2^depth leapfrogs from an identical start; device and oracle differ by float32
+    # rounding (<= 1e-6 relative per leapfrog, growing along the trajectory), so a chain can only take another branch if
+    # one of the oracle's decisions on its path was closer to its boundary than that accumulated difference: 1e-5
+    # relative per the stated tolerance, times the trajectory length headroom below.
+    assert (margins[~same] < 1e-5 * 64).all(), np.sort(margins[~same])[-3:]
+    # and the converse sanity check: chains far from every boundary agree
+    assert same[margins > 1e-2].all()
+
+
+def test_nuts_runs_without_host_round_trips_and_reports_depth_on_request():
+    C, D = 4096, 32
+    tgt = T.Funnel(D)
+    st = bj.nuts.init(0.1 * torch.randn(C, D, device=DEV), tgt)
+    kern = bj.nuts.build_kernel()
+    keys = bj.random.split(bj.random.key(2, DEV), 3)
+    for k in keys:
+        st, info = kern(k, st, tgt, 0.2, torch.ones(D, device=DEV), 10)
+    eng = _engine.get_engine(st.position, tgt)
+    launches, depth = eng.nuts_last_stats()
+    assert launches == 2                                       # fused doublings 0-3, then one launch for the rest
+    assert depth == int(info.num_trajectory_expansions.max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ADVICE: PRNG helpers on side streams; metric cache keyed on content version
+# ---------------------------------------------------------------------------------------------------------
+def test_prng_and_warmup_inside_a_side_stream():
+    s = torch.cuda.Stream(device=DEV)
+    tgt = T.DiagGaussian(np.logspace(-0.3, 0.3, 16))
+    q = torch.randn(512, 16, device=DEV)
+    ref_keys = bj.random.split(bj.random.key(4, DEV), 40)
+    warm = bj.window_adaptation(bj.hmc, tgt, num_integration_steps=5)
+    (ref_state, ref_params), _ = warm.run(bj.random.key(4, DEV), q, 40)
+    alg = bj.dhmc(tgt, 0.3, torch.ones(16, device=DEV))
+    ref_d = alg.init(q, bj.random.key(8, DEV))
+    for k in ref_keys[:5]:
+        ref_d, _ = alg.step(k, ref_d)
+    torch.cuda.synchronize()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        # a long kernel first, so that work issued on the legacy default stream would overtake this stream
+        junk = torch.randn(4096, 4096, device=DEV) @ torch.randn(4096, 4096, device=DEV)
+        keys = bj.random.split(bj.random.key(4, DEV), 40)
+        (state, params), _ = warm.run(bj.random.key(4, DEV), q, 40)
+        d = alg.init(q, bj.random.key(8, DEV))
+        for k in keys[:5]:
+            d, _ = alg.step(k, d)
+    s.synchronize()
+    assert torch.equal(keys, ref_keys)
+    assert torch.equal(state.position, ref_state.position)
+    assert torch.equal(params["step_size"], ref_params["step_size"])
+    assert torch.equal(d.position, ref_d.position)
+    del junk
+
+
+@pytest.mark.parametrize("D, dense", [(16, False), (256, True)])
+def test_inplace_metric_update_is_picked_up(D, dense):
+    C = 64
+    rs = np.random.default_rng(2)
+    if dense:
+        A = rs.standard_normal((D, D))
+        imm_a = (A @ A.T / D + np.eye(D)).astype(F)
+        imm_b = (2.5 * imm_a).astype(F)
+    else:
+        imm_a, imm_b = np.exp(rs.uniform(-1, 1, D)).astype(F), np.exp(rs.uniform(-1, 1, D)).astype(F)
+    tgt = T.DiagGaussian(np.ones(D, F))
+    q = tf(rs.standard_normal((C, D)))
+    key = bj.random.key(1, DEV)
+    kern = bj.hmc.build_kernel(full_info=True)
+    imm = tf(imm_a)
+    _, info_a = kern(key, bj.hmc.init(q, tgt), tgt, 0.1, imm, 3)
+    imm.copy_(tf(imm_b))                                        # same tensor, new contents
+    _, info_b = kern(key, bj.hmc.init(q, tgt), tgt, 0.1, imm, 3)
+    _, info_ref = kern(key, bj.hmc.init(q, tgt), tgt, 0.1, tf(imm_b), 3)
+    assert not torch.equal(info_a.momentum, info_b.momentum)
+    assert torch.equal(info_b.momentum, info_ref.momentum)      # mass_matrix_sqrt / operand planes were re-derived
+    assert torch.equal(info_b.proposal.position, info_ref.proposal.position)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the sharded warm-up does not depend on the GPU count (needs two GPUs: `gpurun --gpus 2`)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_shared_warmup_bit_identical_on_one_and_two_gpus(tmp_path):
+    worker = os.path.join(ROOT, "tests", "helpers", "shared_warmup_worker.py")
+    one, two = str(tmp_path / "g1.npz"), str(tmp_path / "g2.npz")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, worker, one, "16384"], check=True, env=env, timeout=600)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                    "127.0.0.1", "--master-port", "29517", worker, two, "8192"], check=True, env=env, timeout=600)
+    a, b = np.load(one), np.load(two)
+    assert a["n_ranks"] == 1 and b["n_ranks"] == 2
+    for k in ("eps_history", "imm", "step_size", "position", "logdensity"):
+        assert np.array_equal(a[k], b[k]), k

@@ -242,3 +242,14 @@ def test_library_is_sm100a_with_tcgen05_and_packed_fp32_sass():
     for mnemonic in ("UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "FFMA2", "FMUL2", "FADD2"):
         assert mnemonic in sass, f"{mnemonic} missing from libbjx.so SASS"
     assert "HMMA.16816" not in sass and "HGMMA" not in sass      # no mma.sync / wgmma-style fallbacks
+
+
+def test_dense_gaussian_rejects_an_asymmetric_precision():
+    """The fused value_and_grad computes -P x, the gradient of -1/2 x^T P x only for symmetric P."""
+    import numpy as np
+    import pytest
+    from blackjax_b200 import targets as T
+    P = np.eye(4) + 0.1 * np.triu(np.ones((4, 4)), 1)
+    with pytest.raises(ValueError, match="symmetric"):
+        T.DenseGaussian(P)
+    T.DenseGaussian(0.5 * (P + P.T))
