@@ -140,7 +140,8 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
         C, D = position.shape
         dev = position.device
         state = algorithm.init(position, logdensity_fn)
-        eng = get_engine(position, logdensity_fn, max_tree_depth=extra_parameters.get("max_num_doublings", 10))
+        # the engine the transition kernel resolves to (nuts.build_kernel: depth max(10, max_num_doublings))
+        eng = get_engine(position, logdensity_fn, max_tree_depth=max(10, extra_parameters.get("max_num_doublings", 10)))
         schedule = build_schedule(num_steps)
         history = []
         import torch.distributed as dist
@@ -172,6 +173,9 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
                 check(L.bjx_adapt_shared_update(eng.h, comm, n_ranks, ptr(st), ptr(state.position),
                                                 ptr(info.acceptance_rate), int(stage), int(window_end),
                                                 float(target_acceptance_rate), ptr(eps_c), ptr(imm), ptr(eps_hist)), eng.h)
+                if window_end:
+                    imm.add_(0.0)  # in-place no-op: bumps torch's version counter, so that ANY engine the kernel resolves to
+                    #                re-installs the metric the device just rewrote (mass_matrix_sqrt follows the contents)
             step = torch.empty(1, dtype=torch.float32, device=dev)
             check(L.bjx_adapt_shared_final(eng.h, ptr(st), ptr(step)), eng.h)
             step_size = float(step.item())   # the one host read of the warm-up

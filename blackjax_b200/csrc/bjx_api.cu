@@ -610,11 +610,12 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   rc = dispatch(h, K_NUTS_INIT, false, a);
   if (rc) return rc;
 
-  // Tree doubling (trajectory.py:616-725) in two launches and without a host round trip.  The first kFusedDoublings
+  // Tree doubling (trajectory.py:616-725) driven from the host WITHOUT a host round trip.  The first kFusedDoublings
   // doublings run in ONE launch over all chains (every chain needs them and their cost is the fixed per-doubling row
-  // traffic) and compact the chains that keep expanding into list_a; the second launch takes each of those chains
-  // through ALL its remaining doublings (its row count is read on the device from counters[1], the grid covers every
-  // chain and surplus warps exit at once).  Chains never interact, so nothing forces them through the tree in lock step.
+  // traffic) and compact the chains that keep expanding into list_a; every further doubling is one launch over the
+  // compacted list of the chains still expanding (ping-pong lists), whose length is read on the device from
+  // counters[launch]: a fixed grid strides over the list, so a doubling that nobody needs costs one empty launch.
+  // Chains never interact, so nothing forces them through the tree in lock step.
   const int kFusedDoublings = 4;  // (the kernel's lane-parallel key schedule handles up to 10 doublings per launch)
   const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
   const size_t dm_bytes = (h->metric_small_dense || h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
@@ -634,10 +635,9 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
     if (rc) return rc;
     ++launches;
   }
-  for (int d = d_fused; d < max_num_doublings; d += 10) {  // one launch unless max_tree_depth > 14
-    const int d_end = (max_num_doublings - d > 10) ? d + 10 : max_num_doublings;
+  for (int d = d_fused; d < max_num_doublings; ++d) {
     a.depth = d;
-    a.depth_end = d_end;
+    a.depth_end = d + 1;
     a.list_in = (launches & 1) ? h->ws.list_a : h->ws.list_b;
     a.n_in = C;
     a.n_in_dev = h->ws.counters + launches;

@@ -376,7 +376,9 @@ __device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const P
 // fixed per-doubling row traffic) into one launch and gives each deep doubling its own launch over the compacted
 // list of chains that still expand; chains that want doubling d_end are appended to list_out.
 // Checkpoints live in shared memory when depth x D is small enough (ckpt_smem), else in the global workspace.
-template <class R, int TK, bool DM, bool GEN>
+// STRIDE: the row count is read on the device (n_in_dev) and a fixed grid strides over the list; the loop costs ~30
+// registers, so the launch over all chains (row count known on the host) is instantiated without it.
+template <class R, int TK, bool DM, bool GEN, bool STRIDE>
 __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d_begin, int d_end, int max_doublings,
                                                             const int* __restrict__ list_in, int n_in,
                                                             const int* __restrict__ n_in_dev,
@@ -384,12 +386,12 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
                                                             float* q_out, float* logp_out, float* g_out, int ckpt_smem) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int w = blockIdx.x * kWarpsPerBlock + wib;
   extern __shared__ __align__(16) float bjx_smem[];
   float* sm = bjx_smem + (size_t)wib * P.D;  // small dense matvec slice (first kWarpsPerBlock*D floats when used)
-  // n_in_dev: the row count was produced on the device by the previous launch (no host round trip); the grid then
-  // covers every chain and the surplus warps leave here
-  if (w >= (n_in_dev ? *n_in_dev : n_in)) return;
+  // n_in_dev: the row count was produced on the device by the previous launch (no host round trip); the grid is then
+  // a fixed number of CTAs whose warps stride over the compacted list (surplus warps leave at once)
+  const int n_rows = (STRIDE && n_in_dev) ? *n_in_dev : n_in;
+  for (int w = blockIdx.x * kWarpsPerBlock + wib; w < n_rows; w += STRIDE ? gridDim.x * kWarpsPerBlock : n_rows) {
   const int chain = list_in ? list_in[w] : w;
   const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK, DM> c;
@@ -602,6 +604,9 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     ws.step[chain] = d;
     if (run_next && d < max_doublings) list_out[atomicAdd(counter_out, 1)] = chain;
   }
+  if constexpr (!STRIDE) return;  // one row per warp: no loop for the compiler to carry state across
+  __syncwarp();
+  }  // next row of the list
 }
 
 // nuts.py:303-319: acceptance_rate = exp(sum_log_p_accept) / num_states and the NUTSInfo scalars

@@ -57,7 +57,9 @@ struct Launcher {
 template <class R, int TK, bool DM>
 static int launch_one(int kernel_id, const LaunchArgs& a) {
   const int n_rows = (kernel_id == K_NUTS_DOUBLING) ? a.n_in : a.P.C;
-  const dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
+  dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
+  // row count only known on the device: a fixed grid of 6 CTAs per SM strides over the compacted list
+  if (kernel_id == K_NUTS_DOUBLING && a.n_in_dev && grid.x > 148u * 6u) grid.x = 148u * 6u;
   size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
   if (kernel_id == K_NUTS_DOUBLING && a.ckpt_smem) smem += sizeof(float) * kWarpsPerBlock * 2 * a.depth_end * a.P.D;
   cudaStream_t st = a.stream;
@@ -88,14 +90,25 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
                                                                         a.logp_out, a.g_out, a.n, a.info);
       return 0;
     case K_NUTS_DOUBLING:
-      if (a.general_integrator)
-        k_nuts_doubling<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
-                                                                     a.n_in, a.n_in_dev, a.list_out, a.counter, a.q_out,
-                                                                     a.logp_out, a.g_out, a.ckpt_smem);
-      else
-        k_nuts_doubling<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in,
-                                                                      a.n_in, a.n_in_dev, a.list_out, a.counter, a.q_out,
-                                                                      a.logp_out, a.g_out, a.ckpt_smem);
+      if (a.n_in_dev) {
+        if (a.general_integrator)
+          k_nuts_doubling<R, TK, DM, true, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                            a.n_in_dev, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                            a.g_out, a.ckpt_smem);
+        else
+          k_nuts_doubling<R, TK, DM, false, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                             a.n_in_dev, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                             a.g_out, a.ckpt_smem);
+      } else {
+        if (a.general_integrator)
+          k_nuts_doubling<R, TK, DM, true, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                             nullptr, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                             a.g_out, a.ckpt_smem);
+        else
+          k_nuts_doubling<R, TK, DM, false, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                              nullptr, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                              a.g_out, a.ckpt_smem);
+      }
       return 0;
     default:
       break;

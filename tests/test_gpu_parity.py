@@ -36,17 +36,25 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-def close(a, b, rtol=1e-5, scale=None, floor_frac=0.05):
-    """Elementwise: |a - b| <= rtol * max(|b|, floor) for every element, floor = floor_frac * scale with scale = max |b|
-    unless given.  Elements above 5 % of the array's scale are held to rtol relative to THEMSELVES; smaller ones to
-    rtol * floor (their own rounding noise in a float32 reduction is relative to the terms summed, not to the result).
-    floor_frac = 1 (error relative to the array maximum) is used only where stated: outputs of the tensor-core
-    products, whose error is absolute in the row norm."""
+def close(a, b, rtol=1e-5, scale=None, floor_frac=None):
+    """Elementwise: |a - b| <= rtol * max(|b|, floor) for every element.
+    * state vectors (no ``scale``): floor = 5 % of max |b|.  Elements above it are held to rtol relative to THEMSELVES,
+      smaller ones to rtol * floor (their rounding noise comes from terms of the size of the large elements).
+    * reductions (``scale`` given: energies, log-densities, acceptance rates): floor = scale, the magnitude of the terms
+      that were summed -- a sum of D terms that cancels to a small value is not accurate relative to that value.
+    * floor_frac = 1 without scale (``dclose``): outputs of the tensor-core products, whose error is absolute in the row.
+    Non-finite entries must match exactly (inf with inf, NaN with NaN)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    s = np.max(np.abs(b)) if scale is None else scale
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~fin & ~np.isnan(b)], b[~fin & ~np.isnan(b)])
+    if not fin.any():
+        return
+    if floor_frac is None:
+        floor_frac = 1.0 if scale is not None else 0.05
+    s = np.max(np.abs(b[fin])) if scale is None else scale
     floor = floor_frac * max(s, 1e-30)
-    err = np.abs(a - b) / np.maximum(np.abs(b), floor)
-    assert np.all(err <= rtol), f"worst elementwise error {np.nanmax(err):.3e} > rtol {rtol:.1e} (floor {floor:.3e})"
+    err = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), floor)
+    assert np.all(err <= rtol), f"worst elementwise error {np.max(err):.3e} > rtol {rtol:.1e} (floor {floor:.3e})"
 
 
 def dclose(a, b, rtol=1e-5, scale=None):
