@@ -10,6 +10,7 @@ import functools as _functools
 from . import diagnostics, random, targets, util  # noqa: F401
 from ._lib import BjxError  # noqa: F401
 from .adaptation.window_adaptation import build_schedule, window_adaptation  # noqa: F401
+from .adaptation.chees_adaptation import chees_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, GenerateSamplingAPI, SamplingAlgorithm  # noqa: F401
 from . import mcmc  # noqa: F401
 from .mcmc import hmc as _hmc

@@ -88,6 +88,11 @@ _SIGNATURES = {
                                           C.c_float, _f32p, _f32p, _f32p]),
     "bjx_adapt_shared_final": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "bjx_set_default_stream": (C.c_int, [C.c_void_p]),
+    "bjx_chees_state_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "bjx_chees_init": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_int32, C.c_float, _f32p, C.c_void_p]),
+    "bjx_chees_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
+                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _f32p, C.c_void_p, _f32p]),
+    "bjx_chees_final": (C.c_int, [C.c_void_p, _f32p, C.POINTER(C.c_float)]),
     "bjx_potential_scale_reduction": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
     "bjx_ess_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "bjx_effective_sample_size": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),

@@ -332,3 +332,311 @@ extern "C" int bjx_adapt_shared_final(bjx_handle_t h, const float* state, float*
   AD_LAUNCH("k_da_final");
   return 0;
 }
+
+// =====================================================================================================================
+// ChEES-HMC warm-up (blackjax/adaptation/chees_adaptation.py, mass_matrix_estimation=None): dual averaging on the
+// harmonic mean of the acceptance probabilities (:341-360) and Adam ascent on log(trajectory length) along the ChEES
+// gradient jitter * T * (|dx'|^2 - |dx|^2) <dx', p'> (:362-480), both from cross-chain statistics.  Same structure as
+// the shared window adaptation above: fixed blocks of BJX_STAT_BLOCK_CHAINS chains, merged in global chain order after
+// an all-gather (two per step: the centring means must be global before the per-chain dot products can be formed).
+// =====================================================================================================================
+namespace bjx {
+constexpr int kChHdr = 32;
+// header slots
+enum { CH_EPS = 0, CH_LOG_EPS_MA, CH_T, CH_LOG_T_MA, CH_DA_LOGX, CH_DA_LOGX_AVG, CH_DA_STEP, CH_DA_ERR, CH_DA_MU, CH_AD_COUNT,
+       CH_AD_MU, CH_AD_NU, CH_RGA, CH_STEP, CH_MAX_BITS, CH_JITTER_AMOUNT, CH_T_IDX, CH_L, CH_HM_SUM, CH_HM_N, CH_GRAD };
+
+__device__ __forceinline__ float halton_f(int i, int max_bits) {  // dynamic_hmc.py:205-215
+  float s = 0.f;
+  for (int k = 0; k < max_bits; ++k) s += (float)(((i + 1) >> k) & 1) * (0.5f / (float)(1u << k));
+  return s;
+}
+
+// per chain: w' = is_divergent ? 0 : acceptance, zeroed when the proposal row holds a non-finite entry (:239-247)
+__global__ void k_chees_w(int C, int D, const float* __restrict__ prop_q, const float* __restrict__ acc,
+                          const uint8_t* __restrict__ is_div, float* __restrict__ w) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  bool fin = true;
+  for (int i = lane; i < D; i += 32) fin = fin && isfinite(prop_q[(size_t)c * D + i]);
+  fin = __all_sync(0xffffffffu, fin);
+  if (lane == 0) w[c] = (!is_div[c] && fin) ? acc[c] : 0.f;
+}
+
+// block (bx, by): columns [32 bx, +32) over chains of statistic block by.
+// out[by] = (sum_{nd} 1/acc, n_nd, sum w', sum_c w'_c x_c [D], sum_c finite q_c [D], count of non-NaN q [D])
+__global__ void k_chees_pass1(int C, int D, const float* __restrict__ prop_q, const float* __restrict__ init_q,
+                              const float* __restrict__ acc, const uint8_t* __restrict__ is_div, const float* __restrict__ w,
+                              float* __restrict__ out) {
+  __shared__ float red[3][8][33];
+  const int c0 = blockIdx.y * kStatBlock, c1 = min(C, c0 + kStatBlock);
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float* o = out + (size_t)blockIdx.y * (3 + 3 * (size_t)D);
+  float sw = 0.f, sq = 0.f, cq = 0.f;
+  if (col < D)
+    for (int c = c0 + threadIdx.y; c < c1; c += 8) {
+      const float x = prop_q[(size_t)c * D + col], q = init_q[(size_t)c * D + col];
+      sw = fmaf(w[c], isfinite(x) ? x : 0.f, sw);
+      if (!isnan(q)) { sq += q; cq += 1.f; }
+    }
+  red[0][threadIdx.y][threadIdx.x] = sw;
+  red[1][threadIdx.y][threadIdx.x] = sq;
+  red[2][threadIdx.y][threadIdx.x] = cq;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float a = 0.f, b = 0.f, n = 0.f;
+    for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; b += red[1][k][threadIdx.x]; n += red[2][k][threadIdx.x]; }
+    o[3 + col] = a;
+    o[3 + D + col] = b;
+    o[3 + 2 * D + col] = n;
+  }
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    float h = 0.f, n = 0.f, ws = 0.f;
+    for (int c = c0 + t; c < c1; c += 256) {
+      if (!is_div[c]) { h += 1.0f / acc[c]; n += 1.f; }
+      ws += w[c];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      h += __shfl_xor_sync(0xffffffffu, h, off);
+      n += __shfl_xor_sync(0xffffffffu, n, off);
+      ws += __shfl_xor_sync(0xffffffffu, ws, off);
+    }
+    if (threadIdx.x == 0) { red[0][threadIdx.y][0] = h; red[1][threadIdx.y][0] = n; red[2][threadIdx.y][0] = ws; }
+    __syncthreads();
+    if (t == 0) {
+      float a = 0.f, b = 0.f, c_ = 0.f;
+      for (int k = 0; k < 8; ++k) { a += red[0][k][0]; b += red[1][k][0]; c_ += red[2][k][0]; }
+      o[0] = a; o[1] = b; o[2] = c_;
+    }
+  }
+}
+
+// merge the pass-1 blocks in global order: proposal mean (weighted), initial mean (nanmean), harmonic-mean sums
+__global__ void k_chees_means(int D, int nblk, const float* __restrict__ blocks, float* __restrict__ st) {
+  const size_t S = 3 + 3 * (size_t)D;
+  float* pm = st + kChHdr;
+  float* qm = pm + D;
+  float sw = 0.f;
+  for (int b = 0; b < nblk; ++b) sw += blocks[b * S + 2];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a = 0.f, q = 0.f, n = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      a += blocks[b * S + 3 + d];
+      q += blocks[b * S + 3 + D + d];
+      n += blocks[b * S + 3 + 2 * D + d];
+    }
+    pm[d] = a / (sw + 1e-20f);
+    qm[d] = q / n;
+  }
+  if (threadIdx.x == 0) {
+    float h = 0.f, n = 0.f;
+    for (int b = 0; b < nblk; ++b) { h += blocks[b * S]; n += blocks[b * S + 1]; }
+    st[CH_HM_SUM] = h;
+    st[CH_HM_N] = n;
+  }
+}
+
+// per chain (one warp): (|x' - E x'|^2 - |x - E x|^2) <x' - E x', p'>, then its acceptance-weighted terms
+__global__ void k_chees_dots(int C, int D, const float* __restrict__ prop_q, const float* __restrict__ prop_p,
+                             const float* __restrict__ init_q, const float* __restrict__ acc, const uint8_t* __restrict__ is_div,
+                             const float* __restrict__ st, float* __restrict__ num, float* __restrict__ den) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const float* pm = st + kChHdr;
+  const float* qm = pm + D;
+  float a = 0.f, b = 0.f, d = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float pc = prop_q[(size_t)c * D + i] - pm[i];
+    const float ic = init_q[(size_t)c * D + i] - qm[i];
+    a = fmaf(pc, pc, a);
+    b = fmaf(ic, ic, b);
+    d = fmaf(pc, prop_p[(size_t)c * D + i], d);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    d += __shfl_xor_sync(0xffffffffu, d, off);
+  }
+  if (lane == 0) {
+    const bool nd = !is_div[c];
+    num[c] = nd ? acc[c] * ((a - b) * d) : 0.f;
+    den[c] = nd ? acc[c] + 1e-20f : 0.f;
+  }
+}
+// fixed-order sums of the two per-chain arrays over each statistic block -> out[by] = (sum num, sum den)
+__global__ void k_chees_pass2(int C, const float* __restrict__ num, const float* __restrict__ den, float* __restrict__ out) {
+  __shared__ float red[2][8];
+  const int c0 = blockIdx.x * kStatBlock, c1 = min(C, c0 + kStatBlock);
+  float a = 0.f, b = 0.f;
+  for (int c = c0 + threadIdx.x; c < c1; c += 256) { a += num[c]; b += den[c]; }
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.f, y = 0.f;
+    for (int k = 0; k < 8; ++k) { x += red[0][k]; y += red[1][k]; }
+    out[2 * blockIdx.x] = x;
+    out[2 * blockIdx.x + 1] = y;
+  }
+}
+
+// the scalar update (chees_adaptation.py:341-360,470-511) and the next transition's step count
+__global__ void k_chees_finish(int nblk, const float* __restrict__ blocks2, float* __restrict__ st, float lr, float b1, float b2,
+                               float target, float decay, float max_leapfrog, float* __restrict__ hist) {
+  if (threadIdx.x != 0) return;
+  const int max_bits = (int)st[CH_MAX_BITS];
+  const float jam = st[CH_JITTER_AMOUNT];
+  const int rga = (int)st[CH_RGA];
+  const float step = st[CH_STEP];
+  float eps = st[CH_EPS], T = st[CH_T];
+  // step size: dual averaging on target - harmonic mean of the non-divergent acceptance probabilities
+  float hm = 1.0f / (st[CH_HM_SUM] / st[CH_HM_N]);
+  if (!isfinite(hm)) hm = 0.f;
+  float log_x = st[CH_DA_LOGX], log_x_avg = st[CH_DA_LOGX_AVG], da_step = st[CH_DA_STEP], err = st[CH_DA_ERR];
+  const float mu = st[CH_DA_MU];
+  {
+    const float gradient = target - hm;
+    const float reg_step = da_step + 10.f;
+    const float eta_t = powf(da_step, -0.75f);
+    const float nerr = (1.f - (1.f / reg_step)) * err + gradient / reg_step;
+    const float nlog_x = mu - (sqrtf(da_step) / 0.05f) * nerr;
+    const float navg = eta_t * log_x + (1.f - eta_t) * log_x_avg;
+    const float neps = expf(nlog_x);
+    if (isfinite(neps)) { eps = neps; log_x = nlog_x; log_x_avg = navg; da_step += 1.f; err = nerr; }
+  }
+  const float uw = powf(step, -decay);
+  const float log_eps_ma = (1.f - uw) * st[CH_LOG_EPS_MA] + uw * log_x;
+  // trajectory length: Adam on log T along the ChEES gradient
+  float num = 0.f, den = 0.f;
+  for (int b = 0; b < nblk; ++b) { num += blocks2[2 * b]; den += blocks2[2 * b + 1]; }
+  const float jit = halton_f(rga, max_bits) * jam + (1.f - jam);
+  const float grad = (jit * T) * num / den;
+  const float log_T = logf(T);
+  float ad_mu = b1 * st[CH_AD_MU] + (1.f - b1) * grad;
+  float ad_nu = b2 * st[CH_AD_NU] + (1.f - b2) * grad * grad;
+  const float count = st[CH_AD_COUNT] + 1.f;
+  const float mu_hat = ad_mu / (1.f - powf(b1, count));
+  const float nu_hat = ad_nu / (1.f - powf(b2, count));
+  float upd = -lr * (mu_hat / (sqrtf(nu_hat) + 1e-8f));
+  upd = fminf(fmaxf(upd, -0.35f), 0.35f);
+  if (isnan(-lr * (mu_hat / (sqrtf(nu_hat) + 1e-8f)))) upd = __int_as_float(0x7fc00000);
+  float new_log_T = log_T;
+  if (isfinite(log_T + upd)) {
+    new_log_T = log_T + upd;
+    st[CH_AD_MU] = ad_mu; st[CH_AD_NU] = ad_nu; st[CH_AD_COUNT] = count;
+  }
+  const float log_T_ma = (1.f - uw) * st[CH_LOG_T_MA] + uw * new_log_T;
+  float newT = expf(log_T_ma);
+  newT = fminf(fmaxf(newT, eps), max_leapfrog * eps);
+  st[CH_EPS] = eps; st[CH_LOG_EPS_MA] = log_eps_ma; st[CH_T] = newT; st[CH_LOG_T_MA] = log_T_ma;
+  st[CH_DA_LOGX] = log_x; st[CH_DA_LOGX_AVG] = log_x_avg; st[CH_DA_STEP] = da_step; st[CH_DA_ERR] = err;
+  st[CH_RGA] = (float)(rga + 1);
+  st[CH_STEP] = step + 1.f;
+  st[CH_GRAD] = grad;
+  // next transition: ceil(jitter(i + 1) * T / eps) leapfrog steps (integration_steps_fn :775-779)
+  const float jn = halton_f(rga + 1, max_bits) * jam + (1.f - jam);
+  st[CH_L] = ceilf(jn * (newT / eps));
+  const int t = (int)st[CH_T_IDX];
+  if (hist) { hist[4 * t] = eps; hist[4 * t + 1] = newT; hist[4 * t + 2] = st[CH_L]; hist[4 * t + 3] = grad; }
+  st[CH_T_IDX] = (float)(t + 1);
+}
+__global__ void k_chees_init(float* st, float eps0, int max_bits, float jitter_amount) {
+  if (threadIdx.x != 0) return;
+  for (int k = 0; k < kChHdr; ++k) st[k] = 0.f;
+  st[CH_EPS] = eps0; st[CH_T] = eps0;
+  st[CH_DA_LOGX] = logf(eps0); st[CH_DA_STEP] = 1.f; st[CH_DA_MU] = logf(10.f * eps0);
+  st[CH_STEP] = 1.f; st[CH_MAX_BITS] = (float)max_bits; st[CH_JITTER_AMOUNT] = jitter_amount;
+  const float j0 = halton_f(0, max_bits) * jitter_amount + (1.f - jitter_amount);
+  st[CH_L] = ceilf(j0 * (eps0 / eps0));
+}
+__global__ void k_fill_steps(int n, const float* __restrict__ src, int32_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int32_t)src[0];
+}
+}  // namespace bjx
+
+extern "C" int64_t bjx_chees_state_floats(int32_t n_chains_local, int32_t dim, int32_t n_ranks) {
+  if (n_chains_local <= 0 || dim <= 0 || n_ranks <= 0) return 0;
+  const int64_t nb = n_stat_blocks(n_chains_local), D = dim;
+  return kChHdr + 2 * D + 3 * (int64_t)n_chains_local + nb * (3 + 3 * D) * (1 + n_ranks) + nb * 2 * (1 + n_ranks);
+}
+
+extern "C" int bjx_chees_init(bjx_handle_t h, float* state, float step_size, int32_t max_bits, float jitter_amount,
+                              float* step_size_chain_out, int32_t* steps_chain_out) {
+  if (!h || !state || !step_size_chain_out || !steps_chain_out) return bjx_fail(h, BJX_E_INVALID, "null argument");
+  if (!(step_size > 0.f) || max_bits < 1 || max_bits > 30) return bjx_fail(h, BJX_E_INVALID, "bad step_size / max_bits");
+  AD_CUDA(cudaSetDevice(h->cfg.device));
+  const int C = h->cfg.n_chains;
+  k_chees_init<<<1, 32, 0, h->stream>>>(state, step_size, max_bits, jitter_amount);
+  AD_LAUNCH("k_chees_init");
+  k_fill_from<<<(C + 255) / 256, 256, 0, h->stream>>>(C, state + CH_EPS, step_size_chain_out);
+  k_fill_steps<<<(C + 255) / 256, 256, 0, h->stream>>>(C, state + CH_L, steps_chain_out);
+  AD_LAUNCH("k_fill");
+  return 0;
+}
+
+extern "C" int bjx_chees_update(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, float* state, const float* initial_position,
+                                const float* proposal_position, const float* proposal_momentum, const float* acceptance_rate,
+                                const uint8_t* is_divergent, float learning_rate, float b1, float b2, float target_acceptance,
+                                float decay_rate, int32_t max_leapfrog_steps, float* step_size_chain, int32_t* steps_chain,
+                                float* history) {
+  if (!h || !state || !initial_position || !proposal_position || !proposal_momentum || !acceptance_rate || !is_divergent ||
+      !step_size_chain || !steps_chain)
+    return bjx_fail(h, BJX_E_INVALID, "null argument");
+  if (n_ranks < 1 || (n_ranks > 1 && !nccl_comm)) return bjx_fail(h, BJX_E_INVALID, "n_ranks > 1 needs a communicator");
+  AD_CUDA(cudaSetDevice(h->cfg.device));
+  const int C = h->cfg.n_chains, D = h->cfg.dim;
+  const int nb = n_stat_blocks(C);
+  const size_t S1 = 3 + 3 * (size_t)D;
+  float* w = state + kChHdr + 2 * (size_t)D;
+  float* num = w + C;
+  float* den = num + C;
+  float* loc1 = den + C;
+  float* gat1 = loc1 + (size_t)nb * S1;
+  float* loc2 = gat1 + (size_t)nb * S1 * n_ranks;
+  float* gat2 = loc2 + (size_t)nb * 2;
+  cudaStream_t s = h->stream;
+  k_chees_w<<<(C + 7) / 8, 256, 0, s>>>(C, D, proposal_position, acceptance_rate, is_divergent, w);
+  k_chees_pass1<<<dim3((D + 31) / 32, nb), dim3(32, 8), 0, s>>>(C, D, proposal_position, initial_position, acceptance_rate,
+                                                              is_divergent, w, loc1);
+  AD_LAUNCH("k_chees_pass1");
+  const float* m1 = loc1;
+  if (n_ranks > 1) {
+    int rc = bjx_allgather_stats(h, nccl_comm, loc1, (int64_t)(nb * S1), gat1);
+    if (rc) return rc;
+    m1 = gat1;
+  }
+  k_chees_means<<<1, 512, 0, s>>>(D, nb * n_ranks, m1, state);
+  k_chees_dots<<<(C + 7) / 8, 256, 0, s>>>(C, D, proposal_position, proposal_momentum, initial_position, acceptance_rate,
+                                          is_divergent, state, num, den);
+  k_chees_pass2<<<nb, 256, 0, s>>>(C, num, den, loc2);
+  AD_LAUNCH("k_chees_pass2");
+  const float* m2 = loc2;
+  if (n_ranks > 1) {
+    int rc = bjx_allgather_stats(h, nccl_comm, loc2, (int64_t)(nb * 2), gat2);
+    if (rc) return rc;
+    m2 = gat2;
+  }
+  k_chees_finish<<<1, 32, 0, s>>>(nb * n_ranks, m2, state, learning_rate, b1, b2, target_acceptance, decay_rate,
+                                  (float)max_leapfrog_steps, history);
+  k_fill_from<<<(C + 255) / 256, 256, 0, s>>>(C, state + CH_EPS, step_size_chain);
+  k_fill_steps<<<(C + 255) / 256, 256, 0, s>>>(C, state + CH_L, steps_chain);
+  AD_LAUNCH("k_chees_finish");
+  return 0;
+}
+
+extern "C" int bjx_chees_final(bjx_handle_t h, const float* state, float* out2) {
+  if (!h || !state || !out2) return bjx_fail(h, BJX_E_INVALID, "null argument");
+  AD_CUDA(cudaSetDevice(h->cfg.device));
+  float hst[kChHdr];
+  AD_CUDA(cudaMemcpyAsync(hst, state, sizeof(hst), cudaMemcpyDeviceToHost, h->stream));
+  AD_CUDA(cudaStreamSynchronize(h->stream));
+  out2[0] = expf(hst[CH_LOG_EPS_MA]);                       // step_size
+  out2[1] = expf(hst[CH_LOG_T_MA] - hst[CH_LOG_EPS_MA]);    // num_leapfrog_steps (integration_steps_params)
+  return 0;
+}

@@ -246,6 +246,25 @@ int bjx_adapt_shared_update(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, fl
 /* final step size exp(log_step_avg) (staged_adaptation.py:303) into step_size_out [1] (device) */
 int bjx_adapt_shared_final(bjx_handle_t h, const float* state, float* step_size_out);
 
+/* ---- ChEES-HMC warm-up (blackjax/adaptation/chees_adaptation.py, mass_matrix_estimation=None) --------------
+ * Cross-chain adaptation of the step size (dual averaging on the harmonic mean of the acceptance probabilities) and of the
+ * trajectory length (Adam on log T along the ChEES gradient), device resident, two all-gathers of block statistics per
+ * step.  The transition is an HMC step with per-chain arrays the update rewrites: step_size_chain [C] (one value) and
+ * steps_chain int32 [C] = ceil(jitter(i) * T / eps) with the base-2 Halton jitter (dynamic_hmc.py:205-215); pass the
+ * latter to bjx_set_integration_steps and request proposal_position / proposal_momentum in bjx_info. */
+int64_t bjx_chees_state_floats(int32_t n_chains_local, int32_t dim, int32_t n_ranks);
+int bjx_chees_init(bjx_handle_t h, float* state, float step_size, int32_t max_bits, float jitter_amount,
+                   float* step_size_chain_out, int32_t* steps_chain_out);
+/* one warm-up step after the transition; optimiser = Adam(learning_rate, b1, b2, eps 1e-8); history (nullable, device
+ * [num_steps, 4]) receives (step_size, trajectory_length, next step count, ChEES gradient) */
+int bjx_chees_update(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, float* state, const float* initial_position,
+                     const float* proposal_position, const float* proposal_momentum, const float* acceptance_rate,
+                     const uint8_t* is_divergent, float learning_rate, float b1, float b2, float target_acceptance,
+                     float decay_rate, int32_t max_leapfrog_steps, float* step_size_chain, int32_t* steps_chain, float* history);
+/* out2 (HOST, 2 floats): step_size = exp(log_step_size_moving_average), num_leapfrog_steps = exp(log T_ma - log eps_ma);
+ * synchronises the stream */
+int bjx_chees_final(bjx_handle_t h, const float* state, float* out2_host);
+
 /* ---- diagnostics on a device-resident history ---------------------------------------------- */
 /* blackjax.diagnostics.potential_scale_reduction (diagnostics.py:39-89): history float32 [num_samples, C, D] as written
  * by bjx_hmc_sample; rhat_out float32 [D]; scratch: at least 2*C*D + 4 + 4*D floats (device). */

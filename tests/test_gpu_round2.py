@@ -311,3 +311,127 @@ def test_shared_warmup_bit_identical_on_one_and_two_gpus(tmp_path):
     assert a["n_ranks"] == 1 and b["n_ranks"] == 2
     for k in ("eps_history", "imm", "step_size", "position", "logdensity"):
         assert np.array_equal(a[k], b[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 5: the fast sigmoid / softplus (ex2.approx, rcp, lg2.approx) against float64
+# ---------------------------------------------------------------------------------------------------------
+def test_hier_logit_fast_math_error_bounds():
+    """value_and_grad of the hierarchical logistic regression with one exponential, one reciprocal and one logarithm per
+    observation (bjx_big.cu) against a float64 evaluation of the same formulas: per-group gradient entries (sums of 8
+    sigmoids) within 4e-6 absolute, log-density within 1e-6 of the sum of its term magnitudes, including saturated
+    observations (|eta| up to ~40)."""
+    D, C = 2052, 12
+    G = D - 4
+    x, bits = T.HierLogit.synthetic_data(G, seed=3)
+    tgt = T.HierLogit(x, bits)
+    rs = np.random.default_rng(0)
+    q = np.zeros((C, D), F)
+    q[:, 0], q[:, 1], q[:, 2], q[:, 3] = 0.5, np.log(0.7), 1.0, -0.5
+    q[:, 4:] = (0.5 + 0.7 * rs.standard_normal((C, G))).astype(F)
+    q[C // 2:, 4:] *= 25.0                       # saturated logits in half of the chains
+    eng = _engine.Engine(DEV, C, D, tgt)
+    logp, g = eng.init_state(tf(q))
+    q64 = q.astype(np.float64)
+    xs = np.asarray(x, np.float64)
+    y = ((np.asarray(bits, np.uint8)[:, None] >> np.arange(8, dtype=np.uint8)) & 1).astype(np.float64)
+    mu, lt, b0, b1, alpha = q64[:, 0], q64[:, 1], q64[:, 2], q64[:, 3], q64[:, 4:]
+    eta = alpha[:, :, None] + b0[:, None, None] * xs[None, :, :, 0] + b1[:, None, None] * xs[None, :, :, 1]
+    sig = 1.0 / (1.0 + np.exp(-eta))
+    softplus = np.maximum(eta, 0.0) + np.log1p(np.exp(-np.abs(eta)))
+    e2 = np.exp(-2.0 * lt)
+    d = alpha - mu[:, None]
+    ll = np.sum(y * eta - softplus, axis=(1, 2))
+    ref_logp = -0.005 * mu ** 2 - 0.5 * lt ** 2 - 0.08 * (b0 ** 2 + b1 ** 2) + (-0.5 * e2 * np.sum(d * d, 1) - G * lt) + ll
+    ref_ga = -d * e2[:, None] + np.sum(y - sig, axis=2)
+    terms = np.sum(np.abs(y * eta) + softplus, axis=(1, 2)) + 0.5 * e2 * np.sum(d * d, 1)
+    assert np.max(np.abs(npy(logp) - ref_logp) / terms) < 1e-6
+    ga = npy(g)[:, 4:]
+    # the prior part -d e2 is exact float32 arithmetic (relative 1e-6 of its size); the likelihood part is 8 fast sigmoids
+    assert np.max(np.abs(ga - ref_ga) / (1.0 + np.abs(d * e2[:, None]))) < 4e-6
+    gb = npy(g)[:, 2]
+    ref_gb = -0.16 * b0 + np.sum((y - sig) * xs[None, :, :, 0], axis=(1, 2))
+    assert np.max(np.abs(gb - ref_gb)) / np.sum(np.abs(xs[:, :, 0])) < 1e-6
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY 8f item 4: ChEES-HMC warm-up (blackjax/adaptation/chees_adaptation.py), device update vs oracle/chees.py
+# ---------------------------------------------------------------------------------------------------------
+def test_chees_update_teacher_forced_vs_oracle():
+    """Every warm-up step the device update (bjx_chees_update) and the oracle's chees_update are fed the SAME transition
+    (initial positions, proposals, acceptance probabilities, divergence flags): step size, trajectory length and the next
+    step count must agree (1e-5 relative; the step count exactly unless jitter*T/eps sits within 1e-5 of an integer)."""
+    from oracle import chees as ochees
+    D, C, T_ = 24, 4096 + 512, 60
+    scale = np.logspace(-0.5, 1.0, D)
+    tgt = T.DiagGaussian(scale)
+    q = (np.random.default_rng(2).standard_normal((C, D)) * scale).astype(F)
+    kernel = bj.hmc.build_kernel(full_info=True)
+    state = bj.hmc.init(tf(q), tgt)
+    eng = _engine.get_engine(state.position, tgt)
+    L_ = lib()
+    max_bits = 11
+    st = torch.empty(L_.bjx_chees_state_floats(C, D, 1), device=DEV)
+    eps_c = torch.empty(C, device=DEV)
+    steps_c = torch.empty(C, dtype=torch.int32, device=DEV)
+    check(L_.bjx_chees_init(eng.h, ptr(st), 0.05, max_bits, 1.0, ptr(eps_c), ptr(steps_c)), eng.h)
+    imm = torch.ones(D, device=DEV)
+    os_ = ochees.chees_init(0.05)
+    keys = bj.random.split(bj.random.key(5, DEV), T_)
+    for t in range(T_):
+        L_dev = int(steps_c[0])
+        L_or = ochees.integration_steps(os_.random_generator_arg, F(os_.trajectory_length / os_.step_size), 1.0, max_bits)
+        x = float(ochees.jitter(os_.random_generator_arg, 1.0, max_bits)) * float(os_.trajectory_length / os_.step_size)
+        assert L_dev == L_or or abs(x - round(x)) < 1e-4 * max(x, 1.0), (t, L_dev, L_or, x)
+        assert bool((steps_c == L_dev).all()) and bool((eps_c == eps_c[0]).all())
+        init_q = state.position
+        state, info = kernel(keys[t], state, tgt, eps_c, imm, steps_c)
+        div = info.is_divergent.to(torch.uint8)
+        check(L_.bjx_chees_update(eng.h, None, 1, ptr(st), ptr(init_q), ptr(info.proposal.position), ptr(info.proposal.momentum),
+                                  ptr(info.acceptance_rate), ptr(div), 0.1, 0.9, 0.999, 0.651, 0.5, 1000, ptr(eps_c),
+                                  ptr(steps_c), None), eng.h)
+        os_ = ochees.chees_update(os_, npy(info.proposal.position), npy(info.proposal.momentum), npy(init_q),
+                                  npy(info.acceptance_rate), npy(info.is_divergent), lr=0.1, max_bits=max_bits)
+        hdr = npy(st[:16])
+        close_elementwise(hdr[[0, 2]], [os_.step_size, os_.trajectory_length], rtol=1e-5, floor=1e-30)
+        close_elementwise(hdr[[1, 3]], [os_.log_step_size_ma, os_.log_trajectory_length_ma], rtol=2e-5, floor=1e-2)
+        # teacher forcing: continue from the oracle's state bits so that rounding differences cannot accumulate
+        st[0], st[1], st[2], st[3] = float(os_.step_size), float(os_.log_step_size_ma), float(os_.trajectory_length), float(os_.log_trajectory_length_ma)
+        st[4], st[5], st[7] = float(os_.da.log_step_size), float(os_.da.log_step_size_avg), float(os_.da.avg_error)
+        st[10], st[11] = float(os_.optim.mu), float(os_.optim.nu)
+    assert float(os_.trajectory_length) > 3 * float(os_.step_size)     # the criterion did lengthen the trajectories
+
+
+def test_chees_adaptation_reference_test_problem():
+    """tests/adaptation/test_adaptation.py:77-140 of the reference: 2-D normal with std (1, 10), step size 0.1,
+    adam(learning_rate=0.5, b1=0, b2=0.95), target acceptance 0.75; after the warm-up, dynamic HMC with the adapted
+    parameters must show a harmonic-mean acceptance near the target and recover the target's scales.  More chains than
+    the reference's 16 (the statistics are pooled over chains; 16 chains make the comparison with the oracle's free run
+    noisy), same schedule."""
+    from blackjax_b200.adaptation.chees_adaptation import adam
+    from oracle import chees as ochees
+    C, burn = 512, 400
+    std = np.array([1.0, 10.0])
+    tgt, otgt = T.DiagGaussian(std), otargets.DiagGaussian(std)
+    q = np.random.default_rng(1).standard_normal((C, 2)).astype(F)
+    warm = bj.chees_adaptation(tgt, num_chains=C, target_acceptance_rate=0.75)
+    (last, params), hist = warm.run(bj.random.key(346, DEV), tf(q), step_size=0.1, optim=adam(0.5, b1=0.0, b2=0.95), num_steps=burn)
+    ost, oeps, onlf, os_ = ochees.chees_run(otgt, oprng.key(346), q, 0.1, lr=0.5, b1=0.0, b2=0.95, num_steps=burn,
+                                            target_acceptance_rate=0.75)
+    print(f"ChEES: device eps {params['step_size']:.4f} L {params['integration_steps_params'][0]:.2f}; "
+          f"oracle eps {float(oeps):.4f} L {float(onlf):.2f}")
+    assert abs(params["step_size"] / float(oeps) - 1) < 0.15
+    assert abs(params["integration_steps_params"][0] / float(onlf) - 1) < 0.3
+    alg = bj.dhmc(tgt, **params)
+    state = last
+    keys = bj.random.split(bj.random.key(9, DEV), 200)
+    inv_acc, draws = [], []
+    for k in keys:
+        state, info = alg.step(k, state)
+        inv_acc.append((1.0 / info.acceptance_rate).mean())
+        draws.append(state.position)
+    hm = float((1.0 / torch.stack(inv_acc)).mean())
+    assert abs(hm - 0.75) < 0.1, hm
+    x = torch.stack(draws[50:]).reshape(-1, 2)
+    np.testing.assert_allclose(npy(x.std(0)), std, rtol=0.15)

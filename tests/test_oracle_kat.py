@@ -393,3 +393,26 @@ def test_integrators_are_time_reversible_and_conserve_energy(name):
     e1 = -logp1 + metric.kinetic_energy(p1)
     tol = 2e-2 if name == "VELOCITY_VERLET" else 5e-3          # second order vs the higher-order / tuned schemes
     assert np.max(np.abs(e1 - e0)) < tol
+
+
+def test_chees_oracle_reference_test_problem():
+    """oracle/chees.py on the reference's own ChEES test problem (tests/adaptation/test_adaptation.py:77-140: 2-D normal,
+    std (1, 10), step 0.1, adam(0.5, b1=0, b2=0.95), target acceptance 0.75): the Halton sequence is the base-2 radical
+    inverse, the adapted trajectory covers the wide direction and jittered HMC at the adapted parameters accepts near the
+    target (the reference asserts the harmonic mean within 0.1 ... it has no stored vectors for this path)."""
+    from oracle import chees as ochees
+    from oracle import hmc as ohmc_
+    assert [float(ochees.halton(i, 11)) for i in range(7)] == [0.5, 0.25, 0.75, 0.125, 0.625, 0.375, 0.875]
+    tgt = targets.DiagGaussian(np.array([1.0, 10.0]))
+    C = 64
+    q = np.random.default_rng(0).standard_normal((C, 2)).astype(np.float32)
+    st, eps, nlf, s = ochees.chees_run(tgt, prng.key(346), q, 0.1, lr=0.5, b1=0.0, b2=0.95, num_steps=400,
+                                       target_acceptance_rate=0.75)
+    assert 0.5 < float(eps) < 2.5 and 8.0 < float(eps) * float(nlf) < 40.0      # ~ a quarter period of the std-10 direction
+    inv = []
+    keys = prng.split(prng.key(7), 60)
+    for t in range(60):
+        L = ochees.integration_steps(400 + t, nlf, 1.0, 11)
+        st, info = ohmc_.hmc_kernel(prng.split(keys[t], C), st, tgt, eps, np.ones(2, np.float32), L)
+        inv.append(np.mean(1.0 / info.acceptance_rate))
+    assert abs(1.0 / np.mean(inv) - 0.75) < 0.12
