@@ -16,7 +16,7 @@ using namespace bjx;
 
 namespace bjx {
 
-constexpr int kBigThreads = 512;  // one CTA per SM (shared-memory bound): 16 warps hide the SFU / L2 latency
+constexpr int kBigThreads = 768;  // one CTA per SM (shared-memory bound): 24 warps hide the MUFU / L2 latency
 constexpr int kBigWarps = kBigThreads / 32;
 
 struct BigParams {
@@ -88,57 +88,43 @@ __device__ __forceinline__ float big_value_and_grad(const BigParams& P, const fl
     const float mu = q[0], lt = q[1], b0 = q[2], b1 = q[3];
     const float e2 = expf(-2.0f * lt);
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // ll, sum d, sum d^2, grad b0, grad b1
-    // software pipeline over this thread's groups: the 64 bytes of covariates + the outcome byte of the NEXT group are
-    // requested before the 8 observations of the current one are evaluated (the data is L2-resident, ~1 us away at 16
-    // warps per SM; ncu before this change: half of the stall samples on the first FMA that consumes a covariate)
-    float4 xn[4];
-    unsigned bn = 0;
-    float an = 0.f;
-    if (tid < P.G) {
-      const float4* xr = reinterpret_cast<const float4*>(P.data_x + (size_t)tid * 16);
+    // Software pipeline over this thread's groups, two register sets (A, B): the 64 bytes of covariates + the outcome byte
+    // of the NEXT group are requested before the 8 observations of the current one are evaluated (the data is
+    // L2-resident, ~1 us away; ncu before: half of the stall samples on the first FMA that consumes a covariate).
+    auto load_group = [&](int gidx, float4 (&xv)[4], unsigned& bv, float& av) {
+      if (gidx < P.G) {
+        const float4* xr = reinterpret_cast<const float4*>(P.data_x + (size_t)gidx * 16);
 #pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) xn[k2] = __ldg(xr + k2);
-      bn = __ldg(P.data_y + tid);
-      an = q[4 + tid];
-    }
-    for (int gi = tid; gi < P.G; gi += kBigThreads) {
-      const float alpha = an;
-      const unsigned bits = bn;
-      float4 xc[4];
-#pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) xc[k2] = xn[k2];
-      const int gn = gi + kBigThreads;
-      if (gn < P.G) {
-        const float4* xr = reinterpret_cast<const float4*>(P.data_x + (size_t)gn * 16);
-#pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) xn[k2] = __ldg(xr + k2);
-        bn = __ldg(P.data_y + gn);
-        an = q[4 + gn];
+        for (int k2 = 0; k2 < 4; ++k2) xv[k2] = __ldg(xr + k2);
+        bv = __ldg(P.data_y + gidx);
+        av = q[4 + gidx];
       }
+    };
+    auto eval_group = [&](int gidx, const float4 (&xv4)[4], unsigned bits, float alpha) {
       const float d = alpha - mu;
       float ga = 0.f;
 #pragma unroll
       for (int k2 = 0; k2 < 4; ++k2) {
-        const float4 xv = xc[k2];  // (x_{2k2,0}, x_{2k2,1}, x_{2k2+1,0}, x_{2k2+1,1})
+        const float4 xv = xv4[k2];  // (x_{2k2,0}, x_{2k2,1}, x_{2k2+1,0}, x_{2k2+1,1})
         const float xs[2][2] = {{xv.x, xv.y}, {xv.z, xv.w}};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float yv = (float)((bits >> (2 * k2 + u)) & 1u);
+          const bool yb = (bits >> (2 * k2 + u)) & 1u;
           const float eta = alpha + b0 * xs[u][0] + b1 * xs[u][1];
           // One exponential feeds both the sigmoid and the softplus, and the softplus reuses the sigmoid's reciprocal:
           //   ex = exp(-|eta|), r = 1 / (1 + ex), sigmoid = eta >= 0 ? r : ex r, softplus = max(eta, 0) - log(r).
-          // ex2.approx / rcp / lg2.approx (3 MUFU + ~17 FP32 instructions per observation instead of ~70 with expf, an
-          // IEEE division and log1pf).  Error bounds, checked against float64 in tests/test_gpu_round2.py:
-          // |sigmoid error| <= 4e-7 (ex2 2 ulp of an argument |eta| log2e rounded to float32),
-          // |softplus error| <= 3e-7 absolute (lg2.approx is 2^-22 absolute near r = 1).
-          const float ex = __expf(-fabsf(eta));
-          const float rc = __frcp_rn(1.0f + ex);
+          // ex2.approx / rcp.approx / lg2.approx: 3 MUFU + ~20 FP32/ALU instructions per observation (expf + an IEEE
+          // division + log1pf + int-to-float conversions cost 70; __expf / __frcp_rn / (float)bit still 41, of which a
+          // dozen guard subnormal ranges these arguments never reach).  Error bounds, checked against float64 in
+          // tests/test_gpu_round2.py: |sigmoid error| <= 4e-7 (ex2 2 ulp, rcp 1 ulp), |softplus error| <= 3e-7 absolute.
+          float ex, rc, l2;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fabsf(eta) * -1.4426950408889634f));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));   // 1 + ex in [1, 2]
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(rc));          // rc in [1/2, 1]
           const float sig = (eta >= 0.f) ? rc : ex * rc;
-          float l2;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(rc));  // rc in [1/2, 1]: no subnormal handling needed
           const float softplus = fmaf(-0.69314718f, l2, fmaxf(eta, 0.f));
-          const float r = yv - sig;
-          acc[0] += yv * eta - softplus;
+          const float r = (yb ? 1.0f : 0.0f) - sig;
+          acc[0] += (yb ? eta : 0.0f) - softplus;
           ga += r;
           acc[3] = fmaf(r, xs[u][0], acc[3]);
           acc[4] = fmaf(r, xs[u][1], acc[4]);
@@ -146,7 +132,17 @@ __device__ __forceinline__ float big_value_and_grad(const BigParams& P, const fl
       }
       acc[1] += d;
       acc[2] = fmaf(d, d, acc[2]);
-      g[4 + gi] = -d * e2 + ga;
+      g[4 + gidx] = -d * e2 + ga;
+    };
+    float4 xa[4], xb[4];
+    unsigned ba = 0, bb = 0;
+    float aa = 0.f, ab = 0.f;
+    load_group(tid, xa, ba, aa);
+    for (int gi = tid; gi < P.G; gi += 2 * kBigThreads) {
+      load_group(gi + kBigThreads, xb, bb, ab);
+      eval_group(gi, xa, ba, aa);
+      load_group(gi + 2 * kBigThreads, xa, ba, aa);
+      if (gi + kBigThreads < P.G) eval_group(gi + kBigThreads, xb, bb, ab);
     }
     block_sum<5>(acc, red);
     if (tid == 0) {
