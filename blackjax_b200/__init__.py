@@ -16,7 +16,7 @@ from . import mcmc  # noqa: F401
 from .mcmc import hmc as _hmc
 from .mcmc import nuts as _nuts
 from .mcmc import dynamic_hmc as _dynamic_hmc
-from .util import run_inference_algorithm, sample_hmc_native  # noqa: F401
+from .util import run_inference_algorithm, sample_hmc_native, sample_nuts_native  # noqa: F401
 
 hmc = GenerateSamplingAPI(_hmc.as_top_level_api, _hmc.init, _hmc.build_kernel)     # blackjax/__init__.py:111
 nuts = GenerateSamplingAPI(_nuts.as_top_level_api, _nuts.init, _nuts.build_kernel)  # blackjax/__init__.py:112

@@ -63,6 +63,11 @@ _SIGNATURES = {
                                  _f32p, C.c_int32, _f32p]),
     "bjx_nuts_step": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                 C.c_int32, C.POINTER(Info), _f32p, _f32p]),
+    "bjx_nuts_sample": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, C.c_int32, C.c_int32, _f32p,
+                                  C.c_int32, _f32p, C.c_void_p]),
+    "bjx_adapt_shared_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _f32p, C.c_char_p, C.c_int32, _f32p, _f32p, _f32p,
+                                       _f32p, _f32p, _f32p, C.c_float, C.c_int32, C.c_int32, _f32p, _f32p, C.c_void_p,
+                                       C.c_void_p]),
     "bjx_nuts_last_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bjx_prng_split": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int32, _f32p]),
     "bjx_prng_fold_in": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_uint32, _f32p]),

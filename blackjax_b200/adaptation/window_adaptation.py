@@ -165,17 +165,22 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
             eps_hist = torch.empty(num_steps, dtype=torch.float32, device=dev)
             check(L.bjx_adapt_shared_init(eng.h, ptr(st), float(initial_step_size), ptr(eps_c), ptr(imm)), eng.h)
             eng._imm, eng._imm_key = imm, (imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device))
-            for t, (stage, window_end) in enumerate(schedule):
-                state, info = mcmc_kernel(step_keys[t], state, logdensity_fn, eps_c, imm, **extra_parameters)
-                if _leapfrog_counter is not None:  # bench.py: executed leapfrogs, accumulated on the device
-                    n_int = info.num_integration_steps
-                    _leapfrog_counter += (n_int.sum() if isinstance(n_int, torch.Tensor) else n_int * C)
-                check(L.bjx_adapt_shared_update(eng.h, comm, n_ranks, ptr(st), ptr(state.position),
-                                                ptr(info.acceptance_rate), int(stage), int(window_end),
-                                                float(target_acceptance_rate), ptr(eps_c), ptr(imm), ptr(eps_hist)), eng.h)
-                if window_end:
-                    imm.add_(0.0)  # in-place no-op: bumps torch's version counter, so that ANY engine the kernel resolves to
-                    #                re-installs the metric the device just rewrote (mass_matrix_sqrt follows the contents)
+            # the loop itself runs in libbjx (bjx_adapt_shared_run): transition, block statistics, all-gather, device-side
+            # update per warm-up step, nothing waits for the device
+            is_nuts = "num_integration_steps" not in extra_parameters
+            mnd = int(extra_parameters.get("max_num_doublings", 10)) if is_nuts else 0
+            nis = 0 if is_nuts else int(extra_parameters["num_integration_steps"])
+            sched = bytes(int(stage) | (int(window_end) << 1) for stage, window_end in schedule)
+            q, lp, g = state.position.clone(), state.logdensity.clone(), state.logdensity_grad.clone()
+            acc_scratch = torch.empty(C, dtype=torch.float32, device=dev)
+            steps_scratch = torch.empty(C, dtype=torch.int32, device=dev) if _leapfrog_counter is not None else None
+            eng._key_mode(rng_key.to(dev).contiguous(), rank * C)
+            rk = rng_key.to(dev).contiguous()
+            check(L.bjx_adapt_shared_run(eng.h, comm, n_ranks, ptr(rk), sched, int(num_steps), ptr(q), ptr(lp), ptr(g), ptr(st),
+                                         ptr(eps_c), ptr(imm), float(target_acceptance_rate), mnd, nis, ptr(eps_hist),
+                                         ptr(acc_scratch), ptr(steps_scratch), ptr(_leapfrog_counter)), eng.h)
+            imm.add_(0.0)  # version bump: the kernels' metric cache follows the contents the device rewrote
+            state = type(state)(q, lp, g)
             step = torch.empty(1, dtype=torch.float32, device=dev)
             check(L.bjx_adapt_shared_final(eng.h, ptr(st), ptr(step)), eng.h)
             step_size = float(step.item())   # the one host read of the warm-up

@@ -675,6 +675,96 @@ extern "C" int bjx_nuts_last_stats(bjx_handle_t h, int64_t* leaf_launches, int64
   return 0;
 }
 
+// blackjax.util.run_inference_algorithm (util.py:150-213) for NUTS, run natively: step keys = split(rng_key, num_steps) on
+// the device, num_steps in-place transitions enqueued back to back; bjx_nuts_step never waits for the device, so neither
+// does this loop.  Optional outputs per step: positions (every thin-th), acceptance rates and tree sizes.
+extern "C" int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* logp, float* grad, float step_size,
+                               const float* step_size_dev, int32_t max_num_doublings, int32_t num_steps, float* history,
+                               int32_t thin, float* acceptance_history, int32_t* num_integration_steps_history) {
+  if (!h || !rng_key || num_steps < 0 || thin < 1) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  if (num_steps == 0) return 0;
+  if ((size_t)num_steps > h->sample_keys_cap) {
+    if (h->sample_keys) BJX_CUDA(cudaFree(h->sample_keys));
+    h->sample_keys = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->sample_keys, (size_t)num_steps * 2 * sizeof(uint32_t)));
+    h->sample_keys_cap = (size_t)num_steps;
+  }
+  launch_prng_split(rng_key, 1, num_steps, h->sample_keys, h->stream);
+  BJX_CHECK_LAUNCH("k_prng_split");
+  const int saved_mode = h->key_shared;
+  h->key_shared = 1;
+  const size_t C = h->cfg.n_chains, row_bytes = C * h->cfg.dim * sizeof(float);
+  int rc = 0;
+  for (int t = 0; t < num_steps && rc == 0; ++t) {
+    bjx_info info{};
+    info.acceptance_rate = acceptance_history ? acceptance_history + (size_t)t * C : nullptr;
+    info.num_integration_steps = num_integration_steps_history ? num_integration_steps_history + (size_t)t * C : nullptr;
+    rc = bjx_nuts_step(h, h->sample_keys + 2 * (size_t)t, q, logp, grad, q, logp, grad, step_size, step_size_dev,
+                       max_num_doublings, &info, nullptr, nullptr);
+    if (rc == 0 && history && ((t + 1) % thin) == 0) {
+      cudaError_t e = cudaMemcpyAsync(history + (size_t)((t + 1) / thin - 1) * C * h->cfg.dim, q, row_bytes,
+                                      cudaMemcpyDeviceToDevice, h->stream);
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "cudaMemcpyAsync(history)");
+    }
+  }
+  h->key_shared = saved_mode;
+  return rc;
+}
+
+static __global__ void k_accum_steps(int C, const int* __restrict__ n, unsigned long long* __restrict__ out) {
+  unsigned long long a = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) a += (unsigned long long)n[c];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0 && a) atomicAdd(out, a);
+}
+
+// window_adaptation(...).run for the shared (one step size, one diagonal metric) recipe, run natively
+// (staged_adaptation.py:906-966): per warm-up step one transition (NUTS: max_num_doublings > 0, HMC: num_integration_steps
+// > 0) with split(rng_key, num_steps)[t] as the step key, then bjx_adapt_shared_update.  schedule[t] = stage | (window_end
+// << 1) (staged_adaptation.py:315-405).  Nothing in the loop waits for the device.
+extern "C" int bjx_adapt_shared_run(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, const uint32_t* rng_key,
+                                    const uint8_t* schedule, int32_t num_steps, float* q, float* logp, float* grad,
+                                    float* state, float* step_size_chain, float* imm, float target_acceptance,
+                                    int32_t max_num_doublings, int32_t num_integration_steps, float* eps_history,
+                                    float* acceptance_scratch, int32_t* steps_scratch, unsigned long long* leapfrog_counter) {
+  if (!h || !rng_key || !schedule || !q || !logp || !grad || !state || !step_size_chain || !imm || !acceptance_scratch || num_steps < 0)
+    return fail(h, BJX_E_INVALID, "bad argument");
+  if ((max_num_doublings > 0) == (num_integration_steps > 0))
+    return fail(h, BJX_E_INVALID, "give max_num_doublings (NUTS) or num_integration_steps (HMC)");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  if (num_steps == 0) return 0;
+  if ((size_t)num_steps > h->sample_keys_cap) {
+    if (h->sample_keys) BJX_CUDA(cudaFree(h->sample_keys));
+    h->sample_keys = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->sample_keys, (size_t)num_steps * 2 * sizeof(uint32_t)));
+    h->sample_keys_cap = (size_t)num_steps;
+  }
+  launch_prng_split(rng_key, 1, num_steps, h->sample_keys, h->stream);
+  BJX_CHECK_LAUNCH("k_prng_split");
+  const int saved_mode = h->key_shared;
+  h->key_shared = 1;
+  int rc = 0;
+  for (int t = 0; t < num_steps && rc == 0; ++t) {
+    bjx_info info{};
+    info.acceptance_rate = acceptance_scratch;
+    info.num_integration_steps = (leapfrog_counter && steps_scratch) ? steps_scratch : nullptr;
+    const uint32_t* key_t = h->sample_keys + 2 * (size_t)t;
+    rc = max_num_doublings > 0
+             ? bjx_nuts_step(h, key_t, q, logp, grad, q, logp, grad, 0.f, step_size_chain, max_num_doublings, &info, nullptr, nullptr)
+             : bjx_hmc_step(h, key_t, q, logp, grad, q, logp, grad, 0.f, step_size_chain, num_integration_steps, &info);
+    if (rc == 0 && info.num_integration_steps) {  // executed leapfrogs, accumulated on the device (bench.py)
+      k_accum_steps<<<148, 256, 0, h->stream>>>(h->cfg.n_chains, steps_scratch, leapfrog_counter);
+      BJX_CHECK_LAUNCH("k_accum_steps");
+    }
+    if (rc == 0)
+      rc = bjx_adapt_shared_update(h, nccl_comm, n_ranks, state, q, acceptance_scratch, schedule[t] & 1, (schedule[t] >> 1) & 1,
+                                   target_acceptance, step_size_chain, imm, eps_history);
+  }
+  h->key_shared = saved_mode;
+  return rc;
+}
+
 // ---- PRNG ----------------------------------------------------------------------------------------------
 // h may be NULL: the call then runs on the calling thread's registered stream (bjx_set_default_stream; the legacy
 // default stream until one is registered).

@@ -175,6 +175,13 @@ int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   float step_size, const float* step_size_dev, int32_t max_num_doublings,
                   const bjx_info* info, const float* momentum_override,
                   const uint32_t* key_integrator_override);
+/* blackjax.util.run_inference_algorithm (util.py:150-213) for NUTS, run natively like bjx_hmc_sample: step keys =
+ * split(rng_key, num_steps), transitions in place and back to back, no host synchronisation.  history (optional) float32
+ * [num_steps / thin, C, D]; acceptance_history (optional) float32 [num_steps, C]; num_integration_steps_history (optional)
+ * int32 [num_steps, C]. */
+int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* logp, float* grad, float step_size,
+                    const float* step_size_dev, int32_t max_num_doublings, int32_t num_steps, float* history, int32_t thin,
+                    float* acceptance_history, int32_t* num_integration_steps_history);
 /* doubling launches and the deepest tree of the last bjx_nuts_step (host ints; reading the depth synchronises the stream) */
 int bjx_nuts_last_stats(bjx_handle_t h, int64_t* doubling_launches, int64_t* depth_reached);
 
@@ -243,6 +250,17 @@ int bjx_adapt_shared_init(bjx_handle_t h, float* state, float initial_step_size,
 int bjx_adapt_shared_update(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, float* state, const float* q,
                             const float* acceptance_rate, int32_t stage, int32_t window_end, float target_acceptance,
                             float* step_size_chain, float* imm, float* eps_history);
+/* The whole shared warm-up as one call (staged_adaptation.py:906-966): for t < num_steps one in-place transition with step
+ * key split(rng_key, num_steps)[t] (NUTS when max_num_doublings > 0, else HMC with num_integration_steps) followed by
+ * bjx_adapt_shared_update with schedule[t] = stage | window_end << 1 (HOST array, staged_adaptation.py:315-405).
+ * state / step_size_chain / imm as initialised by bjx_adapt_shared_init; acceptance_scratch: device float32 [C];
+ * steps_scratch (device int32 [C]) + leapfrog_counter (device uint64, caller-zeroed): optional, the executed leapfrogs
+ * summed over chains and steps.  Asynchronous: the loop only enqueues. */
+int bjx_adapt_shared_run(bjx_handle_t h, void* nccl_comm, int32_t n_ranks, const uint32_t* rng_key, const uint8_t* schedule,
+                         int32_t num_steps, float* q, float* logp, float* grad, float* state, float* step_size_chain,
+                         float* imm, float target_acceptance, int32_t max_num_doublings, int32_t num_integration_steps,
+                         float* eps_history, float* acceptance_scratch, int32_t* steps_scratch,
+                         unsigned long long* leapfrog_counter);
 /* final step size exp(log_step_avg) (staged_adaptation.py:303) into step_size_out [1] (device) */
 int bjx_adapt_shared_final(bjx_handle_t h, const float* state, float* step_size_out);
 

@@ -435,3 +435,22 @@ def test_chees_adaptation_reference_test_problem():
     assert abs(hm - 0.75) < 0.1, hm
     x = torch.stack(draws[50:]).reshape(-1, 2)
     np.testing.assert_allclose(npy(x.std(0)), std, rtol=0.15)
+
+
+def test_native_nuts_sampler_equals_stepwise_calls():
+    """bjx_nuts_sample (run_inference_algorithm for NUTS without a Python loop) gives the draws of T calls of nuts.step."""
+    C, D, T_ = 2048, 32, 6
+    tgt = T.Funnel(D)
+    q = 0.1 * torch.randn(C, D, device=DEV)
+    imm = torch.ones(D, device=DEV)
+    st0 = bj.nuts.init(q, tgt)
+    key = bj.random.key(12, DEV)
+    fin, hist, acc, n_int = bj.sample_nuts_native(key, st0, tgt, 0.2, imm, T_, max_num_doublings=8)
+    alg = bj.nuts(tgt, 0.2, imm, max_num_doublings=8)
+    st = alg.init(q)
+    keys = bj.random.split(key, T_)
+    for t in range(T_):
+        st, info = alg.step(keys[t], st)
+        assert torch.equal(hist[t], st.position)
+        assert torch.equal(n_int[t], info.num_integration_steps) and torch.equal(acc[t], info.acceptance_rate)
+    assert torch.equal(fin.position, st.position) and torch.equal(fin.logdensity, st.logdensity)
