@@ -81,6 +81,8 @@ class ClockSampler:
         self.idx = gpu_index
 
     def start(self):
+        if os.environ.get("BJX_BENCH_NO_CLOCKS"):   # diagnosis only: does the nvidia-smi poller disturb short launches?
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -320,8 +322,9 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
             if count is not None:
                 count += info.num_integration_steps.sum()
             return state, info
-    for t in range(W):
-        out = one_step(t, None)
+    for t in range(W):   # warm-up runs the SAME code as the timed steps (the leapfrog counter's kernels load lazily)
+        out = one_step(t, lf)
+    lf.zero_()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
