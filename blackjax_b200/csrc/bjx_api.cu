@@ -131,6 +131,8 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   for (int m = 0; m < 3; ++m) { h->dense_mat_s[m] = nullptr; h->dense_mat_src[m] = nullptr; h->dense_mat_ver[m] = 0; }
   h->dense_version = 1;
   h->dense_bytes_built = 0;
+  h->pool_scratch = nullptr;
+  h->pool_scratch_bytes = 0;
   h->dense_streams_ready = false;
   h->dense_stagger_armed = false;
   h->ncoef = 3;
@@ -163,6 +165,7 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->msqrt) cudaFree(h->msqrt);
   if (h->ws_block) cudaFree(h->ws_block);
   if (h->dense_block) cudaFree(h->dense_block);
+  if (h->pool_scratch) cudaFree(h->pool_scratch);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->sample_keys) cudaFree(h->sample_keys);
   if (h->dense_streams_ready) {
@@ -876,16 +879,15 @@ extern "C" int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acc
 
 extern "C" int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acc, float* out) {
   if (!h || !q || !acc || !out) return fail(h, BJX_E_INVALID, "null argument");
-  if (h->cfg.dim > 128) return fail(h, BJX_E_UNSUPPORTED, "dense pooled moments are built for dim <= 128 (dense NUTS/HMC warp path)");
   BJX_CUDA(cudaSetDevice(h->cfg.device));
   const size_t need = pooled_dense_scratch_floats(h->cfg.dim) * sizeof(float);
-  if (h->dense_bytes < need) {  // reuse the dense-path block as scratch (dim <= 128 never uses it otherwise)
-    if (h->dense_block) BJX_CUDA(cudaFree(h->dense_block));
-    h->dense_block = nullptr;
-    BJX_CUDA(cudaMalloc((void**)&h->dense_block, need));
-    h->dense_bytes = need;
+  if (h->pool_scratch_bytes < need) {
+    if (h->pool_scratch) BJX_CUDA(cudaFree(h->pool_scratch));
+    h->pool_scratch = nullptr;
+    BJX_CUDA(cudaMalloc((void**)&h->pool_scratch, need));
+    h->pool_scratch_bytes = need;
   }
-  launch_pooled_stats_dense(h->cfg.n_chains, h->cfg.dim, q, acc, out, h->dense_block, h->stream);
+  launch_pooled_stats_dense(h->cfg.n_chains, h->cfg.dim, q, acc, out, h->pool_scratch, h->stream);
   BJX_CHECK_LAUNCH("k_pooled_stats_dense");
   return 0;
 }

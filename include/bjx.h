@@ -216,7 +216,8 @@ int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t count, flo
  * stats_out float32 [2 + 2*D] = (sum acceptance_rate, n_chains, mean[D], M2[D]).
  * The blocks of all GPUs are exchanged with ONE all-gather and CGL-merged on every rank. */
 int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
-/* Dense variant (welford_dense recipe; metric_buffers.py:396-420 `centered.T @ centered`), dim <= 128:
+/* Dense variant (welford_dense recipe; metric_buffers.py:396-420 `centered.T @ centered`), any dim (float32 SIMT tiles in
+ * a fixed order; dim = 512 x 32768 chains: a few ms):
  * stats_out float32 [2 + D + D*D] = (sum acceptance_rate, n_chains, mean[D], M2[D,D]). */
 int bjx_pooled_stats_dense(bjx_handle_t h, const float* q, const float* acceptance_rate, float* stats_out);
 

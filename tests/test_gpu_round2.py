@@ -454,3 +454,31 @@ def test_native_nuts_sampler_equals_stepwise_calls():
         assert torch.equal(hist[t], st.position)
         assert torch.equal(n_int[t], info.num_integration_steps) and torch.equal(acc[t], info.acceptance_rate)
     assert torch.equal(fin.position, st.position) and torch.equal(fin.logdensity, st.logdensity)
+
+
+def test_dense_shared_window_adaptation_d256_recovers_covariance():
+    """welford_dense recipe, chain-pooled, at dim > 128 (mass_matrix.py:411-442, metric_buffers.py:396-420): HMC on the
+    tensor-core dense path, the D x D co-moment block from bjx_pooled_stats_dense against float64 numpy, and the adapted
+    dense inverse mass matrix against the target covariance."""
+    D, C, T_ = 256, 4096, 150
+    rs = np.random.default_rng(3)
+    A = rs.standard_normal((D, D)) / np.sqrt(D)
+    cov = A @ A.T + 0.5 * np.eye(D)
+    tgt = T.DenseGaussian(np.linalg.inv(cov))
+    q = rs.standard_normal((C, D)).astype(F)
+    warm = bj.window_adaptation(bj.hmc, tgt, is_mass_matrix_diagonal=False, shared=True, num_integration_steps=12)
+    (st, params), hist = warm.run(bj.random.key(6, DEV), tf(q), T_)
+    imm = npy(params["inverse_mass_matrix"])
+    assert imm.shape == (D, D)
+    err = np.abs(imm - cov).max() / np.abs(cov).max()
+    print(f"dense shared adaptation D=256: max |imm - cov| / max|cov| = {err:.3f}, step size {params['step_size']:.3f}")
+    assert err < 0.12                               # 25 pooled draws x 4096 chains
+    eng = _engine.get_engine(st.position, tgt)
+    out = torch.empty(2 + D + D * D, device=DEV)
+    acc = torch.rand(C, device=DEV)
+    check(lib().bjx_pooled_stats_dense(eng.h, ptr(st.position), ptr(acc), ptr(out)), eng.h)
+    x = npy(st.position).astype(np.float64)
+    o = npy(out)
+    ref = (x - x.mean(0)).T @ (x - x.mean(0))
+    assert np.max(np.abs(o[2:2 + D] - x.mean(0))) < 1e-5 * np.abs(x).max()
+    assert np.max(np.abs(o[2 + D:].reshape(D, D) - ref)) < 1e-4 * np.abs(ref).max()
