@@ -81,6 +81,14 @@ class Engine:
         """1-D => diagonal, 2-D [D,D] => dense, 2-D [C,D] with per_chain => per-chain diagonal
         (blackjax/mcmc/metrics.py:701-729 semantics incl. the ValueError)."""
         imm = inverse_mass_matrix
+        from .mcmc.metrics import LowRankMetric
+        if isinstance(imm, LowRankMetric):  # metrics.gaussian_euclidean_low_rank (metrics.py:349-467)
+            sg, U, lam = (t.to(self.device, torch.float32).contiguous() for t in imm)
+            if sg.shape[0] != self.D:
+                raise ValueError(f"low-rank metric has {sg.shape[0]} dimensions, expected {self.D}")
+            check(lib().bjx_set_metric_low_rank(self.h, ptr(sg), ptr(U), ptr(lam), int(lam.shape[0])), self.h)
+            self._imm = (sg, U, lam)
+            return imm
         if not isinstance(imm, torch.Tensor):
             imm = torch.as_tensor(imm, dtype=torch.float32)
         imm = imm.to(self.device, torch.float32).contiguous()
@@ -105,8 +113,12 @@ class Engine:
         shape, torch's in-place version counter), so an in-place update of the caller's tensor re-derives
         mass_matrix_sqrt and the dense operand planes instead of silently keeping stale ones."""
         imm = inverse_mass_matrix
-        key = ((imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device)) if isinstance(imm, torch.Tensor)
-               else None)
+        from .mcmc.metrics import LowRankMetric
+        if isinstance(imm, LowRankMetric):
+            key = tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device)) for t in imm)
+        else:
+            key = ((imm.data_ptr(), tuple(imm.shape), imm._version, str(imm.device)) if isinstance(imm, torch.Tensor)
+                   else None)
         if key is None or key != self._imm_key:
             installed = self.set_metric(imm)
             # a converted copy (dtype / device / layout) is owned by the engine: key on the caller's tensor all the same

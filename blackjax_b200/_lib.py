@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bjx_set_integration_steps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bjx_synchronize": (C.c_int, [C.c_void_p]),
     "bjx_set_metric": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
+    "bjx_set_metric_low_rank": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int32]),
     "bjx_get_mass_matrix_sqrt": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bjx_init_state": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_sample_momentum": (C.c_int, [C.c_void_p, _f32p, _f32p]),

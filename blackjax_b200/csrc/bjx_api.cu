@@ -133,6 +133,8 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->dense_bytes_built = 0;
   h->pool_scratch = nullptr;
   h->pool_scratch_bytes = 0;
+  h->lr_block = nullptr;
+  h->lr_k = 0;
   h->dense_streams_ready = false;
   h->dense_stagger_armed = false;
   h->ncoef = 3;
@@ -166,6 +168,7 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->ws_block) cudaFree(h->ws_block);
   if (h->dense_block) cudaFree(h->dense_block);
   if (h->pool_scratch) cudaFree(h->pool_scratch);
+  if (h->lr_block) cudaFree(h->lr_block);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->sample_keys) cudaFree(h->sample_keys);
   if (h->dense_streams_ready) {
@@ -281,6 +284,44 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
   return 0;
 }
 
+static __global__ void k_low_rank_prepare(int D, int k, const float* __restrict__ sigma, const float* __restrict__ lam,
+                                          float* __restrict__ sg, float* __restrict__ isg, float* __restrict__ lm1,
+                                          float* __restrict__ islm1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D) {
+    sg[i] = sigma[i];
+    isg[i] = 1.0f / sigma[i];                       // inv_sigma (metrics.py:384)
+  }
+  if (i < k) {
+    lm1[i] = lam[i] - 1.0f;
+    islm1[i] = 1.0f / sqrtf(lam[i]) - 1.0f;         // inv_sqrt_lam - 1 (metrics.py:385-386, :141)
+  }
+}
+
+extern "C" int bjx_set_metric_low_rank(bjx_handle_t h, const float* sigma, const float* U, const float* lam, int32_t rank) {
+  if (!h || !sigma || !U || !lam) return fail(h, BJX_E_INVALID, "null argument");
+  if (rank < 1 || rank > kMaxLowRank) return fail(h, BJX_E_UNSUPPORTED, "low-rank metric: 1 <= rank <= 16");
+  const int D = h->cfg.dim;
+  if (h->sc == SC_BIG || h->sc == SC_V8 || h->sc == SC_NONE || use_dense_path(h))
+    return fail(h, BJX_E_UNSUPPORTED, "low-rank metric is built for the warp kernels with dim <= 512 (dim % 4 == 0 above 128)");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t need = ((size_t)D * rank + 2 * (size_t)D + 2 * (size_t)rank) * sizeof(float);
+  if (h->lr_block) BJX_CUDA(cudaFree(h->lr_block));
+  h->lr_block = nullptr;
+  BJX_CUDA(cudaMalloc((void**)&h->lr_block, need));
+  float* Ud = h->lr_block;
+  float* sg = Ud + (size_t)D * rank;
+  BJX_CUDA(cudaMemcpyAsync(Ud, U, (size_t)D * rank * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  k_low_rank_prepare<<<(D + 255) / 256, 256, 0, h->stream>>>(D, rank, sigma, lam, sg, sg + D, sg + 2 * D, sg + 2 * D + rank);
+  BJX_CHECK_LAUNCH("k_low_rank_prepare");
+  h->lr_k = rank;
+  h->metric_kind = BJX_METRIC_LOW_RANK;
+  h->metric_small_dense = false;
+  h->imm = sg;      // (diagonal scaling, for completeness; the low-rank kernels read the lr_* arrays)
+  h->dense_version++;
+  return 0;
+}
+
 extern "C" int bjx_get_mass_matrix_sqrt(bjx_handle_t h, const float** out) {
   if (!h || !out) return fail(h, BJX_E_INVALID, "null argument");
   if (h->metric_kind < 0) return fail(h, BJX_E_STATE, "metric not set");
@@ -299,6 +340,17 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.imm = h->imm;
   P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
   P.msqrt = h->msqrt;
+  P.lr_k = (h->metric_kind == BJX_METRIC_LOW_RANK) ? h->lr_k : 0;
+  if (P.lr_k > 0) {
+    const size_t D = h->cfg.dim, k = h->lr_k;
+    P.lr_U = h->lr_block;
+    P.lr_sigma = h->lr_block + D * k;
+    P.lr_inv_sigma = P.lr_sigma + D;
+    P.lr_lam_m1 = P.lr_inv_sigma + D;
+    P.lr_isl_m1 = P.lr_lam_m1 + k;
+  } else {
+    P.lr_U = P.lr_sigma = P.lr_inv_sigma = P.lr_lam_m1 = P.lr_isl_m1 = nullptr;
+  }
   P.eps = eps;
   P.eps_dev = eps_dev;
   P.div_thr = h->cfg.divergence_threshold;
@@ -313,7 +365,7 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
 static int dispatch(bjx_handle_t h, int kernel_id, bool target_dependent, LaunchArgs& a) {
   a.stream = h->stream;
   a.general_integrator = h->general_integrator;
-  const bool dm = h->metric_small_dense;
+  const bool dm = h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK;
   int rc;
   const int tk = target_dependent ? h->cfg.target.kind : (int)BJX_TARGET_FUNNEL;
   switch (tk) {
@@ -621,7 +673,8 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   // Chains never interact, so nothing forces them through the tree in lock step.
   const int kFusedDoublings = 4;  // (the kernel's lane-parallel key schedule handles up to 10 doublings per launch)
   const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
-  const size_t dm_bytes = (h->metric_small_dense || h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
+  const size_t dm_bytes = (h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK ||
+                           h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
                               ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
   a.ckpt_smem = (ckpt_bytes + dm_bytes <= 40 * 1024) ? 1 : 0;  // stay under the 48 KB default dynamic-smem limit
   int64_t launches = 0;

@@ -30,6 +30,8 @@ struct bjx_handle_s {
   unsigned dense_mat_ver[3];
   unsigned dense_version;        // bumped by bjx_set_metric / bjx_set_target (contents may change behind the same pointer)
   size_t dense_bytes_built;
+  float* lr_block;               // low-rank metric (owned): U [D,k] | sigma [D] | 1/sigma [D] | lambda-1 [k] | 1/sqrt(lambda)-1 [k]
+  int lr_k;
   float* pool_scratch;           // scratch of bjx_pooled_stats_dense (slice partials of the D x D co-moment)
   size_t pool_scratch_bytes;
   cudaStream_t dense_stream[2];  // chain slices of the dense path run on their own streams (bjx_dense.cu)

@@ -150,11 +150,10 @@ int Launcher<TK>::launch(int kernel_id, int sc, bool dm, const LaunchArgs& a) {
       break;
   }
   if constexpr (!small_only) {
-    if (dm) return -2;
-    switch (sc) {
-      case SC_V2: return launch_one<Row<8, true>, TK, false>(kernel_id, a);
-      case SC_V4: return launch_one<Row<16, true>, TK, false>(kernel_id, a);
-      case SC_V8: return launch_one<Row<32, true>, TK, false>(kernel_id, a);
+    switch (sc) {  // dm beyond 128 dims: the low-rank metric (O(D k) per operation) for rows up to 512
+      case SC_V2: return dm ? launch_one<Row<8, true>, TK, true>(kernel_id, a) : launch_one<Row<8, true>, TK, false>(kernel_id, a);
+      case SC_V4: return dm ? launch_one<Row<16, true>, TK, true>(kernel_id, a) : launch_one<Row<16, true>, TK, false>(kernel_id, a);
+      case SC_V8: return dm ? -2 : launch_one<Row<32, true>, TK, false>(kernel_id, a);
       default: break;
     }
   }

@@ -35,6 +35,13 @@ struct Params {
   const float* imm;        // diag: [D] or [C,D]; dense: [D,D]
   long long imm_stride;    // 0 (shared) or D (per chain)
   const float* msqrt;      // mass_matrix_sqrt, same layout as imm
+  // low-rank metric (metrics.py:349-467): M^-1 = diag(sigma) (I + U (Lambda - I) U^T) diag(sigma); lr_k == 0: not in use
+  int lr_k;
+  const float* lr_U;        // [D, k] row-major, orthonormal columns
+  const float* lr_sigma;    // [D]
+  const float* lr_inv_sigma;
+  const float* lr_lam_m1;   // [k] lambda - 1
+  const float* lr_isl_m1;   // [k] 1/sqrt(lambda) - 1
   // step size
   float eps;
   const float* eps_dev;    // [C] or nullptr
@@ -267,6 +274,46 @@ __device__ __forceinline__ void matvec_small(const float* __restrict__ M, const 
   __syncwarp();
 }
 
+// y = x + U ((s - 1) (U^T x))   (_low_rank_matvec, metrics.py:131-177) for a row held by one warp: every lane forms its
+// part of the k <= 16 projections, k interleaved shuffle reductions, then the expansion -- O(D k / 32) per lane, U read
+// through the read-only path (D k floats: L1/L2 resident).
+constexpr int kMaxLowRank = 16;
+template <class R>
+__device__ __forceinline__ void lowrank_apply(const float* __restrict__ U, const float* __restrict__ sm1, int k,
+                                              const float (&x)[R::NS], float (&y)[R::NS], int D, int lane) {
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) y[s] = x[s];
+  // four projections at a time: their shuffle reductions interleave, and the code stays small (the operator is inlined
+  // at every velocity / kinetic-energy / momentum-draw site of every kernel)
+  for (int j0 = 0; j0 < k; j0 += 4) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) {
+      const int e = R::idx(s, lane);
+      if (e < D) {
+        const float* ur = U + (size_t)e * k + j0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < k) t[u] = fmaf(__ldg(ur + u), x[s], t[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = (j0 + u < k) ? warp_sum(t[u]) * __ldg(sm1 + j0 + u) : 0.f;
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) {
+      const int e = R::idx(s, lane);
+      if (e < D) {
+        const float* ur = U + (size_t)e * k + j0;
+        float a = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < k) a = fmaf(__ldg(ur + u), t[u], a);
+        y[s] += a;
+      }
+    }
+  }
+}
+
 // Per-warp constant context: target scales and inverse mass held in registers for the whole kernel.
 template <class R, int TK, bool DM>
 struct Ctx {
@@ -289,7 +336,15 @@ struct Ctx {
   // linear_map(M^-1, p)   blackjax/util.py:57-61
   __device__ __forceinline__ void velocity(const Params& P, const float (&p)[R::NS], float (&v)[R::NS]) {
     if constexpr (DM) {
-      matvec_small<R>(P.imm, p, v, sm, P.D, lane);
+      if (P.lr_k > 0) {  // sigma * lowrank(sigma * p, lambda)   metrics.py:430-432
+        float sg[R::NS], qv[R::NS];
+        R::load_const(sg, P.lr_sigma, P.D, lane);
+        Vec<R::NS>::mul(qv, sg, p);
+        lowrank_apply<R>(P.lr_U, P.lr_lam_m1, P.lr_k, qv, v, P.D, lane);
+        Vec<R::NS>::mul(v, sg, v);
+      } else if constexpr (R::NS <= 4) {  // small dense metrics exist for dim <= 128 only
+        matvec_small<R>(P.imm, p, v, sm, P.D, lane);
+      }
     } else {
       Vec<R::NS>::mul(v, mw, p);
     }
@@ -298,6 +353,15 @@ struct Ctx {
   // kinetic_energy  blackjax/mcmc/metrics.py:263-270: 0.5 * dot(M^-1 p, p)
   __device__ __forceinline__ float kinetic(const Params& P, const float (&p)[R::NS]) {
     float v[R::NS];
+    if constexpr (DM) {
+      if (P.lr_k > 0) {  // 0.5 * dot(q, lowrank(q, lambda)), q = sigma * p   metrics.py:401-408
+        float sg[R::NS], qv[R::NS];
+        R::load_const(sg, P.lr_sigma, P.D, lane);
+        Vec<R::NS>::mul(qv, sg, p);
+        lowrank_apply<R>(P.lr_U, P.lr_lam_m1, P.lr_k, qv, v, P.D, lane);
+        return 0.5f * R::dot(qv, v);
+      }
+    }
     velocity(P, p, v);
     return 0.5f * R::dot(v, p);
   }
@@ -412,7 +476,14 @@ struct Ctx {
       z[s] = (e < P.D) ? normal_at(key, (uint32_t)e) : 0.f;
     }
     if constexpr (DM) {
-      matvec_small<R>(P.msqrt, z, p, sm, P.D, lane);
+      if (P.lr_k > 0) {  // (1/sigma) * lowrank(eps, 1/sqrt(lambda))   metrics.py:389-399
+        float is[R::NS];
+        lowrank_apply<R>(P.lr_U, P.lr_isl_m1, P.lr_k, z, p, P.D, lane);
+        R::load_const(is, P.lr_inv_sigma, P.D, lane);
+        Vec<R::NS>::mul(p, is, p);
+      } else if constexpr (R::NS <= 4) {
+        matvec_small<R>(P.msqrt, z, p, sm, P.D, lane);
+      }
     } else {
       float ms[R::NS];
       R::load_const(ms, P.msqrt + (size_t)chain * P.imm_stride, P.D, lane);

@@ -51,7 +51,8 @@ enum bjx_target_kind {
 enum bjx_metric_kind {
   BJX_METRIC_DIAG = 0,          /* imm [dim]                                    */
   BJX_METRIC_DENSE = 1,         /* imm [dim, dim] symmetric positive definite   */
-  BJX_METRIC_DIAG_PER_CHAIN = 2 /* imm [n_chains, dim] (vmapped window adaptation) */
+  BJX_METRIC_DIAG_PER_CHAIN = 2, /* imm [n_chains, dim] (vmapped window adaptation) */
+  BJX_METRIC_LOW_RANK = 3        /* bjx_set_metric_low_rank */
 };
 
 typedef struct {
@@ -122,6 +123,11 @@ int bjx_synchronize(bjx_handle_t h);
  * mass_matrix_sqrt = 1/sqrt(M^-1) (diag) or L^-T with L = chol(M^-1) (dense), metrics.py:701-729.
  * The dense factorisation runs on the host in float64 and synchronises the stream. */
 int bjx_set_metric(bjx_handle_t h, int32_t metric_kind, const float* inverse_mass_matrix);
+/* metrics.gaussian_euclidean_low_rank(sigma, U, lam) (metrics.py:349-467): M^-1 = diag(sigma) (I + U (Lambda - I) U^T) diag(sigma),
+ * sigma [dim] > 0, U [dim, rank] row-major with orthonormal columns, lam [rank] > 0 (device arrays, copied).  Momentum
+ * draw, kinetic energy, velocity and the U-turn test all cost O(dim * rank).  rank <= 16, dim <= 512 (warp kernels: HMC,
+ * multinomial HMC, NUTS). */
+int bjx_set_metric_low_rank(bjx_handle_t h, const float* sigma, const float* U, const float* lam, int32_t rank);
 /* device pointer to mass_matrix_sqrt as precomputed by bjx_set_metric (for tests) */
 int bjx_get_mass_matrix_sqrt(bjx_handle_t h, const float** out);
 

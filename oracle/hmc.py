@@ -99,6 +99,38 @@ class Metric:
         return out
 
 
+class LowRankMetric(Metric):
+    """gaussian_euclidean_low_rank(sigma, U, lam) (metrics.py:349-467): M^-1 = diag(sigma) (I + U (Lambda - I) U^T) diag(sigma)
+    with orthonormal U [D, k]; every operation is O(D k) through _low_rank_matvec (metrics.py:131-177)."""
+
+    def __init__(self, sigma, U, lam):
+        self.sigma = np.asarray(sigma, F)
+        self.U = np.asarray(U, F)
+        self.lam = np.asarray(lam, F)
+        self.inv_sigma = (F(1.0) / self.sigma).astype(F)
+        self.inv_sqrt_lam = (F(1.0) / np.sqrt(self.lam)).astype(F)
+        self.dense = False
+
+    def _lr(self, y, scales):
+        """y + U ((s - 1) * (U^T y)), batched over the leading axis."""
+        t = (y @ self.U).astype(F)                                  # U^T y
+        return (y + ((scales - F(1.0)) * t) @ self.U.T).astype(F)
+
+    def velocity(self, p):
+        """kinetic-energy gradient M^-1 p = sigma * lowrank(sigma * p, lam) (metrics.py:430-432)."""
+        return (self.sigma * self._lr((self.sigma * p).astype(F), self.lam)).astype(F)
+
+    def sample_momentum(self, keys, dim):
+        """metrics.py:389-399: p = (1/sigma) * lowrank(eps, 1/sqrt(lam))."""
+        z = prng.normal(keys, (dim,))
+        return (self.inv_sigma * self._lr(z, self.inv_sqrt_lam)).astype(F)
+
+    def kinetic_energy(self, p):
+        """metrics.py:401-408: 0.5 * dot(q, lowrank(q, lam)), q = sigma * p."""
+        q = (self.sigma * p).astype(F)
+        return (F(0.5) * np.sum(q * self._lr(q, self.lam), axis=-1, dtype=F)).astype(F)
+
+
 def integrator_step(target, metric, q, p, g, eps, coefficients=VELOCITY_VERLET):
     """One palindromic two-stage step; eps is f32 scalar or [C,1] (signed)."""
     eps = np.asarray(eps, F)

@@ -482,3 +482,73 @@ def test_dense_shared_window_adaptation_d256_recovers_covariance():
     ref = (x - x.mean(0)).T @ (x - x.mean(0))
     assert np.max(np.abs(o[2:2 + D] - x.mean(0))) < 1e-5 * np.abs(x).max()
     assert np.max(np.abs(o[2 + D:].reshape(D, D) - ref)) < 1e-4 * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the low-rank metric (blackjax/mcmc/metrics.py:349-467) in the warp kernels
+# ---------------------------------------------------------------------------------------------------------
+def _low_rank_problem(D, k, seed):
+    rs = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rs.standard_normal((D, k)))
+    sigma = np.exp(rs.uniform(-0.7, 0.7, D)).astype(F)
+    lam = np.exp(rs.uniform(-1.5, 1.5, k)).astype(F)
+    return sigma, U.astype(F), lam
+
+
+@pytest.mark.parametrize("kind, D, k, C, L", [("diag", 64, 3, 48, 7), ("funnel", 128, 8, 40, 6), ("diag", 256, 16, 33, 5),
+                                              ("diag", 512, 5, 24, 4)])
+def test_low_rank_metric_hmc_matches_oracle(kind, D, k, C, L):
+    from blackjax_b200.mcmc.metrics import gaussian_euclidean_low_rank
+    sigma, U, lam = _low_rank_problem(D, k, 7)
+    rs = np.random.default_rng(8)
+    if kind == "funnel":
+        tgt, otgt = T.Funnel(D), otargets.Funnel(D)
+        q = (0.2 * rs.standard_normal((C, D))).astype(F)
+    else:
+        s = np.exp(rs.uniform(-0.5, 0.5, D))
+        tgt, otgt = T.DiagGaussian(s), otargets.DiagGaussian(s)
+        q = (rs.standard_normal((C, D)) * s).astype(F)
+    metric = gaussian_euclidean_low_rank(tf(sigma), tf(U), tf(lam))
+    ometric = ohmc.LowRankMetric(sigma, U, lam)
+    keys = oprng.split(oprng.key(31), C)
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, F(0.05), ometric, L)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), bj.hmc.init(tf(q), tgt), tgt, 0.05, metric, L)
+    torch.cuda.synchronize()
+    from test_gpu_parity import close
+    close(npy(info.momentum), oinfo.momentum, rtol=1e-5)
+    close(npy(info.proposal.position), oinfo.proposal[0], rtol=2e-5)
+    close(npy(info.proposal.momentum), oinfo.proposal[1], rtol=2e-5)
+    close(npy(info.energy), oinfo.energy, rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + D)
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    assert ((npy(info.is_accepted) == oinfo.is_accepted) | (np.abs(u - oinfo.acceptance_rate) < 1e-4)).all()
+    # the momentum draw has covariance M = (M^-1)^-1
+    if D == 64:
+        eng = _engine.get_engine(new.position, tgt)
+        big = _engine.Engine(DEV, 20000, D, tgt)
+        big.ensure_metric(metric)
+        p = npy(big.sample_momentum(bj.random.split(bj.random.key(4, DEV), 20000)))
+        Minv = np.diag(sigma) @ (np.eye(D) + U @ np.diag(lam - 1) @ U.T) @ np.diag(sigma)
+        M = np.linalg.inv(Minv.astype(np.float64))
+        assert np.abs(np.cov(p.T) - M).max() < 0.08 * np.abs(M).max()
+        big.close()
+
+
+def test_low_rank_metric_nuts_matches_oracle():
+    from blackjax_b200.mcmc.metrics import gaussian_euclidean_low_rank
+    D, k, C = 96, 4, 256
+    sigma, U, lam = _low_rank_problem(D, k, 9)
+    s = np.exp(np.random.default_rng(1).uniform(-0.5, 0.5, D))
+    tgt, otgt = T.DiagGaussian(s), otargets.DiagGaussian(s)
+    q = (np.random.default_rng(2).standard_normal((C, D)) * s).astype(F)
+    keys = oprng.split(oprng.key(13), C)
+    margins = np.full(C, np.inf)
+    onew, oinfo = onuts.nuts_kernel(keys, ohmc.init(q, otgt), otgt, F(0.2), ohmc.LowRankMetric(sigma, U, lam), 7, margins=margins)
+    metric = gaussian_euclidean_low_rank(tf(sigma), tf(U), tf(lam))
+    new, info = bj.nuts.build_kernel(max_tree_depth=7)(tk(keys), bj.nuts.init(tf(q), tgt), tgt, 0.2, metric, 7)
+    torch.cuda.synchronize()
+    same = ((npy(info.num_integration_steps) == oinfo.num_integration_steps) & (npy(info.is_turning) == oinfo.is_turning)
+            & np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1))
+    print(f"low-rank NUTS: {same.mean():.4f} identical; margins of the others {np.sort(margins[~same])[:5]}")
+    assert same.mean() >= 0.97
+    assert (margins[~same] < 1e-5 * 64).all()
+    assert oinfo.num_integration_steps.max() >= 15

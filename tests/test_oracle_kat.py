@@ -416,3 +416,26 @@ def test_chees_oracle_reference_test_problem():
         st, info = ohmc_.hmc_kernel(prng.split(keys[t], C), st, tgt, eps, np.ones(2, np.float32), L)
         inv.append(np.mean(1.0 / info.acceptance_rate))
     assert abs(1.0 / np.mean(inv) - 0.75) < 0.12
+
+
+def test_low_rank_metric_oracle_matches_the_dense_formula():
+    """oracle LowRankMetric (metrics.py:349-467) against the explicit matrix M^-1 = D (I + U (Lambda - I) U^T) D: velocity,
+    kinetic energy, momentum covariance M, and the lam = 1 reduction to a diagonal metric with scale sigma (the reference's
+    own statement in the docstring :368-369)."""
+    rs = np.random.default_rng(0)
+    D, k, C = 24, 4, 16
+    U, _ = np.linalg.qr(rs.standard_normal((D, k)))
+    sigma = np.exp(rs.uniform(-1, 1, D))
+    lam = np.array([9.0, 0.25, 4.0, 1.5])
+    m = hmc.LowRankMetric(sigma, U, lam)
+    Minv = np.diag(sigma) @ (np.eye(D) + U @ np.diag(lam - 1) @ U.T) @ np.diag(sigma)
+    p = rs.standard_normal((C, D)).astype(np.float32)
+    np.testing.assert_allclose(m.velocity(p), p @ Minv.T, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(m.kinetic_energy(p), 0.5 * np.einsum("ci,ij,cj->c", p, Minv, p), rtol=2e-5)
+    z = m.sample_momentum(prng.split(prng.key(0), 40000), D)
+    M = np.linalg.inv(Minv)
+    assert np.abs(np.cov(z.T) - M).max() < 0.05 * np.abs(M).max()
+    ones = hmc.LowRankMetric(sigma, U, np.ones(k))
+    diag = hmc.Metric((sigma ** 2).astype(np.float32))
+    np.testing.assert_allclose(ones.velocity(p), diag.velocity(p), rtol=1e-5)
+    assert (ones.is_turning(p, -p, p) == diag.is_turning(p, -p, p)).all()
