@@ -85,6 +85,7 @@ __global__ void k_planes_fixup(int R, int K, const float* __restrict__ y, uint16
   const int lane = threadIdx.x & 31;
   const int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
   const int r = r0 + lane;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // launched programmatically dependent on the product before it
   bool bad = false;
   if (r < R) {
     const float mx = new_max[r];
@@ -488,9 +489,17 @@ static int gemm(bjx_handle_t h, DenseWs& w, const Part& pt, const float* X, int 
   const int rc = gemm_f16x3(g, pt.st);
   if (rc) return bjx_fail(h, BJX_E_UNSUPPORTED, "tensor-core product failed (stage " + std::to_string(rc) + ")");
   if (po.var >= 0) {  // rows whose lift left the exact window are re-split from Y (none in a stable trajectory)
-    k_planes_fixup<<<(pt.n + 255) / 256, 256, 0, pt.st>>>(pt.n, D, Y + ro, g.planes_out, g.epi.stale_max, g.epi.next_max,
-                                                        g.epi.out_unscale);
-    DN_LAUNCH("k_planes_fixup");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((pt.n + 255) / 256);
+    cfg.blockDim = dim3(256);
+    cfg.stream = pt.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DN_CUDA(cudaLaunchKernelEx(&cfg, k_planes_fixup, pt.n, D, (const float*)(Y + ro), g.planes_out, g.epi.stale_max,
+                               (const float*)g.epi.next_max, g.epi.out_unscale));
   }
   return 0;
 }

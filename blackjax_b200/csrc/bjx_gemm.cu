@@ -283,6 +283,9 @@ k_gemm_f16x3(const __grid_constant__ CUtensorMap tm_x,   // [K, 2, M]  binary16 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (descriptor prefetch, barrier init, TMEM allocation, cluster
+  // rendezvous) may run while the previous kernel of the stream drains; nothing below touches its outputs earlier.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: four tiles per stage
@@ -552,6 +555,11 @@ bool make_row_map(CUtensorMap* m, const void* ptr, int rows, int N) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool pdl_enabled() {  // BJX_GEMM_PDL=0 switches programmatic dependent launch off (measurement)
+  static const bool on = [] { const char* e = getenv("BJX_GEMM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int BK, int STAGES, int NY, int NP>
 struct Variant {
   using P = Plan<BK, STAGES, NY, NP>;
@@ -587,9 +595,19 @@ struct Variant {
     const int tiles_m = (g.M + 2 * kBM - 1) / (2 * kBM), tiles_n = (g.N + kBN - 1) / kBN;
     const int n_tiles = tiles_m * tiles_n;
     const int pairs = n_tiles < max_pairs() ? n_tiles : max_pairs();
-    k_gemm_f16x3<BK, STAGES, NY, NP><<<dim3(2 * pairs), dim3(kThreads), P::kSmemBytes, stream>>>(tx, ta, tc, ty, tp, g.epi, g.M,
-                                                                                               g.N, g.K, tiles_n, n_tiles);
-    return cudaGetLastError() == cudaSuccess ? 0 : 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = P::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue overlaps the previous kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_f16x3<BK, STAGES, NY, NP>, tx, ta, tc, ty, tp, g.epi, g.M, g.N, g.K,
+                                             tiles_n, n_tiles);
+    return e == cudaSuccess ? 0 : 8;
   }
 };
 

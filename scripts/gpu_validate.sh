@@ -25,6 +25,8 @@ PY
 python bench.py --impl reference --steps 2 --warmup 1 > "$out/bench_ref.json" 2>> "$out/bench_err.log"
 python bench.py --workload hmc_diag_gaussian_65536x1024_L50 > "$out/bench_diag.json" 2>> "$out/bench_err.log"
 python scripts/bench_nuts.py 65536 128 40 > "$out/nuts40.jsonl" 2>&1
+python bench.py --workload nuts_funnel_65536x128 --steps 20 > "$out/bench_c3.json" 2>> "$out/bench_err.log"
+python bench.py --workload nuts_window_adaptation_512 --steps 2 --warmup 1 > "$out/bench_c4.json" 2>> "$out/bench_err.log"
 python - <<'PY'
 import json
 r = json.load(open("gpurun_out/bench_ref.json")); d = json.load(open("gpurun_out/bench_diag.json"))
@@ -35,8 +37,6 @@ PY
 [ "$mode" = full ] && exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file "$out/launches_dense.csv" \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:device_kernel -s 24 -c 2 -o "$out/prof_gemm" -f \
-  python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rows_split2 -s 24 -c 1 -o "$out/prof_split" -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_f16x3 -s 60 -c 3 -o "$out/prof_gemm" -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ls -la "$out"/*.ncu-rep "$out"/launches_dense.csv
