@@ -11,11 +11,13 @@ from . import diagnostics, random, targets, util  # noqa: F401
 from ._lib import BjxError  # noqa: F401
 from .adaptation.window_adaptation import build_schedule, window_adaptation  # noqa: F401
 from .adaptation.chees_adaptation import chees_adaptation  # noqa: F401
+from .adaptation.meads_adaptation import meads_adaptation  # noqa: F401
 from .base import AdaptationAlgorithm, AdaptationResults, GenerateSamplingAPI, SamplingAlgorithm  # noqa: F401
 from . import mcmc  # noqa: F401
 from .mcmc import hmc as _hmc
 from .mcmc import nuts as _nuts
 from .mcmc import dynamic_hmc as _dynamic_hmc
+from .mcmc import ghmc as _ghmc
 from .util import run_inference_algorithm, sample_hmc_native, sample_nuts_native  # noqa: F401
 
 hmc = GenerateSamplingAPI(_hmc.as_top_level_api, _hmc.init, _hmc.build_kernel)     # blackjax/__init__.py:111
@@ -33,5 +35,7 @@ dmhmc = GenerateSamplingAPI(                                                    
     _dynamic_hmc.init,
     _functools.partial(_dynamic_hmc.build_kernel, build_proposal=_hmc.multinomial_hmc_proposal),
 )
+
+ghmc = GenerateSamplingAPI(_ghmc.as_top_level_api, _ghmc.init, _ghmc.build_kernel)   # blackjax/__init__.py:139
 
 __version__ = "0.1.0"

@@ -99,6 +99,16 @@ _SIGNATURES = {
     "bjx_chees_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _f32p, C.c_void_p, _f32p]),
     "bjx_chees_final": (C.c_int, [C.c_void_p, _f32p, C.POINTER(C.c_float)]),
+    "bjx_ghmc_step": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, C.c_float, _f32p,
+                                C.c_float, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Info)]),
+    "bjx_meads_state_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "bjx_meads_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "bjx_meads_update": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_float, _f32p, _f32p]),
+    "bjx_maximum_eigenvalue_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "bjx_maximum_eigenvalue": (C.c_int, [C.c_void_p, _f32p, C.c_int64, C.c_int32, _f32p, _f32p]),
+    "bjx_permutation_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "bjx_permutation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "bjx_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, _f32p, _f32p, C.c_int64, C.c_int32]),
     "bjx_potential_scale_reduction": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),
     "bjx_ess_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "bjx_effective_sample_size": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p]),

@@ -20,11 +20,14 @@ class AdaptationResults(NamedTuple):
     parameters: dict
 
 
-def build_sampling_algorithm(kernel, init_fn, logdensity_fn, kernel_args=(), init_args=(), kernel_kwargs=None):
+def build_sampling_algorithm(kernel, init_fn, logdensity_fn, kernel_args=(), init_args=(), kernel_kwargs=None,
+                             pass_rng_key_to_init=False):
     """blackjax/base.py:154-206: bind the static arguments, expose (init, step)."""
     kernel_kwargs = kernel_kwargs or {}
 
     def init(position, rng_key=None):
+        if pass_rng_key_to_init:
+            return init_fn(position, logdensity_fn, rng_key, *init_args)
         del rng_key
         return init_fn(position, logdensity_fn, *init_args)
 

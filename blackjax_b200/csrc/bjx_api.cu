@@ -339,6 +339,7 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.logp_offset = h->cfg.target.logp_offset;
   P.imm = h->imm;
   P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
+  P.imm_group = 1;
   P.msqrt = h->msqrt;
   P.lr_k = (h->metric_kind == BJX_METRIC_LOW_RANK) ? h->lr_k : 0;
   if (P.lr_k > 0) {
@@ -532,6 +533,41 @@ extern "C" int bjx_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q
   a.n = L;
   a.info = make_info(info);
   return dispatch(h, K_HMC, true, a);
+}
+
+// ghmc.build_kernel().kernel (ghmc.py:118-189), in place on the persistent (q, p, logp, grad, slice)
+extern "C" int bjx_ghmc_step(bjx_handle_t h, const uint32_t* keys, float* q, float* p, float* logp, float* grad, float* slice,
+                             float step_size, const float* step_size_dev, float alpha, const float* alpha_dev, float delta,
+                             const float* delta_dev, const float* imm_rows, const float* msqrt_rows, int32_t chains_per_group,
+                             int32_t skip_begin, int32_t skip_end, const bjx_info* info) {
+  const void* ptrs[] = {q, grad, p};
+  int rc = check_ready(h, true, ptrs, 3);
+  if (rc) return rc;
+  if (!keys || !logp || !slice) return fail(h, BJX_E_INVALID, "bad argument");
+  if (use_dense_path(h) || use_big_path(h))
+    return fail(h, BJX_E_UNSUPPORTED, "generalized HMC is built for dim <= 1024 (dense metrics: dim <= 128)");
+  if ((imm_rows != nullptr) != (msqrt_rows != nullptr) || chains_per_group < 1)
+    return fail(h, BJX_E_INVALID, "imm_rows and msqrt_rows come together; chains_per_group >= 1");
+  if (imm_rows && (h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK))
+    return fail(h, BJX_E_INVALID, "per-row momentum scales need a diagonal metric on the handle");
+  LaunchArgs a{};
+  a.P = make_params(h, step_size, step_size_dev);
+  if (imm_rows) {  // MEADS: one inverse-mass row per fold (meads_adaptation.py:587-606)
+    a.P.imm = imm_rows;
+    a.P.msqrt = msqrt_rows;
+    a.P.imm_stride = h->cfg.dim;
+    a.P.imm_group = chains_per_group;
+  }
+  a.keys = keys;
+  a.q_out = q; a.logp_out = logp; a.g_out = grad;
+  a.ghmc.p_io = p;
+  a.ghmc.slice_io = slice;
+  a.ghmc.alpha = alpha; a.ghmc.alpha_dev = alpha_dev;
+  a.ghmc.delta = delta; a.ghmc.delta_dev = delta_dev;
+  a.ghmc.param_group = chains_per_group;
+  a.ghmc.skip_begin = skip_begin; a.ghmc.skip_end = skip_end;
+  a.info = make_info(info);
+  return dispatch(h, K_GHMC, true, a);
 }
 
 // hmc.build_kernel(build_proposal=multinomial_hmc_proposal) / blackjax.mhmc (hmc.py:181-248, __init__.py:145-151)

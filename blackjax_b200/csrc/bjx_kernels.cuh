@@ -168,6 +168,89 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
   }
 }
 
+// ---- generalized HMC (ghmc.py:118-189): persistent momentum, ONE leapfrog, non-reversible slice acceptance ------------
+// In place on (q, p, logp, g, slice).  alpha / delta: per chain when the pointers are set.  Chains in [skip_begin,
+// skip_end) draw and integrate like every other chain but keep their state (MEADS' frozen fold,
+// meads_adaptation.py:639-650).  noise_fn is the reference default (identically 0).
+struct GhmcArgs {
+  float* p_io;
+  float* slice_io;
+  float alpha, delta;
+  const float* alpha_dev;
+  const float* delta_dev;
+  int param_group;  // step_size_dev / alpha_dev / delta_dev are indexed by chain / param_group (MEADS: one entry per fold)
+  int skip_begin, skip_end;
+};
+
+template <class R, int TK, bool DM, bool GEN>
+__global__ void __launch_bounds__(kThreads) k_ghmc_transition(Params P, const uint32_t* __restrict__ keys, float* q_io,
+                                                              float* logp_io, float* g_io, GhmcArgs A, InfoPtrs info) {
+  BJX_WARP_PROLOGUE();
+  Ctx<R, TK, DM> c;
+  float q[R::NS], p[R::NS], g[R::NS], z[R::NS];
+  R::load(q, q_io + roff, P.D, lane);
+  R::load(g, g_io + roff, P.D, lane);
+  R::load(p, A.p_io + roff, P.D, lane);
+  c.init(P, chain, lane, sm);
+  const Key rng = chain_key(P, keys, chain);
+  const Key key_momentum = fold_in(rng, 0u);  // ghmc.py:169 (key_noise = fold_in(rng, 1) feeds noise_fn == 0)
+  const int gi = chain / A.param_group;
+  const float alpha = A.alpha_dev ? A.alpha_dev[gi] : A.alpha;
+  const float delta_s = A.delta_dev ? A.delta_dev[gi] : A.delta;
+  c.sample_momentum(P, chain, key_momentum, z);
+  const float keep = sqrtf(1.0f - alpha), mix = sqrtf(alpha);
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) p[s] = __fadd_rn(__fmul_rn(p[s], keep), __fmul_rn(mix, z[s]));  // ghmc.py:205-211
+  if (info.momentum) R::store(p, info.momentum + roff, P.D, lane);
+  float sl = A.slice_io[chain];
+  {  // ((slice + 1 + delta + noise) % 2) - 1   ghmc.py:172; jnp.remainder = fmod + sign fix-up
+    const float x = ((sl + 1.0f) + delta_s) + 0.0f;
+    float r = fmodf(x, 2.0f);
+    if (r != 0.0f && r < 0.0f) r += 2.0f;
+    sl = r - 1.0f;
+  }
+  const float logp0 = logp_io[chain];
+  const float e0 = -logp0 + c.kinetic(P, p);
+  const float eps = P.eps_dev ? P.eps_dev[gi] : P.eps;
+  float logp = logp0;
+  float p0[R::NS];
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) p0[s] = p[s];
+  c.template step<GEN, true>(P, q, p, g, logp, eps);
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) p[s] = -1.0f * p[s];                      // flip_momentum hmc.py:158
+  const float e1 = -logp + c.kinetic(P, p);
+  const float delta = safe_energy_diff(e0, e1);
+  const bool is_div = (-delta) > P.div_thr;
+  const float p_acc = clip_max1(expf(delta));                               // proposal.py:253
+  const bool acc = logf(fabsf(sl)) <= delta;                                // proposal.py:254
+  const float af = acc ? 1.0f : 0.0f;
+  const float sl_next = sl * (expf(-delta) * af + (1.0f - af));             // proposal.py:255 (inf * 0 = NaN kept)
+  if (info.proposal_position) R::store(q, info.proposal_position + roff, P.D, lane);
+  if (info.proposal_momentum) R::store(p, info.proposal_momentum + roff, P.D, lane);
+  if (lane == 0) {
+    if (info.acceptance_rate) info.acceptance_rate[chain] = p_acc;
+    if (info.is_accepted) info.is_accepted[chain] = acc;
+    if (info.is_divergent) info.is_divergent[chain] = is_div;
+    if (info.energy) info.energy[chain] = e1;
+    if (info.num_integration_steps) info.num_integration_steps[chain] = 1;
+  }
+  if (chain >= A.skip_begin && chain < A.skip_end) return;
+  if (acc) {  // the sampled state is flipped once more (ghmc.py:178): +p of the integrator
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) p[s] = -1.0f * p[s];
+    R::store(q, q_io + roff, P.D, lane);
+    R::store(g, g_io + roff, P.D, lane);
+    R::store(p, A.p_io + roff, P.D, lane);
+    if (lane == 0) logp_io[chain] = logp;
+  } else {
+#pragma unroll
+    for (int s = 0; s < R::NS; ++s) p0[s] = -1.0f * p0[s];
+    R::store(p0, A.p_io + roff, P.D, lane);
+  }
+  if (lane == 0) A.slice_io[chain] = sl_next;
+}
+
 // ---- multinomial HMC (hmc.py:181-248 + trajectory.py:170-232 static_progressive_integration) ---------------
 // Same trajectory as k_hmc_transition, but every leaf competes through progressive uniform sampling
 // (proposal.py:118-143) with step key fold_in(key_integrator, i); there is no Metropolis rejection.  The

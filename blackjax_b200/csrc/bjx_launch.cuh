@@ -7,12 +7,13 @@
 namespace bjx {
 
 enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_BIG, SC_NONE };  // SC_BIG: CTA-per-chain (bjx_big.cu)
-enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING, K_MHMC };
+enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING, K_MHMC, K_GHMC };
 
 struct LaunchArgs {
   Params P;
   NutsWs ws;
   InfoPtrs info;
+  GhmcArgs ghmc;
   const uint32_t* keys;
   const float *q_in, *logp_in, *g_in;
   float *q_out, *logp_out, *g_out;
@@ -88,6 +89,12 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       else
         k_mhmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
                                                                         a.logp_out, a.g_out, a.n, a.info);
+      return 0;
+    case K_GHMC:
+      if (a.general_integrator)
+        k_ghmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
+      else
+        k_ghmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
       return 0;
     case K_NUTS_DOUBLING:
       if (a.n_in_dev) {

@@ -33,7 +33,8 @@ struct Params {
   float logp_offset;
   // metric
   const float* imm;        // diag: [D] or [C,D]; dense: [D,D]
-  long long imm_stride;    // 0 (shared) or D (per chain)
+  long long imm_stride;    // 0 (shared) or D (one row per group of imm_group chains)
+  int imm_group;           // chains sharing a metric row (1: per chain; MEADS folds: chains per fold)
   const float* msqrt;      // mass_matrix_sqrt, same layout as imm
   // low-rank metric (metrics.py:349-467): M^-1 = diag(sigma) (I + U (Lambda - I) U^T) diag(sigma); lr_k == 0: not in use
   int lr_k;
@@ -330,7 +331,7 @@ struct Ctx {
 #pragma unroll
       for (int s = 0; s < R::NS; ++s) tw[s] = -tw[s];
     }
-    if constexpr (!DM) R::load_const(mw, P.imm + (size_t)chain * P.imm_stride, P.D, lane);
+    if constexpr (!DM) R::load_const(mw, P.imm + (size_t)(chain / P.imm_group) * P.imm_stride, P.D, lane);
   }
 
   // linear_map(M^-1, p)   blackjax/util.py:57-61
@@ -486,7 +487,7 @@ struct Ctx {
       }
     } else {
       float ms[R::NS];
-      R::load_const(ms, P.msqrt + (size_t)chain * P.imm_stride, P.D, lane);
+      R::load_const(ms, P.msqrt + (size_t)(chain / P.imm_group) * P.imm_stride, P.D, lane);
 #pragma unroll
       for (int s = 0; s < R::NS; ++s) p[s] = ms[s] * z[s];
     }

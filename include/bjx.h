@@ -163,6 +163,35 @@ int bjx_mhmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   const float* grad_in, float* q_out, float* logp_out, float* grad_out,
                   float step_size, const float* step_size_dev, int32_t num_integration_steps,
                   const bjx_info* info);
+/* Generalized HMC: ghmc.build_kernel().kernel (blackjax/mcmc/ghmc.py:118-189; update_momentum :192-213;
+ * nonreversible_slice_sampling blackjax/mcmc/proposal.py:243-264), in place on the persistent state
+ * (q [C,D], p [C,D], logp [C], grad [C,D], slice [C]); noise_fn is the reference default (0).
+ * step_size_dev / alpha_dev / delta_dev (optional) are indexed by chain / chains_per_group; imm_rows + msqrt_rows
+ * (optional, [C / chains_per_group, D]: inverse mass = momentum_inverse_scale^2, ghmc.py:83-84, and 1/sqrt of it)
+ * override the handle's diagonal metric row-wise -- MEADS' per-fold parameters (meads_adaptation.py:587-606).
+ * Chains in [skip_begin, skip_end) are computed but keep their state (the frozen fold, :639-650). */
+int bjx_ghmc_step(bjx_handle_t h, const uint32_t* keys, float* q, float* p, float* logp, float* grad, float* slice,
+                  float step_size, const float* step_size_dev, float alpha, const float* alpha_dev, float delta,
+                  const float* delta_dev, const float* imm_rows, const float* msqrt_rows, int32_t chains_per_group,
+                  int32_t skip_begin, int32_t skip_end, const bjx_info* info);
+/* MEADS fold statistics and parameters (blackjax/adaptation/meads_adaptation.py:507-585, maximum_eigenvalue :787-817)
+ * from the positions and gradients of all chains, folds = contiguous blocks of C / num_folds chains, t = the
+ * adaptation iteration.  state float32 [bjx_meads_state_floats] = step_size[K] | alpha[K] | delta[K] | sigma[K,D] |
+ * imm[K,D] | msqrt[K,D], already rolled by one fold (:560-563), i.e. the arrays bjx_ghmc_step takes.
+ * num_folds = 1 gives base.compute_parameters (:97-152) of all chains. */
+size_t bjx_meads_state_floats(int32_t num_folds, int32_t dim);
+size_t bjx_meads_scratch_floats(int32_t n_chains, int32_t dim, int32_t num_folds);
+int bjx_meads_update(bjx_handle_t h, const float* q, const float* grad, int32_t num_folds, int32_t t,
+                     float step_size_multiplier, float damping_slowdown, float* state, float* scratch);
+/* maximum_eigenvalue (meads_adaptation.py:787-817) of one float32 [n, d] device matrix; out: ONE device float */
+size_t bjx_maximum_eigenvalue_scratch_floats(int64_t n, int32_t d);
+int bjx_maximum_eigenvalue(bjx_handle_t h, const float* x, int64_t n, int32_t d, float* out, float* scratch);
+/* jax.random.permutation(key', n) with key' = fold_in(key, fold_index) (fold_index < 0: key itself): the sort-based
+ * shuffle of jax/_src/random.py.  perm_out int32 [n]; scratch: bjx_permutation_scratch_bytes(n) bytes. */
+size_t bjx_permutation_scratch_bytes(int64_t n);
+int bjx_permutation(bjx_handle_t h, const uint32_t* key, int64_t fold_index, int64_t n, int32_t* perm_out, void* scratch);
+/* dst[r, :] = src[perm[r], :] for float32 [rows, width] (the shuffle of meads_adaptation.py:675-683); out of place */
+int bjx_gather_rows(bjx_handle_t h, const int32_t* perm, const float* src, float* dst, int64_t rows, int32_t width);
 /* blackjax.util.run_inference_algorithm (util.py:150-213) for HMC (multinomial = 0) / multinomial HMC (1), run
  * natively: step keys = jax.random.split(rng_key, num_steps) (util.py:203), num_steps in-place transitions enqueued back
  * to back without host synchronisation; chain c of step t uses split(step_key_t, n_global)[chain_offset + c].

@@ -439,3 +439,59 @@ def test_low_rank_metric_oracle_matches_the_dense_formula():
     diag = hmc.Metric((sigma ** 2).astype(np.float32))
     np.testing.assert_allclose(ones.velocity(p), diag.velocity(p), rtol=1e-5)
     assert (ones.is_turning(p, -p, p) == diag.is_turning(p, -p, p)).all()
+
+
+def test_ghmc_oracle_samples_the_reference_univariate_case():
+    """tests/mcmc/test_sampling.py:1160-1172 of the reference on the restatement: ghmc(step_size=1, scale 1, alpha=0.8,
+    delta=2) on N(1, 2^2); mean and std to the reference's 1e-1 relative tolerance (pooled over 64 chains)."""
+    from oracle import ghmc as oghmc
+    C = 64
+    tgt = targets.DiagGaussian(np.array([2.0]), mean=np.array([1.0]))
+    st = oghmc.init(np.ones((C, 1), np.float32), tgt, prng.split(prng.key(3), C))
+    assert (np.abs(st.slice) <= 1).all() and st.momentum.shape == (C, 1)
+    keys = prng.split(prng.key(4), 1500)
+    draws = []
+    for t in range(1500):
+        st, info = oghmc.ghmc_kernel(prng.split(keys[t], C), st, tgt, 1.0, np.ones(1, np.float32), 0.8, 2.0)
+        assert (np.abs(st.slice) <= 1).all()
+        if t >= 300:
+            draws.append(st.position)
+    x = np.concatenate(draws).ravel()
+    np.testing.assert_allclose(x.mean(), 1.0, rtol=1e-1)
+    np.testing.assert_allclose(x.std(), 2.0, rtol=1e-1)
+
+
+def test_meads_oracle_properties_of_the_reference_tests():
+    """The checkable statements of tests/adaptation/test_meads.py and tests/mcmc/test_sampling.py:606-690 replayed on the
+    restatement: init replicates one parameter set over the folds (:44-56), the step size is linear in the multiplier
+    (:85-97), damping_slowdown raises alpha early on (:99-117), the fold t mod K is frozen at step t (sampling:640-662),
+    the maximum-eigenvalue estimator recovers a dominant eigenvalue, and the shuffle is a permutation."""
+    from oracle import meads as om
+    rs = np.random.default_rng(0)
+    C, D, K = 64, 3, 4
+    q = rs.standard_normal((C, D)).astype(np.float32)
+    tgt = targets.DiagGaussian(np.array([1.0, 2.0, 0.5]))
+    _, g = tgt(q)
+    s1 = om.meads_init(q, g, K)
+    assert (s1.step_size == s1.step_size[0]).all() and (s1.alpha == s1.alpha[0]).all()
+    assert (s1.position_sigma == s1.position_sigma[0]).all() and s1.current_iteration == 0
+    far = 10.0 * q                                           # gradients large enough that min(., 1) does not clip
+    _, gf = tgt(far)
+    a = om.compute_parameters(far, gf, 0, step_size_multiplier=0.25)[0]
+    b = om.compute_parameters(far, gf, 0, step_size_multiplier=0.5)[0]
+    np.testing.assert_allclose(b, 2 * a, rtol=1e-5)
+    lo = om.compute_parameters(q, g, 0, damping_slowdown=1.0)[2]
+    hi = om.compute_parameters(q, g, 0, damping_slowdown=5.0)[2]
+    assert hi >= lo
+    X = (rs.standard_normal((400, 6)) * np.array([10, 1, 1, 1, 1, 1])).astype(np.float32)
+    assert abs(om.maximum_eigenvalue(X) / 100 - 1) < 0.2              # the dominant eigenvalue of the second-moment matrix
+    for n in (1, 7, 2000):
+        np.testing.assert_array_equal(np.sort(om.permutation(prng.key(n), n)), np.arange(n))
+    trace = []
+    om.meads_run(tgt, prng.key(2), q, 3, num_folds=K, trace=trace)
+    n = C // K
+    np.testing.assert_array_equal(trace[0][0].position[:n], q[:n])
+    np.testing.assert_array_equal(trace[1][0].position[n:2 * n], trace[0][0].position[n:2 * n])
+    np.testing.assert_array_equal(trace[2][0].position[2 * n:3 * n], trace[1][0].position[2 * n:3 * n])
+    assert not np.array_equal(trace[0][0].position[n:], q[n:])
+    assert trace[2][1].step_size.shape == (K,) and (trace[2][1].step_size > 0).all()
