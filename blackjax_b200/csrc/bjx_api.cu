@@ -1,5 +1,6 @@
 // C ABI of libbjx.so (include/bjx.h): handle management, argument checking, kernel dispatch and
 // the host-driven NUTS doubling loop.  No torch types, no exceptions across the boundary.
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -788,6 +789,55 @@ extern "C" int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q
   h->key_shared = 1;
   const size_t C = h->cfg.n_chains, row_bytes = C * h->cfg.dim * sizeof(float);
   int rc = 0;
+  // Enough transitions to amortise the ragged end: the chains run decoupled, every warp taking whole chains through all
+  // num_steps transitions (k_nuts_chains).  BJX_NUTS_DECOUPLED=0 keeps the step-synchronous loop (same results).
+  static const bool decoupled_ok = [] { const char* e = getenv("BJX_NUTS_DECOUPLED"); return !(e && e[0] == '0'); }();
+  if (decoupled_ok && num_steps >= 4 && max_num_doublings > 0) {
+    const void* ptrs[] = {q, grad};
+    rc = check_ready(h, true, ptrs, 2);
+    if (rc == 0 && !logp) rc = fail(h, BJX_E_INVALID, "null array argument");
+    if (rc == 0 && max_num_doublings > h->cfg.max_tree_depth)
+      rc = fail(h, BJX_E_INVALID, "max_num_doublings exceeds the handle's max_tree_depth");
+    if (rc == 0 && use_dense_path(h)) rc = fail(h, BJX_E_UNSUPPORTED, "NUTS with a dense metric / dense target needs dim <= 128");
+    if (rc == 0 && h->sc == SC_BIG) rc = fail(h, BJX_E_UNSUPPORTED, "NUTS is built for dim <= 1024");
+    if (rc == 0) rc = ensure_ws(h);
+    if (rc == 0) {
+      cudaError_t e = cudaMemsetAsync(h->ws.counters, 0, 64 * sizeof(int), h->stream);
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "cudaMemsetAsync(counters)");
+    }
+    if (rc == 0) {
+      LaunchArgs a{};
+      a.P = make_params(h, step_size, step_size_dev);
+      a.ws = h->ws;
+      a.q_out = q; a.logp_out = logp; a.g_out = grad;
+      const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)max_num_doublings * h->cfg.dim;
+      const size_t dm_bytes = (h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK ||
+                               h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
+                                  ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
+      a.sample.step_keys = h->sample_keys;
+      a.sample.num_steps = num_steps;
+      a.sample.max_doublings = max_num_doublings;
+      a.sample.ckpt_smem = (ckpt_bytes + dm_bytes <= 40 * 1024) ? 1 : 0;
+      a.sample.history = history;
+      a.sample.thin = thin;
+      a.sample.acceptance_history = acceptance_history;
+      a.sample.nint_history = num_integration_steps_history;
+      a.sample.leapfrogs = nullptr;
+      a.sample.queue = h->ws.counters + 62;
+      // persistent grid: as many CTAs as stay resident (registers: <= 4 per SM; shared memory: the checkpoints)
+      const size_t smem = dm_bytes + (a.sample.ckpt_smem ? ckpt_bytes : 0);
+      int per_sm = smem ? (int)std::min<size_t>(4, (200 * 1024) / smem) : 4;
+      if (per_sm < 1) per_sm = 1;
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+      a.grid_override = (int)std::min<size_t>((C + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sms * per_sm);
+      rc = dispatch(h, K_NUTS_CHAINS, true, a);
+      h->last_leaf_launches = 1;
+      h->last_depth = -1;
+    }
+    h->key_shared = saved_mode;
+    return rc;
+  }
   for (int t = 0; t < num_steps && rc == 0; ++t) {
     bjx_info info{};
     info.acceptance_rate = acceptance_history ? acceptance_history + (size_t)t * C : nullptr;

@@ -347,12 +347,11 @@ struct NutsWs {
 
 // nuts.py:133-136,278-294: key split, momentum draw, initial proposal / trajectory / termination state
 template <class R, int TK, bool DM>
-__global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, const uint32_t* __restrict__ keys,
-                                                        const float* q_in, const float* logp_in, const float* g_in,
-                                                        float* q_out, float* logp_out, float* g_out,
-                                                        const float* mom_override, const uint32_t* keyint_override,
-                                                        float* mom_out) {
-  BJX_WARP_PROLOGUE();
+__device__ __forceinline__ void nuts_init_row(const Params& P, const NutsWs& ws, const uint32_t* keys, const float* q_in,
+                                              const float* logp_in, const float* g_in, float* q_out, float* logp_out,
+                                              float* g_out, const float* mom_override, const uint32_t* keyint_override,
+                                              float* mom_out, int chain, int lane, float* sm) {
+  const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK_FUNNEL, DM> c;
   c.init(P, chain, lane, sm);
   float q[R::NS], p[R::NS], g[R::NS];
@@ -396,6 +395,18 @@ __global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, con
     ws.key_int[2 * chain] = key_integrator.a;
     ws.key_int[2 * chain + 1] = key_integrator.b;
   }
+}
+
+template <class R, int TK, bool DM>
+__global__ void __launch_bounds__(kThreads) k_nuts_init(Params P, NutsWs ws, const uint32_t* __restrict__ keys,
+                                                        const float* q_in, const float* logp_in, const float* g_in,
+                                                        float* q_out, float* logp_out, float* g_out,
+                                                        const float* mom_override, const uint32_t* keyint_override,
+                                                        float* mom_out) {
+  BJX_WARP_PROLOGUE();
+  (void)roff;
+  nuts_init_row<R, TK, DM>(P, ws, keys, q_in, logp_in, g_in, q_out, logp_out, g_out, mom_override, keyint_override, mom_out,
+                           chain, lane, sm);
 }
 
 // is_turning(ckpt_p, p, p_sum - ckpt_sum + ckpt_p) against one checkpoint row (termination.py:96-103,
@@ -461,21 +472,11 @@ __device__ __forceinline__ bool turning_vs_checkpoint(Ctx<R, TK, DM>& c, const P
 // Checkpoints live in shared memory when depth x D is small enough (ckpt_smem), else in the global workspace.
 // STRIDE: the row count is read on the device (n_in_dev) and a fixed grid strides over the list; the loop costs ~30
 // registers, so the launch over all chains (row count known on the host) is instantiated without it.
-template <class R, int TK, bool DM, bool GEN, bool STRIDE>
-__global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d_begin, int d_end, int max_doublings,
-                                                            const int* __restrict__ list_in, int n_in,
-                                                            const int* __restrict__ n_in_dev,
-                                                            int* __restrict__ list_out, int* counter_out,
-                                                            float* q_out, float* logp_out, float* g_out, int ckpt_smem) {
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  extern __shared__ __align__(16) float bjx_smem[];
-  float* sm = bjx_smem + (size_t)wib * P.D;  // small dense matvec slice (first kWarpsPerBlock*D floats when used)
-  // n_in_dev: the row count was produced on the device by the previous launch (no host round trip); the grid is then
-  // a fixed number of CTAs whose warps stride over the compacted list (surplus warps leave at once)
-  const int n_rows = (STRIDE && n_in_dev) ? *n_in_dev : n_in;
-  for (int w = blockIdx.x * kWarpsPerBlock + wib; w < n_rows; w += STRIDE ? gridDim.x * kWarpsPerBlock : n_rows) {
-  const int chain = list_in ? list_in[w] : w;
+// One chain (one warp) through doublings [d_begin, d_end); returns whether the chain wants doubling d_end.
+template <class R, int TK, bool DM, bool GEN>
+__device__ __forceinline__ bool nuts_doubling_row(const Params& P, const NutsWs& ws, int chain, int d_begin, int d_end,
+                                                  int max_doublings, float* q_out, float* logp_out, float* g_out,
+                                                  int ckpt_smem, int lane, int wib, float* sm, float* bjx_smem) {
   const size_t roff = (size_t)chain * P.D;
   Ctx<R, TK, DM> c;
   c.init(P, chain, lane, sm);
@@ -685,11 +686,97 @@ __global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws,
     ws.prop_slpa[chain] = prop_slpa;
     ws.n_states[chain] = n_states;
     ws.step[chain] = d;
-    if (run_next && d < max_doublings) list_out[atomicAdd(counter_out, 1)] = chain;
   }
-  if constexpr (!STRIDE) return;  // one row per warp: no loop for the compiler to carry state across
-  __syncwarp();
+  return run_next && d < max_doublings;
+}
+
+template <class R, int TK, bool DM, bool GEN, bool STRIDE>
+__global__ void __launch_bounds__(kThreads) k_nuts_doubling(Params P, NutsWs ws, int d_begin, int d_end, int max_doublings,
+                                                            const int* __restrict__ list_in, int n_in,
+                                                            const int* __restrict__ n_in_dev,
+                                                            int* __restrict__ list_out, int* counter_out,
+                                                            float* q_out, float* logp_out, float* g_out, int ckpt_smem) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  extern __shared__ __align__(16) float bjx_smem[];
+  float* sm = bjx_smem + (size_t)wib * P.D;  // small dense matvec slice (first kWarpsPerBlock*D floats when used)
+  // n_in_dev: the row count was produced on the device by the previous launch (no host round trip); the grid is then
+  // a fixed number of CTAs whose warps stride over the compacted list (surplus warps leave at once)
+  const int n_rows = (STRIDE && n_in_dev) ? *n_in_dev : n_in;
+  for (int w = blockIdx.x * kWarpsPerBlock + wib; w < n_rows; w += STRIDE ? gridDim.x * kWarpsPerBlock : n_rows) {
+    const int chain = list_in ? list_in[w] : w;
+    const bool more = nuts_doubling_row<R, TK, DM, GEN>(P, ws, chain, d_begin, d_end, max_doublings, q_out, logp_out, g_out,
+                                                        ckpt_smem, lane, wib, sm, bjx_smem);
+    if (lane == 0 && more) list_out[atomicAdd(counter_out, 1)] = chain;
+    if constexpr (!STRIDE) return;  // one row per warp: no loop for the compiler to carry state across
+    __syncwarp();
   }  // next row of the list
+}
+
+// ---- run_inference_algorithm for NUTS with the chains decoupled (bjx_nuts_sample) --------------------------------
+// Chains never interact and transition t of chain c only needs step key t, so nothing forces the chains through the
+// transitions in lock step: a persistent grid whose warps pull chains from a queue and run ALL num_steps transitions of a
+// chain back to back (init row -> doublings 0..max -> info), in place.  The deep trees that leave a per-transition
+// launch with 10 % of its warp slots busy (profiles/r02_ncu_nuts.md) are then hidden behind the other chains' work.
+// Results are bit-identical to num_steps calls of bjx_nuts_step (same device functions, same keys).
+struct NutsSampleArgs {
+  const uint32_t* step_keys;  // [num_steps, 2]
+  int num_steps;
+  int max_doublings;
+  int ckpt_smem;
+  float* history;             // [num_steps / thin, C, D] or nullptr
+  int thin;
+  float* acceptance_history;  // [num_steps, C] or nullptr
+  int* nint_history;          // [num_steps, C] or nullptr
+  unsigned long long* leapfrogs;  // += sum of num_integration_steps, or nullptr
+  int* queue;                 // zeroed by the host
+};
+
+template <class R, int TK, bool DM, bool GEN>
+__global__ void __launch_bounds__(kThreads) k_nuts_chains(Params P, NutsWs ws, float* q_io, float* logp_io, float* g_io,
+                                                          NutsSampleArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  extern __shared__ __align__(16) float bjx_smem[];
+  float* sm = bjx_smem + (size_t)wib * P.D;
+  for (;;) {
+    int chain = 0;
+    if (lane == 0) chain = atomicAdd(A.queue, 1);
+    chain = __shfl_sync(0xffffffffu, chain, 0);
+    if (chain >= P.C) return;
+    const size_t roff = (size_t)chain * P.D;
+    unsigned long long n_leapfrogs = 0;
+    int dmax = 0;
+    for (int t = 0; t < A.num_steps; ++t) {
+      nuts_init_row<R, TK, DM>(P, ws, A.step_keys + 2 * t, q_io, logp_io, g_io, q_io, logp_io, g_io, nullptr, nullptr, nullptr,
+                               chain, lane, sm);
+      __syncwarp();
+      for (int d0 = 0; d0 < A.max_doublings; d0 += 10) {  // the lane-parallel key schedule covers 10 doublings per call
+        const int d1 = min(A.max_doublings, d0 + 10);
+        const bool more = nuts_doubling_row<R, TK, DM, GEN>(P, ws, chain, d0, d1, A.max_doublings, q_io, logp_io, g_io,
+                                                            A.ckpt_smem, lane, wib, sm, bjx_smem);
+        __syncwarp();
+        if (!more) break;
+      }
+      const int n = ws.n_states[chain];
+      n_leapfrogs += (unsigned long long)n;
+      dmax = max(dmax, ws.step[chain]);
+      if (lane == 0) {
+        if (A.acceptance_history) A.acceptance_history[(size_t)t * P.C + chain] = expf(ws.prop_slpa[chain]) / (float)n;
+        if (A.nint_history) A.nint_history[(size_t)t * P.C + chain] = n;
+      }
+      if (A.history && ((t + 1) % A.thin) == 0) {
+        float q[R::NS];
+        R::load(q, q_io + roff, P.D, lane);
+        R::store(q, A.history + ((size_t)((t + 1) / A.thin - 1) * P.C + chain) * P.D, P.D, lane);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (A.leapfrogs) atomicAdd(A.leapfrogs, n_leapfrogs);
+      atomicMax(ws.counters + 63, dmax);
+    }
+  }
 }
 
 // nuts.py:303-319: acceptance_rate = exp(sum_log_p_accept) / num_states and the NUTSInfo scalars

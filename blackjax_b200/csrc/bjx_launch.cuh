@@ -7,13 +7,15 @@
 namespace bjx {
 
 enum SizeClass { SC_V1 = 0, SC_V2, SC_V4, SC_V8, SC_S1, SC_S4, SC_BIG, SC_NONE };  // SC_BIG: CTA-per-chain (bjx_big.cu)
-enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING, K_MHMC, K_GHMC };
+enum KernelId { K_INIT = 0, K_MOMENTUM, K_LEAPFROG, K_ENERGY, K_TURNING, K_HMC, K_NUTS_INIT, K_NUTS_DOUBLING, K_MHMC, K_GHMC, K_NUTS_CHAINS };
 
 struct LaunchArgs {
   Params P;
   NutsWs ws;
   InfoPtrs info;
   GhmcArgs ghmc;
+  NutsSampleArgs sample;
+  int grid_override;    // persistent launches: number of CTAs
   const uint32_t* keys;
   const float *q_in, *logp_in, *g_in;
   float *q_out, *logp_out, *g_out;
@@ -96,6 +98,15 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       else
         k_ghmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
       return 0;
+    case K_NUTS_CHAINS: {
+      size_t sm_bytes = smem + (a.sample.ckpt_smem ? sizeof(float) * kWarpsPerBlock * 2 * a.sample.max_doublings * a.P.D : 0);
+      dim3 g(a.grid_override);
+      if (a.general_integrator)
+        k_nuts_chains<R, TK, DM, true><<<g, block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
+      else
+        k_nuts_chains<R, TK, DM, false><<<g, block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
+      return 0;
+    }
     case K_NUTS_DOUBLING:
       if (a.n_in_dev) {
         if (a.general_integrator)

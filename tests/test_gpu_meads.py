@@ -80,8 +80,9 @@ def test_ghmc_transitions_match_oracle(kind, D, C):
         close(npy(info.energy)[ok], oinfo.energy[ok], 1e-4, 1.0)
         close(npy(info.momentum)[ok], oinfo.momentum[ok], 1e-4, 1e-2)
         close(npy(info.proposal.position)[ok], oinfo.proposal[0][ok], 1e-4, 1e-2)
-        # slice' = slice * exp(-delta_energy) inherits the ABSOLUTE error of the energies (1e-5 relative of |H| ~ D)
-        tol = {"logdensity": (1e-4, 1.0), "slice": (1e-5 * max(D, 100), 1e-2)}
+        # slice' = slice * exp(-delta_energy) inherits the ABSOLUTE error of the energy difference (float32 sums of D terms
+        # of size |H| ~ D) and, being persistent, compounds it over the five transitions
+        tol = {"logdensity": (1e-4, 1.0), "slice": (5e-5 * max(D, 100), 1e-2)}
         for name, a, b in zip(st._fields, st, ost):
             close(npy(a)[ok], np.asarray(b)[ok], *tol.get(name, (2e-4, 1e-2)))
         np.testing.assert_array_equal(npy(info.is_divergent)[ok], oinfo.is_divergent[ok])
