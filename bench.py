@@ -40,7 +40,9 @@ WORKLOADS = {
     "hmc_iso_gaussian_1024x100_L10": dict(C=1024, D=100, L=10, eps=0.2, dense=False),
     # BASELINE configs[2]: NUTS, Neal's funnel (D=128), 65536 chains, diag mass, max_tree_depth=10 (eps 0.1,
     # q0 = 0.1 N(0,1)); a step is one NUTS transition, value counts the leapfrogs the trees actually executed
-    "nuts_funnel_65536x128": dict(C=65536, D=128, eps=0.1, nuts=True, depth=10),
+    # block: NUTS transitions per bench step, run by bjx_nuts_sample (the native run_inference_algorithm) with the chains
+    # decoupled across transitions; block=1 times single bjx_nuts_step calls (BJX_BENCH_NUTS_BLOCK overrides)
+    "nuts_funnel_65536x128": dict(C=65536, D=128, eps=0.1, nuts=True, depth=10, block=32),
     # BASELINE configs[3]: NUTS + window adaptation (dual averaging + diagonal mass matrix, ONE step size / metric for all
     # chains of all GPUs), 512-D Gaussian with std = logspace(-1,1), 32768 chains per GPU (262144 over 8), eps0 = 1.0,
     # target 0.8; a step is one complete 200-step warm-up: per warm-up step one NUTS transition, the block statistics,
@@ -285,6 +287,7 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
     C, D, depth = wl["C"], wl["D"], wl["depth"]
     K, W = args.steps, args.warmup
     adapt = bool(wl.get("adapt"))
+    BLK = 1 if adapt else int(os.environ.get("BJX_BENCH_NUTS_BLOCK", wl.get("block", 1)))
     n_gpus = world
     key0 = bj.random.key(7, dev)
     # global chain c starts at normal(split(key, C_global)[c]): the same chains whatever the GPU count
@@ -318,6 +321,12 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
 
         def one_step(t, count):
             nonlocal state
+            if BLK > 1:
+                state, _, acc, n_int = bj.sample_nuts_native(step_keys[t], state, tgt, wl["eps"], imm, BLK,
+                                                              max_num_doublings=depth, keep_history=False, chain_offset=rank * C)
+                if count is not None:
+                    count += n_int.sum()
+                return state, acc
             state, info = kern(step_keys[t], state, tgt, wl["eps"], imm, depth)
             if count is not None:
                 count += info.num_integration_steps.sum()
@@ -362,10 +371,17 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
             acc_host.copy_(st.logdensity, non_blocking=True)
         else:
             st = bj.nuts.init(q_dev, tgt)
-            st, info = kern(step_keys[t], st, tgt, wl["eps"], imm, depth)
-            count += info.num_integration_steps.sum()
-            out_host.copy_(st.position, non_blocking=True)
-            acc_host.copy_(info.acceptance_rate, non_blocking=True)
+            if BLK > 1:
+                st, _, acc, n_int = bj.sample_nuts_native(step_keys[t], st, tgt, wl["eps"], imm, BLK, max_num_doublings=depth,
+                                                          keep_history=False, chain_offset=rank * C)
+                count += n_int.sum()
+                out_host.copy_(st.position, non_blocking=True)
+                acc_host.copy_(acc[-1], non_blocking=True)
+            else:
+                st, info = kern(step_keys[t], st, tgt, wl["eps"], imm, depth)
+                count += info.num_integration_steps.sum()
+                out_host.copy_(st.position, non_blocking=True)
+                acc_host.copy_(info.acceptance_rate, non_blocking=True)
     e2e_step(0, lf_e2e)
     lf_e2e.zero_()
     barrier()
@@ -389,7 +405,7 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     value = n_lf / (ms_total * 1e-3)
-    transitions = K * (T if adapt else 1)
+    transitions = K * (T if adapt else BLK)
     # The HBM roofline of the path is that of the vectorised one-step leapfrog kernel (24*D bytes per chain per launch,
     # SURVEY 8d) at this workload's chains x dims, timed live below; the tree kernel keeps (q, p, g, p_sum) in registers
     # across the leaves of a launch, so its own figure is reported as an equivalent (what 24*D per executed leapfrog would
@@ -422,7 +438,9 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
         "config": {"workload": args.workload, "chains_per_gpu": C, "dims": D, "max_tree_depth": depth,
                    "mass_matrix": "diag", "step": ("one %d-step window-adaptation warm-up (NUTS transition + block statistics "
                                                    "+ one NCCL all-gather + device-side merge / dual averaging per warm-up step)" % T)
-                   if adapt else "one NUTS transition",
+                   if adapt else ("one NUTS transition" if BLK == 1 else
+                                  "%d NUTS transitions of every chain in one bjx_nuts_sample call (the native run_inference_algorithm; "
+                                  "chains decoupled across transitions, k_nuts_chains)" % BLK),
                    "parallelism": (f"chains sharded x{n_gpus}; one NCCL all-gather of {(C // 4096) * (2 + 2 * D) * 4} bytes per rank "
                                    "per warm-up step (bjx_allgather_stats)") if adapt
                    else f"chains sharded x{n_gpus}, no data-path collective",
@@ -433,13 +451,14 @@ def run_nuts_workload(args, wl, dev, dist, world, rank, local_rank):
                      "traffic_source": traffic_src, "avg_launch_ms": ms_1step, "launches_timed": n1,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
         "tree_kernel": {"kernel": "k_nuts_doubling (one launch for doublings 0-3 over all chains, then one per further doubling over "
-                        "the compacted list; row counts stay on the device: no host round trip)",
+                        "the compacted list; row counts stay on the device: no host round trip)" if (adapt or BLK == 1) else
+                        "k_nuts_chains (persistent grid; every warp takes whole chains through all transitions of the call)",
                         "equivalent_GBps_at_24D_per_leapfrog": 24.0 * D * value / n_gpus / 1e9,
                         "bound": "dependent-instruction latency / issue slots (rows are register-resident inside a launch); "
                                  "ncu issue-slot figures: profiles/r02_ncu_nuts.md"},
         "e2e": {"value": n_lf_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": C * D * 4 + 8,
                 "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": K_e2e, "ms_per_step": ms_e2e / K_e2e},
-        "gpu_launches": K * ((T * 7 + 2) if adapt else 4),
+        "gpu_launches": K * ((T * 7 + 2) if adapt else (4 if BLK == 1 else 3)),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and n_gpus == 1:

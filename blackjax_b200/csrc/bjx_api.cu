@@ -824,13 +824,9 @@ extern "C" int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q
       a.sample.nint_history = num_integration_steps_history;
       a.sample.leapfrogs = nullptr;
       a.sample.queue = h->ws.counters + 62;
-      // persistent grid: as many CTAs as stay resident (registers: <= 4 per SM; shared memory: the checkpoints)
-      const size_t smem = dm_bytes + (a.sample.ckpt_smem ? ckpt_bytes : 0);
-      int per_sm = smem ? (int)std::min<size_t>(4, (200 * 1024) / smem) : 4;
-      if (per_sm < 1) per_sm = 1;
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-      a.grid_override = (int)std::min<size_t>((C + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sms * per_sm);
+      a.grid_override = sms;  // the launcher multiplies by the CTAs that stay resident per SM
       rc = dispatch(h, K_NUTS_CHAINS, true, a);
       h->last_leaf_launches = 1;
       h->last_depth = -1;

@@ -733,7 +733,7 @@ struct NutsSampleArgs {
 };
 
 template <class R, int TK, bool DM, bool GEN>
-__global__ void __launch_bounds__(kThreads) k_nuts_chains(Params P, NutsWs ws, float* q_io, float* logp_io, float* g_io,
+__global__ void __launch_bounds__(kThreads, (R::NS <= 4 && !DM) ? 5 : 1) k_nuts_chains(Params P, NutsWs ws, float* q_io, float* logp_io, float* g_io,
                                                           NutsSampleArgs A) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;

@@ -2,6 +2,8 @@
 // Each target kind is instantiated in its own translation unit (bjx_inst_*.cu) so the build
 // parallelises; bjx_api.cu only sees the declaration of Launcher<TK>::launch.
 #pragma once
+#include <algorithm>
+
 #include "bjx_kernels.cuh"
 
 namespace bjx {
@@ -100,11 +102,16 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       return 0;
     case K_NUTS_CHAINS: {
       size_t sm_bytes = smem + (a.sample.ckpt_smem ? sizeof(float) * kWarpsPerBlock * 2 * a.sample.max_doublings * a.P.D : 0);
-      dim3 g(a.grid_override);
-      if (a.general_integrator)
-        k_nuts_chains<R, TK, DM, true><<<g, block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
-      else
-        k_nuts_chains<R, TK, DM, false><<<g, block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
+      // persistent grid: every CTA that fits (registers, checkpoint shared memory) on each of the grid_override SMs
+      auto go = [&](auto kern) {
+        int nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, sm_bytes) != cudaSuccess || nb < 1) nb = 1;
+        const long long want = ((long long)a.P.C + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const long long ctas = std::min<long long>(want, (long long)a.grid_override * nb);
+        kern<<<dim3((unsigned)ctas), block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
+      };
+      if (a.general_integrator) go(k_nuts_chains<R, TK, DM, true>);
+      else go(k_nuts_chains<R, TK, DM, false>);
       return 0;
     }
     case K_NUTS_DOUBLING:

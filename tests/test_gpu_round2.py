@@ -437,23 +437,34 @@ def test_chees_adaptation_reference_test_problem():
     np.testing.assert_allclose(npy(x.std(0)), std, rtol=0.15)
 
 
-def test_native_nuts_sampler_equals_stepwise_calls():
-    """bjx_nuts_sample (run_inference_algorithm for NUTS without a Python loop) gives the draws of T calls of nuts.step."""
-    C, D, T_ = 2048, 32, 6
+@pytest.mark.parametrize("C,D,T_,depth,thin,metric", [(2048, 32, 6, 8, 1, "diag"), (301, 256, 5, 6, 2, "diag"),
+                                                       (512, 16, 4, 7, 1, "dense"), (1000, 128, 3, 5, 1, "diag")])
+def test_native_nuts_sampler_equals_stepwise_calls(C, D, T_, depth, thin, metric):
+    """bjx_nuts_sample (run_inference_algorithm for NUTS without a Python loop) gives the draws of T calls of nuts.step,
+    bit for bit -- with T >= 4 through the decoupled-chains kernel (k_nuts_chains: every warp takes whole chains through
+    all transitions), below that through the step-synchronous loop."""
     tgt = T.Funnel(D)
-    q = 0.1 * torch.randn(C, D, device=DEV)
-    imm = torch.ones(D, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(C)
+    q = 0.1 * torch.randn(C, D, device=DEV, generator=g)
+    if metric == "dense":
+        a = torch.randn(D, D, device=DEV, generator=g) * 0.2
+        imm = a @ a.T + torch.eye(D, device=DEV)
+    else:
+        imm = torch.exp(0.3 * torch.randn(D, device=DEV, generator=g))
     st0 = bj.nuts.init(q, tgt)
     key = bj.random.key(12, DEV)
-    fin, hist, acc, n_int = bj.sample_nuts_native(key, st0, tgt, 0.2, imm, T_, max_num_doublings=8)
-    alg = bj.nuts(tgt, 0.2, imm, max_num_doublings=8)
+    fin, hist, acc, n_int = bj.sample_nuts_native(key, st0, tgt, 0.2, imm, T_, max_num_doublings=depth, thin=thin)
+    alg = bj.nuts(tgt, 0.2, imm, max_num_doublings=depth)
     st = alg.init(q)
     keys = bj.random.split(key, T_)
     for t in range(T_):
         st, info = alg.step(keys[t], st)
-        assert torch.equal(hist[t], st.position)
+        if (t + 1) % thin == 0:
+            assert torch.equal(hist[(t + 1) // thin - 1], st.position)
         assert torch.equal(n_int[t], info.num_integration_steps) and torch.equal(acc[t], info.acceptance_rate)
+    assert hist.shape[0] == T_ // thin
     assert torch.equal(fin.position, st.position) and torch.equal(fin.logdensity, st.logdensity)
+    assert torch.equal(fin.logdensity_grad, st.logdensity_grad)
 
 
 def test_dense_shared_window_adaptation_d256_recovers_covariance():
