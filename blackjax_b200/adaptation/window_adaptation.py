@@ -190,9 +190,6 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
             step_keys = bjx_random.split(rng_key.to(dev), num_steps)
             da = _da_init(initial_step_size)
             eps = _f32(initial_step_size)
-            if dense and D > 128 and "num_integration_steps" not in extra_parameters:
-                raise NotImplementedError("dense metrics with dim > 128 run on the tensor-core HMC path: use blackjax_b200.hmc "
-                                          "(NUTS with a dense metric is built for dim <= 128)")
             m2_shape = (D, D) if dense else (D,)
             imm = torch.eye(D, dtype=torch.float32, device=dev) if dense else torch.ones(D, dtype=torch.float32, device=dev)
             w_n, w_mean, w_m2 = 0.0, torch.zeros(D, device=dev), torch.zeros(m2_shape, device=dev)

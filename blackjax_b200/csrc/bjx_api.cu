@@ -37,6 +37,10 @@ int bjx_dense_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g
 int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
                        float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,
                        const bjx::InfoPtrs& info);
+int bjx_dense_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
+                        float* q_out, float* logp_out, float* g_out, float step_size, const float* step_size_dev,
+                        int max_num_doublings, bjx::InfoPtrs info, const float* momentum_override,
+                        const uint32_t* key_integrator_override);
 static inline bool target_large_dense(bjx_handle_t h) {
   return h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN && h->cfg.dim > 128;
 }
@@ -133,6 +137,8 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->dense_version = 1;
   h->dense_bytes_built = 0;
   h->pool_scratch = nullptr;
+  h->dn_block = nullptr;
+  h->dn_bytes = 0;
   h->pool_scratch_bytes = 0;
   h->lr_block = nullptr;
   h->lr_k = 0;
@@ -169,6 +175,7 @@ extern "C" int bjx_destroy(bjx_handle_t h) {
   if (h->ws_block) cudaFree(h->ws_block);
   if (h->dense_block) cudaFree(h->dense_block);
   if (h->pool_scratch) cudaFree(h->pool_scratch);
+  if (h->dn_block) cudaFree(h->dn_block);
   if (h->lr_block) cudaFree(h->lr_block);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
   if (h->sample_keys) cudaFree(h->sample_keys);
@@ -667,6 +674,8 @@ static int ensure_ws(bjx_handle_t h) {
   return 0;
 }
 
+int bjx_ensure_nuts_ws(bjx_handle_t h) { return ensure_ws(h); }
+
 extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
                              const float* grad_in, float* q_out, float* logp_out, float* grad_out, float step_size,
                              const float* step_size_dev, int32_t max_num_doublings, const bjx_info* info,
@@ -682,8 +691,24 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
     return fail(h, BJX_E_INVALID, "max_num_doublings exceeds the handle's max_tree_depth");
   if ((q_in == q_out) != (grad_in == grad_out) || (q_in == q_out) != (logp_in == logp_out))
     return fail(h, BJX_E_INVALID, "in-place call must alias all of (q, logp, grad)");
-  if (use_dense_path(h)) return fail(h, BJX_E_UNSUPPORTED, "NUTS with a dense metric / dense target needs dim <= 128");
-  if (h->sc == SC_BIG) return fail(h, BJX_E_UNSUPPORTED, "NUTS is built for dim <= 1024");
+  if (h->sc == SC_BIG && !use_dense_path(h)) return fail(h, BJX_E_UNSUPPORTED, "NUTS is built for dim <= 1024");
+  if (use_dense_path(h) && h->general_integrator)
+    return fail(h, BJX_E_UNSUPPORTED, "only velocity Verlet is built for the tensor-core dense path");
+  auto endpoint_info = [&]() -> int {
+    if (info) {
+      const size_t bytes = (size_t)h->cfg.n_chains * h->cfg.dim * sizeof(float);
+      if (info->left_position) BJX_CUDA(cudaMemcpyAsync(info->left_position, h->ws.left_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      if (info->left_momentum) BJX_CUDA(cudaMemcpyAsync(info->left_momentum, h->ws.left_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      if (info->right_position) BJX_CUDA(cudaMemcpyAsync(info->right_position, h->ws.right_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      if (info->right_momentum) BJX_CUDA(cudaMemcpyAsync(info->right_momentum, h->ws.right_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return 0;
+  };
+  if (use_dense_path(h)) {  // dense metric / dense target beyond 128 dims: lock-step leaves on the tensor-core products
+    rc = bjx_dense_nuts_step(h, keys, q_in, logp_in, grad_in, q_out, logp_out, grad_out, step_size, step_size_dev,
+                             max_num_doublings, make_info(info), momentum_override, key_integrator_override);
+    return rc ? rc : endpoint_info();
+  }
   rc = ensure_ws(h);
   if (rc) return rc;
   const int C = h->cfg.n_chains;
@@ -742,13 +767,8 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   }
   k_nuts_finish<<<(C + 255) / 256, 256, 0, h->stream>>>(C, h->ws, make_info(info));
   BJX_CHECK_LAUNCH("k_nuts_finish");
-  if (info) {
-    const size_t bytes = (size_t)C * h->cfg.dim * sizeof(float);
-    if (info->left_position) BJX_CUDA(cudaMemcpyAsync(info->left_position, h->ws.left_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    if (info->left_momentum) BJX_CUDA(cudaMemcpyAsync(info->left_momentum, h->ws.left_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    if (info->right_position) BJX_CUDA(cudaMemcpyAsync(info->right_position, h->ws.right_q, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    if (info->right_momentum) BJX_CUDA(cudaMemcpyAsync(info->right_momentum, h->ws.right_p, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  }
+  rc = endpoint_info();
+  if (rc) return rc;
   h->last_leaf_launches = launches;
   h->last_depth = -1;  // known on the device only: bjx_nuts_last_stats reads it back on demand
   return 0;

@@ -725,3 +725,5 @@ int bjx_dense_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, 
     return dense_hmc_part(h, w, pt, keys, q_in, logp_in, g_in, q_out, logp_out, g_out, eps, eps_dev, L, info);
   });
 }
+
+#include "bjx_dense_nuts.cuh"

@@ -32,6 +32,8 @@ struct bjx_handle_s {
   size_t dense_bytes_built;
   float* lr_block;               // low-rank metric (owned): U [D,k] | sigma [D] | 1/sigma [D] | lambda-1 [k] | 1/sqrt(lambda)-1 [k]
   int lr_k;
+  void* dn_block;                // NUTS on the dense path (bjx_dense_nuts.cuh): compact rows, checkpoint velocities
+  size_t dn_bytes;
   float* pool_scratch;           // scratch of bjx_pooled_stats_dense (slice partials of the D x D co-moment)
   size_t pool_scratch_bytes;
   cudaStream_t dense_stream[2];  // chain slices of the dense path run on their own streams (bjx_dense.cu)
@@ -50,6 +52,7 @@ struct bjx_handle_s {
 };
 
 int bjx_fail(bjx_handle_t h, int code, const std::string& msg);
+int bjx_ensure_nuts_ws(bjx_handle_t h);  // the NUTS workspace of bjx_api.cu (shared with the dense path)
 int bjx_cuda_fail(bjx_handle_t h, cudaError_t e, const char* where);
 
 

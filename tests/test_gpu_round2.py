@@ -495,6 +495,25 @@ def test_dense_shared_window_adaptation_d256_recovers_covariance():
     assert np.max(np.abs(o[2 + D:].reshape(D, D) - ref)) < 1e-4 * np.abs(ref).max()
 
 
+def test_dense_shared_window_adaptation_with_nuts_beyond_128_dims():
+    """The welford_dense recipe with NUTS at dim > 128 (every warm-up transition runs on the tensor-core dense path):
+    the adapted dense inverse mass matrix approaches the target covariance and the step size is sane."""
+    rs = np.random.default_rng(12)
+    D, C, T_ = 160, 2048, 150
+    a = rs.standard_normal((D, D)) / np.sqrt(D)
+    cov = (a @ a.T + 0.3 * np.eye(D))
+    prec = np.linalg.inv(cov)
+    tgt = T.DenseGaussian((0.5 * (prec + prec.T)).astype(F))
+    q = rs.standard_normal((C, D)).astype(F)
+    warm = bj.window_adaptation(bj.nuts, tgt, is_mass_matrix_diagonal=False, shared=True, max_num_doublings=5)
+    (st, params), hist = warm.run(bj.random.key(3, DEV), tf(q), T_)
+    imm = npy(params["inverse_mass_matrix"])
+    err = np.abs(imm - cov).max() / np.abs(cov).max()
+    print(f"dense shared NUTS adaptation D={D}: max |imm - cov| / max|cov| = {err:.3f}, step size {params['step_size']:.3f}")
+    assert imm.shape == (D, D) and np.isfinite(imm).all()
+    assert err < 0.2 and 0.05 < params["step_size"] < 2.0
+
+
 # ---------------------------------------------------------------------------------------------------------
 # SURVEY 8f item 4: the low-rank metric (blackjax/mcmc/metrics.py:349-467) in the warp kernels
 # ---------------------------------------------------------------------------------------------------------
@@ -563,3 +582,53 @@ def test_low_rank_metric_nuts_matches_oracle():
     assert same.mean() >= 0.97
     assert (margins[~same] < 1e-5 * 64).all()
     assert oinfo.num_integration_steps.max() >= 15
+
+
+@pytest.mark.parametrize("metric,target,D,C,depth,eps", [("dense", "diag", 256, 96, 5, 0.35), ("dense", "dense", 256, 64, 5, 0.3),
+                                                          ("diag", "dense", 192, 64, 4, 0.3), ("dense", "dense", 512, 32, 6, 0.25)])
+def test_dense_path_nuts_matches_oracle(metric, target, D, C, depth, eps):
+    """NUTS beyond 128 dims with a dense metric and / or a dense Gaussian target (lock-step leaves on the tensor-core
+    products, bjx_dense_nuts.cuh) against the oracle: tree sizes, depths, flags and positions agree except for chains one
+    of whose decisions sat on a float tie (the products are good to ~2e-6, so the tie window is wider than for the warp
+    kernels' bit-faithful arithmetic)."""
+    rs = np.random.default_rng(D + C)
+    a = rs.standard_normal((D, D)) / np.sqrt(D)
+    cov = (a @ a.T + 0.5 * np.eye(D)).astype(np.float64)
+    if target == "dense":
+        prec = np.linalg.inv(cov)
+        prec = (0.5 * (prec + prec.T)).astype(F)
+        tgt, otgt = T.DenseGaussian(prec), otargets.DenseGaussian(prec)
+        q = (rs.standard_normal((C, D)) @ np.linalg.cholesky(cov).T).astype(F)
+    else:
+        s = np.exp(rs.uniform(-0.5, 0.5, D))
+        tgt, otgt = T.DiagGaussian(s), otargets.DiagGaussian(s)
+        q = (rs.standard_normal((C, D)) * s).astype(F)
+    if metric == "dense":
+        b = rs.standard_normal((D, D)) / np.sqrt(D)
+        imm = (0.3 * (b @ b.T) + np.eye(D)).astype(F)
+        imm = (0.5 * (imm + imm.T)).astype(F)
+    else:
+        imm = np.exp(rs.uniform(-0.3, 0.3, D)).astype(F)
+    keys = oprng.split(oprng.key(5), C)
+    margins = np.full(C, np.inf)
+    # one step size per chain, from tiny (the tree runs to max depth) to unstable (early U-turns inside sub-trees,
+    # divergences for the chains started far out in the tail)
+    eps_c = (eps * np.logspace(-1.3, 0.9, C)).astype(F)
+    q[-C // 8:] *= 40.0
+    onew, oinfo = onuts.nuts_kernel(keys, ohmc.init(q, otgt), otgt, eps_c, imm, depth, margins=margins)
+    new, info = bj.nuts.build_kernel(max_tree_depth=depth)(tk(keys), bj.nuts.init(tf(q), tgt), tgt, tf(eps_c), tf(imm), depth)
+    torch.cuda.synchronize()
+    same = ((npy(info.num_integration_steps) == oinfo.num_integration_steps)
+            & (npy(info.num_trajectory_expansions) == oinfo.num_trajectory_expansions)
+            & (npy(info.is_turning) == oinfo.is_turning) & (npy(info.is_divergent) == oinfo.is_divergent)
+            & np.all(np.isclose(npy(new.position), onew.position, rtol=2e-3, atol=2e-4), axis=1))
+    print(f"{metric}/{target} D={D}: {same.mean():.3f} identical; margins of the others {np.sort(margins[~same])[:6]}; tree sizes "
+          f"{np.bincount(oinfo.num_integration_steps).nonzero()[0]}; divergent {int(oinfo.is_divergent.sum())}, "
+          f"turning {int(oinfo.is_turning.sum())}, depths {np.bincount(oinfo.num_trajectory_expansions)}")
+    assert len(np.unique(oinfo.num_integration_steps)) >= 3 and oinfo.is_divergent.any()   # the case does exercise the tree
+    assert same.mean() >= 0.9
+    assert (margins[~same] < 2e-3).all(), np.sort(margins[~same])[-3:]
+    ok = same
+    close_elementwise(npy(info.acceptance_rate)[ok], oinfo.acceptance_rate[ok], 2e-3, 1e-2)
+    close_elementwise(npy(info.energy)[ok], oinfo.energy[ok], 1e-4, 1.0)
+    close_elementwise(npy(new.logdensity)[ok], onew.logdensity[ok], 2e-4, 1.0)
