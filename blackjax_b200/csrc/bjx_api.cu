@@ -812,13 +812,12 @@ extern "C" int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q
   // Enough transitions to amortise the ragged end: the chains run decoupled, every warp taking whole chains through all
   // num_steps transitions (k_nuts_chains).  BJX_NUTS_DECOUPLED=0 keeps the step-synchronous loop (same results).
   static const bool decoupled_ok = [] { const char* e = getenv("BJX_NUTS_DECOUPLED"); return !(e && e[0] == '0'); }();
-  if (decoupled_ok && num_steps >= 4 && max_num_doublings > 0) {
+  if (decoupled_ok && num_steps >= 4 && max_num_doublings > 0 && !use_dense_path(h)) {  // (the dense path is lock step)
     const void* ptrs[] = {q, grad};
     rc = check_ready(h, true, ptrs, 2);
     if (rc == 0 && !logp) rc = fail(h, BJX_E_INVALID, "null array argument");
     if (rc == 0 && max_num_doublings > h->cfg.max_tree_depth)
       rc = fail(h, BJX_E_INVALID, "max_num_doublings exceeds the handle's max_tree_depth");
-    if (rc == 0 && use_dense_path(h)) rc = fail(h, BJX_E_UNSUPPORTED, "NUTS with a dense metric / dense target needs dim <= 128");
     if (rc == 0 && h->sc == SC_BIG) rc = fail(h, BJX_E_UNSUPPORTED, "NUTS is built for dim <= 1024");
     if (rc == 0) rc = ensure_ws(h);
     if (rc == 0) {

@@ -12,8 +12,9 @@
  *    per-chain scalars are [n_chains]; PRNG keys are uint32 [n_chains, 2] (raw threefry keys,
  *    i.e. jax.random.key_data layout).
  *  - Every call is asynchronous and ordered on the handle's stream (bjx_nuts_step included: the tree doubling is
- *    driven from host C++ as two launches whose row counts stay on the device); the only calls that wait for the
- *    device are bjx_synchronize, bjx_destroy and bjx_nuts_last_stats.
+ *    driven from host C++ as launches whose row counts stay on the device); the only calls that wait for the
+ *    device are bjx_synchronize, bjx_destroy, bjx_nuts_last_stats and -- once per tree doubling -- bjx_nuts_step on the
+ *    tensor-core dense path (dense metric / dense target with dim > 128: the products are sized from the row count).
  *  - Return value: 0 ok; <0 invalid argument / unsupported configuration (BJX_E_*);
  *    >0 a cudaError_t.  bjx_last_error(handle) returns the text.  No exceptions or
  *    callbacks cross this ABI.  A handle is not thread-safe; distinct handles are independent.
@@ -203,6 +204,9 @@ int bjx_hmc_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* log
 /* nuts.build_kernel(...).kernel (nuts.py:113-145) with iterative_nuts_proposal (nuts.py:223-321).
  * Tree doubling is driven from the host: one launch per doubling over the chains still expanding; each
  * warp integrates its chain's whole sub-tree (up to 2^d leapfrog leaves) inside the launch.
+ * Dense metric / dense Gaussian target with 128 < dim <= 1024: the chains of a doubling advance through its leaves in lock
+ * step, compacted, on the tensor-core products (three per leaf: half-step velocity, gradient, full-step velocity for the
+ * energy and the U-turn tests, metrics.py:263-304); same keys and decisions.
  * momentum_override/key_integrator_override (both or neither, for KATs): skip the key split and
  * the momentum draw and use the given momentum [C,D] and integrator keys [C,2]. */
 int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in,
@@ -211,7 +215,9 @@ int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const
                   const bjx_info* info, const float* momentum_override,
                   const uint32_t* key_integrator_override);
 /* blackjax.util.run_inference_algorithm (util.py:150-213) for NUTS, run natively like bjx_hmc_sample: step keys =
- * split(rng_key, num_steps), transitions in place and back to back, no host synchronisation.  history (optional) float32
+ * split(rng_key, num_steps), transitions in place, no host synchronisation.  With num_steps >= 4 the chains run DECOUPLED:
+ * one persistent launch whose warps take whole chains through all transitions (chains never interact and transition t
+ * of chain c needs only step key t), bit-identical to num_steps calls of bjx_nuts_step.  history (optional) float32
  * [num_steps / thin, C, D]; acceptance_history (optional) float32 [num_steps, C]; num_integration_steps_history (optional)
  * int32 [num_steps, C]. */
 int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q, float* logp, float* grad, float step_size,
