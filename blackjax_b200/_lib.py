@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbjx.so")
 
-TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL, TARGET_DENSE_GAUSSIAN, TARGET_BANANA, TARGET_HIER_LOGIT = 0, 1, 2, 3, 4
+TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL, TARGET_DENSE_GAUSSIAN, TARGET_BANANA, TARGET_HIER_LOGIT, TARGET_USER = 0, 1, 2, 3, 4, 5
 METRIC_DIAG, METRIC_DENSE, METRIC_DIAG_PER_CHAIN = 0, 1, 2
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -15,7 +15,8 @@ _f32p = C.c_void_p  # device pointers travel as integers
 class TargetDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("inv_var", C.c_void_p), ("mean", C.c_void_p),
                 ("precision", C.c_void_p), ("logp_offset", C.c_float), ("data_x", C.c_void_p), ("data_y", C.c_void_p),
-                ("n_groups", C.c_int32)]
+                ("n_groups", C.c_int32), ("n_user_params", C.c_int32), ("user_params", C.c_void_p),
+                ("user_plugin", C.c_void_p)]
 
 
 class Config(C.Structure):
@@ -43,6 +44,8 @@ _SIGNATURES = {
     "bjx_destroy": (C.c_int, [C.c_void_p]),
     "bjx_last_error": (C.c_char_p, [C.c_void_p]),
     "bjx_set_target": (C.c_int, [C.c_void_p, C.POINTER(TargetDesc)]),
+    "bjx_plugin_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bjx_plugin_abi": (C.c_int, []),
     "bjx_set_integrator": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "bjx_set_key_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
     "bjx_set_integration_steps": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,6 +1,7 @@
 // C ABI of libbjx.so (include/bjx.h): handle management, argument checking, kernel dispatch and
 // the host-driven NUTS doubling loop.  No torch types, no exceptions across the boundary.
 #include <algorithm>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -89,9 +90,43 @@ static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
       if (dim <= 1024 || dim % 4 != 0)
         return fail(h, BJX_E_UNSUPPORTED, "HIER_LOGIT target is built for 1024 < dim <= 18432, dim % 4 == 0 (CTA-per-chain kernels)");
       break;
+    case BJX_TARGET_USER:
+      if (!t.user_plugin) return fail(h, BJX_E_INVALID, "USER target needs user_plugin (bjx_plugin_load)");
+      if (t.n_user_params < 0 || (t.n_user_params > 0 && !t.user_params))
+        return fail(h, BJX_E_INVALID, "USER target: user_params is NULL but n_user_params > 0");
+      if (dim > 1024) return fail(h, BJX_E_UNSUPPORTED, "USER targets are built for the warp kernels (dim <= 1024)");
+      break;
     default:
       return fail(h, BJX_E_INVALID, "unknown target kind");
   }
+  return 0;
+}
+
+// ---- plug-ins of user-defined targets (include/bjx_user_target.h) ---------------------------------------------------
+struct bjx_plugin_s {
+  void* dl;
+  int (*launch)(int kernel_id, int sc, int dm, const bjx::LaunchArgs* a);
+  std::string path;
+};
+// what a plug-in must have been built against: the C ABI version and the layout of the launch arguments
+extern "C" int bjx_plugin_abi(void) { return BJX_VERSION * 100000 + (int)sizeof(bjx::LaunchArgs); }
+
+extern "C" int bjx_plugin_load(const char* path, void** plugin_out) {
+  if (!path || !plugin_out) return fail(nullptr, BJX_E_INVALID, "null argument");
+  void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(nullptr, BJX_E_INVALID, std::string("bjx_plugin_load: ") + dlerror());
+  auto abi = (int (*)(void))dlsym(dl, "bjx_plugin_built_for_abi");
+  auto launch = (int (*)(int, int, int, const bjx::LaunchArgs*))dlsym(dl, "bjx_plugin_launch");
+  if (!abi || !launch) {
+    dlclose(dl);
+    return fail(nullptr, BJX_E_INVALID, std::string("bjx_plugin_load: ") + path + " is not a bjx target plug-in");
+  }
+  if (abi() != bjx_plugin_abi()) {
+    dlclose(dl);
+    return fail(nullptr, BJX_E_STATE, std::string("bjx_plugin_load: ") + path +
+                                          " was built against another version of libbjx's kernels: rebuild it");
+  }
+  *plugin_out = new bjx_plugin_s{dl, launch, path};  // never unloaded: handles may refer to it until the process ends
   return 0;
 }
 
@@ -345,6 +380,8 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.mean = h->cfg.target.mean;
   P.prec = h->cfg.target.precision;
   P.logp_offset = h->cfg.target.logp_offset;
+  P.user = h->cfg.target.user_params;
+  P.n_user = h->cfg.target.n_user_params;
   P.imm = h->imm;
   P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
   P.imm_group = 1;
@@ -382,9 +419,13 @@ static int dispatch(bjx_handle_t h, int kernel_id, bool target_dependent, Launch
     case BJX_TARGET_FUNNEL: rc = Launcher<TK_FUNNEL>::launch(kernel_id, h->sc, dm, a); break;
     case BJX_TARGET_DENSE_GAUSSIAN: rc = Launcher<TK_DENSE>::launch(kernel_id, h->sc, dm, a); break;
     case BJX_TARGET_BANANA: rc = Launcher<TK_BANANA>::launch(kernel_id, h->sc, dm, a); break;
+    case BJX_TARGET_USER:
+      rc = static_cast<bjx_plugin_s*>(h->cfg.target.user_plugin)->launch(kernel_id, h->sc, dm ? 1 : 0, &a);
+      if (rc > 0) return cuda_fail(h, (cudaError_t)rc, "plug-in kernel launch");
+      break;
     default: rc = -2;
   }
-  if (rc) return fail(h, BJX_E_UNSUPPORTED, "kernel variant not built for this (target, dim, metric) combination");
+  if (rc) return fail(h, BJX_E_UNSUPPORTED, "kernel variant not built for this (target, dim, metric, integrator) combination");
   BJX_CHECK_LAUNCH("kernel launch");
   return 0;
 }
@@ -736,7 +777,7 @@ extern "C" int bjx_nuts_step(bjx_handle_t h, const uint32_t* keys, const float* 
   const int kFusedDoublings = 4;  // (the kernel's lane-parallel key schedule handles up to 10 doublings per launch)
   const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)h->cfg.max_tree_depth * h->cfg.dim;
   const size_t dm_bytes = (h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK ||
-                           h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
+                           h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN || h->cfg.target.kind == BJX_TARGET_USER)
                               ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
   a.ckpt_smem = (ckpt_bytes + dm_bytes <= 40 * 1024) ? 1 : 0;  // stay under the 48 KB default dynamic-smem limit
   int64_t launches = 0;
@@ -831,7 +872,7 @@ extern "C" int bjx_nuts_sample(bjx_handle_t h, const uint32_t* rng_key, float* q
       a.q_out = q; a.logp_out = logp; a.g_out = grad;
       const size_t ckpt_bytes = sizeof(float) * kWarpsPerBlock * 2 * (size_t)max_num_doublings * h->cfg.dim;
       const size_t dm_bytes = (h->metric_small_dense || h->metric_kind == BJX_METRIC_LOW_RANK ||
-                               h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN)
+                               h->cfg.target.kind == BJX_TARGET_DENSE_GAUSSIAN || h->cfg.target.kind == BJX_TARGET_USER)
                                   ? sizeof(float) * kWarpsPerBlock * h->cfg.dim : 0;
       a.sample.step_keys = h->sample_keys;
       a.sample.num_steps = num_steps;

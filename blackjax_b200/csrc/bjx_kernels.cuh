@@ -489,7 +489,7 @@ __device__ __forceinline__ bool nuts_doubling_row(const Params& P, const NutsWs&
   float* ck_s;
   if (ckpt_smem) {
     // a sub-tree of 2^d leaves touches checkpoint rows 0..d-1, so this launch needs d_end rows per warp
-    float* base = bjx_smem + (size_t)((DM || TK == TK_DENSE) ? kWarpsPerBlock * P.D : 0) +
+    float* base = bjx_smem + (size_t)(needs_row_smem<TK, DM>() ? kWarpsPerBlock * P.D : 0) +
                   (size_t)wib * 2 * d_end * P.D;
     ck_p = base;
     ck_s = base + (size_t)d_end * P.D;

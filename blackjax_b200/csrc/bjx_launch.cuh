@@ -59,13 +59,24 @@ struct Launcher {
 };
 
 #ifdef BJX_INSTANTIATE_TK
-template <class R, int TK, bool DM>
-static int launch_one(int kernel_id, const LaunchArgs& a) {
+// Build-trimming switches (plug-ins of user-defined targets are compiled at run time, for one row size):
+#ifndef BJX_BUILD_SC
+#define BJX_BUILD_SC -1   // -1: every size class; otherwise the one SizeClass to instantiate
+#endif
+#ifndef BJX_BUILD_DM
+#define BJX_BUILD_DM 2    // 0: diagonal metrics only; 1: small dense / low-rank metrics only; 2: both
+#endif
+#ifndef BJX_BUILD_GEN
+#define BJX_BUILD_GEN 2   // 0: velocity Verlet only; 1: general coefficient tables only; 2: both
+#endif
+
+template <class R, int TK, bool DM, bool GEN>
+static int launch_gen(int kernel_id, const LaunchArgs& a) {
   const int n_rows = (kernel_id == K_NUTS_DOUBLING) ? a.n_in : a.P.C;
   dim3 grid((n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kThreads);
   // row count only known on the device: a fixed grid of 6 CTAs per SM strides over the compacted list
   if (kernel_id == K_NUTS_DOUBLING && a.n_in_dev && grid.x > 148u * 6u) grid.x = 148u * 6u;
-  size_t smem = (DM || TK == TK_DENSE) ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
+  size_t smem = needs_row_smem<TK, DM>() ? sizeof(float) * kWarpsPerBlock * a.P.D : 0;
   if (kernel_id == K_NUTS_DOUBLING && a.ckpt_smem) smem += sizeof(float) * kWarpsPerBlock * 2 * a.depth_end * a.P.D;
   cudaStream_t st = a.stream;
   switch (kernel_id) {
@@ -73,67 +84,39 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
       k_init_state<R, TK, DM><<<grid, block, smem, st>>>(a.P, a.q_in, a.logp_out, a.g_out);
       return 0;
     case K_LEAPFROG:
-      if (a.general_integrator)
-        k_leapfrog<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
-      else
-        k_leapfrog<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
+      k_leapfrog<R, TK, DM, GEN><<<grid, block, smem, st>>>(a.P, a.q_out, a.p_io, a.logp_out, a.g_out, a.n);
       return 0;
     case K_HMC:
-      if (a.general_integrator)
-        k_hmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
-                                                                      a.logp_out, a.g_out, a.n, a.info);
-      else
-        k_hmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
-                                                                       a.logp_out, a.g_out, a.n, a.info);
+      k_hmc_transition<R, TK, DM, GEN><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                   a.logp_out, a.g_out, a.n, a.info);
       return 0;
     case K_MHMC:
-      if (a.general_integrator)
-        k_mhmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
-                                                                       a.logp_out, a.g_out, a.n, a.info);
-      else
-        k_mhmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
-                                                                        a.logp_out, a.g_out, a.n, a.info);
+      k_mhmc_transition<R, TK, DM, GEN><<<grid, block, smem, st>>>(a.P, a.keys, a.q_in, a.logp_in, a.g_in, a.q_out,
+                                                                    a.logp_out, a.g_out, a.n, a.info);
       return 0;
     case K_GHMC:
-      if (a.general_integrator)
-        k_ghmc_transition<R, TK, DM, true><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
-      else
-        k_ghmc_transition<R, TK, DM, false><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
+      k_ghmc_transition<R, TK, DM, GEN><<<grid, block, smem, st>>>(a.P, a.keys, a.q_out, a.logp_out, a.g_out, a.ghmc, a.info);
       return 0;
     case K_NUTS_CHAINS: {
       size_t sm_bytes = smem + (a.sample.ckpt_smem ? sizeof(float) * kWarpsPerBlock * 2 * a.sample.max_doublings * a.P.D : 0);
       // persistent grid: every CTA that fits (registers, checkpoint shared memory) on each of the grid_override SMs
-      auto go = [&](auto kern) {
-        int nb = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, sm_bytes) != cudaSuccess || nb < 1) nb = 1;
-        const long long want = ((long long)a.P.C + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        const long long ctas = std::min<long long>(want, (long long)a.grid_override * nb);
-        kern<<<dim3((unsigned)ctas), block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
-      };
-      if (a.general_integrator) go(k_nuts_chains<R, TK, DM, true>);
-      else go(k_nuts_chains<R, TK, DM, false>);
+      auto kern = k_nuts_chains<R, TK, DM, GEN>;
+      int nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, sm_bytes) != cudaSuccess || nb < 1) nb = 1;
+      const long long want = ((long long)a.P.C + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const long long ctas = std::min<long long>(want, (long long)a.grid_override * nb);
+      kern<<<dim3((unsigned)ctas), block, sm_bytes, st>>>(a.P, a.ws, a.q_out, a.logp_out, a.g_out, a.sample);
       return 0;
     }
     case K_NUTS_DOUBLING:
-      if (a.n_in_dev) {
-        if (a.general_integrator)
-          k_nuts_doubling<R, TK, DM, true, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
-                                                                            a.n_in_dev, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                            a.g_out, a.ckpt_smem);
-        else
-          k_nuts_doubling<R, TK, DM, false, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
-                                                                             a.n_in_dev, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                             a.g_out, a.ckpt_smem);
-      } else {
-        if (a.general_integrator)
-          k_nuts_doubling<R, TK, DM, true, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
-                                                                             nullptr, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                             a.g_out, a.ckpt_smem);
-        else
-          k_nuts_doubling<R, TK, DM, false, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
-                                                                              nullptr, a.list_out, a.counter, a.q_out, a.logp_out,
-                                                                              a.g_out, a.ckpt_smem);
-      }
+      if (a.n_in_dev)
+        k_nuts_doubling<R, TK, DM, GEN, true><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                         a.n_in_dev, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                         a.g_out, a.ckpt_smem);
+      else
+        k_nuts_doubling<R, TK, DM, GEN, false><<<grid, block, smem, st>>>(a.P, a.ws, a.depth, a.depth_end, a.n, a.list_in, a.n_in,
+                                                                          nullptr, a.list_out, a.counter, a.q_out, a.logp_out,
+                                                                          a.g_out, a.ckpt_smem);
       return 0;
     default:
       break;
@@ -161,26 +144,40 @@ static int launch_one(int kernel_id, const LaunchArgs& a) {
   return -2;
 }
 
+template <class R, int TK, bool ALLOW_DM = true>
+static int launch_one(int kernel_id, bool dm, const LaunchArgs& a) {
+  if (dm) {
+    if constexpr (ALLOW_DM && BJX_BUILD_DM != 0) {
+      if (a.general_integrator) {
+        if constexpr (BJX_BUILD_GEN != 0) return launch_gen<R, TK, true, true>(kernel_id, a);
+      } else {
+        if constexpr (BJX_BUILD_GEN != 1) return launch_gen<R, TK, true, false>(kernel_id, a);
+      }
+    }
+  } else {
+    if constexpr (BJX_BUILD_DM != 1) {
+      if (a.general_integrator) {
+        if constexpr (BJX_BUILD_GEN != 0) return launch_gen<R, TK, false, true>(kernel_id, a);
+      } else {
+        if constexpr (BJX_BUILD_GEN != 1) return launch_gen<R, TK, false, false>(kernel_id, a);
+      }
+    }
+  }
+  return -2;
+}
+
+constexpr bool sc_built(int sc) { return BJX_BUILD_SC < 0 || BJX_BUILD_SC == sc; }
+
 template <int TK>
 int Launcher<TK>::launch(int kernel_id, int sc, bool dm, const LaunchArgs& a) {
   constexpr bool small_only = (TK == TK_DENSE || TK == TK_BANANA);
-  switch (sc) {
-    case SC_V1:
-      return dm ? launch_one<Row<4, true>, TK, true>(kernel_id, a) : launch_one<Row<4, true>, TK, false>(kernel_id, a);
-    case SC_S1:
-      return dm ? launch_one<Row<1, false>, TK, true>(kernel_id, a) : launch_one<Row<1, false>, TK, false>(kernel_id, a);
-    case SC_S4:
-      return dm ? launch_one<Row<4, false>, TK, true>(kernel_id, a) : launch_one<Row<4, false>, TK, false>(kernel_id, a);
-    default:
-      break;
-  }
-  if constexpr (!small_only) {
-    switch (sc) {  // dm beyond 128 dims: the low-rank metric (O(D k) per operation) for rows up to 512
-      case SC_V2: return dm ? launch_one<Row<8, true>, TK, true>(kernel_id, a) : launch_one<Row<8, true>, TK, false>(kernel_id, a);
-      case SC_V4: return dm ? launch_one<Row<16, true>, TK, true>(kernel_id, a) : launch_one<Row<16, true>, TK, false>(kernel_id, a);
-      case SC_V8: return dm ? -2 : launch_one<Row<32, true>, TK, false>(kernel_id, a);
-      default: break;
-    }
+  if constexpr (sc_built(SC_V1)) { if (sc == SC_V1) return launch_one<Row<4, true>, TK>(kernel_id, dm, a); }
+  if constexpr (sc_built(SC_S1)) { if (sc == SC_S1) return launch_one<Row<1, false>, TK>(kernel_id, dm, a); }
+  if constexpr (sc_built(SC_S4)) { if (sc == SC_S4) return launch_one<Row<4, false>, TK>(kernel_id, dm, a); }
+  if constexpr (!small_only) {  // dm beyond 128 dims: the low-rank metric (O(D k) per operation) for rows up to 512
+    if constexpr (sc_built(SC_V2)) { if (sc == SC_V2) return launch_one<Row<8, true>, TK>(kernel_id, dm, a); }
+    if constexpr (sc_built(SC_V4)) { if (sc == SC_V4) return launch_one<Row<16, true>, TK>(kernel_id, dm, a); }
+    if constexpr (sc_built(SC_V8)) { if (sc == SC_V8) return launch_one<Row<32, true>, TK, false>(kernel_id, dm, a); }
   }
   return -2;
 }

@@ -22,7 +22,11 @@
 
 namespace bjx {
 
-enum { TK_DIAG = 0, TK_FUNNEL = 1, TK_DENSE = 2, TK_BANANA = 3 };
+enum { TK_DIAG = 0, TK_FUNNEL = 1, TK_DENSE = 2, TK_BANANA = 3, TK_USER = 4 };
+
+// kernels whose warps need a D-float shared-memory slice (small dense matvec staging; scratch of user-defined targets)
+template <int TK, bool DM>
+__host__ __device__ constexpr bool needs_row_smem() { return DM || TK == TK_DENSE || TK == TK_USER; }
 
 struct Params {
   int C, D;
@@ -31,6 +35,8 @@ struct Params {
   const float* mean;
   const float* prec;
   float logp_offset;
+  const float* user;       // TK_USER: the user's parameter block (n_user floats: data, hyper-parameters)
+  int n_user;
   // metric
   const float* imm;        // diag: [D] or [C,D]; dense: [D,D]
   long long imm_stride;    // 0 (shared) or D (one row per group of imm_group chains)
@@ -92,6 +98,29 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, f
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+
+// ---- user-defined targets (TK_USER; include/bjx_user_target.h) -----------------------------------------------------
+// BlackJAX differentiates any `logdensity_fn` with jax.value_and_grad (mcmc/hmc.py:91, integrators.py:189).  Without a
+// tracing compiler the plug-in point is the fused value_and_grad itself: the user writes ONE device function against the
+// row layout above; bjx_plugin.cu instantiates every transition kernel of the path around it (nvcc, one small .so per
+// target) and libbjx dispatches to it like to a built-in target.
+struct UserCtx {
+  const float* theta;  // parameter block [n_theta] (device memory, read-only)
+  int n_theta;
+  int D;               // row length; slots with Row::idx(s, lane) >= D hold 0 on entry and must be left 0 in g
+  int lane;
+  float* row_smem;     // this warp's scratch of D floats in shared memory (see row_stage)
+};
+}  // namespace bjx
+namespace bjx_user {
+// value_and_grad of the user's log-density for the row held by one warp: q[s] / g[s] are the slots of this lane
+// (element index R::idx(s, lane)); logp must come back identical on all lanes when WANT_LOGP (otherwise it is dead and
+// the reduction may be skipped).  Defined by the plug-in's source, never by libbjx itself.
+template <class R, bool WANT_LOGP>
+__device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS], float (&g)[R::NS],
+                                               float& logp);
+}  // namespace bjx_user
+namespace bjx {
 
 template <int NS>
 struct Vec {
@@ -275,6 +304,27 @@ __device__ __forceinline__ void matvec_small(const float* __restrict__ M, const 
   __syncwarp();
 }
 
+// Helpers for user-defined targets: random access to the row.
+// row_stage: copy the row into the warp's shared-memory scratch (element e at u.row_smem[e]); every lane can then read
+// any element.  row_at<E>: broadcast element E (compile-time index) straight from the owner's register.
+template <class R>
+__device__ __forceinline__ void row_stage(const UserCtx& u, const float (&x)[R::NS]) {
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < R::NS; ++s) {
+    const int e = R::idx(s, u.lane);
+    if (e < u.D) u.row_smem[e] = x[s];
+  }
+  __syncwarp();
+}
+template <class R, int E>
+__device__ __forceinline__ float row_at(const float (&x)[R::NS]) {
+  constexpr int slot = R::VEC ? ((E >> 7) * 4 + (E & 3)) : (E >> 5);
+  constexpr int owner = R::VEC ? ((E & 127) >> 2) : (E & 31);
+  static_assert(slot < R::NS, "element index beyond the row");
+  return __shfl_sync(0xffffffffu, x[slot], owner);
+}
+
 // y = x + U ((s - 1) (U^T x))   (_low_rank_matvec, metrics.py:131-177) for a row held by one warp: every lane forms its
 // part of the k <= 16 projections, k interleaved shuffle reductions, then the expansion -- O(D k / 32) per lane, U read
 // through the read-only path (D k floats: L1/L2 resident).
@@ -409,6 +459,12 @@ struct Ctx {
       logp = -0.5f * R::dot(q, g) + P.logp_offset;
 #pragma unroll
       for (int s = 0; s < R::NS; ++s) g[s] = -g[s];
+    } else if constexpr (TK == TK_USER) {
+      const UserCtx u{P.user, P.n_user, P.D, lane, sm};
+      float lp = 0.f;
+      bjx_user::value_and_grad<R, WANT_LOGP>(u, q, g, lp);
+      if (WANT_LOGP) logp = lp + P.logp_offset;
+      __syncwarp();  // the scratch slice is shared with the small dense metric's matvec
     } else {  // TK_BANANA, D == 2, scalar layout: x0 at lane 0, x1 at lane 1
       const float x0 = __shfl_sync(0xffffffffu, q[0], 0);
       const float x1 = __shfl_sync(0xffffffffu, q[0], 1);

@@ -4,8 +4,9 @@ BlackJAX accepts any JAX callable as ``logdensity_fn`` and differentiates it wit
 ``jax.value_and_grad`` (blackjax/mcmc/hmc.py:91, integrators.py:189).  Without a tracing compiler the
 B200 path takes a *target descriptor* in the ``logdensity_fn`` slot instead: one of the named models
 below, each with a hand-derived gradient fused into the leapfrog kernels
-(blackjax_b200/csrc/bjx_row.cuh ``Ctx::value_and_grad``).  This is the deliberate scope limit of the
-drop-in (SURVEY.md section 7 "logdensity boundary").
+(blackjax_b200/csrc/bjx_row.cuh ``Ctx::value_and_grad``), or a ``UserTarget``: the user's own fused
+``value_and_grad`` as CUDA source, compiled into a plug-in that holds every kernel of the path
+(include/bjx_user_target.h, blackjax_b200/plugin.py).
 """
 import numpy as np
 import torch
@@ -165,3 +166,65 @@ class HierLogit(Target):
         d.n_groups = self.n_groups
         d.logp_offset = 0.0
         return d
+
+
+class UserTarget(Target):
+    """A model of the user's own: ``source`` is CUDA text defining ``bjx_user::value_and_grad`` (contract:
+    include/bjx_user_target.h); ``params`` is the float32 parameter block the function reads as ``u.theta`` (data,
+    hyper-parameters).  This is the slot of BlackJAX's arbitrary ``logdensity_fn`` (mcmc/hmc.py:91): the gradient comes
+    from the author instead of from autodiff, everything downstream (HMC / multinomial / generalized HMC, NUTS, window
+    adaptation, ChEES, MEADS, every metric and integrator of the warp kernels) is the same code as for the built-in
+    targets.  The plug-in is compiled by nvcc on first use and cached in-tree (blackjax_b200/_plugins/)."""
+
+    kind = _lib.TARGET_USER
+
+    def __init__(self, dim, source, params=None, name="user", logp_offset=0.0, dense_metric=True,
+                 general_integrators=True):
+        from . import plugin
+        self.dim = int(dim)
+        plugin.size_class(self.dim)  # validates the row size
+        self.source = source
+        self.name = name
+        self.params = None if params is None else np.ascontiguousarray(params, np.float32).reshape(-1)
+        self.logp_offset = float(logp_offset)
+        self.build_options = dict(dense_metric=bool(dense_metric), general_integrators=bool(general_integrators))
+        self._plugin_path = None
+
+    def plugin_path(self):
+        """Build the plug-in if it is not cached yet and return its path."""
+        from . import plugin
+        if self._plugin_path is None:
+            self._plugin_path = plugin.build_plugin(self.source, self.dim, self.name, **self.build_options)
+        return self._plugin_path
+
+    def _desc(self, device):
+        from . import plugin
+        d = _lib.TargetDesc()
+        d.kind, d.dim = self.kind, self.dim
+        d.logp_offset = self.logp_offset
+        d.user_plugin = plugin.load_plugin(self.plugin_path())
+        if self.params is not None and self.params.size:
+            d.user_params = self._cached("params", self.params, device).data_ptr()
+            d.n_user_params = int(self.params.size)
+        return d
+
+
+class LinearRegression(UserTarget):
+    """The regression posterior of the reference's sampling tests (tests/mcmc/test_sampling.py:103-111
+    ``regression_logprob``; position = [log_scale, coefs_0 .. coefs_{K-1}]) as a user-defined target:
+    blackjax_b200/user_targets/linear_regression.cuh.  ``x`` is [N, K] (K <= 16), ``y`` is [N]."""
+
+    def __init__(self, x, y, **build_options):
+        from . import plugin
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(y, np.float32).reshape(-1)
+        if x.ndim == 1:
+            x = x[:, None]
+        if x.ndim != 2 or x.shape[0] != y.shape[0] or not (1 <= x.shape[1] <= 16):
+            raise ValueError("x must be [N, K] with 1 <= K <= 16 and y [N]")
+        if x.shape[0] >= 1 << 24:
+            raise ValueError("N must be below 2^24 (it travels as a float)")
+        self.x, self.y = x, y
+        theta = np.concatenate([np.asarray([x.shape[0], x.shape[1]], np.float32), x.reshape(-1), y])
+        super().__init__(1 + x.shape[1], plugin.read_example("linear_regression"), theta, name="linear_regression",
+                         **build_options)

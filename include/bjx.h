@@ -44,8 +44,10 @@ enum bjx_target_kind {
   BJX_TARGET_FUNNEL = 1,         /* Neal's funnel                       tests/fixtures.py:81-98   */
   BJX_TARGET_DENSE_GAUSSIAN = 2, /* -1/2 x^T P x + offset               tests/mcmc/test_mclmc_lrd.py:86-88 */
   BJX_TARGET_BANANA = 3,         /* -(1-x0)^2 - 1.5 (x1-x0^2)^2, dim=2  tests/mcmc/test_trajectory.py:79-80 */
-  BJX_TARGET_HIER_LOGIT = 4      /* hierarchical logistic regression (BASELINE config 5; builder-defined, see
+  BJX_TARGET_HIER_LOGIT = 4,     /* hierarchical logistic regression (BASELINE config 5; builder-defined, see
                                     DESIGN.md): x = [mu, log tau, beta0, beta1, alpha_0..alpha_{G-1}], dim = 4 + G */
+  BJX_TARGET_USER = 5            /* user-defined value_and_grad compiled into a plug-in (bjx_plugin_load; dim <= 1024):
+                                    the slot of the arbitrary `logdensity_fn` callable of hmc.py:91 / nuts.py:133 */
 };
 
 /* inverse-mass-matrix layouts (metrics.py:701-729: 1-D => diagonal, 2-D => dense) */
@@ -66,6 +68,9 @@ typedef struct {
   const float* data_x;    /* HIER_LOGIT: covariates [G, 8, 2] (device)     */
   const uint8_t* data_y;  /* HIER_LOGIT: outcomes, bit k of byte g = y_gk  */
   int32_t n_groups;       /* HIER_LOGIT: G (dim = 4 + G)                   */
+  int32_t n_user_params;  /* USER: floats in user_params                   */
+  const float* user_params; /* USER: parameter block (device) or NULL      */
+  void* user_plugin;      /* USER: plug-in from bjx_plugin_load            */
 } bjx_target_desc;
 
 typedef struct {
@@ -105,6 +110,15 @@ int bjx_create(const bjx_config* cfg, bjx_handle_t* out);
 int bjx_destroy(bjx_handle_t h);
 const char* bjx_last_error(bjx_handle_t h); /* h may be NULL: last global error */
 int bjx_set_target(bjx_handle_t h, const bjx_target_desc* target);
+/* User-defined targets.  BlackJAX takes any callable and differentiates it (`jax.value_and_grad(logdensity_fn)`,
+ * mcmc/hmc.py:91, integrators.py:189); here the plug-in point is the fused value_and_grad device function
+ * (`bjx_user::value_and_grad`, contract in include/bjx_user_target.h).  A plug-in is a small shared library built from
+ * blackjax_b200/csrc/bjx_plugin.cu + the user's source (nvcc; blackjax_b200/plugin.py does it from Python) holding every
+ * transition kernel of the path instantiated around that function.  bjx_plugin_load opens it (host path), checks that it
+ * was built against this library's kernel ABI (bjx_plugin_abi) and returns the pointer to put into
+ * bjx_target_desc.user_plugin with kind = BJX_TARGET_USER.  Plug-ins stay loaded for the life of the process. */
+int bjx_plugin_load(const char* path, void** plugin_out);
+int bjx_plugin_abi(void);
 /* Palindromic two-stage integrator (integrators.py:62-152): host array of n coefficients, n odd in 3..11.
  * {0.5, 1, 0.5} = velocity_verlet (default, :321-322); mclachlan :335-340, yoshida :351-357, omelyan :363-369. */
 int bjx_set_integrator(bjx_handle_t h, const float* coefficients, int32_t n);

@@ -10,6 +10,7 @@ integrators.py:189,204); without JAX the named models are differentiated by hand
                                     tests/adaptation/test_staged_adaptation.py:1029-1040
 * ``Banana``                        tests/mcmc/test_trajectory.py:79-80
 * ``NormLogpdf``                    tests/mcmc/test_trajectory.py:27 (jax.scipy.stats.norm.logpdf)
+* ``LinearRegression``              tests/mcmc/test_sampling.py:103-111 ``regression_logprob``
 
 Each target maps ``q: f32[C, D]`` to ``(logp: f32[C], grad: f32[C, D])``.
 """
@@ -170,4 +171,52 @@ class HierLogit:
             g[..., 2] = F(-0.16) * b0 + np.sum(r * self.x[:, :, 0], axis=(-1, -2), dtype=F)
             g[..., 3] = F(-0.16) * b1 + np.sum(r * self.x[:, :, 1], axis=(-1, -2), dtype=F)
             g[..., 4:] = -d * e2[..., None] + np.sum(r, axis=-1, dtype=F)
+        return logp.astype(F), g.astype(F)
+
+
+class LinearRegression:
+    """``regression_logprob`` of the reference's sampling tests (tests/mcmc/test_sampling.py:103-111), K coefficients:
+
+        scale = exp(log_scale)
+        logp  = expon.logpdf(scale, 0, 1) + log_scale + sum_k norm.logpdf(coefs_k, 0, 5)
+              + sum_n norm.logpdf(y_n, X_n . coefs, scale)
+
+    position = [log_scale, coefs_0 .. coefs_{K-1}].  The gradient is what ``jax.grad`` of that expression gives,
+    written out:  d/d log_scale = -scale + 1 - N + sum_n r_n^2 / scale^2,  d/d coefs_k = -coefs_k/25 + sum_n r_n X_nk / scale^2
+    (r_n = y_n - X_n . coefs).  Checked against central differences of the float64 density in tests/test_oracle_kat.py."""
+
+    kind = "linear_regression"
+
+    def __init__(self, x, y):
+        x = np.asarray(x, F)
+        self.x = x[:, None] if x.ndim == 1 else x
+        self.y = np.asarray(y, F).reshape(-1)
+        self.N, self.K = self.x.shape
+        self.dim = 1 + self.K
+
+    def logp64(self, q):
+        """The reference's expression in float64 (jax.scipy.stats formulas), for gradient checks."""
+        q = np.asarray(q, np.float64)
+        ls, c = q[..., 0], q[..., 1:]
+        scale = np.exp(ls)
+        r = self.y.astype(np.float64) - c @ self.x.astype(np.float64).T
+        prior = -scale + ls + np.sum(-c * c / 50.0 - np.log(5.0) - 0.5 * np.log(2 * np.pi), axis=-1)
+        lik = np.sum(-r * r / (2.0 * scale[..., None] ** 2) - ls[..., None] - 0.5 * np.log(2 * np.pi), axis=-1)
+        return prior + lik
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        ls, c = q[..., 0], q[..., 1:]
+        with np.errstate(over="ignore", invalid="ignore"):
+            scale = np.exp(ls).astype(F)
+            w = np.exp(F(-2.0) * ls).astype(F)
+            r = (self.y - (c @ self.x.T).astype(F)).astype(F)                    # [C, N]
+            ss = np.sum(r * r, axis=-1, dtype=F)
+            rx = (r @ self.x).astype(F)                                          # [C, K]
+            cc = np.sum(c * c, axis=-1, dtype=F)
+            k0 = F(np.log(5.0)) + F(0.5 * np.log(2 * np.pi))
+            logp = (ls - scale) - (cc / F(50.0) + F(self.K) * k0) - (F(0.5) * w * ss + F(self.N) * (ls + F(0.5 * np.log(2 * np.pi))))
+            g = np.empty_like(q)
+            g[..., 0] = (w * ss - scale) + (F(1.0) - F(self.N))
+            g[..., 1:] = w[..., None] * rx - c / F(25.0)
         return logp.astype(F), g.astype(F)

@@ -33,10 +33,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from blackjax_b200 import _lib
-    # bjx_target_desc: 2 x int32, 3 pointers, float (+pad); bjx_info: 14 pointers
-    assert C.sizeof(_lib.TargetDesc) == 64
+    # bjx_target_desc: 2 x int32, 3 pointers, float (+pad), 2 pointers, 2 x int32, 2 pointers; bjx_info: 14 pointers
+    assert C.sizeof(_lib.TargetDesc) == 80
+    assert _lib.TargetDesc.user_params.offset == 64 and _lib.TargetDesc.user_plugin.offset == 72
     assert C.sizeof(_lib.Info) == 14 * 8
-    assert C.sizeof(_lib.Config) == 16 + 8 + 8 + 64
+    assert C.sizeof(_lib.Config) == 16 + 8 + 8 + 80
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -253,3 +254,61 @@ def test_dense_gaussian_rejects_an_asymmetric_precision():
     with pytest.raises(ValueError, match="symmetric"):
         T.DenseGaussian(P)
     T.DenseGaussian(0.5 * (P + P.T))
+
+
+# ---- user-defined target plug-ins (include/bjx_user_target.h): host-side machinery, no compute ---------------------
+def test_plugin_builds_exports_and_loads():
+    from blackjax_b200 import _lib, plugin
+    path = plugin.build_plugin(plugin.read_example("diag_gaussian"), 18, "diag_gaussian", dense_metric=False,
+                               general_integrators=False)
+    assert path.startswith(plugin.PLUGIN_DIR) and os.path.exists(path)
+    so = C.CDLL(path)
+    assert so.bjx_plugin_built_for_abi() == _lib.lib().bjx_plugin_abi()
+    assert hasattr(so, "bjx_plugin_launch")
+    p = plugin.load_plugin(path)
+    assert p and plugin.load_plugin(path) == p            # cached per path
+    # same source, another row size class or other options: another build
+    other, _ = plugin.plugin_path(plugin.read_example("diag_gaussian"), 100, "diag_gaussian", False, False)
+    assert other != path
+    same, _ = plugin.plugin_path(plugin.read_example("diag_gaussian"), 21, "diag_gaussian", False, False)
+    assert same == path                                    # 18 and 21 dims share the scalar <= 32 size class
+
+
+def test_plugin_load_rejects_foreign_libraries_and_missing_files():
+    from blackjax_b200 import _lib
+    out = C.c_void_p()
+    assert _lib.lib().bjx_plugin_load(b"/nonexistent/libbjxt.so", C.byref(out)) == -1
+    assert b"bjx_plugin_load" in _lib.lib().bjx_last_error(None)
+    assert _lib.lib().bjx_plugin_load(_lib.LIB_PATH.encode(), C.byref(out)) == -1     # libbjx itself is not a plug-in
+    assert b"not a bjx target plug-in" in _lib.lib().bjx_last_error(None)
+
+
+def test_plugin_compile_error_is_reported_with_the_compiler_output():
+    from blackjax_b200 import BjxError, plugin
+    bad = "namespace bjx_user { this is not CUDA }"
+    with pytest.raises(BjxError, match="nvcc failed"):
+        plugin.build_plugin(bad, 8, "broken", dense_metric=False, general_integrators=False)
+    path, _ = plugin.plugin_path(bad, 8, "broken", False, False)
+    assert not os.path.exists(path)
+
+
+def test_plugin_size_classes_mirror_the_launcher():
+    from blackjax_b200 import plugin
+    assert [plugin.size_class(d) for d in (4, 128, 132, 256, 260, 512, 516, 1024, 1, 31, 33, 127)] == \
+        [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5]
+    for d in (0, 130, 1028, 2048):
+        with pytest.raises(ValueError):
+            plugin.size_class(d)
+
+
+def test_user_target_descriptor_without_gpu():
+    # building the descriptor loads the plug-in and needs the parameter block on a device: without a GPU the
+    # constructor and the build still work, and the linear regression packs [N, K, X, y]
+    from blackjax_b200 import targets
+    x = np.arange(12, dtype=np.float32).reshape(4, 3)
+    y = np.ones(4, np.float32)
+    t = targets.LinearRegression(x, y, dense_metric=False, general_integrators=False)
+    assert t.dim == 4 and t.params.shape == (2 + 12 + 4,) and t.params[0] == 4 and t.params[1] == 3
+    assert os.path.exists(t.plugin_path())
+    with pytest.raises(ValueError):
+        targets.LinearRegression(np.zeros((4, 17), np.float32), y)

@@ -495,3 +495,26 @@ def test_meads_oracle_properties_of_the_reference_tests():
     np.testing.assert_array_equal(trace[2][0].position[2 * n:3 * n], trace[1][0].position[2 * n:3 * n])
     assert not np.array_equal(trace[0][0].position[n:], q[n:])
     assert trace[2][1].step_size.shape == (K,) and (trace[2][1].step_size > 0).all()
+
+
+def test_linear_regression_oracle_gradient_matches_float64_differences():
+    """oracle/targets.py LinearRegression (tests/mcmc/test_sampling.py:103-111 regression_logprob): the hand-derived
+    float32 value_and_grad against the float64 restatement of the reference's expression and its central differences."""
+    from oracle import targets as otargets
+    rs = np.random.default_rng(3)
+    x = rs.standard_normal((300, 4)).astype(np.float32)
+    y = (x @ np.array([3.0, -1.0, 0.5, 2.0]) + rs.standard_normal(300)).astype(np.float32)
+    t = otargets.LinearRegression(x, y)
+    q = np.concatenate([0.3 * rs.standard_normal((9, 1)), np.array([3.0, -1.0, 0.5, 2.0]) + 0.2 * rs.standard_normal((9, 4))],
+                       axis=1).astype(np.float32)
+    lp, g = t(q)
+    np.testing.assert_allclose(lp, t.logp64(q), rtol=2e-6)
+    h = 1e-5
+    for i in range(5):
+        e = np.zeros(5)
+        e[i] = h
+        fd = (t.logp64(q.astype(np.float64) + e) - t.logp64(q.astype(np.float64) - e)) / (2 * h)
+        np.testing.assert_allclose(g[:, i], fd, rtol=1e-4, atol=1e-3)
+    # the reference's own call shape: x [N, 1], scalar coefficient
+    t1 = otargets.LinearRegression(x[:, :1], y)
+    assert t1.dim == 2 and t1(np.array([[0.0, 4.0]], np.float32))[1].shape == (1, 2)
