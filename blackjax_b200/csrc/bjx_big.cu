@@ -62,8 +62,11 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[NV*kBigW
   }
 }
 
-// value_and_grad of the target at the row q (shared memory) -> g (shared memory), returns logp (all threads)
-template <int TK>
+// value_and_grad of the target at the row q (shared memory) -> g (shared memory), returns logp (all threads).
+// WANT_LOGP = false: only the gradient is consumed (interior steps of a fixed-length trajectory, where the value is
+// dead -- as in the warp kernels); the hierarchical logistic model then skips the softplus (one MUFU of three and a
+// quarter of the instructions per observation).
+template <int TK, bool WANT_LOGP = true>
 __device__ __forceinline__ float big_value_and_grad(const BigParams& P, const float* q, float* g, float* red) {
   const int D = P.D, tid = threadIdx.x;
   if constexpr (TK == BJX_TARGET_DIAG_GAUSSIAN) {
@@ -74,6 +77,7 @@ __device__ __forceinline__ float big_value_and_grad(const BigParams& P, const fl
       acc[0] = fmaf(d, t, acc[0]);
       g[i] = t;
     }
+    if constexpr (!WANT_LOGP) return 0.f;
     block_sum<1>(acc, red);
     return 0.5f * acc[0] + P.logp_offset;
   } else if constexpr (TK == BJX_TARGET_FUNNEL) {
@@ -117,14 +121,17 @@ __device__ __forceinline__ float big_value_and_grad(const BigParams& P, const fl
           // division + log1pf + int-to-float conversions cost 70; __expf / __frcp_rn / (float)bit still 41, of which a
           // dozen guard subnormal ranges these arguments never reach).  Error bounds, checked against float64 in
           // tests/test_gpu_round2.py: |sigmoid error| <= 4e-7 (ex2 2 ulp, rcp 1 ulp), |softplus error| <= 3e-7 absolute.
-          float ex, rc, l2;
+          float ex, rc;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fabsf(eta) * -1.4426950408889634f));
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));   // 1 + ex in [1, 2]
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(rc));          // rc in [1/2, 1]
           const float sig = (eta >= 0.f) ? rc : ex * rc;
-          const float softplus = fmaf(-0.69314718f, l2, fmaxf(eta, 0.f));
           const float r = (yb ? 1.0f : 0.0f) - sig;
-          acc[0] += (yb ? eta : 0.0f) - softplus;
+          if constexpr (WANT_LOGP) {
+            float l2;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(rc));        // rc in [1/2, 1]
+            const float softplus = fmaf(-0.69314718f, l2, fmaxf(eta, 0.f));
+            acc[0] += (yb ? eta : 0.0f) - softplus;
+          }
           ga += r;
           acc[3] = fmaf(r, xs[u][0], acc[3]);
           acc[4] = fmaf(r, xs[u][1], acc[4]);
@@ -163,17 +170,33 @@ __device__ __forceinline__ float big_kinetic(const BigParams& P, const float* im
   return 0.5f * acc[0];
 }
 
+// n velocity-Verlet steps (integrators.py:104-150) on the row in shared memory; returns the log-density after the last
+// one.  Between two steps the closing half kick of one and the opening half kick of the next run in the same pass over
+// the row (two separately rounded FMAs, bit-identical to the step-by-step form), so an interior step is one pass +
+// one gradient evaluation (gradient only: its log-density is dead) instead of two passes.
 template <int TK>
-__device__ __forceinline__ float big_leapfrog(const BigParams& P, const float* imm, float* q, float* p, float* g,
-                                              float eps, float* red) {
+__device__ __forceinline__ float big_trajectory(const BigParams& P, const float* imm, float* q, float* p, float* g,
+                                                float eps, int n, float* red) {
   const float eh = eps * 0.5f, e1 = eps * 1.0f;
+  if (n <= 0) return 0.f;
   for (int i = threadIdx.x; i < P.D; i += kBigThreads) {
     const float pn = fmaf(eh, g[i], p[i]);
     p[i] = pn;
     q[i] = fmaf(e1, __ldg(imm + i) * pn, q[i]);
   }
   __syncthreads();
-  const float logp = big_value_and_grad<TK>(P, q, g, red);
+  for (int s = 0; s + 1 < n; ++s) {
+    big_value_and_grad<TK, false>(P, q, g, red);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.D; i += kBigThreads) {
+      float pn = fmaf(eh, g[i], p[i]);   // second half kick of step s
+      pn = fmaf(eh, g[i], pn);           // first half kick of step s + 1
+      p[i] = pn;
+      q[i] = fmaf(e1, __ldg(imm + i) * pn, q[i]);
+    }
+    __syncthreads();
+  }
+  const float logp = big_value_and_grad<TK, true>(P, q, g, red);
   __syncthreads();
   for (int i = threadIdx.x; i < P.D; i += kBigThreads) p[i] = fmaf(eh, g[i], p[i]);
   __syncthreads();
@@ -238,8 +261,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_leapfrog(BigParams P, float
   __syncthreads();
   const float* imm = P.imm + (size_t)c * P.imm_stride;
   const float eps = P.eps_dev ? P.eps_dev[c] : P.eps;
-  float logp = 0.f;
-  for (int s = 0; s < n_steps; ++s) logp = big_leapfrog<TK>(P, imm, q, p, g, eps, red);
+  const float logp = big_trajectory<TK>(P, imm, q, p, g, eps, n_steps, red);
   big_store(q_io + ro, q, P.D);
   big_store(p_io + ro, p, P.D);
   big_store(g_io + ro, g, P.D);
@@ -270,8 +292,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_hmc(BigParams P, const uint
   const float logp0 = logp_in[c];
   const float e0 = -logp0 + big_kinetic(P, imm, p, red);  // hmc.py:159
   const float eps = P.eps_dev ? P.eps_dev[c] : P.eps;
-  float logp = logp0;
-  for (int s = 0; s < L; ++s) logp = big_leapfrog<TK>(P, imm, q, p, g, eps, red);  // trajectory.py:165
+  const float logp = L > 0 ? big_trajectory<TK>(P, imm, q, p, g, eps, L, red) : logp0;  // trajectory.py:165
   const float e1 = -logp + big_kinetic(P, imm, p, red);  // hmc.py:160 (kinetic energy is even in p: the flip is implicit)
   float delta = e0 - e1;
   if (isnan(delta)) delta = -__int_as_float(0x7f800000);  // proposal.py:45-48
