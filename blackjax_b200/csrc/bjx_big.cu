@@ -336,6 +336,10 @@ __global__ void __launch_bounds__(kBigThreads) k_big_hmc(BigParams P, const uint
 // intercepts are thread-private -- p lives in registers, q and grad in shared memory (2 x 2 x 40 KB) that only the owner
 // touches, and no barrier orders the row passes.  Only the four hyper-parameters (elements 0..3) are shared: one barrier
 // after the position update, and the block reduction of the 5 + 5 sums.
+// Measured at 32768 x 10000, L = 20 (scripts/bench_c5.py): one chain per CTA 65.0 ms; this kernel with 768 threads (80
+// registers) 55.2 ms, 640 threads 48.0 ms, 512 threads (128 registers: nothing spills) 41.8 ms, 384 threads 49.2 ms; with
+// the next group's covariates prefetched into a second register set 47.8 ms (512 threads) -- two chains already put 16
+// independent observations behind every load, the extra registers cost more than the prefetch hides.
 template <int T>
 __device__ __forceinline__ void block_sum2(float (&v)[10], float* red /*[10 * T/32]*/) {
   constexpr int W = T / 32;
