@@ -78,8 +78,9 @@ class Engine:
 
     # -- metric ---------------------------------------------------------------------------------
     def set_metric(self, inverse_mass_matrix):
-        """1-D => diagonal, 2-D [D,D] => dense, 2-D [C,D] with per_chain => per-chain diagonal
-        (blackjax/mcmc/metrics.py:701-729 semantics incl. the ValueError)."""
+        """1-D => diagonal, 2-D [D,D] => dense, 2-D [C,D] => per-chain diagonal, 3-D [C,D,D] => per-chain dense
+        (blackjax/mcmc/metrics.py:701-729 semantics incl. the ValueError; the per-chain layouts are what jax.vmap
+        over chains gives the reference)."""
         imm = inverse_mass_matrix
         from .mcmc.metrics import LowRankMetric
         if isinstance(imm, LowRankMetric):  # metrics.gaussian_euclidean_low_rank (metrics.py:349-467)
@@ -100,6 +101,8 @@ class Engine:
             kind = _lib.METRIC_DENSE
         elif imm.ndim == 2 and tuple(imm.shape) == (self.C, self.D):
             kind = _lib.METRIC_DIAG_PER_CHAIN
+        elif imm.ndim == 3 and tuple(imm.shape) == (self.C, self.D, self.D):
+            kind = _lib.METRIC_DENSE_PER_CHAIN   # one dense matrix per chain (vmapped dense adaptation), dim <= 64
         else:
             raise ValueError(
                 "The mass matrix has the wrong number of dimensions:"

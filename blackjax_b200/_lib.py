@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbjx.so")
 
 TARGET_DIAG_GAUSSIAN, TARGET_FUNNEL, TARGET_DENSE_GAUSSIAN, TARGET_BANANA, TARGET_HIER_LOGIT, TARGET_USER = 0, 1, 2, 3, 4, 5
-METRIC_DIAG, METRIC_DENSE, METRIC_DIAG_PER_CHAIN = 0, 1, 2
+METRIC_DIAG, METRIC_DENSE, METRIC_DIAG_PER_CHAIN, METRIC_LOW_RANK, METRIC_DENSE_PER_CHAIN = 0, 1, 2, 3, 4
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -85,6 +85,8 @@ _SIGNATURES = {
     "bjx_da_final": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "bjx_welford_update": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int32]),
     "bjx_welford_final": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p]),
+    "bjx_welford_dense_update": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int32]),
+    "bjx_welford_dense_final": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p]),
     "bjx_pooled_stats": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_pooled_stats_dense": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p]),
     "bjx_nccl_unique_id": (C.c_int, [C.c_void_p]),

@@ -131,9 +131,6 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
     ``blackjax_b200.nuts``; ``extra_parameters`` go to the kernel (``num_integration_steps`` /
     ``max_num_doublings``).  Returns an :class:`AdaptationAlgorithm` with ``run(rng_key, position, num_steps)``."""
     dense = not is_mass_matrix_diagonal
-    if dense and not shared:
-        raise NotImplementedError("dense (welford_dense) adaptation is built for the chain-pooled mode: pass shared=True "
-                                  "(a per-chain dense metric would need [C, D, D] mass matrices in the kernels)")
     def run(rng_key, position, num_steps: int = 1000, _leapfrog_counter=None):
         from .._engine import get_engine
         position = position.contiguous()
@@ -234,20 +231,29 @@ def window_adaptation(algorithm, logdensity_fn, is_mass_matrix_diagonal: bool = 
         da_state = torch.empty(C, 5, dtype=torch.float32, device=dev)
         eps = torch.full((C,), float(initial_step_size), dtype=torch.float32, device=dev)
         check(lib().bjx_da_init(eng.h, ptr(da_state), ptr(eps), ptr(eps)), eng.h)
-        imm = torch.ones(C, D, dtype=torch.float32, device=dev)
+        if dense:  # one dense matrix per chain (what jax.vmap(warmup.run) carries with is_mass_matrix_diagonal=False)
+            if D > 64:
+                raise NotImplementedError("per-chain dense adaptation is built for dim <= 64 ([C, D, D] metrics); use "
+                                          "shared=True (pooled dense metric, any dim) beyond")
+            imm = torch.eye(D, dtype=torch.float32, device=dev).repeat(C, 1, 1).contiguous()
+            w_m2 = torch.zeros(C, D, D, dtype=torch.float32, device=dev)
+            wf_update, wf_final = lib().bjx_welford_dense_update, lib().bjx_welford_dense_final
+        else:
+            imm = torch.ones(C, D, dtype=torch.float32, device=dev)
+            w_m2 = torch.zeros(C, D, dtype=torch.float32, device=dev)
+            wf_update, wf_final = lib().bjx_welford_update, lib().bjx_welford_final
         w_mean = torch.zeros(C, D, dtype=torch.float32, device=dev)
-        w_m2 = torch.zeros(C, D, dtype=torch.float32, device=dev)
         w_n = 0
         for t, (stage, window_end) in enumerate(schedule):
             state, info = mcmc_kernel(keys[t], state, logdensity_fn, eps, imm, **extra_parameters)
             if stage == 1:
                 w_n += 1
-                check(lib().bjx_welford_update(eng.h, ptr(state.position), ptr(w_mean), ptr(w_m2), w_n), eng.h)
+                check(wf_update(eng.h, ptr(state.position), ptr(w_mean), ptr(w_m2), w_n), eng.h)
             check(lib().bjx_da_update(eng.h, ptr(da_state), ptr(info.acceptance_rate), float(target_acceptance_rate),
                                       ptr(eps)), eng.h)
             if window_end:
                 new_imm = torch.empty_like(imm)
-                check(lib().bjx_welford_final(eng.h, ptr(w_mean), ptr(w_m2), w_n, ptr(new_imm)), eng.h)
+                check(wf_final(eng.h, ptr(w_mean), ptr(w_m2), w_n, ptr(new_imm)), eng.h)
                 imm = new_imm   # new tensor identity => the kernel re-derives mass_matrix_sqrt
                 w_n = 0
                 check(lib().bjx_da_reset(eng.h, ptr(da_state), ptr(eps)), eng.h)

@@ -276,7 +276,10 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
   size_t elems;
   if (kind == BJX_METRIC_DIAG) elems = D;
   else if (kind == BJX_METRIC_DIAG_PER_CHAIN) elems = (size_t)C * D;
-  else if (kind == BJX_METRIC_DENSE) {
+  else if (kind == BJX_METRIC_DENSE_PER_CHAIN) {
+    if (D > 64) return fail(h, BJX_E_UNSUPPORTED, "per-chain dense metrics are built for dim <= 64");
+    elems = (size_t)C * D * D;
+  } else if (kind == BJX_METRIC_DENSE) {
     if (D > 128 && D % 4 != 0)
       return fail(h, BJX_E_UNSUPPORTED, "dense metric with dim > 128 needs dim % 4 == 0 (tensor-core GEMM path)");
     elems = (size_t)D * D;
@@ -316,13 +319,16 @@ extern "C" int bjx_set_metric(bjx_handle_t h, int32_t kind, const float* imm) {
       for (int j = 0; j < D; ++j) m[(size_t)i * D + j] = (float)Li[(size_t)j * D + i];  // (L^-1)^T
     BJX_CUDA(cudaMemcpyAsync(h->msqrt, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     BJX_CUDA(cudaStreamSynchronize(h->stream));
+  } else if (kind == BJX_METRIC_DENSE_PER_CHAIN) {
+    launch_chol_linv_t(C, D, imm, h->msqrt, h->stream);  // L^-T per chain on the device (float64)
+    BJX_CHECK_LAUNCH("k_chol_linv_t");
   } else {
     launch_diag_mass_sqrt(imm, (long long)elems, h->msqrt, h->stream);
     BJX_CHECK_LAUNCH("k_diag_mass_sqrt");
   }
   h->dense_version++;
   h->metric_kind = kind;
-  h->metric_small_dense = (kind == BJX_METRIC_DENSE) && D <= 128;
+  h->metric_small_dense = ((kind == BJX_METRIC_DENSE) && D <= 128) || kind == BJX_METRIC_DENSE_PER_CHAIN;
   h->imm = imm;
   return 0;
 }
@@ -383,7 +389,8 @@ static Params make_params(bjx_handle_t h, float eps, const float* eps_dev) {
   P.user = h->cfg.target.user_params;
   P.n_user = h->cfg.target.n_user_params;
   P.imm = h->imm;
-  P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim : 0;
+  P.imm_stride = (h->metric_kind == BJX_METRIC_DIAG_PER_CHAIN) ? h->cfg.dim
+                 : (h->metric_kind == BJX_METRIC_DENSE_PER_CHAIN) ? (long long)h->cfg.dim * h->cfg.dim : 0;
   P.imm_group = 1;
   P.msqrt = h->msqrt;
   P.lr_k = (h->metric_kind == BJX_METRIC_LOW_RANK) ? h->lr_k : 0;
@@ -1062,6 +1069,20 @@ extern "C" int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t
   BJX_CUDA(cudaSetDevice(h->cfg.device));
   launch_welford_final((long long)h->cfg.n_chains * h->cfg.dim, mean, m2, count, imm_out, h->stream);
   BJX_CHECK_LAUNCH("k_welford_final");
+  return 0;
+}
+extern "C" int bjx_welford_dense_update(bjx_handle_t h, const float* q, float* mean, float* m2, int32_t new_count) {
+  if (!h || !q || !mean || !m2 || new_count < 1) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_welford_dense_update(h->cfg.n_chains, h->cfg.dim, q, mean, m2, new_count, h->stream);
+  BJX_CHECK_LAUNCH("k_welford_dense_m2");
+  return 0;
+}
+extern "C" int bjx_welford_dense_final(bjx_handle_t h, float* mean, float* m2, int32_t count, float* imm_out) {
+  if (!h || !mean || !m2 || !imm_out || count < 2) return fail(h, BJX_E_INVALID, "bad argument");
+  BJX_CUDA(cudaSetDevice(h->cfg.device));
+  launch_welford_dense_final(h->cfg.n_chains, h->cfg.dim, mean, m2, count, imm_out, h->stream);
+  BJX_CHECK_LAUNCH("k_welford_dense_final");
   return 0;
 }
 extern "C" int bjx_pooled_stats(bjx_handle_t h, const float* q, const float* acc, float* out) {

@@ -11,6 +11,9 @@ void launch_diag_mass_sqrt(const float* imm, long long n, float* out, cudaStream
 void launch_da(int op, int C, float* st, const float* in, float target, float* eps_out, cudaStream_t s);
 void launch_welford_update(long long n, const float* x, float* mean, float* m2, int count, cudaStream_t s);
 void launch_welford_final(long long n, float* mean, float* m2, int count, float* imm, cudaStream_t s);
+void launch_welford_dense_update(int C, int D, const float* x, float* mean, float* m2, int count, cudaStream_t s);
+void launch_welford_dense_final(int C, int D, float* mean, float* m2, int count, float* imm, cudaStream_t s);
+void launch_chol_linv_t(int C, int D, const float* imm, float* msqrt, cudaStream_t s);
 void launch_pooled_stats(int C, int D, const float* x, const float* acc, float* out, cudaStream_t s);
 void launch_pooled_stats_dense(int C, int D, const float* x, const float* acc, float* out, float* scratch, cudaStream_t s);
 size_t pooled_dense_scratch_floats(int D);

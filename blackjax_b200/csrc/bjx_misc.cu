@@ -165,6 +165,98 @@ void launch_welford_final(long long n, float* mean, float* m2, int count, float*
   if (n > 0) k_welford_final<<<grid1d(n), 256, 0, s>>>(n, mean, m2, (float)count, imm);
 }
 
+// ---- Welford, dense, one accumulator per chain (adaptation/mass_matrix.py:411-442 with is_diagonal_matrix=False: what
+// jax.vmap(window_adaptation(..., is_mass_matrix_diagonal=False).run) carries per chain) ----------------------------------
+// m2[c,i,j] += (x_i - mean_new_i) * (x_j - mean_old_j)   (jnp.outer(updated_delta, delta), :427-433); the mean is
+// updated by a second launch so that every element of the outer product sees the OLD mean.
+__global__ void k_welford_dense_m2(int C, int D, const float* __restrict__ x, const float* __restrict__ mean,
+                                   float* __restrict__ m2, float count) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)C * D * D) return;
+  const int j = (int)(t % D), i = (int)((t / D) % D);
+  const long long c = t / ((long long)D * D);
+  const float xi = x[c * D + i], mi = mean[c * D + i], xj = x[c * D + j], mj = mean[c * D + j];
+  const float di = xi - mi;
+  const float ui = xi - (mi + di / count);
+  m2[t] = m2[t] + ui * (xj - mj);
+}
+__global__ void k_welford_mean(long long n, const float* __restrict__ x, float* __restrict__ mean, float count) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float m = mean[t];
+  mean[t] = m + (x[t] - m) / count;
+}
+// regularised dense inverse mass matrix (mass_matrix.py:335-357: the shrinkage target is 1e-3 * identity) and reset
+__global__ void k_welford_dense_final(int C, int D, float* __restrict__ mean, float* __restrict__ m2, float count,
+                                      float* __restrict__ imm) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)C * D * D) return;
+  const int j = (int)(t % D), i = (int)((t / D) % D);
+  const float cov = m2[t] / (count - 1.f);
+  const float denom = count + 5.f;
+  imm[t] = count / denom * cov + ((i == j) ? 5.f / denom * 1e-3f : 0.f);
+  m2[t] = 0.f;
+  if (j == 0) mean[(t / ((long long)D * D)) * D + i] = 0.f;
+}
+void launch_welford_dense_update(int C, int D, const float* x, float* mean, float* m2, int count, cudaStream_t s) {
+  const long long n = (long long)C * D * D;
+  if (n <= 0) return;
+  k_welford_dense_m2<<<grid1d(n), 256, 0, s>>>(C, D, x, mean, m2, (float)count);
+  k_welford_mean<<<grid1d((long long)C * D), 256, 0, s>>>((long long)C * D, x, mean, (float)count);
+}
+void launch_welford_dense_final(int C, int D, float* mean, float* m2, int count, float* imm, cudaStream_t s) {
+  const long long n = (long long)C * D * D;
+  if (n > 0) k_welford_dense_final<<<grid1d(n), 256, 0, s>>>(C, D, mean, m2, (float)count, imm);
+}
+
+// mass_matrix_sqrt of one dense inverse mass matrix PER CHAIN (metrics.py:712-715: L = chol(M^-1) lower,
+// mass_matrix_sqrt = solve_triangular(L, I, lower, trans) = L^-T), float64 like the shared dense metric's host
+// factorisation.  One CTA per chain, D <= 64: L (strict lower triangle) and L^-1 (stored transposed in the strict upper
+// triangle) share one D x D shared-memory matrix, the two diagonals sit beside it.  A matrix that is not positive
+// definite yields NaNs (as jnp.linalg.cholesky does).
+__global__ void __launch_bounds__(64) k_chol_linv_t(int D, const float* __restrict__ imm, float* __restrict__ msqrt) {
+  extern __shared__ double chol_sm[];
+  double* S = chol_sm;            // [D, D]
+  double* dL = chol_sm + D * D;   // diag(L)
+  double* dI = dL + D;            // diag(L^-1)
+  const int t = threadIdx.x;
+  const float* A = imm + (size_t)blockIdx.x * D * D;
+  float* out = msqrt + (size_t)blockIdx.x * D * D;
+  for (int j = 0; j < D; ++j) {   // column j of L (Cholesky-Crout): thread t owns row t
+    if (t == j) {
+      double s = (double)A[(size_t)j * D + j];
+      for (int k = 0; k < j; ++k) s -= S[j * D + k] * S[j * D + k];
+      dL[j] = sqrt(s);
+    }
+    __syncthreads();
+    if (t > j && t < D) {
+      double s = (double)A[(size_t)t * D + j];
+      for (int k = 0; k < j; ++k) s -= S[t * D + k] * S[j * D + k];
+      S[t * D + j] = s / dL[j];
+    }
+    __syncthreads();
+  }
+  if (t < D) {                    // column t of L^-1 by forward substitution (thread-private column, stored at S[t][i])
+    dI[t] = 1.0 / dL[t];
+    for (int i = t + 1; i < D; ++i) {
+      double s = -S[i * D + t] * dI[t];
+      for (int k = t + 1; k < i; ++k) s -= S[i * D + k] * S[t * D + k];
+      S[t * D + i] = s / dL[i];
+    }
+  }
+  __syncthreads();
+  // msqrt = (L^-1)^T: msqrt[i][j] = Linv[j][i] = (j > i ? S[i][j] : j == i ? dI[i] : 0)
+  for (int e = t; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    out[e] = (float)(j > i ? S[i * D + j] : (j == i ? dI[i] : 0.0));
+  }
+}
+void launch_chol_linv_t(int C, int D, const float* imm, float* msqrt, cudaStream_t s) {
+  if (C <= 0) return;
+  const size_t smem = ((size_t)D * D + 2 * D) * sizeof(double);
+  k_chol_linv_t<<<C, 64, smem, s>>>(D, imm, msqrt);
+}
+
 // ---- chain-pooled summary block (metric_buffers.py:396-420 cgl_update_batch statistics) -------------------
 // out[0] = sum acceptance_rate, out[1] = C, out[2:2+D] = mean over chains, out[2+D:2+2D] = sum (x-mean)^2.
 // Column reductions over the chain axis: block (32 x 8) owns 32 columns, threads stride over chains

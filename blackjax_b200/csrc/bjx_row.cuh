@@ -39,7 +39,7 @@ struct Params {
   int n_user;
   // metric
   const float* imm;        // diag: [D] or [C,D]; dense: [D,D]
-  long long imm_stride;    // 0 (shared) or D (one row per group of imm_group chains)
+  long long imm_stride;    // 0 (shared), D (one row per group of imm_group chains) or D*D (one dense matrix per chain)
   int imm_group;           // chains sharing a metric row (1: per chain; MEADS folds: chains per fold)
   const float* msqrt;      // mass_matrix_sqrt, same layout as imm
   // low-rank metric (metrics.py:349-467): M^-1 = diag(sigma) (I + U (Lambda - I) U^T) diag(sigma); lr_k == 0: not in use
@@ -371,6 +371,7 @@ struct Ctx {
   float tw[(TK == TK_DIAG) ? R::NS : 1];  // target -1/s^2 (negated once: grad = q * tw, exactly -(q/s^2))
   float mw[DM ? 1 : R::NS];               // diagonal inverse mass
   float* sm;                              // shared-memory slice (small dense paths)
+  size_t moff;                            // small dense metric: offset of this chain's matrix (0 when shared)
   int lane;
 
   __device__ __forceinline__ void init(const Params& P, int chain, int lane_, float* sm_) {
@@ -381,7 +382,9 @@ struct Ctx {
 #pragma unroll
       for (int s = 0; s < R::NS; ++s) tw[s] = -tw[s];
     }
+    moff = 0;
     if constexpr (!DM) R::load_const(mw, P.imm + (size_t)(chain / P.imm_group) * P.imm_stride, P.D, lane);
+    else moff = (size_t)(chain / P.imm_group) * P.imm_stride;  // D*D per chain for per-chain dense metrics
   }
 
   // linear_map(M^-1, p)   blackjax/util.py:57-61
@@ -394,7 +397,7 @@ struct Ctx {
         lowrank_apply<R>(P.lr_U, P.lr_lam_m1, P.lr_k, qv, v, P.D, lane);
         Vec<R::NS>::mul(v, sg, v);
       } else if constexpr (R::NS <= 4) {  // small dense metrics exist for dim <= 128 only
-        matvec_small<R>(P.imm, p, v, sm, P.D, lane);
+        matvec_small<R>(P.imm + moff, p, v, sm, P.D, lane);
       }
     } else {
       Vec<R::NS>::mul(v, mw, p);
@@ -539,7 +542,7 @@ struct Ctx {
         R::load_const(is, P.lr_inv_sigma, P.D, lane);
         Vec<R::NS>::mul(p, is, p);
       } else if constexpr (R::NS <= 4) {
-        matvec_small<R>(P.msqrt, z, p, sm, P.D, lane);
+        matvec_small<R>(P.msqrt + moff, z, p, sm, P.D, lane);
       }
     } else {
       float ms[R::NS];

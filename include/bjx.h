@@ -55,7 +55,8 @@ enum bjx_metric_kind {
   BJX_METRIC_DIAG = 0,          /* imm [dim]                                    */
   BJX_METRIC_DENSE = 1,         /* imm [dim, dim] symmetric positive definite   */
   BJX_METRIC_DIAG_PER_CHAIN = 2, /* imm [n_chains, dim] (vmapped window adaptation) */
-  BJX_METRIC_LOW_RANK = 3        /* bjx_set_metric_low_rank */
+  BJX_METRIC_LOW_RANK = 3,       /* bjx_set_metric_low_rank */
+  BJX_METRIC_DENSE_PER_CHAIN = 4 /* imm [n_chains, dim, dim], dim <= 64 (vmapped dense window adaptation) */
 };
 
 typedef struct {
@@ -266,6 +267,11 @@ int bjx_da_final(bjx_handle_t h, const float* da_state, float* step_size_out);
 int bjx_welford_update(bjx_handle_t h, const float* q, float* mean, float* m2, int32_t new_count);
 /* regularised IMM (mass_matrix.py:335-357): imm = n/(n+5) m2/(n-1) + 1e-3*5/(n+5); resets mean,m2 */
 int bjx_welford_final(bjx_handle_t h, float* mean, float* m2, int32_t count, float* imm_out);
+/* Per-chain dense Welford (mass_matrix.py:411-442 with is_diagonal_matrix=False): mean [C,D], m2 [C,D,D];
+ * m2 += outer(x - mean_new, x - mean_old) */
+int bjx_welford_dense_update(bjx_handle_t h, const float* q, float* mean, float* m2, int32_t new_count);
+/* regularised dense IMM per chain (mass_matrix.py:335-357): imm = n/(n+5) m2/(n-1) + 1e-3*5/(n+5) I; resets mean,m2 */
+int bjx_welford_dense_final(bjx_handle_t h, float* mean, float* m2, int32_t count, float* imm_out);
 /* Chain-pooled summary block of THIS GPU's chains for the shared-epsilon warm-up
  * (staged_adaptation.py:153-171,906-966; metric_buffers.py:396-420):
  * stats_out float32 [2 + 2*D] = (sum acceptance_rate, n_chains, mean[D], M2[D]).

@@ -179,8 +179,11 @@ def window_adaptation_run(kernel, target, rng_key, position, num_steps, *, is_ma
     for t, (stage, window_end) in enumerate(schedule):
         if diag:
             state, info = kernel(keys[:, t], state, target, eps, _PerChainDiag(imm), **kernel_kwargs)
-        else:
-            raise NotImplementedError("per-chain dense adaptation: run chains one at a time")
+        else:  # one dense metric per chain: the batched kernel takes ONE metric, so the chains go through it one by one
+            parts = [kernel(keys[c:c + 1, t], type(state)(*(a[c:c + 1] for a in state)), target, eps[c], imm[c],
+                            **kernel_kwargs) for c in range(C)]
+            state = type(state)(*(np.concatenate([p[0][k] for p in parts]) for k in range(len(state))))
+            info = _Acc(np.concatenate([p[1].acceptance_rate for p in parts]))
         for c in range(C):
             if stage == 1:
                 wfs[c] = welford_update(wfs[c], state.position[c])
@@ -194,6 +197,10 @@ def window_adaptation_run(kernel, target, rng_key, position, num_steps, *, is_ma
         hist.append(eps.copy())
     final_eps = np.array([da_final(d) for d in das], F)
     return state, final_eps, imm, np.array(hist, F)
+
+
+class _Acc(NamedTuple):
+    acceptance_rate: np.ndarray
 
 
 from .hmc import Metric as _Metric  # noqa: E402

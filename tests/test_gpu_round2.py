@@ -632,3 +632,125 @@ def test_dense_path_nuts_matches_oracle(metric, target, D, C, depth, eps):
     close_elementwise(npy(info.acceptance_rate)[ok], oinfo.acceptance_rate[ok], 2e-3, 1e-2)
     close_elementwise(npy(info.energy)[ok], oinfo.energy[ok], 1e-4, 1.0)
     close_elementwise(npy(new.logdensity)[ok], onew.logdensity[ok], 2e-4, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# per-chain dense metrics and per-chain dense Welford (what jax.vmap(window_adaptation(..., is_mass_matrix_diagonal=False)
+# .run) carries: mass_matrix.py:411-442 outer-product update, metrics.py:712-715 factorisation per chain)
+# ---------------------------------------------------------------------------------------------------------------------
+from test_gpu_parity import close  # noqa: E402
+
+
+def _spd_stack(rs, C, D, scale=1.0):
+    A = rs.standard_normal((C, D, D))
+    return (scale * (A @ A.transpose(0, 2, 1) / D + np.eye(D))).astype(F)
+
+
+@pytest.mark.parametrize("kind, D", [("diag", 6), ("funnel", 20), ("diag", 64), ("banana", 2)])
+def test_per_chain_dense_metric_matches_oracle(kind, D):
+    from test_gpu_parity import make_target
+    rs = np.random.default_rng(31 + D)
+    tgt, otgt = make_target(kind, D, rs)
+    C = 12
+    imm = _spd_stack(rs, C, D)
+    q = (0.4 * rs.standard_normal((C, D))).astype(F)
+    keys = oprng.split(oprng.key(5), C)
+    eng = _engine.Engine(DEV, C, D, tgt)
+    eng.set_metric(tf(imm))
+    # momentum draw p = L_c^-T z and velocity / energy with every chain's own matrix
+    p_dev = npy(eng.sample_momentum(tk(keys)))
+    p_ref = np.concatenate([ohmc.Metric(imm[c]).sample_momentum(keys[c:c + 1], D) for c in range(C)])
+    close(p_dev, p_ref, rtol=1e-5)
+    lp, _ = otgt(q)
+    e_dev = npy(eng.energy(tf(p_ref), tf(lp)))
+    e_ref = np.concatenate([-lp[c:c + 1] + ohmc.Metric(imm[c]).kinetic_energy(p_ref[c:c + 1]) for c in range(C)])
+    close(e_dev, e_ref, rtol=1e-5, scale=np.max(np.abs(e_ref)) + 1)
+    # HMC and NUTS transitions, teacher-forced, chain by chain through the oracle
+    st = bj.hmc.init(tf(q), tgt)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), st, tgt, 0.1, tf(imm), 6)
+    nnew, ninfo = bj.nuts.build_kernel(full_info=True)(tk(keys), st, tgt, 0.15, tf(imm), 6)
+    torch.cuda.synchronize()
+    for c in range(C):
+        ost = ohmc.init(q[c:c + 1], otgt)
+        onew, oinfo = ohmc.hmc_kernel(keys[c:c + 1], ost, otgt, F(0.1), imm[c], 6)
+        close(npy(info.proposal.position)[c:c + 1], oinfo.proposal[0], rtol=2e-5)
+        close(npy(info.energy)[c:c + 1], oinfo.energy, rtol=1e-5, scale=np.abs(oinfo.energy).max() + 1)
+        if bool(npy(info.is_accepted)[c]) == bool(oinfo.is_accepted[0]):
+            close(npy(new.position)[c:c + 1], onew.position, rtol=2e-5)
+        o2, oi2 = onuts.nuts_kernel(keys[c:c + 1], ost, otgt, F(0.15), imm[c], 6)
+        if int(npy(ninfo.num_integration_steps)[c]) == int(oi2.num_integration_steps[0]):
+            assert np.allclose(npy(nnew.position)[c:c + 1], o2.position, rtol=1e-4, atol=1e-5) or \
+                abs(float(npy(ninfo.acceptance_rate)[c]) - float(oi2.acceptance_rate[0])) < 1e-4
+    n_same = sum(int(npy(ninfo.num_integration_steps)[c]) ==
+                 int(onuts.nuts_kernel(keys[c:c + 1], ohmc.init(q[c:c + 1], otgt), otgt, F(0.15), imm[c], 6)[1]
+                     .num_integration_steps[0]) for c in range(C))
+    assert n_same >= C - 1
+    with pytest.raises(bj.BjxError, match="dim <= 64"):
+        e2 = _engine.Engine(DEV, 3, 100, T.StdNormal(100))
+        e2.set_metric(torch.eye(100, device=DEV).repeat(3, 1, 1).contiguous())
+
+
+def test_per_chain_dense_factorisation_non_pd_stays_in_its_chain():
+    # L^-T per chain on the device (float64): a matrix that is not positive definite gives NaN momenta for ITS chain only
+    # (jnp.linalg.cholesky semantics); the other chains match the oracle's factorisation
+    C, D = 9, 48
+    rs = np.random.default_rng(2)
+    imm = _spd_stack(rs, C, D, scale=3.0)
+    imm[4] = -imm[4]
+    eng = _engine.Engine(DEV, C, D, T.StdNormal(D))
+    eng.set_metric(tf(imm))
+    keys = oprng.split(oprng.key(1), C)
+    p = npy(eng.sample_momentum(tk(keys)))
+    assert np.isnan(p[4]).any()
+    for c in range(C):
+        if c != 4:
+            close(p[c:c + 1], ohmc.Metric(imm[c]).sample_momentum(keys[c:c + 1], D), rtol=1e-5)
+
+
+def test_welford_dense_per_chain_kernels():
+    from blackjax_b200._lib import check, lib, ptr
+    C, D = 7, 10
+    rs = np.random.default_rng(8)
+    eng = _engine.Engine(DEV, C, D, T.StdNormal(D))
+    mean = torch.zeros(C, D, device=DEV)
+    m2 = torch.zeros(C, D, D, device=DEV)
+    ws = [oadapt.welford_init(D, diagonal=False) for _ in range(C)]
+    for n in range(1, 12):
+        x = (rs.standard_normal((C, D)) * np.linspace(0.5, 3, D) + 1.0).astype(F)
+        dx = tf(x)
+        check(lib().bjx_welford_dense_update(eng.h, ptr(dx), ptr(mean), ptr(m2), n), eng.h)
+        ws = [oadapt.welford_update(w, xi) for w, xi in zip(ws, x)]
+    close(npy(mean), np.stack([w.mean for w in ws]), rtol=1e-5)
+    close(npy(m2), np.stack([w.m2 for w in ws]), rtol=1e-5, scale=np.max([np.abs(w.m2).max() for w in ws]))
+    imm = torch.empty(C, D, D, device=DEV)
+    check(lib().bjx_welford_dense_final(eng.h, ptr(mean), ptr(m2), 11, ptr(imm)), eng.h)
+    ref = np.stack([oadapt.welford_final(w) for w in ws])
+    close(npy(imm), ref, rtol=1e-5, scale=np.abs(ref).max())
+    assert float(mean.abs().max()) == 0.0 and float(m2.abs().max()) == 0.0
+
+
+def test_window_adaptation_per_chain_dense_recovers_each_chains_covariance():
+    """window_adaptation(nuts, target, is_mass_matrix_diagonal=False) with per-chain state (shared=False): every chain
+    ends with its own dense inverse mass matrix [C, D, D] and step size; on a correlated Gaussian the matrices must
+    approach the target covariance (Stan's regularisation and ~200 draws leave ~25 % element noise) and the adapted sampler
+    must run with them."""
+    D, C = 4, 64
+    rs = np.random.default_rng(0)
+    A = rs.standard_normal((D, D))
+    cov = A @ A.T / D + 0.5 * np.eye(D)
+    tgt = T.DenseGaussian(np.linalg.inv(cov))
+    q0 = tf(rs.standard_normal((C, D)))
+    warmup = bj.window_adaptation(bj.nuts, tgt, is_mass_matrix_diagonal=False)
+    (state, params), _ = warmup.run(bj.random.key(3, DEV), q0, 400)
+    imm = npy(params["inverse_mass_matrix"])
+    assert imm.shape == (C, D, D) and npy(params["step_size"]).shape == (C,)
+    assert np.all(np.isfinite(imm))
+    mean_imm = imm.mean(0)
+    assert np.max(np.abs(mean_imm - cov)) < 0.12 * np.max(np.abs(cov))       # averaged over chains: close to Sigma
+    assert np.all(np.linalg.eigvalsh(imm.astype(np.float64)) > 0)            # every chain's matrix is SPD
+    alg = bj.nuts(tgt, **params)
+    st, acc = state, []
+    for k in bj.random.split(bj.random.key(4, DEV), 30):
+        st, info = alg.step(k, st)
+        acc.append(float(info.acceptance_rate.mean()))
+    assert 0.6 < np.mean(acc) < 0.98
