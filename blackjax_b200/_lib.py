@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bjx_plugin_abi": (C.c_int, []),
     "bjx_set_integrator": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "bjx_set_key_mode": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
+    "bjx_set_ghmc_noise": (C.c_int, [C.c_void_p, _f32p]),
     "bjx_set_integration_steps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bjx_synchronize": (C.c_int, [C.c_void_p]),
     "bjx_set_metric": (C.c_int, [C.c_void_p, C.c_int32, _f32p]),

@@ -184,6 +184,7 @@ extern "C" int bjx_create(const bjx_config* cfg, bjx_handle_t* out) {
   h->general_integrator = false;
   h->key_shared = 0;
   h->steps_dev = nullptr;
+  h->ghmc_noise = nullptr;
   h->chain_offset = 0;
   h->sample_keys = nullptr;
   h->sample_keys_cap = 0;
@@ -259,6 +260,14 @@ extern "C" int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_
 extern "C" int bjx_set_integration_steps(bjx_handle_t h, const int32_t* steps_dev) {
   if (!h) return fail(h, BJX_E_INVALID, "null handle");
   h->steps_dev = steps_dev;
+  return 0;
+}
+
+// Generalized HMC's slice noise (blackjax/mcmc/ghmc.py:90,172 `noise_fn(key_noise)`): per-chain values float32 [C]
+// (device) added to the slice translation of the following bjx_ghmc_step calls; NULL restores the default (0).
+extern "C" int bjx_set_ghmc_noise(bjx_handle_t h, const float* noise_dev) {
+  if (!h) return fail(h, BJX_E_INVALID, "null handle");
+  h->ghmc_noise = noise_dev;
   return 0;
 }
 
@@ -622,6 +631,7 @@ extern "C" int bjx_ghmc_step(bjx_handle_t h, const uint32_t* keys, float* q, flo
   a.ghmc.delta = delta; a.ghmc.delta_dev = delta_dev;
   a.ghmc.param_group = chains_per_group;
   a.ghmc.skip_begin = skip_begin; a.ghmc.skip_end = skip_end;
+  a.ghmc.noise_dev = h->ghmc_noise;
   a.info = make_info(info);
   return dispatch(h, K_GHMC, true, a);
 }

@@ -45,6 +45,7 @@ struct bjx_handle_s {
   bool general_integrator;
   int key_shared;          // see bjx_set_key_mode
   const int32_t* steps_dev;  // see bjx_set_integration_steps
+  const float* ghmc_noise;   // see bjx_set_ghmc_noise
   uint32_t chain_offset;
   uint32_t* sample_keys;   // [num_steps, 2] step keys of bjx_hmc_sample
   size_t sample_keys_cap;

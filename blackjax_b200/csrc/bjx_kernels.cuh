@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kThreads) k_hmc_transition(Params P, const uin
 // ---- generalized HMC (ghmc.py:118-189): persistent momentum, ONE leapfrog, non-reversible slice acceptance ------------
 // In place on (q, p, logp, g, slice).  alpha / delta: per chain when the pointers are set.  Chains in [skip_begin,
 // skip_end) draw and integrate like every other chain but keep their state (MEADS' frozen fold,
-// meads_adaptation.py:639-650).  noise_fn is the reference default (identically 0).
+// meads_adaptation.py:639-650).  noise_dev: the values noise_fn(key_noise) of ghmc.py:172 per chain, evaluated by the caller
+// (key_noise = split(rng_key)[1]); nullptr = the reference default (identically 0).
 struct GhmcArgs {
   float* p_io;
   float* slice_io;
@@ -180,6 +181,7 @@ struct GhmcArgs {
   const float* delta_dev;
   int param_group;  // step_size_dev / alpha_dev / delta_dev are indexed by chain / param_group (MEADS: one entry per fold)
   int skip_begin, skip_end;
+  const float* noise_dev;
 };
 
 template <class R, int TK, bool DM, bool GEN>
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) k_ghmc_transition(Params P, const ui
   R::load(p, A.p_io + roff, P.D, lane);
   c.init(P, chain, lane, sm);
   const Key rng = chain_key(P, keys, chain);
-  const Key key_momentum = fold_in(rng, 0u);  // ghmc.py:169 (key_noise = fold_in(rng, 1) feeds noise_fn == 0)
+  const Key key_momentum = fold_in(rng, 0u);  // ghmc.py:169 (key_noise = fold_in(rng, 1): see noise_dev)
   const int gi = chain / A.param_group;
   const float alpha = A.alpha_dev ? A.alpha_dev[gi] : A.alpha;
   const float delta_s = A.delta_dev ? A.delta_dev[gi] : A.delta;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_ghmc_transition(Params P, const ui
   if (info.momentum) R::store(p, info.momentum + roff, P.D, lane);
   float sl = A.slice_io[chain];
   {  // ((slice + 1 + delta + noise) % 2) - 1   ghmc.py:172; jnp.remainder = fmod + sign fix-up
-    const float x = ((sl + 1.0f) + delta_s) + 0.0f;
+    const float x = ((sl + 1.0f) + delta_s) + (A.noise_dev ? A.noise_dev[chain] : 0.0f);
     float r = fmodf(x, 2.0f);
     if (r != 0.0f && r < 0.0f) r += 2.0f;
     sl = r - 1.0f;

@@ -4,7 +4,7 @@ Persistent momentum (partial refresh with weight ``alpha``), ONE velocity-Verlet
 non-reversible slice acceptance (translation ``delta``): one fused kernel launch per transition (``bjx_ghmc_step``).
 Batched like :mod:`blackjax_b200.mcmc.hmc`: ``position`` is ``[n_chains, dim]``, ``rng_key`` one raw key or one per chain.
 ``momentum_inverse_scale`` in its 1-D form is an inverse SCALE, squared into the inverse mass matrix (ghmc.py:64-84);
-a 2-D array or a ``LowRankMetric`` is an inverse mass matrix as in ``hmc``.  ``noise_fn`` must be the default (0).
+a 2-D array or a ``LowRankMetric`` is an inverse mass matrix as in ``hmc``.  ``noise_fn`` maps the per-chain noise keys to per-chain values (see ``build_kernel``).
 """
 import ctypes as C
 from typing import NamedTuple
@@ -68,9 +68,9 @@ def _param(v, eng, name):
 
 def build_kernel(noise_fn=None, divergence_threshold: float = 1000, integrator=velocity_verlet, full_info: bool = False,
                  inplace: bool = False, chain_offset: int = 0):
-    """blackjax/mcmc/ghmc.py:87-189."""
-    if noise_fn is not None:
-        raise NotImplementedError("generalized HMC is built for the default noise_fn (identically 0)")
+    """blackjax/mcmc/ghmc.py:87-189.  ``noise_fn`` (ghmc.py:90,172): a callable mapping the per-chain noise keys
+    ``key_noise = split(rng_key)[1]`` (uint32 [C, 2] on the device) to the per-chain noise values float32 [C] added to the
+    slice translation, e.g. ``lambda k: 0.1 * blackjax.random.normal(k)``; None = the reference default (0)."""
     coefficients = integrators.as_coefficients(integrator)
 
     def kernel(rng_key, state, logdensity_fn, step_size, momentum_inverse_scale, alpha, delta, *, _rows=None):
@@ -92,6 +92,17 @@ def build_kernel(noise_fn=None, divergence_threshold: float = 1000, integrator=v
             fields.update(momentum=torch.empty_like(q), proposal_position=torch.empty_like(q),
                           proposal_momentum=torch.empty_like(q))
         info = eng._info(fields)
+        noise = None
+        if noise_fn is not None:
+            # the chain keys of this transition (given, or split(step_key, C_global)[offset + c]), then ghmc.py:169
+            chain_keys = keys
+            if keys.ndim == 1:
+                chain_keys = bjx_random.split(keys, Cn + int(chain_offset))[int(chain_offset):int(chain_offset) + Cn]
+            noise = noise_fn(bjx_random.split(chain_keys.contiguous(), 2).view(torch.int32)[:, 1].contiguous()
+                             .view(torch.uint32))
+            noise = torch.as_tensor(noise, dtype=torch.float32, device=dev).expand(Cn).contiguous()
+        check(lib().bjx_set_ghmc_noise(eng.h, ptr(noise)), eng.h)
+        eng._ghmc_noise_keepalive = noise   # the launch is asynchronous
         if _rows is not None:   # MEADS: per-fold device parameters (step_size, alpha, delta: [K]; imm, msqrt: [K, D])
             eps_d, a_d, d_d, imm_rows, msqrt_rows, group, skip = _rows
             check(lib().bjx_ghmc_step(eng.h, ptr(keys), ptr(q), ptr(p), ptr(logp), ptr(g), ptr(sl), 0.0, ptr(eps_d), 0.0,

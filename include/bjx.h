@@ -133,6 +133,9 @@ int bjx_set_key_mode(bjx_handle_t h, int32_t shared_step_key, uint32_t chain_off
  * [n_chains] device array read by the following bjx_hmc_step / bjx_mhmc_step calls (their scalar L is then ignored);
  * NULL restores the scalar.  The caller keeps the array alive until those calls have run.  dim <= 1024 only. */
 int bjx_set_integration_steps(bjx_handle_t h, const int32_t* steps_dev);
+/* Generalized HMC slice noise (mcmc/ghmc.py:90,172 `noise_fn(key_noise)`, key_noise = split(rng_key)[1]): per-chain values
+ * float32 [C] (device) for the following bjx_ghmc_step calls, evaluated by the caller; NULL = the default noise_fn (0). */
+int bjx_set_ghmc_noise(bjx_handle_t h, const float* noise_dev);
 int bjx_synchronize(bjx_handle_t h);
 
 /* metrics.default_metric / gaussian_euclidean (metrics.py:180-218,221-346): precomputes

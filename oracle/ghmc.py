@@ -10,7 +10,7 @@ Follows
 * blackjax/mcmc/ghmc.py:192-213   update_momentum
 * blackjax/mcmc/proposal.py:243-264 nonreversible_slice_sampling
 * blackjax/mcmc/hmc.py:153-176    the proposal generator (energies, divergence, HMCInfo)
-Only the default ``noise_fn`` (identically 0) is restated.
+``noise_fn`` (ghmc.py:90,172): a callable on the per-chain noise keys ``split(rng_key)[1]`` returning float32 [C]; default 0.
 """
 from typing import NamedTuple
 
@@ -55,7 +55,7 @@ def _remainder2(x):
 
 
 def ghmc_kernel(keys, state, target, step_size, momentum_inverse_scale, alpha, delta, divergence_threshold=1000.0,
-                margins=None):
+                margins=None, noise_fn=None):
     """One GHMC transition for every chain.  step_size, alpha, delta: scalars or [C]; momentum_inverse_scale: [D], [C, D]
     (inverse scale, squared here) or a ready ``Metric``.  ``margins`` (test aid, a list): receives |log|slice| - delta_energy|
     per chain, the distance of the accept decision from a tie."""
@@ -69,10 +69,11 @@ def ghmc_kernel(keys, state, target, step_size, momentum_inverse_scale, alpha, d
     alpha = np.broadcast_to(np.asarray(alpha, F), (C,))
     delta = np.broadcast_to(np.asarray(delta, F), (C,))
     eps = np.broadcast_to(np.asarray(step_size, F), (C,))[:, None]
-    ks = prng.split(keys, 2)                                         # ghmc.py:169 (key_noise unused: noise_fn == 0)
+    ks = prng.split(keys, 2)                                         # ghmc.py:169: key_momentum, key_noise
+    noise = F(0.0) if noise_fn is None else np.asarray(noise_fn(ks[:, 1]), F)
     fresh = metric.sample_momentum(ks[:, 0], D)
     p0 = (p_prev * np.sqrt(F(1.0) - alpha)[:, None] + np.sqrt(alpha)[:, None] * fresh).astype(F)   # ghmc.py:205-211
-    sl = (_remainder2(((sl + F(1.0)) + delta) + F(0.0)) - F(1.0)).astype(F)                       # ghmc.py:172
+    sl = (_remainder2(((sl + F(1.0)) + delta) + noise) - F(1.0)).astype(F)                        # ghmc.py:172
     q1, p1, logp1, g1 = integrator_step(target, metric, q0, p0, g0, eps)
     p1 = (F(-1.0) * p1).astype(F)                                    # hmc.py:158
     e0 = (-logp0 + metric.kinetic_energy(p0)).astype(F)

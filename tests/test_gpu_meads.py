@@ -89,6 +89,33 @@ def test_ghmc_transitions_match_oracle(kind, D, C):
     assert ok.mean() > 0.97
 
 
+def test_ghmc_noise_fn_matches_oracle():
+    """ghmc.py:90,172: ``noise_fn(key_noise)`` added to the slice translation; key_noise = split(rng_key)[1] per chain.
+    Per-chain keys and a shared step key (per-chain keys derived from the global chain index) give the same draws."""
+    D, C = 12, 256
+    tgt, otgt = _targets("diag", D)
+    rng = np.random.default_rng(5)
+    q0 = (rng.standard_normal((C, D)) * 0.7).astype(F)
+    key0 = oprng.split(oprng.key(21), C)
+    ost = oghmc.init(q0, otgt, key0)
+    st = bj.ghmc.init(tf(q0), tgt, tk(key0))
+    kernel = bj.ghmc.build_kernel(noise_fn=lambda k: 0.4 * bj.random.normal(k) + 0.05)
+    onoise = lambda k: (F(0.4) * oprng.normal(k) + F(0.05)).astype(F)
+    scale = np.ones(D, F)
+    sk = oprng.key(22)
+    keys = oprng.split(sk, C)
+    onew, oinfo = oghmc.ghmc_kernel(keys, ost, otgt, F(0.1), scale, F(0.5), F(0.3), noise_fn=onoise)
+    for k_dev in (tk(keys), tk(sk)):      # explicit per-chain keys | one step key
+        new, info = kernel(k_dev, st, tgt, 0.1, tf(scale), 0.5, 0.3)
+        same = npy(info.is_accepted) == oinfo.is_accepted
+        assert same.mean() > 0.98
+        close(npy(new.slice)[same], onew.slice[same], 2e-4, 1e-2)
+        close(npy(new.position)[same], onew.position[same], 1e-4, 1e-2)
+    # and the noise does change the chain: without it the slice variables differ
+    plain, _ = bj.ghmc.build_kernel()(tk(keys), st, tgt, 0.1, tf(scale), 0.5, 0.3)
+    assert float((plain.slice - new.slice).abs().max()) > 0.1
+
+
 def test_ghmc_skipped_chains_keep_their_state():
     D, C = 16, 256
     tgt, _ = _targets("diag", D)
