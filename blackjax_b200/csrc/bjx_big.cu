@@ -250,24 +250,64 @@ __global__ void __launch_bounds__(kBigThreads) k_big_energy(BigParams P, const f
   if (threadIdx.x == 0) e[c] = -logp[c] + 0.5f * acc[0];
 }
 
-template <int TK>
-__global__ void __launch_bounds__(kBigThreads) k_big_leapfrog(BigParams P, float* q_io, float* p_io, float* logp_io,
-                                                              float* g_io, int n_steps) {
+// n leapfrog steps per launch (bjx_leapfrog; n = 1 is the one-step kernel the HBM roofline is quoted on).  Thread t owns
+// elements t + 768 k of the row, so the momentum is thread-private and stays in REGISTERS (NK per thread); only q and grad,
+// which the target's value_and_grad addresses freely, live in shared memory: 2 x 4 D bytes instead of 3 x 4 D, and for
+// rows up to 10752 dims two CTAs fit an SM, so one CTA's loads and stores overlap the other's arithmetic (with three rows
+// and one CTA per SM the phases load -> compute -> store ran back to back: 0.45 of the HBM peak at 32768 x 10000).
+template <int TK, int NK>
+__global__ void __launch_bounds__(kBigThreads, (NK <= 14 && TK != BJX_TARGET_HIER_LOGIT) ? 2 : 1)
+    k_big_leapfrog(BigParams P, float* q_io, float* p_io, float* logp_io, float* g_io, int n_steps) {
   extern __shared__ __align__(16) float sm[];
-  float *q = sm, *p = sm + P.D, *g = sm + 2 * (size_t)P.D, *red = sm + 3 * (size_t)P.D;
-  const int c = blockIdx.x;
-  const size_t ro = (size_t)c * P.D;
-  big_load(q, q_io + ro, P.D);
-  big_load(p, p_io + ro, P.D);
-  big_load(g, g_io + ro, P.D);
-  __syncthreads();
+  float *q = sm, *g = sm + P.D, *red = sm + 2 * (size_t)P.D;
+  const int c = blockIdx.x, D = P.D, tid = threadIdx.x;
+  const size_t ro = (size_t)c * D;
   const float* imm = P.imm + (size_t)c * P.imm_stride;
   const float eps = P.eps_dev ? P.eps_dev[c] : P.eps;
-  const float logp = big_trajectory<TK>(P, imm, q, p, g, eps, n_steps, red);
-  big_store(q_io + ro, q, P.D);
-  big_store(p_io + ro, p, P.D);
-  big_store(g_io + ro, g, P.D);
-  if (threadIdx.x == 0 && n_steps > 0) logp_io[c] = logp;
+  const float eh = eps * 0.5f, e1 = eps * 1.0f;
+  float p[NK];
+  if (n_steps <= 0) return;
+  // load + first half kick + position update in one pass (integrators.py:199-203,235-245)
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int i = tid + kBigThreads * k;
+    p[k] = 0.f;
+    if (i < D) {
+      const float pn = fmaf(eh, __ldcs(g_io + ro + i), __ldcs(p_io + ro + i));
+      p[k] = pn;
+      q[i] = fmaf(e1, __ldg(imm + i) * pn, __ldcs(q_io + ro + i));
+    }
+  }
+  __syncthreads();
+  for (int s = 0; s + 1 < n_steps; ++s) {
+    big_value_and_grad<TK, false>(P, q, g, red);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int i = tid + kBigThreads * k;
+      if (i < D) {
+        const float gv = g[i];
+        float pn = fmaf(eh, gv, p[k]);   // second half kick of step s
+        pn = fmaf(eh, gv, pn);           // first half kick of step s + 1
+        p[k] = pn;
+        q[i] = fmaf(e1, __ldg(imm + i) * pn, q[i]);
+      }
+    }
+    __syncthreads();
+  }
+  const float logp = big_value_and_grad<TK, true>(P, q, g, red);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int i = tid + kBigThreads * k;
+    if (i < D) {
+      const float gv = g[i];
+      __stcs(p_io + ro + i, fmaf(eh, gv, p[k]));
+      __stcs(g_io + ro + i, gv);
+      __stcs(q_io + ro + i, q[i]);
+    }
+  }
+  if (tid == 0) logp_io[c] = logp;
 }
 
 // whole HMC transition (hmc.py:279-312) with the row resident in shared memory
@@ -654,10 +694,28 @@ int bjx_big_energy(bjx_handle_t h, const float* p, const float* logp, float* e_o
   BG_LAUNCH("k_big_energy");
   return 0;
 }
+template <int TK>
+static int big_leapfrog_launch(bjx_handle_t h, const BigParams& P, float* q, float* p, float* logp, float* g, int n) {
+  const size_t smem = (2 * (size_t)h->cfg.dim + 5 * kBigWarps) * sizeof(float);
+  int rc;
+  if (h->cfg.dim <= 14 * kBigThreads) {
+    if ((rc = big_smem(h, k_big_leapfrog<TK, 14>, smem))) return rc;
+    k_big_leapfrog<TK, 14><<<h->cfg.n_chains, kBigThreads, smem, h->stream>>>(P, q, p, logp, g, n);
+  } else {
+    if ((rc = big_smem(h, k_big_leapfrog<TK, 24>, smem))) return rc;
+    k_big_leapfrog<TK, 24><<<h->cfg.n_chains, kBigThreads, smem, h->stream>>>(P, q, p, logp, g, n);
+  }
+  BG_LAUNCH("k_big_leapfrog");
+  return 0;
+}
 int bjx_big_leapfrog(bjx_handle_t h, float* q, float* p, float* logp, float* g, float eps, const float* eps_dev, int n) {
   BigParams P = big_params(h, eps, eps_dev);
-  BIG_DISPATCH(k_big_leapfrog, 3, P, q, p, logp, g, n);
-  return 0;
+  switch (h->cfg.target.kind) {
+    case BJX_TARGET_DIAG_GAUSSIAN: return big_leapfrog_launch<BJX_TARGET_DIAG_GAUSSIAN>(h, P, q, p, logp, g, n);
+    case BJX_TARGET_FUNNEL: return big_leapfrog_launch<BJX_TARGET_FUNNEL>(h, P, q, p, logp, g, n);
+    case BJX_TARGET_HIER_LOGIT: return big_leapfrog_launch<BJX_TARGET_HIER_LOGIT>(h, P, q, p, logp, g, n);
+    default: return bjx_fail(h, BJX_E_UNSUPPORTED, "target not built for dim > 1024");
+  }
 }
 int bjx_big_hmc_step(bjx_handle_t h, const uint32_t* keys, const float* q_in, const float* logp_in, const float* g_in,
                      float* q_out, float* logp_out, float* g_out, float eps, const float* eps_dev, int L,

@@ -6,13 +6,13 @@
 //        blackjax_b200/csrc/bjx_plugin.cu -o libbjxt_my_target.so
 //
 // It holds every transition kernel of the path (init, leapfrog, HMC, multinomial HMC, generalized HMC, NUTS doubling,
-// the decoupled NUTS sampler) instantiated around the user's bjx_user::value_and_grad, exactly as bjx_inst_*.cu does
+// the decoupled NUTS sampler) instantiated around the user's bjx_user::Model, exactly as bjx_inst_*.cu does
 // for the built-in targets, and exports the two symbols bjx_plugin_load resolves.
 #define BJX_INSTANTIATE_TK 4  // bjx::TK_USER
 #include "bjx_row.cuh"
 
 #ifndef BJX_USER_SOURCE
-#error "define BJX_USER_SOURCE to the file that defines bjx_user::value_and_grad (see include/bjx_user_target.h)"
+#error "define BJX_USER_SOURCE to the file that defines bjx_user::Model (see include/bjx_user_target.h)"
 #endif
 #include BJX_USER_SOURCE
 

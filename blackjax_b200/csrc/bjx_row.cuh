@@ -101,7 +101,7 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, f
 
 // ---- user-defined targets (TK_USER; include/bjx_user_target.h) -----------------------------------------------------
 // BlackJAX differentiates any `logdensity_fn` with jax.value_and_grad (mcmc/hmc.py:91, integrators.py:189).  Without a
-// tracing compiler the plug-in point is the fused value_and_grad itself: the user writes ONE device function against the
+// tracing compiler the plug-in point is the fused value_and_grad itself: the user writes ONE small device struct against the
 // row layout above; bjx_plugin.cu instantiates every transition kernel of the path around it (nvcc, one small .so per
 // target) and libbjx dispatches to it like to a built-in target.
 struct UserCtx {
@@ -113,12 +113,18 @@ struct UserCtx {
 };
 }  // namespace bjx
 namespace bjx_user {
-// value_and_grad of the user's log-density for the row held by one warp: q[s] / g[s] are the slots of this lane
-// (element index R::idx(s, lane)); logp must come back identical on all lanes when WANT_LOGP (otherwise it is dead and
-// the reduction may be skipped).  Defined by the plug-in's source, never by libbjx itself.
-template <class R, bool WANT_LOGP>
-__device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS], float (&g)[R::NS],
-                                               float& logp);
+// The user's model, defined by the plug-in's source (never by libbjx itself):
+//   template <class R> struct Model {
+//     /* per-kernel state in registers, e.g. float w[R::NS]; */
+//     __device__ __forceinline__ void init(const bjx::UserCtx& u);            // once per kernel launch and chain row
+//     template <bool WANT_LOGP>
+//     __device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS], float (&g)[R::NS],
+//                                                    float& logp) const;
+//   };
+// value_and_grad: q[s] / g[s] are the slots of this lane (element index R::idx(s, lane)); logp must come back identical on
+// all lanes when WANT_LOGP (otherwise it is dead and the reduction may be skipped).
+template <class R>
+struct Model;
 }  // namespace bjx_user
 namespace bjx {
 
@@ -365,9 +371,16 @@ __device__ __forceinline__ void lowrank_apply(const float* __restrict__ U, const
   }
 }
 
+struct NoUserModel {};
+template <class R, int TK>
+struct UserModelOf { using type = NoUserModel; };
+template <class R>
+struct UserModelOf<R, TK_USER> { using type = bjx_user::Model<R>; };
+
 // Per-warp constant context: target scales and inverse mass held in registers for the whole kernel.
 template <class R, int TK, bool DM>
 struct Ctx {
+  typename UserModelOf<R, TK>::type um;   // TK_USER: the user's model (its per-kernel state lives here)
   float tw[(TK == TK_DIAG) ? R::NS : 1];  // target -1/s^2 (negated once: grad = q * tw, exactly -(q/s^2))
   float mw[DM ? 1 : R::NS];               // diagonal inverse mass
   float* sm;                              // shared-memory slice (small dense paths)
@@ -382,6 +395,7 @@ struct Ctx {
 #pragma unroll
       for (int s = 0; s < R::NS; ++s) tw[s] = -tw[s];
     }
+    if constexpr (TK == TK_USER) um.init(UserCtx{P.user, P.n_user, P.D, lane, sm});
     moff = 0;
     if constexpr (!DM) R::load_const(mw, P.imm + (size_t)(chain / P.imm_group) * P.imm_stride, P.D, lane);
     else moff = (size_t)(chain / P.imm_group) * P.imm_stride;  // D*D per chain for per-chain dense metrics
@@ -465,7 +479,7 @@ struct Ctx {
     } else if constexpr (TK == TK_USER) {
       const UserCtx u{P.user, P.n_user, P.D, lane, sm};
       float lp = 0.f;
-      bjx_user::value_and_grad<R, WANT_LOGP>(u, q, g, lp);
+      um.template value_and_grad<WANT_LOGP>(u, q, g, lp);
       if (WANT_LOGP) logp = lp + P.logp_offset;
       __syncwarp();  // the scratch slice is shared with the small dense metric's matvec
     } else {  // TK_BANANA, D == 2, scalar layout: x0 at lane 0, x1 at lane 1

@@ -69,7 +69,7 @@ def plugin_path(source, dim, name="user", dense_metric=True, general_integrators
 
 
 def build_plugin(source, dim, name="user", dense_metric=True, general_integrators=True, verbose=False):
-    """Compile (once) the plug-in for ``source`` -- CUDA text defining ``bjx_user::value_and_grad`` -- at this row size.
+    """Compile (once) the plug-in for ``source`` -- CUDA text defining ``bjx_user::Model`` -- at this row size.
 
     ``dense_metric`` / ``general_integrators``: also build the small-dense / low-rank metric variants and the
     mclachlan / yoshida / omelyan integrator variants (each doubles the compile time: about 8 s without both, 30 s with

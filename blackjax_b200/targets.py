@@ -169,7 +169,7 @@ class HierLogit(Target):
 
 
 class UserTarget(Target):
-    """A model of the user's own: ``source`` is CUDA text defining ``bjx_user::value_and_grad`` (contract:
+    """A model of the user's own: ``source`` is CUDA text defining the device struct ``bjx_user::Model`` (contract:
     include/bjx_user_target.h); ``params`` is the float32 parameter block the function reads as ``u.theta`` (data,
     hyper-parameters).  This is the slot of BlackJAX's arbitrary ``logdensity_fn`` (mcmc/hmc.py:91): the gradient comes
     from the author instead of from autodiff, everything downstream (HMC / multinomial / generalized HMC, NUTS, window

@@ -17,9 +17,13 @@
 namespace bjx_user {
 constexpr int kMaxCoefs = 16;
 
-template <class R, bool WANT_LOGP>
-__device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS], float (&g)[R::NS],
-                                               float& logp) {
+template <class R>
+struct Model {
+  __device__ __forceinline__ void init(const bjx::UserCtx&) {}  // nothing to keep between calls: the data is read per call
+
+  template <bool WANT_LOGP>
+  __device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS], float (&g)[R::NS],
+                                                 float& logp) const {
   const int N = (int)__ldg(u.theta), K = u.D - 1;
   const float* __restrict__ X = u.theta + 2;
   const float* __restrict__ y = X + (size_t)N * K;
@@ -70,5 +74,6 @@ __device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const floa
     logp = (ls - scale) - (cc / 50.0f + (float)K * (kLog5 + kHalfLog2Pi)) -
            (0.5f * w * ss + (float)N * (ls + kHalfLog2Pi));
   }
-}
+  }
+};
 }  // namespace bjx_user

@@ -113,7 +113,7 @@ const char* bjx_last_error(bjx_handle_t h); /* h may be NULL: last global error 
 int bjx_set_target(bjx_handle_t h, const bjx_target_desc* target);
 /* User-defined targets.  BlackJAX takes any callable and differentiates it (`jax.value_and_grad(logdensity_fn)`,
  * mcmc/hmc.py:91, integrators.py:189); here the plug-in point is the fused value_and_grad device function
- * (`bjx_user::value_and_grad`, contract in include/bjx_user_target.h).  A plug-in is a small shared library built from
+ * (`bjx_user::Model<R>::value_and_grad`, contract in include/bjx_user_target.h).  A plug-in is a small shared library built from
  * blackjax_b200/csrc/bjx_plugin.cu + the user's source (nvcc; blackjax_b200/plugin.py does it from Python) holding every
  * transition kernel of the path instantiated around that function.  bjx_plugin_load opens it (host path), checks that it
  * was built against this library's kernel ABI (bjx_plugin_abi) and returns the pointer to put into

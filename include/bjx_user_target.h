@@ -3,8 +3,8 @@
  *
  * BlackJAX accepts any JAX callable as `logdensity_fn` and obtains its gradient with
  * `jax.value_and_grad(logdensity_fn)` (blackjax/mcmc/hmc.py:91, nuts.py:133, integrators.py:189,204).  There is no
- * tracing compiler on this side of the boundary, so the plug-in point is the fused value_and_grad itself: ONE CUDA
- * device function, written against the row layout of the kernels, compiled by nvcc together with
+ * tracing compiler on this side of the boundary, so the plug-in point is the fused value_and_grad itself: ONE small CUDA
+ * device struct, written against the row layout of the kernels, compiled by nvcc together with
  * blackjax_b200/csrc/bjx_plugin.cu into a small shared library that holds every transition kernel of the path
  * (HMC, multinomial / generalized HMC, NUTS, the leapfrog and init kernels) instantiated around it.  The warm-up schemes,
  * samplers, metrics (diagonal, per-chain diagonal, dense and low-rank up to their row limits) and integrators then work with
@@ -14,9 +14,14 @@
  * blackjax_b200/csrc/bjx_row.cuh which the plug-in translation unit includes first):
  *
  *   namespace bjx_user {
- *   template <class R, bool WANT_LOGP>
- *   __device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u,
- *                                                  const float (&q)[R::NS], float (&g)[R::NS], float& logp);
+ *   template <class R>
+ *   struct Model {
+ *     // optional per-kernel state, held in registers for the whole launch (e.g. float w[R::NS];)
+ *     __device__ __forceinline__ void init(const bjx::UserCtx& u);          // once per kernel launch and chain row
+ *     template <bool WANT_LOGP>
+ *     __device__ __forceinline__ void value_and_grad(const bjx::UserCtx& u, const float (&q)[R::NS],
+ *                                                    float (&g)[R::NS], float& logp) const;
+ *   };
  *   }
  *
  * Layout.  One warp owns one chain row of length u.D.  Lane `u.lane` holds R::NS slots of it in registers; slot s is
@@ -30,6 +35,10 @@
  *   bjx::row_at<R, E>(q) element E (compile-time index) broadcast from its owner's register.
  *   bjx::warp_sum(x)     all-lanes sum (xor-shuffle tree: the same value, bit for bit, on every lane).
  *   bjx::Vec<R::NS>      packed-FP32 helpers (axpy, mul, scale, add, dot_partial).
+ *
+ * init.  Called once per kernel launch for the chain row the warp owns, before any value_and_grad: load what every
+ * evaluation needs (scales, a few hyper-parameters) into the struct's members so that it stays in registers across the
+ * leapfrog steps of the launch.
  *
  * Results.  g = d logp / d q for the slots of this lane.  When WANT_LOGP is true, `logp` must come back with the
  * log-density, identical on all 32 lanes (finish reductions with bjx::warp_sum); when it is false the value is dead

@@ -285,7 +285,7 @@ def test_plugin_load_rejects_foreign_libraries_and_missing_files():
 
 def test_plugin_compile_error_is_reported_with_the_compiler_output():
     from blackjax_b200 import BjxError, plugin
-    bad = "namespace bjx_user { this is not CUDA }"
+    bad = "namespace bjx_user { template <class R> struct Model { this is not CUDA }; }"
     with pytest.raises(BjxError, match="nvcc failed"):
         plugin.build_plugin(bad, 8, "broken", dense_metric=False, general_integrators=False)
     path, _ = plugin.plugin_path(bad, 8, "broken", False, False)
