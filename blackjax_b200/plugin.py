@@ -126,7 +126,7 @@ PREBUILT = (
     ("diag_gaussian", 512, False, False),   # SC_V4
     ("diag_gaussian", 1024, False, False),  # SC_V8
     ("linear_regression", 2, True, True),   # SC_S1: the reference's regression posterior (log_scale + K <= 16 coefficients)
-    ("linear_regression", 4, False, False), # SC_V1 (three coefficients)
+    ("linear_regression", 4, True, True),   # SC_V1 (three or seven coefficients: 4 or 8 dims)
 )
 
 
