@@ -127,6 +127,8 @@ PREBUILT = (
     ("diag_gaussian", 1024, False, False),  # SC_V8
     ("linear_regression", 2, True, True),   # SC_S1: the reference's regression posterior (log_scale + K <= 16 coefficients)
     ("linear_regression", 4, True, True),   # SC_V1 (three or seven coefficients: 4 or 8 dims)
+    ("rosenbrock", 5, False, False), ("rosenbrock", 100, False, False), ("rosenbrock", 70, False, False),
+    ("rosenbrock", 256, False, False), ("rosenbrock", 1024, False, False),   # SC_S1, V1, S4, V2, V8
 )
 
 

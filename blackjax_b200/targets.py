@@ -228,3 +228,15 @@ class LinearRegression(UserTarget):
         theta = np.concatenate([np.asarray([x.shape[0], x.shape[1]], np.float32), x.reshape(-1), y])
         super().__init__(1 + x.shape[1], plugin.read_example("linear_regression"), theta, name="linear_regression",
                          **build_options)
+
+
+class Rosenbrock(UserTarget):
+    """-beta * sum_{i<D-1} [a (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]: a neighbour-coupled model shipped as a user-defined target
+    (blackjax_b200/user_targets/rosenbrock.cuh; the row is staged in the warp's shared-memory scratch)."""
+
+    def __init__(self, dim, a=5.0, beta=0.05, **build_options):
+        from . import plugin
+        if dim < 2:
+            raise ValueError("Rosenbrock needs dim >= 2")
+        super().__init__(dim, plugin.read_example("rosenbrock"), np.asarray([a, beta], np.float32), name="rosenbrock",
+                         **build_options)

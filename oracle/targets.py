@@ -11,6 +11,7 @@ integrators.py:189,204); without JAX the named models are differentiated by hand
 * ``Banana``                        tests/mcmc/test_trajectory.py:79-80
 * ``NormLogpdf``                    tests/mcmc/test_trajectory.py:27 (jax.scipy.stats.norm.logpdf)
 * ``LinearRegression``              tests/mcmc/test_sampling.py:103-111 ``regression_logprob``
+* ``Rosenbrock``                    builder-defined neighbour-coupled model (blackjax_b200/user_targets/rosenbrock.cuh)
 
 Each target maps ``q: f32[C, D]`` to ``(logp: f32[C], grad: f32[C, D])``.
 """
@@ -220,3 +221,31 @@ class LinearRegression:
             g[..., 0] = (w * ss - scale) + (F(1.0) - F(self.N))
             g[..., 1:] = w[..., None] * rx - c / F(25.0)
         return logp.astype(F), g.astype(F)
+
+
+class Rosenbrock:
+    """logp(x) = -beta * sum_{i<D-1} [a (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]; the neighbour-coupled user-defined target of
+    blackjax_b200/user_targets/rosenbrock.cuh (builder-defined: not in the reference)."""
+
+    kind = "rosenbrock"
+
+    def __init__(self, dim, a=5.0, beta=0.05):
+        self.dim, self.a, self.beta = dim, F(a), F(beta)
+
+    def logp64(self, q):
+        q = np.asarray(q, np.float64)
+        t = q[..., 1:] - q[..., :-1] ** 2
+        return -float(self.beta) * np.sum(float(self.a) * t * t + (1.0 - q[..., :-1]) ** 2, axis=-1)
+
+    def __call__(self, q):
+        q = np.asarray(q, F)
+        a, beta = self.a, self.beta
+        with np.errstate(over="ignore", invalid="ignore"):
+            xi = q[..., :-1]
+            t = (q[..., 1:] - xi * xi).astype(F)
+            o = (F(1.0) - xi).astype(F)
+            logp = -beta * np.sum(a * t * t + o * o, axis=-1, dtype=F)
+            d = np.zeros_like(q)
+            d[..., :-1] = F(-4.0) * a * xi * t - F(2.0) * o
+            d[..., 1:] += F(2.0) * a * t
+        return logp.astype(F), (-beta * d).astype(F)

@@ -258,3 +258,54 @@ def test_user_target_failure_modes():
                                                                         torch.ones(256, device=DEV), 3)
     with pytest.raises(bj.BjxError):   # dense metric beyond 128 dims is the tensor-core path: Gaussian targets only
         bj.hmc.build_kernel()(bj.random.key(0, DEV), st, tgt, 0.1, torch.eye(256, device=DEV), 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a neighbour-coupled model (every element needs elements other lanes hold): row staging in the warp's scratch, at every
+# row size class
+# ---------------------------------------------------------------------------------------------------------------------
+ROSEN_OPTS = dict(dense_metric=False, general_integrators=False)
+
+
+@pytest.mark.parametrize("D", [5, 100, 70, 256, 1024])
+def test_user_rosenbrock_value_and_grad_matches_oracle(D):
+    tgt, otgt = T.Rosenbrock(D, **ROSEN_OPTS), otargets.Rosenbrock(D)
+    rs = np.random.default_rng(D)
+    q = (0.7 + 0.4 * rs.standard_normal((41, D))).astype(F)
+    st = bj.hmc.init(tf(q), tgt)
+    lp, g = otgt(q)
+    close(npy(st.logdensity), lp, rtol=1e-5, scale=np.max(np.abs(lp)))
+    close(npy(st.logdensity_grad), g, rtol=1e-5, scale=np.max(np.abs(g)))
+
+
+@pytest.mark.parametrize("D, algo", [(256, "hmc"), (70, "hmc"), (100, "nuts"), (5, "nuts"), (1024, "hmc")])
+def test_user_rosenbrock_transitions_match_oracle(D, algo):
+    tgt, otgt = T.Rosenbrock(D, **ROSEN_OPTS), otargets.Rosenbrock(D)
+    rs = np.random.default_rng(300 + D)
+    C = 48
+    q = (0.7 + 0.3 * rs.standard_normal((C, D))).astype(F)
+    imm = np.exp(rs.uniform(-0.2, 0.2, D)).astype(F)
+    keys = oprng.split(oprng.key(D), C)
+    if algo == "hmc":
+        onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, F(0.05), imm, 8)
+        new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), bj.hmc.init(tf(q), tgt), tgt, 0.05, tf(imm), 8)
+        torch.cuda.synchronize()
+        close(npy(info.proposal.position), oinfo.proposal[0])
+        close(npy(info.proposal.momentum), oinfo.proposal[1], rtol=2e-5)
+        close(npy(info.energy), oinfo.energy, rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + 1)
+        u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+        acc = npy(info.is_accepted)
+        assert ((acc == oinfo.is_accepted) | (np.abs(u - oinfo.acceptance_rate) < 1e-4)).all()
+        same = acc == oinfo.is_accepted
+        close(npy(new.position)[same], onew.position[same])
+    else:
+        eps = 0.2 if D >= 100 else 0.35   # trees of ~10-15 leaves (longer ones amplify float32 rounding on this nonlinear model)
+        onew, oinfo = onuts.nuts_kernel(keys, ohmc.init(q, otgt), otgt, F(eps), imm, 7)
+        new, info = bj.nuts.build_kernel(full_info=True)(tk(keys), bj.nuts.init(tf(q), tgt), tgt, eps, tf(imm), 7)
+        torch.cuda.synchronize()
+        same = ((npy(info.num_integration_steps) == oinfo.num_integration_steps)
+                & (npy(info.is_turning) == oinfo.is_turning)
+                & np.all(np.isclose(npy(new.position), onew.position, rtol=1e-4, atol=1e-5), axis=1))
+        assert same.mean() >= 0.9, same.mean()
+        assert npy(info.num_integration_steps).mean() > 3
+        close(npy(new.logdensity)[same], onew.logdensity[same], rtol=1e-5, scale=np.max(np.abs(onew.logdensity)) + 1)
