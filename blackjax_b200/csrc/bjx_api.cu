@@ -12,6 +12,7 @@
 #include "../../include/bjx.h"
 #include "bjx_internal.h"
 #include "bjx_launch.cuh"
+#include "bjx_big.cuh"
 #include "bjx_handle.h"
 
 using namespace bjx;
@@ -94,7 +95,14 @@ static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
       if (!t.user_plugin) return fail(h, BJX_E_INVALID, "USER target needs user_plugin (bjx_plugin_load)");
       if (t.n_user_params < 0 || (t.n_user_params > 0 && !t.user_params))
         return fail(h, BJX_E_INVALID, "USER target: user_params is NULL but n_user_params > 0");
-      if (dim > 1024) return fail(h, BJX_E_UNSUPPORTED, "USER targets are built for the warp kernels (dim <= 1024)");
+      {
+        auto* pl = static_cast<bjx_plugin_s*>(t.user_plugin);
+        if (dim > 1024 && !pl->launch_big)
+          return fail(h, BJX_E_UNSUPPORTED, "this USER target's plug-in holds the warp kernels only (dim <= 1024): build it with "
+                                            "bjx_user::BigModel for rows beyond");
+        if (dim <= 1024 && !pl->launch)
+          return fail(h, BJX_E_UNSUPPORTED, "this USER target's plug-in holds the big-row kernels only (dim > 1024)");
+      }
       break;
     default:
       return fail(h, BJX_E_INVALID, "unknown target kind");
@@ -103,13 +111,10 @@ static int validate_target(bjx_handle_t h, const bjx_target_desc& t, int dim) {
 }
 
 // ---- plug-ins of user-defined targets (include/bjx_user_target.h) ---------------------------------------------------
-struct bjx_plugin_s {
-  void* dl;
-  int (*launch)(int kernel_id, int sc, int dm, const bjx::LaunchArgs* a);
-  std::string path;
-};
 // what a plug-in must have been built against: the C ABI version and the layout of the launch arguments
-extern "C" int bjx_plugin_abi(void) { return BJX_VERSION * 100000 + (int)sizeof(bjx::LaunchArgs); }
+extern "C" int bjx_plugin_abi(void) {
+  return BJX_VERSION * 100000 + (int)sizeof(bjx::LaunchArgs) + 7 * (int)sizeof(bjx::BigLaunchArgs);
+}
 
 extern "C" int bjx_plugin_load(const char* path, void** plugin_out) {
   if (!path || !plugin_out) return fail(nullptr, BJX_E_INVALID, "null argument");
@@ -117,7 +122,8 @@ extern "C" int bjx_plugin_load(const char* path, void** plugin_out) {
   if (!dl) return fail(nullptr, BJX_E_INVALID, std::string("bjx_plugin_load: ") + dlerror());
   auto abi = (int (*)(void))dlsym(dl, "bjx_plugin_built_for_abi");
   auto launch = (int (*)(int, int, int, const bjx::LaunchArgs*))dlsym(dl, "bjx_plugin_launch");
-  if (!abi || !launch) {
+  auto launch_big = (int (*)(int, const bjx::BigLaunchArgs*))dlsym(dl, "bjx_plugin_launch_big");
+  if (!abi || (!launch && !launch_big)) {
     dlclose(dl);
     return fail(nullptr, BJX_E_INVALID, std::string("bjx_plugin_load: ") + path + " is not a bjx target plug-in");
   }
@@ -126,7 +132,7 @@ extern "C" int bjx_plugin_load(const char* path, void** plugin_out) {
     return fail(nullptr, BJX_E_STATE, std::string("bjx_plugin_load: ") + path +
                                           " was built against another version of libbjx's kernels: rebuild it");
   }
-  *plugin_out = new bjx_plugin_s{dl, launch, path};  // never unloaded: handles may refer to it until the process ends
+  *plugin_out = new bjx_plugin_s{dl, launch, launch_big};  // never unloaded: handles may refer to it until the process ends
   return 0;
 }
 
@@ -436,6 +442,7 @@ static int dispatch(bjx_handle_t h, int kernel_id, bool target_dependent, Launch
     case BJX_TARGET_DENSE_GAUSSIAN: rc = Launcher<TK_DENSE>::launch(kernel_id, h->sc, dm, a); break;
     case BJX_TARGET_BANANA: rc = Launcher<TK_BANANA>::launch(kernel_id, h->sc, dm, a); break;
     case BJX_TARGET_USER:
+      if (!static_cast<bjx_plugin_s*>(h->cfg.target.user_plugin)->launch) { rc = -2; break; }
       rc = static_cast<bjx_plugin_s*>(h->cfg.target.user_plugin)->launch(kernel_id, h->sc, dm ? 1 : 0, &a);
       if (rc > 0) return cuda_fail(h, (cudaError_t)rc, "plug-in kernel launch");
       break;

@@ -5,6 +5,17 @@
 #include "../../include/bjx.h"
 #include "bjx_kernels.cuh"
 
+namespace bjx {
+struct LaunchArgs;
+struct BigLaunchArgs;
+}
+// A loaded target plug-in (bjx_plugin_load): the warp-kernel launcher (rows up to 1024 dims) and / or the big-row launcher
+struct bjx_plugin_s {
+  void* dl;
+  int (*launch)(int kernel_id, int sc, int dm, const bjx::LaunchArgs* a);
+  int (*launch_big)(int kernel_id, const bjx::BigLaunchArgs* a);
+};
+
 struct bjx_handle_s {
   bjx_config cfg;
   cudaStream_t stream;

@@ -21,13 +21,15 @@ PLUGIN_DIR = os.path.join(_HERE, "_plugins")
 USER_TARGETS = os.path.join(_HERE, "user_targets")
 
 # everything a plug-in is compiled from besides the user's source: a change in any of these is a new build
-_ABI_SOURCES = ("bjx_plugin.cu", "bjx_row.cuh", "bjx_kernels.cuh", "bjx_launch.cuh", "bjx_prng.cuh")
+_ABI_SOURCES = ("bjx_plugin.cu", "bjx_row.cuh", "bjx_kernels.cuh", "bjx_launch.cuh", "bjx_prng.cuh", "bjx_big.cuh")
 
+SC_BIG = 6
 _LOADED = {}  # path -> bjx_plugin pointer (plug-ins stay loaded for the life of the process)
 
 
 def size_class(dim):
-    """Row size class of the warp kernels (csrc/bjx_launch.cuh ``size_class_for``); user targets stop at 1024 dims."""
+    """Row size class of the kernels (csrc/bjx_launch.cuh ``size_class_for``): 0..5 the warp kernels (rows up to 1024 dims,
+    the model is a ``bjx_user::Model<R>``), 6 the CTA-per-chain kernels (1024 < dim <= 18432, ``bjx_user::BigModel``)."""
     if dim <= 0:
         raise ValueError("dim must be positive")
     if dim % 4 == 0 and dim <= 1024:
@@ -36,7 +38,9 @@ def size_class(dim):
         return 4
     if dim <= 128:
         return 5
-    raise ValueError("user-defined targets need dim <= 1024 with dim % 4 == 0, or dim <= 128 otherwise")
+    if dim % 4 == 0 and dim <= 18432:
+        return SC_BIG
+    raise ValueError("user-defined targets need dim <= 18432 with dim % 4 == 0, or dim <= 128 otherwise")
 
 
 def _nvcc():
@@ -62,6 +66,8 @@ def plugin_path(source, dim, name="user", dense_metric=True, general_integrators
     h = _abi_digest()
     sc = size_class(dim)
     flags = (sc, 2 if dense_metric else 0, 2 if general_integrators else 0)
+    if sc == SC_BIG:  # diagonal metrics and velocity Verlet only in this size class: the options do not apply
+        flags = (sc, 0, 0)
     h.update(repr(flags).encode())
     h.update(source.encode())
     safe = "".join(ch if ch.isalnum() else "_" for ch in name)[:40]
@@ -87,8 +93,12 @@ def build_plugin(source, dim, name="user", dense_metric=True, general_integrator
         f.write(source)
     tmp = path + f".tmp{os.getpid()}"
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-           "-shared", "-I", CSRC, "-I", INCLUDE, f"-DBJX_USER_SOURCE=\"{src}\"", f"-DBJX_BUILD_SC={sc}",
-           f"-DBJX_BUILD_DM={dm}", f"-DBJX_BUILD_GEN={gen}", os.path.join(CSRC, "bjx_plugin.cu"), "-o", tmp]
+           "-shared", "-I", CSRC, "-I", INCLUDE, f"-DBJX_USER_SOURCE=\"{src}\""]
+    if sc == SC_BIG:
+        cmd += ["-DBJX_PLUGIN_BIG=1"]
+    else:
+        cmd += [f"-DBJX_BUILD_SC={sc}", f"-DBJX_BUILD_DM={dm}", f"-DBJX_BUILD_GEN={gen}"]
+    cmd += [os.path.join(CSRC, "bjx_plugin.cu"), "-o", tmp]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -129,6 +139,7 @@ PREBUILT = (
     ("linear_regression", 4, True, True),   # SC_V1 (three or seven coefficients: 4 or 8 dims)
     ("rosenbrock", 5, False, False), ("rosenbrock", 100, False, False), ("rosenbrock", 70, False, False),
     ("rosenbrock", 256, False, False), ("rosenbrock", 1024, False, False),   # SC_S1, V1, S4, V2, V8
+    ("diag_gaussian_big", 2048, False, False), ("hier_logit_big", 1504, False, False),   # CTA-per-chain rows (SC_BIG)
 )
 
 

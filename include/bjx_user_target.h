@@ -46,6 +46,24 @@
  * bjx_target_desc.logp_offset is added by the caller.  The function must be deterministic and must not write global
  * memory.  All 32 lanes call it together (no divergent early return around warp-level primitives).
  *
+ * Rows beyond a warp (1024 < dim <= 18432, dim % 4 == 0).  One CTA of bjx::kBigThreads (768) threads owns the chain row,
+ * held in shared memory; the plug-in is built with -DBJX_PLUGIN_BIG=1 and the source defines instead
+ *
+ *   namespace bjx_user {
+ *   struct BigModel {
+ *     template <bool WANT_LOGP>
+ *     __device__ static __forceinline__ float value_and_grad(const bjx::BigUserCtx& u, const float* q, float* g,
+ *                                                            float* red);
+ *   };
+ *   }
+ *
+ * q[0..D) is complete on entry (shared memory, read-only); the function writes every g[i], i < D, and returns the
+ * log-density on ALL threads (bjx::block_sum<NV>(acc, red), NV <= 5, sums per-thread partials over the CTA; `red` is its
+ * scratch).  All kBigThreads threads call it together; the caller places the barriers before and after.  u.tid is
+ * threadIdx.x; by convention thread t walks elements t, t + kBigThreads, ...  HMC, the leapfrog / init / momentum / energy
+ * building blocks and diagonal metrics exist in this size class (as for the built-in targets); NUTS does not.
+ * Examples: blackjax_b200/user_targets/diag_gaussian_big.cuh, hier_logit_big.cuh (BASELINE config 5's model).
+ *
  * Example (the linear regression posterior of the reference's own sampling tests, tests/mcmc/test_sampling.py:103-111):
  * blackjax_b200/user_targets/linear_regression.cuh.
  */

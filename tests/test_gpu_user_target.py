@@ -249,7 +249,7 @@ def test_window_adaptation_on_the_reference_regression_posterior(algo):
 def test_user_target_failure_modes():
     # rows beyond the warp kernels, a dense metric on the tensor-core path: loud errors, no fallback
     with pytest.raises(ValueError):
-        T.UserTarget(2048, plugin.read_example("diag_gaussian"), np.ones(2048, F))
+        T.UserTarget(20000, plugin.read_example("diag_gaussian"), np.ones(20000, F))
     tgt = user_diag(np.ones(256), 256, dense_metric=False, general_integrators=False)
     q = torch.zeros(8, 256, device=DEV)
     st = bj.hmc.init(q, tgt)
@@ -309,3 +309,73 @@ def test_user_rosenbrock_transitions_match_oracle(D, algo):
         assert same.mean() >= 0.9, same.mean()
         assert npy(info.num_integration_steps).mean() > 3
         close(npy(new.logdensity)[same], onew.logdensity[same], rtol=1e-5, scale=np.max(np.abs(onew.logdensity)) + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rows beyond a warp (1024 < dim <= 18432): the CTA-level contract bjx_user::BigModel
+# ---------------------------------------------------------------------------------------------------------------------
+def test_user_big_row_diag_gaussian_bit_identical_to_builtin():
+    from blackjax_b200 import _engine
+    D, C = 2048, 21
+    rs = np.random.default_rng(3)
+    s = np.exp(rs.uniform(-1, 1, D))
+    builtin = T.DiagGaussian(s)
+    user = T.UserTarget(D, plugin.read_example("diag_gaussian_big"), (1.0 / (s * s)).astype(F), name="diag_gaussian_big")
+    q = tf(rs.standard_normal((C, D)))
+    imm = tf(np.exp(rs.uniform(-0.5, 0.5, D)))
+    keys = tk(oprng.split(oprng.key(4), C))
+    out = {}
+    for name, tgt in (("builtin", builtin), ("user", user)):
+        st = bj.hmc.init(q, tgt)
+        new, info = bj.hmc.build_kernel(full_info=True)(keys, st, tgt, 0.05, imm, 6)
+        eng = _engine.get_engine(q, tgt)
+        eng.ensure_metric(imm)
+        p = eng.sample_momentum(keys)
+        ql, lp, g = q.clone(), st.logdensity.clone(), st.logdensity_grad.clone()
+        eng.leapfrog_(ql, p, lp, g, 0.05, 3)
+        out[name] = [st.logdensity, st.logdensity_grad, new.position, new.logdensity, info.energy, info.acceptance_rate,
+                     info.is_accepted, info.proposal.momentum, ql, p, lp, g]
+    torch.cuda.synchronize()
+    for a, b in zip(out["builtin"], out["user"]):
+        assert torch.equal(a, b)
+    st = bj.hmc.init(q, user)
+    with pytest.raises(bj.BjxError):     # NUTS is not built for this size class (built-in targets neither)
+        bj.nuts.build_kernel()(keys, st, user, 0.05, imm, 3)
+
+
+def test_user_big_row_hier_logit_matches_builtin_and_oracle():
+    from blackjax_b200 import _engine
+    D, C = 1504, 10
+    G = D - 4
+    x, bits = T.HierLogit.synthetic_data(G, seed=1)
+    builtin, otgt = T.HierLogit(x, bits), otargets.HierLogit(x, bits)
+    theta = np.concatenate([np.asarray([G, 0, 0, 0], F), x.reshape(-1).astype(F), bits.astype(F)])
+    user = T.UserTarget(D, plugin.read_example("hier_logit_big"), theta, name="hier_logit_big")
+    rs = np.random.default_rng(6)
+    q = (0.3 * rs.standard_normal((C, D))).astype(F)
+    imm = np.exp(rs.uniform(-0.3, 0.3, D)).astype(F)
+    keys = oprng.split(oprng.key(2), C)
+    res = {}
+    for name, tgt in (("builtin", builtin), ("user", user)):
+        eng = _engine.Engine(DEV, C, D, tgt)
+        eng.set_metric(tf(imm))
+        dq = tf(q)
+        lp, g = eng.init_state(dq)
+        p = eng.sample_momentum(tk(keys))
+        lp0, g0 = lp.clone(), g.clone()
+        eng.leapfrog_(dq, p, lp, g, 0.01, 4)
+        res[name] = [lp0, g0, dq, p, lp, g]
+    torch.cuda.synchronize()
+    for a, b in zip(res["builtin"], res["user"]):   # the same one-chain-per-CTA arithmetic and summation order: equal to rounding
+        close(npy(a), npy(b), rtol=2e-6, scale=float(b.abs().max()) + 1.0)
+    # whole transition through the plug-in's k_big_hmc against the oracle
+    onew, oinfo = ohmc.hmc_kernel(keys, ohmc.init(q, otgt), otgt, F(0.01), ohmc.Metric(imm), 6)
+    new, info = bj.hmc.build_kernel(full_info=True)(tk(keys), bj.hmc.init(tf(q), user), user, 0.01, tf(imm), 6)
+    torch.cuda.synchronize()
+    close(npy(info.proposal.position), oinfo.proposal[0], rtol=1e-5)
+    close(npy(info.energy), oinfo.energy, rtol=1e-5, scale=np.max(np.abs(oinfo.energy)) + D)
+    u = oprng.uniform(oprng.split(keys, 2)[:, 1])
+    acc = npy(info.is_accepted)
+    assert ((acc == oinfo.is_accepted) | (np.abs(u - oinfo.acceptance_rate) < 1e-3)).all()
+    same = acc == oinfo.is_accepted
+    close(npy(new.position)[same], onew.position[same], rtol=1e-5)

@@ -274,6 +274,19 @@ def test_plugin_builds_exports_and_loads():
     assert same == path                                    # 18 and 21 dims share the scalar <= 32 size class
 
 
+def test_big_row_plugin_builds_and_exports_its_launcher():
+    # rows beyond a warp: the CTA-level contract (bjx_user::BigModel); the plug-in exports bjx_plugin_launch_big only
+    from blackjax_b200 import _lib, plugin
+    assert plugin.size_class(2048) == plugin.SC_BIG and plugin.size_class(18432) == plugin.SC_BIG
+    path = plugin.build_plugin(plugin.read_example("diag_gaussian_big"), 2048, "diag_gaussian_big", False, False)
+    so = C.CDLL(path)
+    assert so.bjx_plugin_built_for_abi() == _lib.lib().bjx_plugin_abi()
+    assert hasattr(so, "bjx_plugin_launch_big") and not hasattr(so, "bjx_plugin_launch")
+    assert plugin.load_plugin(path)
+    # the options of the warp kernels do not apply to this size class: one build whatever they say
+    assert plugin.plugin_path(plugin.read_example("diag_gaussian_big"), 4096, "diag_gaussian_big", True, True)[0] == path
+
+
 def test_plugin_load_rejects_foreign_libraries_and_missing_files():
     from blackjax_b200 import _lib
     out = C.c_void_p()
@@ -296,7 +309,7 @@ def test_plugin_size_classes_mirror_the_launcher():
     from blackjax_b200 import plugin
     assert [plugin.size_class(d) for d in (4, 128, 132, 256, 260, 512, 516, 1024, 1, 31, 33, 127)] == \
         [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5]
-    for d in (0, 130, 1028, 2048):
+    for d in (0, 130, 1030, 18436):
         with pytest.raises(ValueError):
             plugin.size_class(d)
 
