@@ -23,6 +23,7 @@
 #ifndef BJX_H_
 #define BJX_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -325,3 +325,15 @@ def test_user_target_descriptor_without_gpu():
     assert os.path.exists(t.plugin_path())
     with pytest.raises(ValueError):
         targets.LinearRegression(np.zeros((4, 17), np.float32), y)
+
+
+def test_headers_are_valid_c99(tmp_path):
+    """include/bjx.h is the drop-in boundary for non-C++ hosts (cgo, JNI, ctypes generators): it must compile as plain C."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "bjx.h"\n#include "bjx_user_target.h"\n'
+                   'int probe(void) { bjx_config c; bjx_info i; bjx_target_desc t; (void)c; (void)i; (void)t;\n'
+                   '  return (int)sizeof(bjx_handle_t) + BJX_TARGET_USER + BJX_METRIC_DENSE_PER_CHAIN + BJX_E_STATE; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
+                        str(tmp_path / "abi.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
