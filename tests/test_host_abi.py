@@ -337,3 +337,24 @@ def test_headers_are_valid_c99(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
                         str(tmp_path / "abi.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_plugin_cubins_are_sm100a_with_the_same_kernels_as_the_library():
+    """A user-defined target's plug-in holds the path's kernels compiled for sm_100a only, with the packed FP32
+    instructions of the built-in row kernels (FFMA2 / FMUL2) -- the same templates, another translation unit."""
+    import shutil
+    from blackjax_b200 import plugin
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    path = plugin.build_plugin(plugin.read_example("diag_gaussian"), 256, "diag_gaussian", dense_metric=False,
+                               general_integrators=False)
+    elf = subprocess.run([cuobjdump, "-lelf", path], capture_output=True, text=True, timeout=120).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, timeout=600).stdout
+    for kern in ("k_hmc_transition", "k_mhmc_transition", "k_ghmc_transition", "k_nuts_doubling", "k_nuts_chains", "k_leapfrog",
+                 "k_init_state"):
+        assert kern in sass, kern
+    assert "FFMA2" in sass and "FMUL2" in sass
+    assert re.search(r"k_hmc_transitionINS_3RowILi8ELb1EEELi4E", sass), "HMC kernel of the user target (Row<8,true>, TK=4) missing"
