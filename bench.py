@@ -237,28 +237,35 @@ def cpu_nuts_rate(wl, budget_s=12.0):
 
 
 def cpu_hier_rate(wl, budget_s=12.0):
-    """leapfrog-steps/s of the numpy oracle (oracle/hmc.py + oracle/targets.py HierLogit) on a bounded chain sample of
-    config 5: one process, numpy's own threading."""
+    """leapfrog-steps/s of the C/pthreads oracle twin (oracle/c/oracle_hmc.c, target kind 2 = oracle/targets.py HierLogit
+    with the library's exact expf / log1pf) on all host cores it may use, on a bounded chain sample of config 5."""
     import numpy as np
     from blackjax_b200.targets import HierLogit
-    from oracle import hmc as ohmc, prng, targets as otargets
+    from oracle import cport, hmc as ohmc, prng, targets as otargets
     D, L = wl["D"], wl["L"]
     F = np.float32
     x, bits = HierLogit.synthetic_data(D - 4, seed=1)
-    tgt = otargets.HierLogit(x, bits)
-    Cs = 16
+    cores = cport.num_threads()
+    Cs = max(cores, 8)
     rs = np.random.default_rng(0)
     q = np.empty((Cs, D), F)
     q[:, :4] = [0.5, np.log(0.7), 1.0, -0.5]
     q[:, 4:] = 0.5 + 0.7 * rs.standard_normal((Cs, D - 4))
-    st = ohmc.init(q, tgt)
+    st = ohmc.init(q, otargets.HierLogit(x, bits))
+    qc, lc, gc = q.copy(), st.logdensity.copy(), st.logdensity_grad.copy()
     imm = np.ones(D, F)
-    t0, reps = time.perf_counter(), 0
-    while time.perf_counter() - t0 < budget_s and reps < 50:
-        st, _ = ohmc.hmc_kernel(prng.split(prng.fold_in(prng.key(1), reps), Cs), st, tgt, F(wl["eps"]), imm, L)
-        reps += 1
-    t = time.perf_counter() - t0
-    return Cs * L * reps / t, 1, f"{Cs} of {wl['C']} chains x {D} dims x L={L}, {reps} transition(s) ({t:.1f} s)", t / reps * 1e3, {}
+
+    def run(n):
+        t0 = time.perf_counter()
+        for r in range(n):
+            cport.hmc_hier_step(x, bits, imm, prng.split(prng.fold_in(prng.key(1), r), Cs), qc, lc, gc, wl["eps"], L)
+        return time.perf_counter() - t0
+    t1 = run(1)
+    n = int(max(1, min(50, budget_s / 3.0 / max(t1, 1e-9))))
+    ts = sorted(run(n) for _ in range(3))
+    t = ts[1]
+    sample = f"{Cs} of {wl['C']} chains x {D} dims x L={L}, {n} transition(s) x 3 repeats (median {t:.2f} s)"
+    return Cs * L * n / t, cores, sample, t / n * 1e3, {"repeats_s": [round(v, 3) for v in ts]}
 
 
 def cpu_rate(wl, budget_s, steps=1, warmup=0):
@@ -281,7 +288,7 @@ def run_reference(args, wl_name, wl):
         "config": {"workload": wl_name, **{k: v for k, v in wl.items()},
                    "note": "baseline/_ref (BlackJAX on JAX) was tried first and cannot be installed in this image (no jax / "
                            "jaxlib wheel, no network); this arm times the restated oracle instead: the C/pthreads twin of "
-                           "oracle/hmc.py (HMC workloads) or the numpy oracle (NUTS workloads)"},
+                           "oracle/hmc.py (HMC workloads, config 5's hierarchical model included) or the numpy oracle (NUTS workloads)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **extra},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

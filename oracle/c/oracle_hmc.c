@@ -71,8 +71,11 @@ static inline float normal_at(uint32_t k0, uint32_t k1, uint32_t i) {
   return 1.41421356237309515f * erfinv_f32(u);
 }
 
-/* target kinds: 0 diagonal Gaussian (inv_var[D]), 1 Neal's funnel */
-static float value_and_grad(int kind, int D, const float* inv_var, const float* q, float* g) {
+/* target kinds: 0 diagonal Gaussian (inv_var[D]), 1 Neal's funnel, 2 hierarchical logistic regression (BASELINE config 5:
+ * x = [mu, log_tau, beta0, beta1, alpha_0 .. alpha_{G-1}], data_x [G,8,2], data_y [G] outcome bits; oracle/targets.py
+ * HierLogit, with the library's exact expf / log1pf as a CPU implementation would use them) */
+static float value_and_grad(int kind, int D, const float* inv_var, const float* data_x, const unsigned char* data_y,
+                            const float* q, float* g) {
   if (kind == 0) {
     float acc = 0.f;
 #pragma omp simd reduction(+ : acc)
@@ -82,6 +85,38 @@ static float value_and_grad(int kind, int D, const float* inv_var, const float* 
       g[i] = -t;
     }
     return -0.5f * acc;
+  }
+  if (kind == 2) {
+    const int G = D - 4;
+    const float mu = q[0], lt = q[1], b0 = q[2], b1 = q[3];
+    const float e2 = expf(-2.0f * lt);
+    float ll = 0.f, sd = 0.f, sd2 = 0.f, gb0 = 0.f, gb1 = 0.f;
+    for (int gi = 0; gi < G; ++gi) {
+      const float alpha = q[4 + gi], d = alpha - mu;
+      const float* xr = data_x + (size_t)gi * 16;
+      const unsigned bits = data_y[gi];
+      float ga = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float x0 = xr[2 * k], x1 = xr[2 * k + 1];
+        const float y = (float)((bits >> k) & 1u);
+        const float eta = alpha + b0 * x0 + b1 * x1;
+        const float sig = 1.0f / (1.0f + expf(-eta));
+        const float softplus = fmaxf(eta, 0.f) + log1pf(expf(-fabsf(eta)));
+        const float r = y - sig;
+        ll += y * eta - softplus;
+        ga += r;
+        gb0 += r * x0;
+        gb1 += r * x1;
+      }
+      sd += d;
+      sd2 += d * d;
+      g[4 + gi] = -d * e2 + ga;
+    }
+    g[0] = -0.01f * mu + e2 * sd;
+    g[1] = -lt + e2 * sd2 - (float)G;
+    g[2] = -0.16f * b0 + gb0;
+    g[3] = -0.16f * b1 + gb1;
+    return -0.005f * mu * mu - 0.5f * lt * lt - 0.08f * (b0 * b0 + b1 * b1) + (-0.5f * e2 * sd2 - (float)G * lt) + ll;
   }
   float y = q[0], ss = 0.f;
 #pragma omp simd reduction(+ : ss)
@@ -98,6 +133,8 @@ typedef struct {
   const uint32_t* keys;
   float *q, *logp, *g, eps, *acc_rate;
   unsigned char* accepted;
+  const float* data_x;
+  const unsigned char* data_y;
 } job_t;
 
 static void* worker(void* arg) {
@@ -128,7 +165,7 @@ static void* worker(void* arg) {
         p[i] = p[i] + eh * g1[i];
         q1[i] = q1[i] + e1s * (imm[i] * p[i]);
       }
-      lp = value_and_grad(J->kind, D, J->inv_var, q1, g1);
+      lp = value_and_grad(J->kind, D, J->inv_var, J->data_x, J->data_y, q1, g1);
       for (int i = 0; i < D; ++i) p[i] = p[i] + eh * g1[i];
     }
     float k1 = 0.f;
@@ -210,10 +247,9 @@ static void pin_thread(pthread_t th, int t) {
   pthread_setaffinity_np(th, sizeof(one), &one);
 }
 
-/* One HMC transition for chains [0, C): in-place on q, logp, g.  Returns the number of leapfrogs done. */
-long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const float* imm /*[D]*/,
-                          const uint32_t* keys /*[C,2]*/, float* q, float* logp, float* g, float eps, int L,
-                          float* acc_rate /*[C] or NULL*/, unsigned char* accepted /*[C] or NULL*/, int n_threads) {
+static long long hmc_step_impl(int C, int D, int kind, const float* inv_var, const float* data_x, const unsigned char* data_y,
+                               const float* imm, const uint32_t* keys, float* q, float* logp, float* g, float eps, int L,
+                               float* acc_rate, unsigned char* accepted, int n_threads) {
   float* msqrt = (float*)malloc(sizeof(float) * D);
   for (int i = 0; i < D; ++i) msqrt[i] = 1.0f / sqrtf(imm[i]);
   int T = n_threads > 0 ? n_threads : oracle_num_threads();
@@ -223,7 +259,7 @@ long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const fl
   job_t* jobs = (job_t*)malloc(sizeof(job_t) * T);
   for (int t = 0; t < T; ++t) {
     job_t j = {(int)((long long)C * t / T), (int)((long long)C * (t + 1) / T), D, kind, L, inv_var, imm, msqrt, keys,
-               q, logp, g, eps, acc_rate, accepted};
+               q, logp, g, eps, acc_rate, accepted, data_x, data_y};
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
     pin_thread(th[t], t);
@@ -233,6 +269,20 @@ long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const fl
   free(jobs);
   free(msqrt);
   return (long long)C * L;
+}
+
+/* One HMC transition for chains [0, C): in-place on q, logp, g.  Returns the number of leapfrogs done. */
+long long oracle_hmc_step(int C, int D, int kind, const float* inv_var, const float* imm /*[D]*/,
+                          const uint32_t* keys /*[C,2]*/, float* q, float* logp, float* g, float eps, int L,
+                          float* acc_rate /*[C] or NULL*/, unsigned char* accepted /*[C] or NULL*/, int n_threads) {
+  return hmc_step_impl(C, D, kind, inv_var, NULL, NULL, imm, keys, q, logp, g, eps, L, acc_rate, accepted, n_threads);
+}
+
+/* The same transition on the hierarchical logistic regression of BASELINE config 5 (D = 4 + G). */
+long long oracle_hmc_step_hier(int C, int D, const float* data_x /*[G,8,2]*/, const unsigned char* data_y /*[G]*/,
+                               const float* imm, const uint32_t* keys, float* q, float* logp, float* g, float eps, int L,
+                               float* acc_rate, unsigned char* accepted, int n_threads) {
+  return hmc_step_impl(C, D, 2, NULL, data_x, data_y, imm, keys, q, logp, g, eps, L, acc_rate, accepted, n_threads);
 }
 
 /* ------------------------------------------------------------------------------------------------------

@@ -27,6 +27,9 @@ def lib():
         l.oracle_hmc_dense_step.restype = C.c_longlong
         l.oracle_hmc_dense_step.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        l.oracle_hmc_step_hier.restype = C.c_longlong
+        l.oracle_hmc_step_hier.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         l.oracle_num_threads.restype = C.c_int
         _lib = l
     return _lib
@@ -49,6 +52,24 @@ def hmc_step(kind, inv_var, imm, keys, q, logp, g, eps, L, n_threads=0):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     lib().oracle_hmc_step(Cn, D, int(kind), p(inv_var), p(imm), p(keys), p(q), p(logp), p(g), float(eps), int(L),
                           p(acc), p(ok), int(n_threads))
+    return acc, ok.astype(bool)
+
+
+def hmc_hier_step(covariates, outcome_bits, imm, keys, q, logp, g, eps, L, n_threads=0):
+    """In-place HMC transition on the hierarchical logistic regression (oracle/targets.py HierLogit; D = 4 + G)."""
+    Cn, D = q.shape
+    for a in (q, logp, g):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    x = np.ascontiguousarray(covariates, np.float32)
+    y = np.ascontiguousarray(outcome_bits, np.uint8)
+    assert x.shape == (D - 4, 8, 2) and y.shape == (D - 4,)
+    imm = np.ascontiguousarray(imm, np.float32)
+    keys = np.ascontiguousarray(keys, np.uint32)
+    acc = np.empty(Cn, np.float32)
+    ok = np.empty(Cn, np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().oracle_hmc_step_hier(Cn, D, p(x), p(y), p(imm), p(keys), p(q), p(logp), p(g), float(eps), int(L), p(acc), p(ok),
+                               int(n_threads))
     return acc, ok.astype(bool)
 
 

@@ -204,14 +204,15 @@ def test_allgather_merge_world_size_2_gloo(tmp_path):
         assert "OK" in o
 
 
-def test_bench_reference_arm_contract():
+@pytest.mark.parametrize("workload", ["hmc_iso_gaussian_1024x100_L10", "hmc_hier_logit_32768x10000_L20"])
+def test_bench_reference_arm_contract(workload):
     """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU, prints exactly one
     JSON line on stdout and carries the contract's keys; the product arm refuses to run without a GPU."""
     import json
     import subprocess
     import sys
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
-           "hmc_iso_gaussian_1024x100_L10", "--steps", "2", "--warmup", "1"]
+           workload, "--steps", "2", "--warmup", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -221,8 +222,8 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "hmc_iso_gaussian_1024x100_L10"
-    if not torch.cuda.is_available():
+    assert d["config"]["workload"] == workload
+    if not torch.cuda.is_available() and workload.startswith("hmc_iso"):
         ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                               capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert ours.returncode != 0          # no silent CPU path
