@@ -199,14 +199,15 @@ def cpu_hmc_rate(wl, budget_s=12.0, steps=1, warmup=0):
     return rate, cores, sample, t / n_steps * 1e3, extra
 
 
-def cpu_nuts_rate(wl, budget_s=12.0):
-    """leapfrog-steps/s of the restated numpy oracle (oracle/nuts.py, oracle/adaptation.py) on a bounded chain sample of
-    the NUTS workloads: one process, numpy's own threading (the port is vectorised over chains, not multi-threaded)."""
+def _cpu_nuts_worker(args):
+    """One process of the NUTS CPU arm: the restated numpy oracle (oracle/nuts.py, oracle/adaptation.py) on its own chain
+    sample, numpy's own threading off (one process per granted core).  Returns (leapfrogs, seconds, repetitions)."""
+    wl, budget_s, seed = args
     import numpy as np
     from oracle import adaptation as oadapt, hmc as ohmc, nuts as onuts, prng, targets as otargets
     D = wl["D"]
     F = np.float32
-    rs = np.random.default_rng(0)
+    rs = np.random.default_rng(seed)
     if wl.get("adapt"):
         tgt = otargets.DiagGaussian(np.logspace(-1, 1, D))
         Cs, T = 64, 12
@@ -218,22 +219,45 @@ def cpu_nuts_rate(wl, budget_s=12.0):
             count["n"] += int(info.num_integration_steps.sum())
             return st, info
         t0 = time.perf_counter()
-        oadapt.window_adaptation_run(kernel, tgt, prng.key(11), q, T, shared=True)
-        t = time.perf_counter() - t0
-        return count["n"] / t, 1, f"{Cs} of {wl['C']} chains x {D} dims, first {T} of {wl['warmup_steps']} warm-up steps ({t:.1f} s)", t * 1e3, {}
+        oadapt.window_adaptation_run(kernel, tgt, prng.key(11 + seed), q, T, shared=True)
+        return count["n"], time.perf_counter() - t0, T
     tgt = otargets.Funnel(D)
     Cs = 256
     q = (0.1 * rs.standard_normal((Cs, D))).astype(F)
     st = ohmc.init(q, tgt)
-    keys = prng.split(prng.key(1), Cs)
     imm = np.ones(D, F)
     n, t0, reps = 0, time.perf_counter(), 0
     while time.perf_counter() - t0 < budget_s and reps < 20:
-        st, info = onuts.nuts_kernel(prng.split(prng.fold_in(prng.key(1), reps), Cs), st, tgt, F(wl["eps"]), imm, wl["depth"])
+        st, info = onuts.nuts_kernel(prng.split(prng.fold_in(prng.key(1 + seed), reps), Cs), st, tgt, F(wl["eps"]), imm, wl["depth"])
         n += int(info.num_integration_steps.sum())
         reps += 1
-    t = time.perf_counter() - t0
-    return n / t, 1, f"{Cs} of {wl['C']} chains x {D} dims, {reps} NUTS transition(s) ({t:.1f} s)", t / reps * 1e3, {}
+    return n, time.perf_counter() - t0, reps
+
+
+def cpu_nuts_rate(wl, budget_s=12.0):
+    """leapfrog-steps/s of the restated numpy oracle on a bounded chain sample of the NUTS workloads: one process per core
+    this job may use (scheduler affinity and cgroup quota, as for the C twin), each on its own chains; value = all
+    leapfrogs / the slowest process's time."""
+    import multiprocessing as mp
+    from oracle import cport
+    cores = max(1, cport.num_threads())
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(v, "1")           # inherited by the spawned workers: one thread per process
+    jobs = [(wl, budget_s, s) for s in range(cores)]
+    if cores == 1:
+        res = [_cpu_nuts_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_nuts_worker, jobs)
+    n = sum(r[0] for r in res)
+    t = max(r[1] for r in res)
+    reps = res[0][2]
+    D = wl["D"]
+    if wl.get("adapt"):
+        sample = f"{cores} x 64 of {wl['C']} chains x {D} dims, first {reps} of {wl['warmup_steps']} warm-up steps ({t:.1f} s)"
+    else:
+        sample = f"{cores} x 256 of {wl['C']} chains x {D} dims, {reps} NUTS transition(s) each ({t:.1f} s)"
+    return n / t, cores, sample, t / max(reps, 1) * 1e3, {}
 
 
 def cpu_hier_rate(wl, budget_s=12.0):
