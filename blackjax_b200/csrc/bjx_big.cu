@@ -1,9 +1,10 @@
-// Large rows (1024 < D <= 18432, D % 4 == 0): one CTA owns one chain and keeps the whole row triple
-// (q, p, grad) in shared memory for the entire launch -- the same "state never round-trips HBM between
-// leapfrogs" design as the warp-per-chain kernels (bjx_kernels.cuh), for rows that no longer fit a warp's
-// registers.  BASELINE config 5 (hierarchical logistic regression, D = 10000) runs here: at 3 x 40 KB of
-// shared memory per chain one CTA is resident per SM, and the step is bound by the 8*G sigmoid / softplus
-// evaluations per leapfrog (SFU), not by HBM.
+// Large rows (1024 < D <= 18432, D % 4 == 0): one CTA owns one chain and keeps the row in shared memory for the entire
+// launch -- the same "state never round-trips HBM between leapfrogs" design as the warp-per-chain kernels
+// (bjx_kernels.cuh), for rows that no longer fit a warp's registers.  The kernels shared with the plug-ins of user-defined
+// big-row targets (init, n-step leapfrog with the momentum in registers, the one-chain-per-CTA HMC transition) live in
+// bjx_big.cuh; this file holds the target-independent kernels (momentum draw, energy), the host dispatch, and BASELINE
+// config 5's transition kernel: the hierarchical logistic regression (D = 10000) with TWO chains per CTA
+// (k_big2_hmc_hier), bound by the 8 G sigmoid evaluations per leapfrog (MUFU pipe 56 %, issue slots 66 %), not by HBM.
 //
 // Same reference functions as the warp kernels: hmc.py:90-92 (init), metrics.py:260-270 (momentum draw,
 // kinetic energy), integrators.py:104-150 (velocity Verlet), hmc.py:279-312 (transition),
