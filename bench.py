@@ -240,7 +240,7 @@ def cpu_nuts_rate(wl, budget_s=12.0):
     leapfrogs / the slowest process's time."""
     import multiprocessing as mp
     from oracle import cport
-    cores = max(1, cport.num_threads())
+    cores = max(1, min(cport.num_threads(), 32))   # (32 processes bound the arm's memory and start-up time on big hosts)
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ.setdefault(v, "1")           # inherited by the spawned workers: one thread per process
     jobs = [(wl, budget_s, s) for s in range(cores)]
